@@ -1,0 +1,144 @@
+/*
+ * polymc.h — C ABI of libpolymc_b200.so: the B200 (sm_100a) fixed-force-ensemble MCMC hot path
+ * of grasingerm/polymer-stats, i.e. everything inside `mcmc(nsteps, pargs)` of
+ * mcmc_eap_chain.jl:171-376 for thousands of independent chains at once.
+ *
+ * The reference has no FFI of its own (pure Julia).  The seams this ABI replaces are ordinary
+ * Julia functions; each entry point below cites the one it stands in for.  A Julia host binds
+ * these with `ccall` (see INTEGRATION.md and polymer-stats_b200/julia/mcmc_eap_chain.jl); the
+ * Python host in polymer-stats_b200/polymc/ binds them with ctypes.
+ *
+ * Conventions
+ *   - plain C, POD only; the caller owns every host buffer and passes pointer + implied length;
+ *     the library owns all device memory behind the opaque handle.
+ *   - every function returns 0 on success or a negative pmc_status; the message for the calling
+ *     thread is available from pmc_last_error().  No exception or exit() crosses the boundary.
+ *   - calls are synchronous (they return after the stream work has completed) and a handle is
+ *     not re-entrant, like the single-threaded reference (`julia -t 1`).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     PMC_ERR_NO_DEVICE.
+ *   - monomer indices are 0-based at this boundary (the Julia host passes idx-1).
+ *   - one handle holds chains of ONE chain length n and ONE energy type (they select the
+ *     kernel); all other parameters may differ per case.  Hosts bucket mixed sweeps by (n, energy).
+ */
+#ifndef POLYMC_H
+#define POLYMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMC_ABI_VERSION 1
+
+typedef enum pmc_status {
+  PMC_OK = 0,
+  PMC_ERR_INVALID = -1,    /* bad argument / unsupported option combination        */
+  PMC_ERR_NO_DEVICE = -2,  /* no CUDA device, or device index out of range         */
+  PMC_ERR_CUDA = -3,       /* a CUDA runtime call or kernel failed                 */
+  PMC_ERR_NOMEM = -4,      /* host or device allocation failed                     */
+  PMC_ERR_UNSUPPORTED = -5 /* chain too long for one CTA's shared memory, etc.     */
+} pmc_status;
+
+/* --chain-type (mcmc_eap_chain.jl:25-28; inc/eap_chain.jl:81-87) */
+enum { PMC_CHAIN_DIELECTRIC = 0, PMC_CHAIN_POLAR = 1 };
+/* --energy-type (mcmc_eap_chain.jl:41-44; inc/eap_chain.jl:95-105; "Ising" is accepted by the ctor) */
+enum { PMC_ENERGY_NONINTERACTING = 0, PMC_ENERGY_INTERACTING = 1, PMC_ENERGY_ISING = 2 };
+
+/* One case = one command line of mcmc_eap_chain.jl (ArgParse table :19-153). */
+typedef struct pmc_case {
+  double E0, K1, K2, mu, kT, Fz, Fx, b;   /* --E0 --K1 --K2 --mu --kT --Fz --Fx --mlen            */
+  double phi_step, theta_step;            /* --phi-step --theta-step                              */
+  double adj_lb, adj_ub, adj_scale;       /* --step-adjust-lb/-ub/-scale (scale 1.0 disables)     */
+  int64_t n;                              /* --num-monomers                                       */
+  int64_t steps_per_adjust;               /* --steps-per-adjust                                   */
+  int32_t chain_type;                     /* PMC_CHAIN_*                                          */
+  int32_t energy_type;                    /* PMC_ENERGY_*                                         */
+  int32_t do_flips;                       /* --do-flips                                           */
+  int32_t umbrella;                       /* --umbrella-sampling                                  */
+  int32_t force_init;                     /* --force-init                                         */
+  int32_t reserved;                       /* must be 0                                            */
+} pmc_case;
+
+typedef struct pmc_handle pmc_handle;
+
+/* ---- library / device ------------------------------------------------------------------ */
+int32_t pmc_abi_version(void);
+const char* pmc_last_error(void);                 /* replaces Julia `error(...)` text, mcmc_eap_chain.jl:184,195 */
+int32_t pmc_device_count(int32_t* count);
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* Builds ncases*replicas_per_case chains on CUDA device `device` and draws their random initial
+ * state (phi~U(0,2pi), theta~U(0,pi)) — replaces `EAPChain(pargs)`, inc/eap_chain.jl:60-135, and
+ * the set-up half of mcmc(), mcmc_eap_chain.jl:171-265.  Chain c belongs to case c/replicas_per_case.
+ * Its Philox stream is keyed by (seed, chain_id_base + c), so results do not depend on how a sweep
+ * is sharded over GPUs. */
+int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_case, uint64_t seed,
+                   int32_t device, uint32_t chain_id_base, pmc_handle** out);
+void pmc_destroy(pmc_handle* h);
+int64_t pmc_num_chains(const pmc_handle* h);
+int64_t pmc_num_monomers(const pmc_handle* h);
+/* Work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
+int32_t pmc_set_stream(pmc_handle* h, void* cuda_stream);
+
+/* ---- state ------------------------------------------------------------------------------ */
+/* Overwrite / read the independent state (phi, theta), n doubles each — the fields `ϕs`, `θs` of
+ * EAPChain (inc/eap_chain.jl:22,25); all caches are rebuilt on device.  *_all: [chains][n]. */
+int32_t pmc_set_state(pmc_handle* h, int64_t chain, const double* phi, const double* theta);
+int32_t pmc_get_state(pmc_handle* h, int64_t chain, double* phi, double* theta);
+int32_t pmc_set_state_all(pmc_handle* h, const double* phi, const double* theta);
+int32_t pmc_get_state_all(pmc_handle* h, double* phi, double* theta);
+
+/* ---- energies (parity seams) ------------------------------------------------------------ */
+/* out[4] = {U, sum(us), U_dipole_dipole, Omega}: `U(chain)` inc/eap_chain.jl:411 → inc/energy.jl:7-23
+ * with U_interaction :196-211 / U_Ising :215-228; Omega = Σ log sin θ (fix of :117). */
+int32_t pmc_energy(pmc_handle* h, int64_t chain, double out[4]);
+int32_t pmc_energy_all(pmc_handle* h, double* out /* [chains][4] */);
+/* Observables of the current state: out[6] = {r1,r2,r3,p1,p2,p3} — end_to_end :405, chain_μ :408. */
+int32_t pmc_observables(pmc_handle* h, int64_t chain, double out[6]);
+/* Energy change of the single-monomer trial `move!(trial, idx, dphi, dtheta)` (inc/eap_chain.jl:230-257)
+ * WITHOUT mutating the chain: out[3] = {dU, dOmega, theta_was_clamped}.  Same device code as pmc_run. */
+int32_t pmc_delta_u(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, double dtheta, double out[3]);
+
+/* ---- the hot loop ------------------------------------------------------------------------ */
+/* Runs `nsteps` Metropolis trials on every chain — the `for step=1:nsteps` loop,
+ * mcmc_eap_chain.jl:276-350: proposal :277-280, ΔU (replacing the deep copy + full recompute
+ * :281-283), Metropolis inc/acceptance.jl:29-37, step adaptation :301-322, the 8 averagers
+ * :327-328 (inc/average.jl:40-48, umbrella :63-97) and, every `stepout` steps, one trajectory row
+ * (step,r1..3,p1..3,U) :330-333 and one rolling row (step + 16 running averages) :334-346.
+ * traj: [chains][rows][8], roll: [chains][rows][17], rows = number of multiples of stepout in
+ * (step0, step0+nsteps]; either may be NULL (rows are then left on the device).  stepout<=0: no rows.
+ * The step counter continues across calls within one init. */
+int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll);
+int64_t pmc_rows_for(const pmc_handle* h, int64_t nsteps, int64_t stepout);
+/* Device time of the last pmc_run's MCMC kernel, CUDA events on the handle's stream. */
+int32_t pmc_last_run_ms(const pmc_handle* h, float* ms);
+
+/* Re-initialisation between inits, mcmc_eap_chain.jl:352-361 (metropolis_acc, inc/acceptance.jl:1-3):
+ * draws a fresh random chain per chain and swaps it in iff force_init or
+ * eps <= exp(-dU/kT) Π sinθ_new / Π sinθ_old.  replaced: [chains] 0/1, may be NULL.  Restarts the
+ * step counter; accumulators keep accumulating. */
+int32_t pmc_reinit(pmc_handle* h, int32_t* replaced);
+
+/* ---- results ----------------------------------------------------------------------------- */
+/* get_avg of the 8 averagers (inc/average.jl:38): avg [chains][16] in rolling.csv column order
+ * (r1,r2,r3,r1sq,r2sq,r3sq,rsq,p1,p2,p3,p1sq,p2sq,p3sq,psq,U,Usq); acc_rate [chains] = nacc_total /
+ * trials (mcmc_eap_chain.jl:365); normalizer [chains] = Σ of averaging weights (trial count unless
+ * umbrella).  Any pointer may be NULL. */
+int32_t pmc_averages(pmc_handle* h, double* avg, double* acc_rate, double* normalizer);
+/* Raw accumulators for pooling replicas exactly: sums [chains][17] (16 sums + normaliser). */
+int32_t pmc_accumulators(pmc_handle* h, double* sums);
+/* diag [chains][8] = {phi_step, theta_step, nacc, natt, nacc_total, trials, U_running, max |U_running -
+ * U_recomputed| seen at re-synchronisation}. */
+int32_t pmc_diagnostics(pmc_handle* h, double* diag);
+
+/* ---- measurement helper ------------------------------------------------------------------ */
+/* Dependent-free DFMA loop on all SMs of `device`; returns achieved FP64 TFLOP/s (2 flop per DFMA)
+ * and the device time in ms.  Used by bench.py as the measured FP64 roofline denominator. */
+int32_t pmc_fp64_peak_probe(int32_t device, int32_t iters, double* tflops, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYMC_H */

@@ -1,0 +1,78 @@
+"""Closed-form (quadrature) ensemble averages for NON-INTERACTING chains — pin P2 of SURVEY.md §8c.
+
+TEST INFRASTRUCTURE ONLY (same rule as oracle.py).
+
+With `--energy-type noninteracting` (inc/energy.jl:7-9) the chain energy is a sum of
+single-monomer terms e(θ,ϕ) = u(θ) − b (Fx n̂x + Fz n̂z), u = −½ E0 μz (inc/eap_chain.jl:53),
+so the monomers are independent with density ∝ sinθ · exp(−e/kT) on the sphere.  The sampler
+clamps θ to [0,π] (eap_chain.jl:236), and a clamped proposal has sinθ = 0 (or 1.2e-16) and is
+rejected, which is plain Metropolis on the restricted domain — the target density is unchanged.
+
+For E0 = 0, Fx = 0 the result reduces to the Langevin function ⟨cosθ⟩ = coth f − 1/f, f = bFz/kT
+(the inverse of which the reference approximates in inc/langevin.jl:1-3).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _mu(x, sth, cph, sph, *, chain_type, E0, K1, K2, mu):
+    """Dipole response, inc/dipole_response.jl:7-11 (dielectric) / :27-29 with M = mu·I (polar)."""
+    nx, ny, nz = cph * sth, sph * sth, x
+    if chain_type == "dielectric":
+        f = (K1 - K2) * E0 * x
+        return f * nx, f * ny, f * nz + K2 * E0
+    return mu * nx, mu * ny, mu * nz
+
+
+def single_monomer_moments(*, chain_type="dielectric", E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0,
+                           Fz=0.0, Fx=0.0, b=1.0, nx_quad=400, nphi_quad=256):
+    """Moments of one monomer under density ∝ exp(−e/kT) dx dϕ (x = cosθ).
+
+    Gauss–Legendre in x, periodic trapezoid in ϕ (spectrally accurate)."""
+    xs, wx = np.polynomial.legendre.leggauss(nx_quad)
+    ph = np.arange(nphi_quad) * (2 * np.pi / nphi_quad)
+    X, P = np.meshgrid(xs, ph, indexing="ij")
+    W = wx[:, None] * np.full_like(P, 2 * np.pi / nphi_quad)
+    sth = np.sqrt(np.maximum(0.0, 1 - X * X))
+    cph, sph = np.cos(P), np.sin(P)
+    mx, my, mz = _mu(X, sth, cph, sph, chain_type=chain_type, E0=E0, K1=K1, K2=K2, mu=mu)
+    nx, ny, nz = cph * sth, sph * sth, X
+    e = -0.5 * E0 * mz - b * (Fx * nx + Fz * nz)
+    logw = -e / kT
+    logw -= logw.max()
+    dens = np.exp(logw) * W
+    Z = dens.sum()
+
+    def avg(f):
+        return float((f * dens).sum() / Z)
+
+    return {
+        "n": np.array([avg(nx), avg(ny), avg(nz)]),
+        "n2": np.array([avg(nx * nx), avg(ny * ny), avg(nz * nz)]),
+        "mu": np.array([avg(mx), avg(my), avg(mz)]),
+        "mu2": np.array([avg(mx * mx), avg(my * my), avg(mz * mz)]),
+        "e": avg(e),
+        "e2": avg(e * e),
+    }
+
+
+def chain_averages(n, **kw):
+    """The 16 averages in rolling.csv order (mcmc_eap_chain.jl:259) for n independent monomers."""
+    b = kw.get("b", 1.0)
+    m = single_monomer_moments(**kw)
+    r = n * b * m["n"]
+    rj2 = b * b * (n * m["n2"] + n * (n - 1) * m["n"] ** 2)
+    p = n * m["mu"]
+    pj2 = n * m["mu2"] + n * (n - 1) * m["mu"] ** 2
+    U = n * m["e"]
+    U2 = n * (m["e2"] - m["e"] ** 2) + (n * m["e"]) ** 2
+    return np.concatenate([r, rj2, [rj2.sum()], p, pj2, [pj2.sum()], [U, U2]])
+
+
+def langevin(f):
+    """⟨cosθ⟩ of a freely-jointed monomer under reduced force f = bF/kT: coth f − 1/f."""
+    f = np.asarray(f, dtype=float)
+    small = np.abs(f) < 1e-4
+    fs = np.where(small, 1.0, f)
+    return np.where(small, f / 3 - f ** 3 / 45, 1 / np.tanh(fs) - 1 / fs)

@@ -1,0 +1,240 @@
+// chain_math.cuh — device-side chain physics shared by every kernel of libpolymc_b200.
+//
+// Restates, for one monomer / one pair at a time, the arithmetic of
+//   inc/eap_chain.jl:40-58 (n̂, u), :200-207 (pair term), :230-257 (move!),
+//   inc/dipole_response.jl:7-29, inc/acceptance.jl:29-37, mcmc_eap_chain.jl:277-280
+// in the changed-pair ΔU form of SURVEY.md §8a.  All arithmetic is FP64.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pmc {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kInv4Pi = 0.07957747154594767;  // 1/(4π), hoisted out of the pair term
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Same stream definition as oracle/polymc_oracle.c:
+//   key = (seed_lo, seed_hi), counter = (pos_lo, pos_hi, chain_id, (init << 8) | sub)
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { SUB_STEP_A = 0, SUB_STEP_B = 1, SUB_INIT = 2, SUB_REINIT = 3 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint4 philox_at(uint64_t seed, uint32_t chain_id, uint32_t init, uint32_t sub,
+                                           uint64_t pos) {
+  return philox4x32_10(make_uint4((uint32_t)pos, (uint32_t)(pos >> 32), chain_id, (init << 8) | sub),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
+  const uint64_t v = ((uint64_t)hi << 32) | lo;
+  return (double)(v >> 11) * 0x1.0p-53;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-monomer record in HBM.  (phi, theta) is the independent state (EAPChain.ϕs/θs,
+// eap_chain.jl:22,25); n̂ and sinθ are the caches a proposal needs (n̂s, sθs, :27,:28).
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) MonoRec {
+  double phi, theta;
+  double nx, ny;
+  double nz, sth;
+};
+
+// Per-chain constants (one case of the sweep).
+struct ChainParams {
+  double alpha, beta, m;  // μ = (alpha·n̂z + m)·n̂ + beta·ẑ : dielectric alpha=(K1-K2)E0, beta=K2·E0; polar m=mu
+  double E0, kT, inv_kT, Fz, Fx, b;
+  double adj_lb, adj_ub, adj_scale;
+  double cF;              // 0.2 + 0.8 exp(-(Fx²+Fz²)/kT), average.jl:121-122
+  double gauge0;          // log_gauge without Ω0: -(K1+2K2)E0² n/(3kT)  or  -mu·E0·n/(3kT) (average.jl:109-118)
+  double phi_step0, theta_step0;
+  long long steps_per_adjust;
+  int do_flips, umbrella, force_init, pad;
+};
+
+constexpr int kNumAcc = 17;  // 16 sums (rolling.csv order) + normaliser
+
+// Per-chain mutable scalars.
+struct ChainDyn {
+  double U, Omega, su;    // running energy, Σ log sinθ, Σ u_i
+  double r[3], p[3];      // end-to-end vector, net dipole
+  double phi_step, theta_step;
+  double log_gauge;       // AntiDipoleWeightFunction.log_gauge (fixed at construction)
+  double drift_max;       // max |U_running - U_recomputed| seen at re-synchronisation
+  double acc[kNumAcc], comp[kNumAcc];  // Neumaier-compensated sums
+  long long nacc, natt, nacc_total, steps_total, step;
+  int init, valid;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Small math helpers
+// ---------------------------------------------------------------------------------------------
+// 1/sqrt(x) to ≈1 ulp: MUFU.RSQ64H seed + one cubically convergent correction
+//   y ← y (1 + e/2 + 3e²/8), e = 1 - x y²   (seed error ≲2^-20 ⇒ result error ≲2^-60).
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y * y, 1.0);
+  const double t = fma(e, 0.375, 0.5);
+  return fma(y * e, t, y);
+}
+
+// 4π × one dipole-dipole pair term (eap_chain.jl:200-207): μa·μb/r³ − 3(μa·r)(μb·r)/r⁵.
+__device__ __forceinline__ double pair_g(double ax, double ay, double az, double bx, double by, double bz,
+                                         double rx, double ry, double rz) {
+  const double r2 = fma(rz, rz, fma(ry, ry, rx * rx));
+  const double mm = fma(az, bz, fma(ay, by, ax * bx));
+  const double a = fma(az, rz, fma(ay, ry, ax * rx));
+  const double b = fma(bz, rz, fma(by, ry, bx * rx));
+  const double y = rsqrt_fast(r2);
+  const double y2 = y * y;
+  const double t = fma(-3.0 * a * b, y2, mm);
+  return t * (y2 * y);
+}
+
+__device__ __forceinline__ void mu_of(const ChainParams& P, double nx, double ny, double nz, double& mx,
+                                      double& my, double& mz) {
+  const double f = P.alpha * nz + P.m;
+  mx = f * nx;
+  my = f * ny;
+  mz = f * nz + P.beta;
+}
+
+// Neumaier compensated add: (s, c) += v.
+__device__ __forceinline__ void comp_add(double& s, double& c, double v) {
+  const double t = s + v;
+  c += (fabs(s) >= fabs(v)) ? ((s - t) + v) : ((v - t) + s);
+  s = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One trial move of monomer idx (steps 1-4 of SURVEY Appendix A).
+// ---------------------------------------------------------------------------------------------
+struct Proposal {
+  double nx, ny, nz;      // n̂'
+  double mx, my, mz;      // μ'
+  double dnx, dny, dnz;   // Δn̂
+  double dmx, dmy, dmz;   // Δμ
+  double phi, theta, sth; // new angles and sinθ'
+  double du, drF, dOmega; // Δu_idx, −b(FxΔn̂x+FzΔn̂z), log(sinθ'/sinθ)
+  double single;          // −(du+drF)/kT + dΩ [+ Δw]: everything but the pair sum
+  double eps;
+  int idx;
+  int skip;               // sinθ' == 0 ⇒ logπ' = −Inf ⇒ certain rejection (eap_chain.jl:236-238)
+  int clamped;
+  int pad;
+};
+
+// Raw random draws of one trial: idx, dϕ, [Bool], dθ, ϵ (mcmc_eap_chain.jl:277-280,287).
+struct Draws {
+  double u_phi, u_theta, eps;
+  int idx, flipbit;
+};
+
+__device__ __forceinline__ Draws draw_step(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
+                                           int n) {
+  const uint4 a = philox_at(seed, chain_id, init, SUB_STEP_A, (uint64_t)step);
+  const uint4 b = philox_at(seed, chain_id, init, SUB_STEP_B, (uint64_t)step);
+  Draws d;
+  const uint64_t v = ((uint64_t)a.y << 32) | a.x;
+  d.idx = (int)__umul64hi(v, (uint64_t)n);
+  d.u_phi = u53(a.z, a.w);
+  d.flipbit = (int)(a.z & 1u);
+  d.u_theta = u53(b.x, b.y);
+  d.eps = u53(b.z, b.w);
+  return d;
+}
+
+// move! up to the energy (eap_chain.jl:232-251) for given increments.
+__device__ __forceinline__ void build_proposal(const ChainParams& P, const MonoRec& rec, int idx, double dphi,
+                                               double dtheta, double eps, Proposal& q) {
+  q.idx = idx;
+  q.eps = eps;
+  q.phi = rec.phi + dphi;  // never wrapped (:232)
+  const double traw = rec.theta + dtheta;
+  q.theta = fmin(kPi, fmax(0.0, traw));  // clamped, not reflected (:236)
+  q.clamped = (q.theta != traw);
+  double sph, cph, sth, cth;
+  sincos(q.phi, &sph, &cph);
+  sincos(q.theta, &sth, &cth);
+  q.sth = sth;
+  q.nx = cph * sth;
+  q.ny = sph * sth;
+  q.nz = cth;
+  mu_of(P, q.nx, q.ny, q.nz, q.mx, q.my, q.mz);
+  double omx, omy, omz;
+  mu_of(P, rec.nx, rec.ny, rec.nz, omx, omy, omz);
+  q.dnx = q.nx - rec.nx;
+  q.dny = q.ny - rec.ny;
+  q.dnz = q.nz - rec.nz;
+  q.dmx = q.mx - omx;
+  q.dmy = q.my - omy;
+  q.dmz = q.mz - omz;
+  q.dOmega = log(sth / rec.sth);                       // :238
+  q.du = -0.5 * P.E0 * q.mz - (-0.5 * P.E0 * omz);     // u = −½E0μz, :53
+  q.drF = -P.b * (q.dnx * P.Fx + q.dnz * P.Fz);        // −Δr·F, energy.jl:8
+  const double dw = P.umbrella ? q.du * P.inv_kT * P.cF : 0.0;  // average.jl:120-124
+  q.single = -(q.du + q.drF) * P.inv_kT + q.dOmega + dw;
+  q.skip = (sth == 0.0);
+}
+
+// Proposal increments from raw draws: rand(Uniform(-s,s)) = -s + 2s·u (mcmc_eap_chain.jl:278-280).
+__device__ __forceinline__ void increments(const ChainParams& P, const Draws& d, double theta_old,
+                                           double phi_step, double theta_step, double& dphi, double& dtheta) {
+  dphi = -phi_step + (2.0 * phi_step) * d.u_phi;
+  dtheta = ((P.do_flips && d.flipbit) ? kPi - 2.0 * theta_old : 0.0) + (-theta_step + (2.0 * theta_step) * d.u_theta);
+}
+
+// Metropolis on Δlogπ (acceptance.jl:32): NaN and −Inf both reject.
+__device__ __forceinline__ bool metropolis(double dlogpi, double eps) {
+  return (dlogpi >= 0.0) || (eps < exp(dlogpi));
+}
+
+// Step-size adaptation, mcmc_eap_chain.jl:301-322 (counters reset only when a change fires).
+__device__ __forceinline__ void adapt_steps(const ChainParams& P, long long step, double& phi_step,
+                                            double& theta_step, long long& nacc, long long& natt) {
+  if (P.adj_scale != 1.0 && P.steps_per_adjust > 0 && step % P.steps_per_adjust == 0) {
+    const double ratio = (double)nacc / (double)natt;
+    if (ratio > P.adj_ub && phi_step != kPi && theta_step != kPi / 2) {
+      nacc = 0;
+      natt = 0;
+      phi_step = fmin(kPi, phi_step * P.adj_scale);
+      theta_step = fmin(kPi / 2, theta_step * P.adj_scale);
+    } else if (ratio < P.adj_lb) {
+      nacc = 0;
+      natt = 0;
+      phi_step /= P.adj_scale;
+      theta_step /= P.adj_scale;
+    }
+  }
+}
+
+// record! of the 8 averagers (average.jl:40-48; umbrella :63-73) on the current state.
+__device__ __forceinline__ void record_averages(const ChainParams& P, double* acc, double* comp,
+                                                const double* r, const double* p, double U, double su,
+                                                double log_gauge) {
+  double wgt = 1.0;
+  if (P.umbrella) wgt = 1.0 / exp(su * P.inv_kT * P.cF - log_gauge);
+  const double v[kNumAcc] = {r[0], r[1], r[2], r[0] * r[0], r[1] * r[1], r[2] * r[2],
+                             r[0] * r[0] + r[1] * r[1] + r[2] * r[2],
+                             p[0], p[1], p[2], p[0] * p[0], p[1] * p[1], p[2] * p[2],
+                             p[0] * p[0] + p[1] * p[1] + p[2] * p[2],
+                             U, U * U, 1.0};
+#pragma unroll
+  for (int k = 0; k < kNumAcc; ++k) comp_add(acc[k], comp[k], v[k] * wgt);
+}
+
+}  // namespace pmc

@@ -1,0 +1,532 @@
+// cta_kernels.cuh — one CTA per chain: the interacting (all-pairs dipole-dipole) hot path.
+//
+// The chain (positions x, dipoles μ; eap_chain.jl:31,33 `μs`, `xs`) is staged in shared memory as
+// SoA FP64 arrays.  A single-monomer rotation at idx translates the whole tail j>idx rigidly
+// (positions are a cumulative sum of directions, eap_chain.jl:49-51), so the exact energy change
+// touches the row {idx}×rest and the rectangle heads(i<idx)×tails(j>idx) — (idx)(n-1-idx)+(n-1)
+// pairs.  The rectangle is flattened over the CTA's warps: one side of the
+// rectangle is held in registers one item per lane, the other side is read from shared memory as
+// warp-wide broadcasts, and the partial sums are reduced with warp shuffles.
+#pragma once
+
+#include "chain_math.cuh"
+
+namespace pmc {
+
+constexpr int kPartDoubles = 96;  // 3 × 32 warp partials (block scan of n̂ needs three)
+constexpr int kRowDoubles = 26;   // 8 trajectory + 17 rolling values (+1 pad)
+
+struct CtaView {
+  double *sx, *sy, *sz;   // positions x_i (eap_chain.jl:49-51)
+  double *mx, *my, *mz;   // dipoles μ_i
+  double *E;              // μ_B · D_eff of the broadcast-side items of the current trial
+  double *part;           // warp partial sums
+  double *rowbuf;         // staging of one output row
+  Proposal* prop;         // [2] ping-pong
+  ChainDyn* dyn;
+  ChainParams* par;
+};
+
+__host__ __device__ inline size_t cta_smem_bytes(int n) {
+  size_t b = (size_t)7 * n * sizeof(double);
+  b += (kPartDoubles + kRowDoubles) * sizeof(double);
+  b += 2 * sizeof(Proposal) + sizeof(ChainDyn) + sizeof(ChainParams);
+  return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ CtaView carve(unsigned char* base, int n) {
+  CtaView S;
+  double* d = reinterpret_cast<double*>(base);
+  S.sx = d; S.sy = d + n; S.sz = d + 2 * n;
+  S.mx = d + 3 * n; S.my = d + 4 * n; S.mz = d + 5 * n;
+  S.E = d + 6 * n;
+  S.part = d + 7 * n;
+  S.rowbuf = S.part + kPartDoubles;
+  S.prop = reinterpret_cast<Proposal*>(S.rowbuf + kRowDoubles);
+  S.dyn = reinterpret_cast<ChainDyn*>(S.prop + 2);
+  S.par = reinterpret_cast<ChainParams*>(S.dyn + 1);
+  return S;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA, result in every thread.  `trailing_sync` protects `part` for immediate reuse.
+template <int T>
+__device__ __forceinline__ double block_sum(double v, double* part, bool trailing_sync = true) {
+  constexpr int W = T / 32;
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) s += part[w];
+  if (trailing_sync) __syncthreads();
+  return s;
+}
+
+// Stage one chain: x = b(cumsum(n̂) − n̂/2) (update_xs!, eap_chain.jl:49-51) by a block scan, and
+// μ (dipole_response.jl).  Ends with a barrier.
+template <int T>
+__device__ void load_chain(const MonoRec* __restrict__ mono, const ChainParams& P, int n, const CtaView& S) {
+  constexpr int W = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = (n + T - 1) / T;
+  const int i0 = min(n, tid * C), i1 = min(n, i0 + C);
+  double lx = 0, ly = 0, lz = 0;
+  for (int i = i0; i < i1; ++i) {
+    lx += mono[i].nx;
+    ly += mono[i].ny;
+    lz += mono[i].nz;
+  }
+  // inclusive warp scan
+  double ix = lx, iy = ly, iz = lz;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double tx = __shfl_up_sync(0xffffffffu, ix, o);
+    const double ty = __shfl_up_sync(0xffffffffu, iy, o);
+    const double tz = __shfl_up_sync(0xffffffffu, iz, o);
+    if (lane >= o) { ix += tx; iy += ty; iz += tz; }
+  }
+  if (lane == 31) { S.part[warp] = ix; S.part[32 + warp] = iy; S.part[64 + warp] = iz; }
+  __syncthreads();
+  double ox = 0, oy = 0, oz = 0;
+  for (int w = 0; w < warp && w < W; ++w) { ox += S.part[w]; oy += S.part[32 + w]; oz += S.part[64 + w]; }
+  double sxx = ox + (ix - lx), syy = oy + (iy - ly), szz = oz + (iz - lz);  // exclusive prefix
+  for (int i = i0; i < i1; ++i) {
+    const MonoRec r = mono[i];
+    sxx += r.nx; syy += r.ny; szz += r.nz;
+    S.sx[i] = P.b * (sxx - 0.5 * r.nx);
+    S.sy[i] = P.b * (syy - 0.5 * r.ny);
+    S.sz[i] = P.b * (szz - 0.5 * r.nz);
+    double ux, uy, uz;
+    mu_of(P, r.nx, r.ny, r.nz, ux, uy, uz);
+    S.mx[i] = ux; S.my[i] = uy; S.mz[i] = uz;
+  }
+  __syncthreads();
+}
+
+// 4π × dipole-dipole energy of the staged chain: U_interaction (eap_chain.jl:196-211) or
+// U_Ising (:215-228).  Result in every thread.
+template <int T>
+__device__ double cta_pair_energy(const CtaView& S, int n, int energy_type) {
+  constexpr int W = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double acc = 0.0;
+  if (energy_type == 1) {
+    for (int i = warp; i < n - 1; i += W) {
+      const double xi = S.sx[i], yi = S.sy[i], zi = S.sz[i];
+      const double ax = S.mx[i], ay = S.my[i], az = S.mz[i];
+      for (int j = i + 1 + lane; j < n; j += 32)
+        acc += pair_g(ax, ay, az, S.mx[j], S.my[j], S.mz[j], xi - S.sx[j], yi - S.sy[j], zi - S.sz[j]);
+    }
+  } else if (energy_type == 2) {
+    for (int i = tid; i < n - 1; i += T)
+      acc += pair_g(S.mx[i], S.my[i], S.mz[i], S.mx[i + 1], S.my[i + 1], S.mz[i + 1],
+                    S.sx[i] - S.sx[i + 1], S.sy[i] - S.sy[i + 1], S.sz[i] - S.sz[i + 1]);
+  }
+  return block_sum<T>(acc, S.part);
+}
+
+// The rectangle heads×tails, 43 FP64 instructions per pair (old and new energy of one pair):
+//   lane item L in registers (x_L, μ_L, −3μ_L, cL = −3μ_L·D), broadcast item B from shared memory
+//   (x_B, μ_B, eB = μ_B·D);  r = x_L − x_B,  r' = r − D;
+//   μ_L·r' = μ_L·r − μ_L·D and μ_B·r' = μ_B·r − eB save two dot products;
+//   g = y³(μ_L·μ_B + (−3μ_L·r)(μ_B·r) y²),  y = 1/|r|.
+template <int T>
+__device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, int baseB, int B, double Dx,
+                                           double Dy, double Dz) {
+  constexpr int W = T / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = (A + 31) >> 5;
+  const int U = G * B;
+  int u = (int)(((long long)U * warp) / W);
+  const int u1 = (int)(((long long)U * (warp + 1)) / W);
+  double acc = 0.0;
+  if (u >= u1) return acc;
+  int g = u / B;
+  int k = u - g * B;
+  while (u < u1) {
+    const int li = g * 32 + lane;
+    const bool valid = li < A;
+    const int L = baseA + min(li, A - 1);
+    const double xL = S.sx[L], yL = S.sy[L], zL = S.sz[L];
+    const double ax = S.mx[L], ay = S.my[L], az = S.mz[L];
+    const double tx = -3.0 * ax, ty = -3.0 * ay, tz = -3.0 * az;
+    const double cL = fma(tz, Dz, fma(ty, Dy, tx * Dx));
+    const int kend = min(B, k + (u1 - u));
+    u += kend - k;
+    double a0 = 0.0, a1 = 0.0;
+    const double* __restrict__ bxp = S.sx + baseB;
+    const double* __restrict__ byp = S.sy + baseB;
+    const double* __restrict__ bzp = S.sz + baseB;
+    const double* __restrict__ mxp = S.mx + baseB;
+    const double* __restrict__ myp = S.my + baseB;
+    const double* __restrict__ mzp = S.mz + baseB;
+    const double* __restrict__ ep = S.E + baseB;
+#define PMC_RECT_PAIR(KK, ACC)                                                      \
+  {                                                                                 \
+    const double rx = xL - bxp[KK], ry = yL - byp[KK], rz = zL - bzp[KK];           \
+    const double ux = mxp[KK], uy = myp[KK], uz = mzp[KK];                          \
+    const double mm = fma(az, uz, fma(ay, uy, ax * ux));                            \
+    const double r2 = fma(rz, rz, fma(ry, ry, rx * rx));                            \
+    const double a3 = fma(tz, rz, fma(ty, ry, tx * rx));                            \
+    const double bb = fma(uz, rz, fma(uy, ry, ux * rx));                            \
+    const double qx = rx - Dx, qy = ry - Dy, qz = rz - Dz;                          \
+    const double q2 = fma(qz, qz, fma(qy, qy, qx * qx));                            \
+    const double a3n = a3 - cL;                                                     \
+    const double bn = bb - ep[KK];                                                  \
+    const double y = rsqrt_fast(r2);                                                \
+    const double yn = rsqrt_fast(q2);                                               \
+    const double y2 = y * y, yn2 = yn * yn;                                         \
+    const double t = fma(a3 * bb, y2, mm);                                          \
+    const double tn = fma(a3n * bn, yn2, mm);                                       \
+    ACC = fma(tn, yn2 * yn, ACC);                                                   \
+    ACC = fma(-t, y2 * y, ACC);                                                     \
+  }
+    for (; k + 1 < kend; k += 2) {
+      PMC_RECT_PAIR(k, a0)
+      PMC_RECT_PAIR(k + 1, a1)
+    }
+    if (k < kend) PMC_RECT_PAIR(k, a0)
+#undef PMC_RECT_PAIR
+    acc += valid ? (a0 + a1) : 0.0;
+    k = 0;
+    ++g;
+  }
+  return acc;
+}
+
+// 4π × Σ over changed pairs of (new − old), summed over the CTA (result in every thread).
+// Contains two barriers (after E, and inside the reduction); no trailing barrier.
+template <int T>
+__device__ __forceinline__ double cta_delta_pairs(const CtaView& S, int n, int energy_type, double b, int idx,
+                                                  double npx, double npy, double npz,   // μ'
+                                                  double dnx, double dny, double dnz) { // Δn̂
+  const int tid = threadIdx.x;
+  const double Dx = b * dnx, Dy = b * dny, Dz = b * dnz;  // tail translation
+  const double hx = 0.5 * Dx, hy = 0.5 * Dy, hz = 0.5 * Dz;
+  const int H = idx, Tl = n - 1 - idx;
+  // lane side = the one that wastes fewer lanes
+  bool rect = (energy_type == 1) && H > 0 && Tl > 0;
+  bool lanes_are_heads = true;
+  if (rect) {
+    const long long costH = (long long)((H + 31) >> 5) * Tl;
+    const long long costT = (long long)((Tl + 31) >> 5) * H;
+    lanes_are_heads = costH <= costT;
+  }
+  // D_eff: r = x_L − x_B.  L=head,B=tail: r' = r − D.  L=tail,B=head: r' = r + D.
+  const double sgn = lanes_are_heads ? 1.0 : -1.0;
+  const double ex = sgn * Dx, ey = sgn * Dy, ez = sgn * Dz;
+  const int baseA = lanes_are_heads ? 0 : idx + 1, A = lanes_are_heads ? H : Tl;
+  const int baseB = lanes_are_heads ? idx + 1 : 0, B = lanes_are_heads ? Tl : H;
+  if (rect)
+    for (int k = tid; k < B; k += T)
+      S.E[baseB + k] = fma(S.mz[baseB + k], ez, fma(S.my[baseB + k], ey, S.mx[baseB + k] * ex));
+  // row {idx}×rest: both μ_idx and the separation change.
+  double acc = 0.0;
+  {
+    const double xi = S.sx[idx], yi = S.sy[idx], zi = S.sz[idx];
+    const double ox = S.mx[idx], oy = S.my[idx], oz = S.mz[idx];
+    int jlo = 0, jhi = n - 1;
+    if (energy_type == 2) { jlo = max(0, idx - 1); jhi = min(n - 1, idx + 1); }
+    if (energy_type == 0) { jlo = 1; jhi = 0; }
+    for (int j = jlo + tid; j <= jhi; j += T) {
+      if (j == idx) continue;
+      const double rx = xi - S.sx[j], ry = yi - S.sy[j], rz = zi - S.sz[j];
+      const double s = (j < idx) ? 1.0 : -1.0;  // x'_idx − x'_j = r ± (b/2)Δn̂
+      const double ux = S.mx[j], uy = S.my[j], uz = S.mz[j];
+      acc += pair_g(npx, npy, npz, ux, uy, uz, fma(s, hx, rx), fma(s, hy, ry), fma(s, hz, rz)) -
+             pair_g(ox, oy, oz, ux, uy, uz, rx, ry, rz);
+    }
+  }
+  __syncthreads();  // E visible
+  if (rect) acc += rect_sum<T>(S, baseA, A, baseB, B, ex, ey, ez);
+  return block_sum<T>(acc, S.part, /*trailing_sync=*/false);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernels
+// ---------------------------------------------------------------------------------------------
+struct RunArgs {
+  MonoRec* mono;
+  const ChainParams* par;
+  ChainDyn* dyn;
+  double* traj;  // [chains][rows][8]
+  double* roll;  // [chains][rows][17]
+  long long nsteps, stepout, rows;
+  uint64_t seed;
+  uint32_t chain_id_base;
+  int n;
+  int nchains;
+  int energy_type;
+};
+
+// Thread 0: draw and build the proposal of trial `step`.
+__device__ __forceinline__ void make_proposal(const RunArgs& a, const ChainParams& P, const ChainDyn& D,
+                                              const MonoRec* mono, uint32_t chain_id, long long step,
+                                              Proposal& q) {
+  const Draws d = draw_step(a.seed, chain_id, (uint32_t)D.init, step, a.n);
+  const MonoRec rec = mono[d.idx];
+  double dphi, dtheta;
+  increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
+  build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+}
+
+// Thread 0 (lane kernel: every thread): bookkeeping after the accept/reject decision —
+// counters (mcmc_eap_chain.jl:288-292), adaptation (:301-322), averagers (:327-328).
+__device__ __forceinline__ void after_decision(const ChainParams& P, ChainDyn& D, const Proposal& q, bool accept,
+                                               double dU_pairs, long long step) {
+  if (accept) {
+    D.U += q.du + q.drF + dU_pairs;
+    D.Omega += q.dOmega;
+    D.su += q.du;
+    D.r[0] += P.b * q.dnx; D.r[1] += P.b * q.dny; D.r[2] += P.b * q.dnz;
+    D.p[0] += q.dmx; D.p[1] += q.dmy; D.p[2] += q.dmz;
+    D.nacc += 1;
+    D.nacc_total += 1;
+  }
+  D.natt += 1;
+  D.steps_total += 1;
+  D.step = step;
+  adapt_steps(P, step, D.phi_step, D.theta_step, D.nacc, D.natt);
+  record_averages(P, D.acc, D.comp, D.r, D.p, D.U, D.su, D.log_gauge);
+}
+
+__device__ __forceinline__ void stage_row(const ChainDyn& D, long long step, double* rowbuf) {
+  rowbuf[0] = (double)step;  // the reference's hcat promotes step to Float64 (mcmc_eap_chain.jl:331)
+  rowbuf[1] = D.r[0]; rowbuf[2] = D.r[1]; rowbuf[3] = D.r[2];
+  rowbuf[4] = D.p[0]; rowbuf[5] = D.p[1]; rowbuf[6] = D.p[2];
+  rowbuf[7] = D.U;
+  rowbuf[8] = (double)step;
+  const double nrm = D.acc[16] + D.comp[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) rowbuf[9 + k] = (D.acc[k] + D.comp[k]) / nrm;
+}
+
+// The hot loop (mcmc_eap_chain.jl:276-350) for one interacting chain per CTA.
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_run_cta(const RunArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = a.n;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  if (tid == 0) {
+    *S.par = a.par[c];
+    *S.dyn = a.dyn[c];
+  }
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const double b = P.b, inv_kT = P.inv_kT;
+  const long long step0 = S.dyn->step;
+  long long row = 0;
+  if (tid == 0) make_proposal(a, P, *S.dyn, mono, chain_id, step0 + 1, S.prop[1]);
+
+  for (long long s = 1; s <= a.nsteps; ++s) {
+    const long long step = step0 + s;
+    __syncthreads();  // (A) proposal of this trial and state updates of the previous one are visible
+    const Proposal* q = &S.prop[s & 1];
+    const int idx = q->idx;
+    const bool skip = q->skip;
+    const double dnx = q->dnx, dny = q->dny, dnz = q->dnz;
+    double dsum = 0.0;
+    bool accept = false;
+    if (!skip) {
+      dsum = kInv4Pi * cta_delta_pairs<T>(S, n, 1, b, idx, q->mx, q->my, q->mz, dnx, dny, dnz);
+      accept = metropolis(q->single - dsum * inv_kT, q->eps);
+    }
+    if (accept) {  // apply move!: x_idx += (b/2)Δn̂, x_{j>idx} += bΔn̂, μ_idx = μ'
+      const double Dx = b * dnx, Dy = b * dny, Dz = b * dnz;
+      for (int j = idx + 1 + tid; j < n; j += T) {
+        S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
+      }
+    }
+    if (tid == 0) {
+      if (accept) {
+        S.sx[idx] += 0.5 * b * dnx; S.sy[idx] += 0.5 * b * dny; S.sz[idx] += 0.5 * b * dnz;
+        S.mx[idx] = q->mx; S.my[idx] = q->my; S.mz[idx] = q->mz;
+        MonoRec rec;
+        rec.phi = q->phi; rec.theta = q->theta;
+        rec.nx = q->nx; rec.ny = q->ny; rec.nz = q->nz; rec.sth = q->sth;
+        mono[idx] = rec;
+      }
+      after_decision(P, *S.dyn, *q, accept, dsum, step);
+    }
+    const bool isrow = a.stepout > 0 && (step % a.stepout) == 0;
+    if (isrow && tid < 32) {
+      if (tid == 0) stage_row(*S.dyn, step, S.rowbuf);
+      __syncwarp();
+      if (row < a.rows) {
+        if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = S.rowbuf[tid];
+        if (tid < 17) a.roll[((size_t)c * a.rows + row) * 17 + tid] = S.rowbuf[8 + tid];
+      }
+      __syncwarp();
+    }
+    if (isrow) ++row;
+    if (tid == 0 && s < a.nsteps) make_proposal(a, P, *S.dyn, mono, chain_id, step + 1, S.prop[(s + 1) & 1]);
+  }
+  __syncthreads();
+  if (tid == 0) a.dyn[c] = *S.dyn;
+}
+
+// Recompute {U, Σu, U_dd, Ω, r, p} of chains from their records (EAPChain ctor tail,
+// eap_chain.jl:124-133).  Optionally writes them to out4 / obs6 and/or re-synchronises dyn.
+struct EnergyArgs {
+  const MonoRec* mono;
+  const ChainParams* par;
+  ChainDyn* dyn;
+  double* out4;  // [nchains][4] or null
+  double* obs6;  // [nchains][6] or null
+  int n, energy_type, first_chain;
+  int update_dyn, rebind_gauge;
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) k_energy_cta(const EnergyArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  const int c = a.first_chain + blockIdx.x;
+  const int tid = threadIdx.x, n = a.n;
+  const MonoRec* mono = a.mono + (size_t)c * n;
+  if (tid == 0) *S.par = a.par[c];
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  double su = 0, om = 0, px = 0, py = 0, pz = 0;
+  for (int i = tid; i < n; i += T) {
+    su += -0.5 * P.E0 * S.mz[i];
+    om += log(mono[i].sth);
+    px += S.mx[i]; py += S.my[i]; pz += S.mz[i];
+  }
+  su = block_sum<T>(su, S.part);
+  om = block_sum<T>(om, S.part);
+  px = block_sum<T>(px, S.part);
+  py = block_sum<T>(py, S.part);
+  pz = block_sum<T>(pz, S.part);
+  const double udd = kInv4Pi * cta_pair_energy<T>(S, n, a.energy_type);
+  if (tid == 0) {
+    // end_to_end (eap_chain.jl:405): x_n + (b/2) n̂_n
+    const double rx = S.sx[n - 1] + 0.5 * P.b * mono[n - 1].nx;
+    const double ry = S.sy[n - 1] + 0.5 * P.b * mono[n - 1].ny;
+    const double rz = S.sz[n - 1] + 0.5 * P.b * mono[n - 1].nz;
+    const double U = su + udd - (rx * P.Fx + rz * P.Fz);  // energy.jl:7-23
+    if (a.out4) {
+      double* o = a.out4 + (size_t)blockIdx.x * 4;
+      o[0] = U; o[1] = su; o[2] = udd; o[3] = om;
+    }
+    if (a.obs6) {
+      double* o = a.obs6 + (size_t)blockIdx.x * 6;
+      o[0] = rx; o[1] = ry; o[2] = rz; o[3] = px; o[4] = py; o[5] = pz;
+    }
+    if (a.update_dyn) {
+      ChainDyn& D = a.dyn[c];
+      if (D.valid) D.drift_max = fmax(D.drift_max, fabs(D.U - U));
+      D.U = U; D.su = su; D.Omega = om;
+      D.r[0] = rx; D.r[1] = ry; D.r[2] = rz;
+      D.p[0] = px; D.p[1] = py; D.p[2] = pz;
+      if (a.rebind_gauge || !D.valid) D.log_gauge = P.gauge0 + om;
+      D.valid = 1;
+    }
+  }
+}
+
+// Non-mutating ΔU of one scripted move on one interacting chain (same device code as k_run_cta).
+struct DeltaArgs {
+  const MonoRec* mono;
+  const ChainParams* par;
+  double* out;  // {dU, dOmega, clamped, dU_pairs}
+  int n, energy_type, chain, idx;
+  double dphi, dtheta;
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) k_delta_cta(const DeltaArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  const int tid = threadIdx.x, n = a.n;
+  const MonoRec* mono = a.mono + (size_t)a.chain * n;
+  if (tid == 0) *S.par = a.par[a.chain];
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  if (tid == 0) build_proposal(P, mono[a.idx], a.idx, a.dphi, a.dtheta, 0.0, S.prop[0]);
+  __syncthreads();
+  const Proposal* q = &S.prop[0];
+  const double dsum =
+      kInv4Pi * cta_delta_pairs<T>(S, n, a.energy_type, P.b, a.idx, q->mx, q->my, q->mz, q->dnx, q->dny, q->dnz);
+  if (tid == 0) {
+    a.out[0] = q->du + q->drF + dsum;
+    a.out[1] = q->dOmega;
+    a.out[2] = (double)q->clamped;
+    a.out[3] = dsum;
+  }
+}
+
+// Re-initialisation (mcmc_eap_chain.jl:352-361): candidate records are in `cand`.
+struct ReinitArgs {
+  MonoRec* mono;
+  const MonoRec* cand;
+  const ChainParams* par;
+  ChainDyn* dyn;
+  int* replaced;  // may be null
+  uint64_t seed;
+  uint32_t chain_id_base;
+  int n, energy_type, new_init;
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) k_reinit_cta(const ReinitArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  const int c = blockIdx.x, tid = threadIdx.x, n = a.n;
+  const MonoRec* cand = a.cand + (size_t)c * n;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  if (tid == 0) *S.par = a.par[c];
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(cand, P, n, S);
+  double su = 0, om = 0, px = 0, py = 0, pz = 0;
+  for (int i = tid; i < n; i += T) {
+    su += -0.5 * P.E0 * S.mz[i];
+    om += log(cand[i].sth);
+    px += S.mx[i]; py += S.my[i]; pz += S.mz[i];
+  }
+  su = block_sum<T>(su, S.part);
+  om = block_sum<T>(om, S.part);
+  px = block_sum<T>(px, S.part);
+  py = block_sum<T>(py, S.part);
+  pz = block_sum<T>(pz, S.part);
+  const double udd = kInv4Pi * cta_pair_energy<T>(S, n, a.energy_type);
+  const double rx = S.sx[n - 1] + 0.5 * P.b * cand[n - 1].nx;
+  const double ry = S.sy[n - 1] + 0.5 * P.b * cand[n - 1].ny;
+  const double rz = S.sz[n - 1] + 0.5 * P.b * cand[n - 1].nz;
+  const double U = su + udd - (rx * P.Fx + rz * P.Fz);
+  const ChainDyn& D0 = a.dyn[c];
+  const uint4 w = philox_at(a.seed, a.chain_id_base + (uint32_t)c, (uint32_t)a.new_init, SUB_REINIT, 0);
+  const double eps = u53(w.x, w.y);
+  // metropolis_acc (acceptance.jl:1-3) with Π sinθ written as exp(Σ log sinθ)
+  const bool take = P.force_init || (eps <= exp(-(U - D0.U) * P.inv_kT + (om - D0.Omega)));
+  __syncthreads();
+  if (take)
+    for (int i = tid; i < n; i += T) mono[i] = cand[i];
+  if (tid == 0) {
+    ChainDyn& D = a.dyn[c];
+    if (take) {
+      D.U = U; D.su = su; D.Omega = om;
+      D.r[0] = rx; D.r[1] = ry; D.r[2] = rz;
+      D.p[0] = px; D.p[1] = py; D.p[2] = pz;
+    }
+    D.init = a.new_init;
+    D.step = 0;
+    if (a.replaced) a.replaced[c] = take ? 1 : 0;
+  }
+}
+
+}  // namespace pmc

@@ -1,0 +1,666 @@
+// polymc.cu — host side of libpolymc_b200.so: the C ABI declared in include/polymc.h.
+//
+// No CPU fallback: every compute entry point needs a CUDA device and reports
+// PMC_ERR_NO_DEVICE / PMC_ERR_CUDA otherwise.
+#include "../../include/polymc.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lane_kernels.cuh"
+
+using namespace pmc;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PMC_CU(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      cudaGetLastError();                                                                         \
+      return fail((e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? PMC_ERR_NO_DEVICE \
+                  : (e__ == cudaErrorMemoryAllocation)                              ? PMC_ERR_NOMEM \
+                                                                                    : PMC_ERR_CUDA, \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                           \
+    }                                                                                             \
+  } while (0)
+
+constexpr int kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct pmc_handle {
+  int device = 0;
+  int64_t nchains = 0;
+  int n = 0;
+  int energy_type = 0;
+  uint64_t seed = 0;
+  uint32_t chain_id_base = 0;
+  int init = 0;
+  cudaStream_t stream = nullptr;
+  MonoRec* mono = nullptr;
+  MonoRec* cand = nullptr;
+  ChainParams* par = nullptr;
+  ChainDyn* dyn = nullptr;
+  double* traj = nullptr;
+  double* roll = nullptr;
+  size_t traj_cap = 0, roll_cap = 0;
+  double* scratch = nullptr;  // 2·nchains·n doubles (state staging) — also small outputs
+  size_t scratch_cap = 0;
+  int* flags = nullptr;       // nchains ints
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int cta_threads = 256;      // block size of the CTA-per-chain kernels
+  std::vector<ChainDyn> host_dyn;
+};
+
+namespace {
+
+int ensure_scratch(pmc_handle* h, size_t doubles) {
+  if (h->scratch_cap >= doubles) return PMC_OK;
+  if (h->scratch) cudaFree(h->scratch);
+  h->scratch = nullptr;
+  h->scratch_cap = 0;
+  PMC_CU(cudaMalloc(&h->scratch, doubles * sizeof(double)));
+  h->scratch_cap = doubles;
+  return PMC_OK;
+}
+
+int check_handle(const pmc_handle* h) {
+  if (!h) return fail(PMC_ERR_INVALID, "null handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail(PMC_ERR_NO_DEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  return PMC_OK;
+}
+
+int check_chain(const pmc_handle* h, int64_t chain) {
+  if (chain < 0 || chain >= h->nchains) return fail(PMC_ERR_INVALID, "chain index out of range");
+  return PMC_OK;
+}
+
+// Block size for the CTA-per-chain kernels: enough threads to cover the mean rectangle
+// (n²/6 pairs) without leaving most lanes idle on short chains.  PMC_CTA_THREADS overrides.
+int pick_cta_threads(int n) {
+  int t = n <= 96 ? 64 : n <= 256 ? 128 : n <= 1536 ? 256 : 512;
+  const int o = env_int("PMC_CTA_THREADS", 0);
+  if (o == 64 || o == 128 || o == 256 || o == 512 || o == 1024) t = o;
+  return t;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  PMC_CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return PMC_OK;
+}
+
+// Launch helpers: dispatch on the block size chosen at create time.
+int launch_energy(pmc_handle* h, const EnergyArgs& a, int nblocks) {
+  const size_t smem = cta_smem_bytes(h->n);
+#define PMC_CASE(TT)                                                        \
+  case TT: {                                                                \
+    int rc = set_smem(k_energy_cta<TT>, smem);                              \
+    if (rc) return rc;                                                      \
+    k_energy_cta<TT><<<nblocks, TT, smem, h->stream>>>(a);                  \
+    break;                                                                  \
+  }
+  switch (h->cta_threads) {
+    PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
+    default: return fail(PMC_ERR_INVALID, "bad cta_threads");
+  }
+#undef PMC_CASE
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+
+int launch_run_cta(pmc_handle* h, const RunArgs& a) {
+  const size_t smem = cta_smem_bytes(h->n);
+  const int nblocks = (int)h->nchains;
+#define PMC_CASE(TT, MB)                                                    \
+  case TT: {                                                                \
+    int rc = set_smem(k_run_cta<TT, MB>, smem);                             \
+    if (rc) return rc;                                                      \
+    k_run_cta<TT, MB><<<nblocks, TT, smem, h->stream>>>(a);                 \
+    break;                                                                  \
+  }
+  switch (h->cta_threads) {
+    PMC_CASE(64, 8) PMC_CASE(128, 6) PMC_CASE(256, 3) PMC_CASE(512, 1) PMC_CASE(1024, 1)
+    default: return fail(PMC_ERR_INVALID, "bad cta_threads");
+  }
+#undef PMC_CASE
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+
+int launch_delta_cta(pmc_handle* h, const DeltaArgs& a) {
+  const size_t smem = cta_smem_bytes(h->n);
+#define PMC_CASE(TT)                                                        \
+  case TT: {                                                                \
+    int rc = set_smem(k_delta_cta<TT>, smem);                               \
+    if (rc) return rc;                                                      \
+    k_delta_cta<TT><<<1, TT, smem, h->stream>>>(a);                         \
+    break;                                                                  \
+  }
+  switch (h->cta_threads) {
+    PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
+    default: return fail(PMC_ERR_INVALID, "bad cta_threads");
+  }
+#undef PMC_CASE
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+
+int launch_reinit(pmc_handle* h, const ReinitArgs& a) {
+  const size_t smem = cta_smem_bytes(h->n);
+  const int nblocks = (int)h->nchains;
+#define PMC_CASE(TT)                                                        \
+  case TT: {                                                                \
+    int rc = set_smem(k_reinit_cta<TT>, smem);                              \
+    if (rc) return rc;                                                      \
+    k_reinit_cta<TT><<<nblocks, TT, smem, h->stream>>>(a);                  \
+    break;                                                                  \
+  }
+  switch (h->cta_threads) {
+    PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
+    default: return fail(PMC_ERR_INVALID, "bad cta_threads");
+  }
+#undef PMC_CASE
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+
+// Recompute the running scalars of every chain from its records (re-synchronisation).
+int refresh(pmc_handle* h, bool rebind_gauge, int first = 0, int count = -1) {
+  EnergyArgs a{};
+  a.mono = h->mono; a.par = h->par; a.dyn = h->dyn;
+  a.out4 = nullptr; a.obs6 = nullptr;
+  a.n = h->n; a.energy_type = h->energy_type; a.first_chain = first;
+  a.update_dyn = 1; a.rebind_gauge = rebind_gauge ? 1 : 0;
+  return launch_energy(h, a, count < 0 ? (int)h->nchains : count);
+}
+
+int validate_case(const pmc_case& c, const pmc_case& first) {
+  if (c.n < 1) return fail(PMC_ERR_INVALID, "num-monomers must be >= 1");
+  if (c.n != first.n || c.energy_type != first.energy_type)
+    return fail(PMC_ERR_INVALID, "all cases of one handle must share num-monomers and energy-type; bucket the sweep");
+  if (c.chain_type != PMC_CHAIN_DIELECTRIC && c.chain_type != PMC_CHAIN_POLAR)
+    return fail(PMC_ERR_INVALID, "chain-type is not understood.");  // eap_chain.jl:86
+  if (c.energy_type < 0 || c.energy_type > 2)
+    return fail(PMC_ERR_INVALID, "energy-type is not understood.");  // eap_chain.jl:104
+  if (!(c.kT > 0.0)) return fail(PMC_ERR_INVALID, "kT must be positive");
+  if (c.reserved != 0) return fail(PMC_ERR_INVALID, "pmc_case.reserved must be 0");
+  return PMC_OK;
+}
+
+ChainParams params_of(const pmc_case& c) {
+  ChainParams P{};
+  if (c.chain_type == PMC_CHAIN_DIELECTRIC) {  // dipole_response.jl:7-11
+    P.alpha = (c.K1 - c.K2) * c.E0;
+    P.beta = c.K2 * c.E0;
+    P.m = 0.0;
+    P.gauge0 = -(c.K1 + 2 * c.K2) * c.E0 * c.E0 * (double)c.n / (3 * c.kT);  // average.jl:109-112
+  } else {  // dipole_response.jl:27-29 with M = mu·I (eap_chain.jl:84)
+    P.alpha = 0.0;
+    P.beta = 0.0;
+    P.m = c.mu;
+    P.gauge0 = -c.mu * c.E0 * (double)c.n / (3 * c.kT);  // average.jl:114-118, eigvals(mu·I)[end] = mu
+  }
+  P.E0 = c.E0; P.kT = c.kT; P.inv_kT = 1.0 / c.kT;
+  P.Fz = c.Fz; P.Fx = c.Fx; P.b = c.b;
+  P.adj_lb = c.adj_lb; P.adj_ub = c.adj_ub; P.adj_scale = c.adj_scale;
+  P.cF = 0.2 + 0.8 * std::exp(-(c.Fx * c.Fx + c.Fz * c.Fz) / c.kT);
+  P.phi_step0 = c.phi_step; P.theta_step0 = c.theta_step;
+  P.steps_per_adjust = c.steps_per_adjust;
+  P.do_flips = c.do_flips; P.umbrella = c.umbrella; P.force_init = c.force_init;
+  return P;
+}
+
+int fetch_dyn(pmc_handle* h) {
+  h->host_dyn.resize((size_t)h->nchains);
+  PMC_CU(cudaMemcpyAsync(h->host_dyn.data(), h->dyn, sizeof(ChainDyn) * (size_t)h->nchains, cudaMemcpyDeviceToHost,
+                         h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  return PMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t pmc_abi_version(void) { return PMC_ABI_VERSION; }
+
+const char* pmc_last_error(void) { return g_err.c_str(); }
+
+int32_t pmc_device_count(int32_t* count) {
+  if (!count) return fail(PMC_ERR_INVALID, "null count");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    return fail(PMC_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = c;
+  return PMC_OK;
+}
+
+int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_case, uint64_t seed, int32_t device,
+                   uint32_t chain_id_base, pmc_handle** out) {
+  if (!out) return fail(PMC_ERR_INVALID, "null out handle");
+  *out = nullptr;
+  if (!cases || ncases < 1 || replicas_per_case < 1) return fail(PMC_ERR_INVALID, "need >= 1 case and >= 1 replica");
+  for (int64_t i = 0; i < ncases; ++i) {
+    int rc = validate_case(cases[i], cases[0]);
+    if (rc) return rc;
+  }
+  const int64_t nchains = ncases * (int64_t)replicas_per_case;
+  if (nchains > (int64_t)0x7fffffff) return fail(PMC_ERR_INVALID, "too many chains for one handle");
+  int ndev = 0;
+  {
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) {
+      cudaGetLastError();
+      return fail(PMC_ERR_NO_DEVICE, "no CUDA device available (libpolymc_b200 has no CPU fallback)");
+    }
+  }
+  if (device < 0 || device >= ndev) return fail(PMC_ERR_NO_DEVICE, "device index out of range");
+  PMC_CU(cudaSetDevice(device));
+  const int n = (int)cases[0].n;
+  if (cases[0].n > 1 << 20) return fail(PMC_ERR_UNSUPPORTED, "num-monomers too large");
+  if (cta_smem_bytes(n) > (size_t)kSmemMax)
+    return fail(PMC_ERR_UNSUPPORTED, "chain too long: x and mu of one chain must fit one CTA's 227 KB shared memory "
+                                     "(num-monomers <= ~4100)");
+  pmc_handle* h = new (std::nothrow) pmc_handle();
+  if (!h) return fail(PMC_ERR_NOMEM, "host allocation failed");
+  h->device = device;
+  h->nchains = nchains;
+  h->n = n;
+  h->energy_type = cases[0].energy_type;
+  h->seed = seed;
+  h->chain_id_base = chain_id_base;
+  h->cta_threads = pick_cta_threads(n);
+
+  std::vector<ChainParams> par((size_t)nchains);
+  std::vector<ChainDyn> dyn((size_t)nchains);
+  for (int64_t c = 0; c < nchains; ++c) {
+    const pmc_case& cs = cases[c / replicas_per_case];
+    par[(size_t)c] = params_of(cs);
+    ChainDyn d{};
+    d.phi_step = cs.phi_step;
+    d.theta_step = cs.theta_step;
+    dyn[(size_t)c] = d;
+  }
+  auto cleanup = [&](int rc) {
+    pmc_destroy(h);
+    return rc;
+  };
+#define PMC_TRY(expr)                    \
+  do {                                   \
+    int rc__ = [&]() -> int {            \
+      expr;                              \
+      return PMC_OK;                     \
+    }();                                 \
+    if (rc__) return cleanup(rc__);      \
+  } while (0)
+  const size_t total = (size_t)nchains * (size_t)n;
+  PMC_TRY(PMC_CU(cudaMalloc(&h->mono, total * sizeof(MonoRec))));
+  PMC_TRY(PMC_CU(cudaMalloc(&h->par, (size_t)nchains * sizeof(ChainParams))));
+  PMC_TRY(PMC_CU(cudaMalloc(&h->dyn, (size_t)nchains * sizeof(ChainDyn))));
+  PMC_TRY(PMC_CU(cudaMalloc(&h->flags, (size_t)nchains * sizeof(int))));
+  PMC_TRY(PMC_CU(cudaEventCreate(&h->ev0)));
+  PMC_TRY(PMC_CU(cudaEventCreate(&h->ev1)));
+  PMC_TRY(PMC_CU(cudaMemcpy(h->par, par.data(), (size_t)nchains * sizeof(ChainParams), cudaMemcpyHostToDevice)));
+  PMC_TRY(PMC_CU(cudaMemcpy(h->dyn, dyn.data(), (size_t)nchains * sizeof(ChainDyn), cudaMemcpyHostToDevice)));
+  {
+    const int tb = 256;
+    const long long blocks = ((long long)total + tb - 1) / tb;
+    k_fill_random<<<(unsigned)blocks, tb, 0, h->stream>>>(h->mono, (long long)total, n, seed, chain_id_base, 0u);
+    PMC_TRY(PMC_CU(cudaGetLastError()));
+  }
+  {
+    int rc = refresh(h, /*rebind_gauge=*/true);
+    if (rc) return cleanup(rc);
+  }
+  PMC_TRY(PMC_CU(cudaStreamSynchronize(h->stream)));
+#undef PMC_TRY
+  *out = h;
+  return PMC_OK;
+}
+
+void pmc_destroy(pmc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->mono) cudaFree(h->mono);
+  if (h->cand) cudaFree(h->cand);
+  if (h->par) cudaFree(h->par);
+  if (h->dyn) cudaFree(h->dyn);
+  if (h->traj) cudaFree(h->traj);
+  if (h->roll) cudaFree(h->roll);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->flags) cudaFree(h->flags);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+}
+
+int64_t pmc_num_chains(const pmc_handle* h) { return h ? h->nchains : 0; }
+int64_t pmc_num_monomers(const pmc_handle* h) { return h ? h->n : 0; }
+
+int32_t pmc_set_stream(pmc_handle* h, void* cuda_stream) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return PMC_OK;
+}
+
+static int set_state_range(pmc_handle* h, int64_t first, int64_t count, const double* phi, const double* theta) {
+  if (!phi || !theta) return fail(PMC_ERR_INVALID, "null state pointer");
+  const size_t m = (size_t)count * (size_t)h->n;
+  int rc = ensure_scratch(h, 2 * m);
+  if (rc) return rc;
+  PMC_CU(cudaMemcpyAsync(h->scratch, phi, m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  PMC_CU(cudaMemcpyAsync(h->scratch + m, theta, m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int tb = 256;
+  k_build_records<<<(unsigned)((m + tb - 1) / tb), tb, 0, h->stream>>>(h->mono + (size_t)first * h->n, h->scratch,
+                                                                         h->scratch + m, (long long)m);
+  PMC_CU(cudaGetLastError());
+  // a new state replaces the chain the weight function was built from (mcmc_eap_chain.jl:175-177)
+  rc = refresh(h, /*rebind_gauge=*/true, (int)first, (int)count);
+  if (rc) return rc;
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  return PMC_OK;
+}
+
+static int get_state_range(pmc_handle* h, int64_t first, int64_t count, double* phi, double* theta) {
+  if (!phi || !theta) return fail(PMC_ERR_INVALID, "null state pointer");
+  const size_t m = (size_t)count * (size_t)h->n;
+  int rc = ensure_scratch(h, 2 * m);
+  if (rc) return rc;
+  const int tb = 256;
+  k_extract_state<<<(unsigned)((m + tb - 1) / tb), tb, 0, h->stream>>>(h->mono + (size_t)first * h->n, h->scratch,
+                                                                         h->scratch + m, (long long)m);
+  PMC_CU(cudaGetLastError());
+  PMC_CU(cudaMemcpyAsync(phi, h->scratch, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaMemcpyAsync(theta, h->scratch + m, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  return PMC_OK;
+}
+
+int32_t pmc_set_state(pmc_handle* h, int64_t chain, const double* phi, const double* theta) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = check_chain(h, chain))) return rc;
+  return set_state_range(h, chain, 1, phi, theta);
+}
+
+int32_t pmc_get_state(pmc_handle* h, int64_t chain, double* phi, double* theta) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = check_chain(h, chain))) return rc;
+  return get_state_range(h, chain, 1, phi, theta);
+}
+
+int32_t pmc_set_state_all(pmc_handle* h, const double* phi, const double* theta) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  return set_state_range(h, 0, h->nchains, phi, theta);
+}
+
+int32_t pmc_get_state_all(pmc_handle* h, double* phi, double* theta) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  return get_state_range(h, 0, h->nchains, phi, theta);
+}
+
+static int energy_range(pmc_handle* h, int64_t first, int64_t count, double* out4, double* obs6) {
+  int rc = ensure_scratch(h, (size_t)count * 10);
+  if (rc) return rc;
+  EnergyArgs a{};
+  a.mono = h->mono; a.par = h->par; a.dyn = h->dyn;
+  a.out4 = h->scratch;
+  a.obs6 = h->scratch + (size_t)count * 4;
+  a.n = h->n; a.energy_type = h->energy_type; a.first_chain = (int)first;
+  a.update_dyn = 0; a.rebind_gauge = 0;
+  rc = launch_energy(h, a, (int)count);
+  if (rc) return rc;
+  if (out4)
+    PMC_CU(cudaMemcpyAsync(out4, a.out4, (size_t)count * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (obs6)
+    PMC_CU(cudaMemcpyAsync(obs6, a.obs6, (size_t)count * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  return PMC_OK;
+}
+
+int32_t pmc_energy(pmc_handle* h, int64_t chain, double out[4]) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = check_chain(h, chain))) return rc;
+  if (!out) return fail(PMC_ERR_INVALID, "null out");
+  return energy_range(h, chain, 1, out, nullptr);
+}
+
+int32_t pmc_energy_all(pmc_handle* h, double* out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!out) return fail(PMC_ERR_INVALID, "null out");
+  return energy_range(h, 0, h->nchains, out, nullptr);
+}
+
+int32_t pmc_observables(pmc_handle* h, int64_t chain, double out[6]) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = check_chain(h, chain))) return rc;
+  if (!out) return fail(PMC_ERR_INVALID, "null out");
+  return energy_range(h, chain, 1, nullptr, out);
+}
+
+int32_t pmc_delta_u(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, double dtheta, double out[3]) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = check_chain(h, chain))) return rc;
+  if (!out) return fail(PMC_ERR_INVALID, "null out");
+  if (idx0 < 0 || idx0 >= h->n) return fail(PMC_ERR_INVALID, "monomer index out of range");
+  if ((rc = ensure_scratch(h, 8))) return rc;
+  DeltaArgs a{};
+  a.mono = h->mono; a.par = h->par; a.out = h->scratch;
+  a.n = h->n; a.energy_type = h->energy_type; a.chain = (int)chain; a.idx = (int)idx0;
+  a.dphi = dphi; a.dtheta = dtheta;
+  if (h->energy_type == PMC_ENERGY_INTERACTING) {
+    if ((rc = launch_delta_cta(h, a))) return rc;
+  } else {
+    k_delta_lane<<<1, 32, 0, h->stream>>>(a);
+    PMC_CU(cudaGetLastError());
+  }
+  double tmp[4];
+  PMC_CU(cudaMemcpyAsync(tmp, h->scratch, sizeof(tmp), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  out[0] = tmp[0]; out[1] = tmp[1]; out[2] = tmp[2];
+  return PMC_OK;
+}
+
+int64_t pmc_rows_for(const pmc_handle* h, int64_t nsteps, int64_t stepout) {
+  if (!h || stepout <= 0 || nsteps <= 0) return 0;
+  // all chains share the step counter (same number of pmc_run trials since the last init)
+  const int64_t step0 = h->host_dyn.empty() ? 0 : (int64_t)h->host_dyn[0].step;
+  return (step0 + nsteps) / stepout - step0 / stepout;
+}
+
+int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (nsteps < 0) return fail(PMC_ERR_INVALID, "nsteps must be >= 0");
+  if (nsteps == 0) return PMC_OK;
+  // re-synchronise running scalars against a full recompute (records drift, SURVEY §7 "hard parts")
+  if ((rc = refresh(h, false))) return rc;
+  // step0 (shared by all chains) decides the row count
+  {
+    ChainDyn d0;
+    PMC_CU(cudaMemcpyAsync(&d0, h->dyn, sizeof(ChainDyn), cudaMemcpyDeviceToHost, h->stream));
+    PMC_CU(cudaStreamSynchronize(h->stream));
+    if (h->host_dyn.empty()) h->host_dyn.resize((size_t)h->nchains);
+    h->host_dyn[0] = d0;
+  }
+  const int64_t rows = pmc_rows_for(h, nsteps, stepout);
+  const size_t ntraj = (size_t)h->nchains * (size_t)rows * 8, nroll = (size_t)h->nchains * (size_t)rows * 17;
+  if (ntraj > h->traj_cap) {
+    if (h->traj) cudaFree(h->traj);
+    h->traj = nullptr; h->traj_cap = 0;
+    PMC_CU(cudaMalloc(&h->traj, ntraj * sizeof(double)));
+    h->traj_cap = ntraj;
+  }
+  if (nroll > h->roll_cap) {
+    if (h->roll) cudaFree(h->roll);
+    h->roll = nullptr; h->roll_cap = 0;
+    PMC_CU(cudaMalloc(&h->roll, nroll * sizeof(double)));
+    h->roll_cap = nroll;
+  }
+  RunArgs a{};
+  a.mono = h->mono; a.par = h->par; a.dyn = h->dyn;
+  a.traj = h->traj; a.roll = h->roll;
+  a.nsteps = nsteps; a.stepout = stepout; a.rows = rows;
+  a.seed = h->seed; a.chain_id_base = h->chain_id_base;
+  a.n = h->n; a.nchains = (int)h->nchains; a.energy_type = h->energy_type;
+  PMC_CU(cudaEventRecord(h->ev0, h->stream));
+  if (h->energy_type == PMC_ENERGY_INTERACTING) {
+    if ((rc = launch_run_cta(h, a))) return rc;
+  } else {
+    constexpr int TB = 64;
+    k_run_lane<TB><<<(unsigned)((h->nchains + TB - 1) / TB), TB, 0, h->stream>>>(a);
+    PMC_CU(cudaGetLastError());
+  }
+  PMC_CU(cudaEventRecord(h->ev1, h->stream));
+  if (traj && rows > 0)
+    PMC_CU(cudaMemcpyAsync(traj, h->traj, ntraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (roll && rows > 0)
+    PMC_CU(cudaMemcpyAsync(roll, h->roll, nroll * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  PMC_CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->host_dyn[0].step += nsteps;
+  return PMC_OK;
+}
+
+int32_t pmc_last_run_ms(const pmc_handle* h, float* ms) {
+  if (!h || !ms) return fail(PMC_ERR_INVALID, "null argument");
+  *ms = h->last_ms;
+  return PMC_OK;
+}
+
+int32_t pmc_reinit(pmc_handle* h, int32_t* replaced) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  const size_t total = (size_t)h->nchains * (size_t)h->n;
+  if (!h->cand) PMC_CU(cudaMalloc(&h->cand, total * sizeof(MonoRec)));
+  h->init += 1;
+  const int tb = 256;
+  k_fill_random<<<(unsigned)((total + tb - 1) / tb), tb, 0, h->stream>>>(h->cand, (long long)total, h->n, h->seed,
+                                                                        h->chain_id_base, (uint32_t)h->init);
+  PMC_CU(cudaGetLastError());
+  if ((rc = refresh(h, false))) return rc;  // current U, Ω exact before comparing
+  ReinitArgs a{};
+  a.mono = h->mono; a.cand = h->cand; a.par = h->par; a.dyn = h->dyn; a.replaced = h->flags;
+  a.seed = h->seed; a.chain_id_base = h->chain_id_base;
+  a.n = h->n; a.energy_type = h->energy_type; a.new_init = h->init;
+  if ((rc = launch_reinit(h, a))) return rc;
+  if (replaced)
+    PMC_CU(cudaMemcpyAsync(replaced, h->flags, (size_t)h->nchains * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  if (!h->host_dyn.empty()) h->host_dyn[0].step = 0;
+  return PMC_OK;
+}
+
+int32_t pmc_averages(pmc_handle* h, double* avg, double* acc_rate, double* normalizer) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = fetch_dyn(h))) return rc;
+  for (int64_t c = 0; c < h->nchains; ++c) {
+    const ChainDyn& d = h->host_dyn[(size_t)c];
+    const double nrm = d.acc[16] + d.comp[16];
+    if (avg)
+      for (int k = 0; k < 16; ++k) avg[c * 16 + k] = (d.acc[k] + d.comp[k]) / nrm;  // get_avg, average.jl:38
+    if (acc_rate) acc_rate[c] = d.steps_total ? (double)d.nacc_total / (double)d.steps_total : 0.0;
+    if (normalizer) normalizer[c] = nrm;
+  }
+  return PMC_OK;
+}
+
+int32_t pmc_accumulators(pmc_handle* h, double* sums) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!sums) return fail(PMC_ERR_INVALID, "null sums");
+  if ((rc = fetch_dyn(h))) return rc;
+  for (int64_t c = 0; c < h->nchains; ++c) {
+    const ChainDyn& d = h->host_dyn[(size_t)c];
+    for (int k = 0; k < kNumAcc; ++k) sums[c * kNumAcc + k] = d.acc[k] + d.comp[k];
+  }
+  return PMC_OK;
+}
+
+int32_t pmc_diagnostics(pmc_handle* h, double* diag) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!diag) return fail(PMC_ERR_INVALID, "null diag");
+  if ((rc = fetch_dyn(h))) return rc;
+  for (int64_t c = 0; c < h->nchains; ++c) {
+    const ChainDyn& d = h->host_dyn[(size_t)c];
+    double* o = diag + c * 8;
+    o[0] = d.phi_step; o[1] = d.theta_step;
+    o[2] = (double)d.nacc; o[3] = (double)d.natt;
+    o[4] = (double)d.nacc_total; o[5] = (double)d.steps_total;
+    o[6] = d.U; o[7] = d.drift_max;
+  }
+  return PMC_OK;
+}
+
+int32_t pmc_fp64_peak_probe(int32_t device, int32_t iters, double* tflops, float* ms) {
+  if (!tflops) return fail(PMC_ERR_INVALID, "null tflops");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return fail(PMC_ERR_NO_DEVICE, "no CUDA device available");
+  }
+  if (device < 0 || device >= ndev) return fail(PMC_ERR_NO_DEVICE, "device index out of range");
+  PMC_CU(cudaSetDevice(device));
+  if (iters < 1) iters = 1 << 16;
+  cudaDeviceProp prop;
+  PMC_CU(cudaGetDeviceProperties(&prop, device));
+  double* sink = nullptr;
+  PMC_CU(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  PMC_CU(cudaEventCreate(&e0));
+  PMC_CU(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  k_fp64_probe<<<blocks, threads>>>(sink, 1024, 1.0000001, 1e-9);  // warm-up
+  PMC_CU(cudaEventRecord(e0));
+  k_fp64_probe<<<blocks, threads>>>(sink, iters, 1.0000001, 1e-9);
+  PMC_CU(cudaEventRecord(e1));
+  PMC_CU(cudaEventSynchronize(e1));
+  PMC_CU(cudaGetLastError());
+  float t = 0.f;
+  PMC_CU(cudaEventElapsedTime(&t, e0, e1));
+  const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops = flops / ((double)t * 1e-3) / 1e12;
+  if (ms) *ms = t;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return PMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+"""ctypes binding of libpolymc_b200.so (include/polymc.h) — the only compute path of this package.
+
+There is deliberately no CPU fallback: if the shared library is missing, or no CUDA device is
+present, every compute call raises `PolymcError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG_DIR)                      # polymer-stats_b200/
+LIB_PATH = os.path.join(_ROOT, "libpolymc_b200.so")
+CSRC_DIR = os.path.join(_ROOT, "csrc")
+
+CHAIN_TYPES = {"dielectric": 0, "polar": 1}
+ENERGY_TYPES = {"noninteracting": 0, "interacting": 1, "Ising": 2}
+
+AVG_NAMES = ["r1", "r2", "r3", "r1sq", "r2sq", "r3sq", "rsq",
+             "p1", "p2", "p3", "p1sq", "p2sq", "p3sq", "psq", "U", "Usq"]
+
+EXPORTS = [
+    "pmc_abi_version", "pmc_last_error", "pmc_device_count", "pmc_create", "pmc_destroy",
+    "pmc_num_chains", "pmc_num_monomers", "pmc_set_stream", "pmc_set_state", "pmc_get_state",
+    "pmc_set_state_all", "pmc_get_state_all", "pmc_energy", "pmc_energy_all", "pmc_observables",
+    "pmc_delta_u", "pmc_run", "pmc_rows_for", "pmc_last_run_ms", "pmc_reinit", "pmc_averages",
+    "pmc_accumulators", "pmc_diagnostics", "pmc_fp64_peak_probe",
+]
+
+
+class PolymcError(RuntimeError):
+    """Raised for any non-zero pmc_status (mirrors the reference's `error(...)` convention,
+    mcmc_eap_chain.jl:184,195)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"libpolymc_b200 error {code}: {msg}")
+        self.code = code
+
+
+class PmcCase(C.Structure):
+    """Mirror of `pmc_case` (include/polymc.h): one command line of mcmc_eap_chain.jl:19-153."""
+    _fields_ = [
+        ("E0", C.c_double), ("K1", C.c_double), ("K2", C.c_double), ("mu", C.c_double),
+        ("kT", C.c_double), ("Fz", C.c_double), ("Fx", C.c_double), ("b", C.c_double),
+        ("phi_step", C.c_double), ("theta_step", C.c_double),
+        ("adj_lb", C.c_double), ("adj_ub", C.c_double), ("adj_scale", C.c_double),
+        ("n", C.c_int64), ("steps_per_adjust", C.c_int64),
+        ("chain_type", C.c_int32), ("energy_type", C.c_int32),
+        ("do_flips", C.c_int32), ("umbrella", C.c_int32),
+        ("force_init", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=1.0,
+              chain_type="dielectric", energy_type="noninteracting",
+              phi_step=3 * math.pi / 8, theta_step=3 * math.pi / 16,
+              adj_lb=0.15, adj_ub=0.55, adj_scale=1.1, steps_per_adjust=2500,
+              do_flips=False, umbrella=False, force_init=False) -> PmcCase:
+    """Defaults are the ArgParse defaults of mcmc_eap_chain.jl:19-153."""
+    if chain_type not in CHAIN_TYPES:
+        raise PolymcError(-1, "chain-type is not understood.")      # eap_chain.jl:86
+    if energy_type not in ENERGY_TYPES:
+        raise PolymcError(-1, "energy-type is not understood.")     # eap_chain.jl:104
+    return PmcCase(E0, K1, K2, mu, kT, Fz, Fx, b, phi_step, theta_step, adj_lb, adj_ub, adj_scale,
+                   n, steps_per_adjust, CHAIN_TYPES[chain_type], ENERGY_TYPES[energy_type],
+                   int(do_flips), int(umbrella), int(force_init), 0)
+
+
+def build(force: bool = False) -> str:
+    """Compile libpolymc_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_ROOT), "include", "polymc.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs if os.path.exists(s))
+    if force or stale:
+        subprocess.check_call(["make", "-C", CSRC_DIR, "-s"] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare the prototypes.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PolymcError(-2, f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    dp = C.POINTER(C.c_double)
+    hp = C.c_void_p
+    L.pmc_abi_version.restype = C.c_int32
+    L.pmc_last_error.restype = C.c_char_p
+    L.pmc_device_count.argtypes = [C.POINTER(C.c_int32)]
+    L.pmc_create.argtypes = [C.POINTER(PmcCase), C.c_int64, C.c_int32, C.c_uint64, C.c_int32, C.c_uint32,
+                             C.POINTER(hp)]
+    L.pmc_destroy.argtypes = [hp]
+    L.pmc_destroy.restype = None
+    L.pmc_num_chains.argtypes = [hp]
+    L.pmc_num_chains.restype = C.c_int64
+    L.pmc_num_monomers.argtypes = [hp]
+    L.pmc_num_monomers.restype = C.c_int64
+    L.pmc_set_stream.argtypes = [hp, C.c_void_p]
+    L.pmc_set_state.argtypes = [hp, C.c_int64, dp, dp]
+    L.pmc_get_state.argtypes = [hp, C.c_int64, dp, dp]
+    L.pmc_set_state_all.argtypes = [hp, dp, dp]
+    L.pmc_get_state_all.argtypes = [hp, dp, dp]
+    L.pmc_energy.argtypes = [hp, C.c_int64, dp]
+    L.pmc_energy_all.argtypes = [hp, dp]
+    L.pmc_observables.argtypes = [hp, C.c_int64, dp]
+    L.pmc_delta_u.argtypes = [hp, C.c_int64, C.c_int64, C.c_double, C.c_double, dp]
+    L.pmc_run.argtypes = [hp, C.c_int64, C.c_int64, dp, dp]
+    L.pmc_rows_for.argtypes = [hp, C.c_int64, C.c_int64]
+    L.pmc_rows_for.restype = C.c_int64
+    L.pmc_last_run_ms.argtypes = [hp, C.POINTER(C.c_float)]
+    L.pmc_reinit.argtypes = [hp, C.POINTER(C.c_int32)]
+    L.pmc_averages.argtypes = [hp, dp, dp, dp]
+    L.pmc_accumulators.argtypes = [hp, dp]
+    L.pmc_diagnostics.argtypes = [hp, dp]
+    L.pmc_fp64_peak_probe.argtypes = [C.c_int32, C.c_int32, dp, C.POINTER(C.c_float)]
+    for name in EXPORTS:
+        f = getattr(L, name)
+        if f.restype is C.c_int:  # default restype: every status-returning entry point
+            f.restype = C.c_int32
+    if L.pmc_abi_version() != 1:
+        raise PolymcError(-1, "ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise PolymcError(rc, load().pmc_last_error().decode("utf-8", "replace"))
+
+
+def _dp(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    rc = load().pmc_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def fp64_peak_probe(device=0, iters=1 << 17):
+    t = C.c_double()
+    ms = C.c_float()
+    _check(load().pmc_fp64_peak_probe(device, iters, C.byref(t), C.byref(ms)))
+    return t.value, ms.value
+
+
+class Ensemble:
+    """A batch of independent chains on one GPU: ncases × replicas, uniform n and energy type.
+
+    The methods map 1:1 onto the C ABI; docstrings there cite the reference seams."""
+
+    def __init__(self, cases, replicas=1, seed=0, device=0, chain_id_base=0):
+        if isinstance(cases, PmcCase):
+            cases = [cases]
+        self.cases = list(cases)
+        self.replicas = int(replicas)
+        arr = (PmcCase * len(self.cases))(*self.cases)
+        h = C.c_void_p()
+        _check(load().pmc_create(arr, len(self.cases), self.replicas, seed, device, chain_id_base, C.byref(h)))
+        self._h = h
+        self.nchains = int(load().pmc_num_chains(h))
+        self.n = int(load().pmc_num_monomers(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().pmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr: int):
+        _check(load().pmc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_state(self, chain, phi, theta):
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if phi.shape != (self.n,) or theta.shape != (self.n,):
+            raise PolymcError(-1, "state arrays must have num-monomers entries")
+        _check(load().pmc_set_state(self._h, chain, _dp(phi), _dp(theta)))
+
+    def get_state(self, chain):
+        phi, theta = np.empty(self.n), np.empty(self.n)
+        _check(load().pmc_get_state(self._h, chain, _dp(phi), _dp(theta)))
+        return phi, theta
+
+    def set_state_all(self, phi, theta):
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if phi.shape != (self.nchains, self.n) or theta.shape != (self.nchains, self.n):
+            raise PolymcError(-1, "state arrays must be [chains][num-monomers]")
+        _check(load().pmc_set_state_all(self._h, _dp(phi), _dp(theta)))
+
+    def get_state_all(self):
+        phi, theta = np.empty((self.nchains, self.n)), np.empty((self.nchains, self.n))
+        _check(load().pmc_get_state_all(self._h, _dp(phi), _dp(theta)))
+        return phi, theta
+
+    def energy(self, chain):
+        o = np.empty(4)
+        _check(load().pmc_energy(self._h, chain, _dp(o)))
+        return {"U": o[0], "su": o[1], "Udd": o[2], "Omega": o[3]}
+
+    def energy_all(self):
+        o = np.empty((self.nchains, 4))
+        _check(load().pmc_energy_all(self._h, _dp(o)))
+        return o
+
+    def observables(self, chain):
+        o = np.empty(6)
+        _check(load().pmc_observables(self._h, chain, _dp(o)))
+        return o[:3].copy(), o[3:].copy()
+
+    def delta_u(self, chain, idx0, dphi, dtheta):
+        o = np.empty(3)
+        _check(load().pmc_delta_u(self._h, chain, idx0, dphi, dtheta, _dp(o)))
+        return {"dU": o[0], "dOmega": o[1], "clamped": bool(o[2])}
+
+    def rows_for(self, nsteps, stepout):
+        return int(load().pmc_rows_for(self._h, nsteps, stepout))
+
+    def run(self, nsteps, stepout=0, fetch_rows=True, traj=None, roll=None):
+        """The hot loop for every chain.  Returns (traj [chains][rows][8], roll [chains][rows][17])
+        or (None, None) when fetch_rows is False (rows stay on the device)."""
+        rows = self.rows_for(nsteps, stepout)
+        if fetch_rows and rows > 0:
+            if traj is None:
+                traj = np.empty((self.nchains, rows, 8))
+            if roll is None:
+                roll = np.empty((self.nchains, rows, 17))
+        else:
+            traj = roll = None
+        _check(load().pmc_run(self._h, nsteps, stepout, _dp(traj), _dp(roll)))
+        return traj, roll
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        _check(load().pmc_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def reinit(self):
+        flags = (C.c_int32 * self.nchains)()
+        _check(load().pmc_reinit(self._h, flags))
+        return np.frombuffer(flags, dtype=np.int32).copy()
+
+    def averages(self):
+        avg = np.empty((self.nchains, 16))
+        ar = np.empty(self.nchains)
+        nrm = np.empty(self.nchains)
+        _check(load().pmc_averages(self._h, _dp(avg), _dp(ar), _dp(nrm)))
+        return avg, ar, nrm
+
+    def accumulators(self):
+        s = np.empty((self.nchains, 17))
+        _check(load().pmc_accumulators(self._h, _dp(s)))
+        return s
+
+    def diagnostics(self):
+        d = np.empty((self.nchains, 8))
+        _check(load().pmc_diagnostics(self._h, _dp(d)))
+        return d
