@@ -114,6 +114,8 @@ int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, do
 int64_t pmc_rows_for(const pmc_handle* h, int64_t nsteps, int64_t stepout);
 /* Device time of the last pmc_run's MCMC kernel, CUDA events on the handle's stream. */
 int32_t pmc_last_run_ms(const pmc_handle* h, float* ms);
+/* Number of CUDA kernels this handle has launched so far (bench.py's `gpu_launches`). */
+int64_t pmc_launch_count(const pmc_handle* h);
 
 /* Re-initialisation between inits, mcmc_eap_chain.jl:352-361 (metropolis_acc, inc/acceptance.jl:1-3):
  * draws a fresh random chain per chain and swaps it in iff force_init or

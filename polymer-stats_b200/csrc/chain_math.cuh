@@ -15,7 +15,7 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr double kInv4Pi = 0.07957747154594767;  // 1/(4π), hoisted out of the pair term
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. SC'11).  Same stream definition as oracle/polymc_oracle.c:
+// Philox4x32-10 (Salmon et al. SC'11).  Stream definition (DESIGN.md "RNG streams"):
 //   key = (seed_lo, seed_hi), counter = (pos_lo, pos_hi, chain_id, (init << 8) | sub)
 // ---------------------------------------------------------------------------------------------
 enum : uint32_t { SUB_STEP_A = 0, SUB_STEP_B = 1, SUB_INIT = 2, SUB_REINIT = 3 };

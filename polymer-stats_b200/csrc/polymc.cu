@@ -67,6 +67,7 @@ struct pmc_handle {
   int* flags = nullptr;       // nchains ints
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
+  int64_t launches = 0;
   int cta_threads = 256;      // block size of the CTA-per-chain kernels
   std::vector<ChainDyn> host_dyn;
 };
@@ -117,7 +118,8 @@ int launch_energy(pmc_handle* h, const EnergyArgs& a, int nblocks) {
   case TT: {                                                                \
     int rc = set_smem(k_energy_cta<TT>, smem);                              \
     if (rc) return rc;                                                      \
-    k_energy_cta<TT><<<nblocks, TT, smem, h->stream>>>(a);                  \
+    k_energy_cta<TT><<<nblocks, TT, smem, h->stream>>>(a);              \
+    ++h->launches;                  \
     break;                                                                  \
   }
   switch (h->cta_threads) {
@@ -136,7 +138,8 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
   case TT: {                                                                \
     int rc = set_smem(k_run_cta<TT, MB>, smem);                             \
     if (rc) return rc;                                                      \
-    k_run_cta<TT, MB><<<nblocks, TT, smem, h->stream>>>(a);                 \
+    k_run_cta<TT, MB><<<nblocks, TT, smem, h->stream>>>(a);             \
+    ++h->launches;                 \
     break;                                                                  \
   }
   switch (h->cta_threads) {
@@ -154,7 +157,8 @@ int launch_delta_cta(pmc_handle* h, const DeltaArgs& a) {
   case TT: {                                                                \
     int rc = set_smem(k_delta_cta<TT>, smem);                               \
     if (rc) return rc;                                                      \
-    k_delta_cta<TT><<<1, TT, smem, h->stream>>>(a);                         \
+    k_delta_cta<TT><<<1, TT, smem, h->stream>>>(a);                     \
+    ++h->launches;                         \
     break;                                                                  \
   }
   switch (h->cta_threads) {
@@ -173,7 +177,8 @@ int launch_reinit(pmc_handle* h, const ReinitArgs& a) {
   case TT: {                                                                \
     int rc = set_smem(k_reinit_cta<TT>, smem);                              \
     if (rc) return rc;                                                      \
-    k_reinit_cta<TT><<<nblocks, TT, smem, h->stream>>>(a);                  \
+    k_reinit_cta<TT><<<nblocks, TT, smem, h->stream>>>(a);              \
+    ++h->launches;                  \
     break;                                                                  \
   }
   switch (h->cta_threads) {
@@ -331,6 +336,7 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
     const int tb = 256;
     const long long blocks = ((long long)total + tb - 1) / tb;
     k_fill_random<<<(unsigned)blocks, tb, 0, h->stream>>>(h->mono, (long long)total, n, seed, chain_id_base, 0u);
+    ++h->launches;
     PMC_TRY(PMC_CU(cudaGetLastError()));
   }
   {
@@ -380,6 +386,7 @@ static int set_state_range(pmc_handle* h, int64_t first, int64_t count, const do
   const int tb = 256;
   k_build_records<<<(unsigned)((m + tb - 1) / tb), tb, 0, h->stream>>>(h->mono + (size_t)first * h->n, h->scratch,
                                                                          h->scratch + m, (long long)m);
+  ++h->launches;
   PMC_CU(cudaGetLastError());
   // a new state replaces the chain the weight function was built from (mcmc_eap_chain.jl:175-177)
   rc = refresh(h, /*rebind_gauge=*/true, (int)first, (int)count);
@@ -396,6 +403,7 @@ static int get_state_range(pmc_handle* h, int64_t first, int64_t count, double* 
   const int tb = 256;
   k_extract_state<<<(unsigned)((m + tb - 1) / tb), tb, 0, h->stream>>>(h->mono + (size_t)first * h->n, h->scratch,
                                                                          h->scratch + m, (long long)m);
+  ++h->launches;
   PMC_CU(cudaGetLastError());
   PMC_CU(cudaMemcpyAsync(phi, h->scratch, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   PMC_CU(cudaMemcpyAsync(theta, h->scratch + m, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -486,6 +494,7 @@ int32_t pmc_delta_u(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, dou
     if ((rc = launch_delta_cta(h, a))) return rc;
   } else {
     k_delta_lane<<<1, 32, 0, h->stream>>>(a);
+    ++h->launches;
     PMC_CU(cudaGetLastError());
   }
   double tmp[4];
@@ -543,6 +552,7 @@ int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, do
   } else {
     constexpr int TB = 64;
     k_run_lane<TB><<<(unsigned)((h->nchains + TB - 1) / TB), TB, 0, h->stream>>>(a);
+    ++h->launches;
     PMC_CU(cudaGetLastError());
   }
   PMC_CU(cudaEventRecord(h->ev1, h->stream));
@@ -562,6 +572,8 @@ int32_t pmc_last_run_ms(const pmc_handle* h, float* ms) {
   return PMC_OK;
 }
 
+int64_t pmc_launch_count(const pmc_handle* h) { return h ? h->launches : 0; }
+
 int32_t pmc_reinit(pmc_handle* h, int32_t* replaced) {
   int rc = check_handle(h);
   if (rc) return rc;
@@ -571,6 +583,7 @@ int32_t pmc_reinit(pmc_handle* h, int32_t* replaced) {
   const int tb = 256;
   k_fill_random<<<(unsigned)((total + tb - 1) / tb), tb, 0, h->stream>>>(h->cand, (long long)total, h->n, h->seed,
                                                                         h->chain_id_base, (uint32_t)h->init);
+  ++h->launches;
   PMC_CU(cudaGetLastError());
   if ((rc = refresh(h, false))) return rc;  // current U, Ω exact before comparing
   ReinitArgs a{};

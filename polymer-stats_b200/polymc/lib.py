@@ -28,7 +28,7 @@ EXPORTS = [
     "pmc_num_chains", "pmc_num_monomers", "pmc_set_stream", "pmc_set_state", "pmc_get_state",
     "pmc_set_state_all", "pmc_get_state_all", "pmc_energy", "pmc_energy_all", "pmc_observables",
     "pmc_delta_u", "pmc_run", "pmc_rows_for", "pmc_last_run_ms", "pmc_reinit", "pmc_averages",
-    "pmc_accumulators", "pmc_diagnostics", "pmc_fp64_peak_probe",
+    "pmc_accumulators", "pmc_diagnostics", "pmc_fp64_peak_probe", "pmc_launch_count",
 ]
 
 
@@ -119,6 +119,8 @@ def load():
     L.pmc_rows_for.argtypes = [hp, C.c_int64, C.c_int64]
     L.pmc_rows_for.restype = C.c_int64
     L.pmc_last_run_ms.argtypes = [hp, C.POINTER(C.c_float)]
+    L.pmc_launch_count.argtypes = [hp]
+    L.pmc_launch_count.restype = C.c_int64
     L.pmc_reinit.argtypes = [hp, C.POINTER(C.c_int32)]
     L.pmc_averages.argtypes = [hp, dp, dp, dp]
     L.pmc_accumulators.argtypes = [hp, dp]
@@ -261,6 +263,9 @@ class Ensemble:
         ms = C.c_float()
         _check(load().pmc_last_run_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def launch_count(self) -> int:
+        return int(load().pmc_launch_count(self._h))
 
     def reinit(self):
         flags = (C.c_int32 * self.nchains)()

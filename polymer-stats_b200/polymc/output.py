@@ -1,0 +1,70 @@
+"""The output contract of mcmc_eap_chain.jl: the 10 `key = value` stdout lines
+(:386-395) and the two CSV files (:256-259, :329-348), formatted the way Julia prints Float64 so
+run/*.jl launchers, scripts/aggregate_mcmc.jl (:61-75) and scripts/plot_hermans.py keep parsing them.
+"""
+from __future__ import annotations
+
+import math
+from decimal import Decimal
+
+TRAJ_HEADER = "step,r1,r2,r3,p1,p2,p3,U"                                   # mcmc_eap_chain.jl:257
+ROLL_HEADER = ("step,r1,r2,r3,r1sq,r2sq,r3sq,rsq,p1,p2,p3,p1sq,p2sq,p3sq,psq,U,Usq")  # :259
+
+
+def julia_float(x: float) -> str:
+    """Julia `print(::Float64)`: shortest round-trip digits; positional notation for decimal
+    exponents with -4 < pt <= 6 (Base.Ryu.writeshortest), otherwise `d.ddde±x`; `NaN`, `Inf`, `-Inf`."""
+    x = float(x)
+    if math.isnan(x):
+        return "NaN"
+    if math.isinf(x):
+        return "Inf" if x > 0 else "-Inf"
+    if x == 0.0:
+        return "-0.0" if math.copysign(1.0, x) < 0 else "0.0"
+    sign, digits, exp = Decimal(repr(x)).as_tuple()
+    digs = "".join(map(str, digits)).rstrip("0") or "0"
+    exp += len(digits) - len(digs)          # value = 0.digs… × 10^(len(digs)+exp) → point position
+    pt = len(digs) + exp                    # number of digits before the decimal point
+    s = "-" if sign else ""
+    if -4 < pt <= 6:
+        if pt <= 0:
+            body = "0." + "0" * (-pt) + digs
+        elif pt >= len(digs):
+            body = digs + "0" * (pt - len(digs)) + ".0"
+        else:
+            body = digs[:pt] + "." + digs[pt:]
+        return s + body
+    mant = digs[0] + "." + (digs[1:] or "0")
+    return f"{s}{mant}e{pt - 1}"
+
+
+def julia_vector(v) -> str:
+    """Julia `show(::Vector{Float64})`: `[a, b, c]`."""
+    return "[" + ", ".join(julia_float(x) for x in v) + "]"
+
+
+def result_lines(avg16, acc_rate, mlen, n):
+    """The 10 stdout lines, mcmc_eap_chain.jl:386-395.  avg16 is in rolling.csv column order."""
+    r, rj2, r2 = avg16[0:3], avg16[3:6], avg16[6]
+    p, pj2, p2 = avg16[7:10], avg16[10:13], avg16[13]
+    U, U2 = avg16[14], avg16[15]
+    nb = mlen * n
+    return [
+        f"<r>    =   {julia_vector(r)}",
+        f"<r/nb> =   {julia_vector([x / nb for x in r])}",
+        f"<rj2>  =   {julia_vector(rj2)}",
+        f"<r2>   =   {julia_float(r2)}",
+        f"<p>    =   {julia_vector(p)}",
+        f"<pj2>  =   {julia_vector(pj2)}",
+        f"<p2>   =   {julia_float(p2)}",
+        f"<U>    =   {julia_float(U)}",
+        f"<U2>   =   {julia_float(U2)}",
+        f"AR     =   {julia_float(acc_rate)}",
+    ]
+
+
+def write_rows(fh, rows):
+    """`writedlm(file, hcat(...), ',')` of Float64 rows (step is promoted to Float64, :331,:336)."""
+    for row in rows:
+        fh.write(",".join(julia_float(x) for x in row))
+        fh.write("\n")

@@ -1,0 +1,182 @@
+"""CPU tests of the host side: CLI table vs the reference's ArgParse table (golden fixture), output
+formatting, the C ABI surface, and failure without a GPU."""
+import ast
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _julia_default(s):
+    s = s.strip()
+    if s.startswith('"'):
+        return s.strip('"')
+    s = s.replace("π", "math.pi")
+    m = re.fullmatch(r"convert\(Int,\s*(.*)\)", s)   # e.g. convert(Int, 1e5)
+    if m:
+        return int(float(m.group(1)))
+    return eval(s, {"math": math})
+
+
+def test_cli_table_matches_reference(pm, cli_table):
+    """Every option of mcmc_eap_chain.jl:19-153 exists with the same long/short names and default."""
+    from polymc import mcmc
+    parser = mcmc.build_parser()
+    by_long = {}
+    for a in parser._actions:
+        for o in a.option_strings:
+            if o.startswith("--"):
+                by_long[o] = a
+    assert len(cli_table) == 34
+    for e in cli_table:
+        assert e["long"] in by_long, e["long"]
+        a = by_long[e["long"]]
+        if e["short"]:
+            assert e["short"] in a.option_strings, (e["long"], e["short"])
+        if e["action"] == ":store_true":
+            assert a.default is False and a.nargs == 0
+        else:
+            want = _julia_default(e["default"])
+            assert a.default == pytest.approx(want) if isinstance(want, float) else a.default == want, e["long"]
+            assert a.type is {"Float64": float, "Int": int, "String": str}[e["arg_type"]]
+
+
+def test_cli_parses_launcher_style_argv(pm):
+    """argv exactly as run/interacting_dielectric_study.jl:41 builds it."""
+    from polymc import mcmc
+    argv = ("--chain-type dielectric --energy-type interacting -b 1.0 --E0 0.5 --K1 1.0 --K2 0.0 --kT 1.0 "
+            "--Fz 0.25 --Fx 0.0 -n 100 --num-steps 500000 -v 2 --prefix out/E0-0000500_run-001").split()
+    pargs = mcmc.parse_args(argv)
+    assert pargs["energy-type"] == "interacting" and pargs["mlen"] == 1.0 and pargs["num-monomers"] == 100
+    assert pargs["num-steps"] == 500000 and pargs["verbose"] == 2 and pargs["stepout"] == 500
+    c = mcmc.case_from_pargs(pargs)
+    assert c.n == 100 and c.energy_type == 1 and c.E0 == 0.5 and c.steps_per_adjust == 2500
+    assert c.phi_step == pytest.approx(3 * math.pi / 8) and c.theta_step == pytest.approx(3 * math.pi / 16)
+
+
+def test_reference_refusals(pm):
+    from polymc import mcmc
+    with pytest.raises(pm.PolymcError, match="acceptance criteria has not yet been implemented"):
+        mcmc.validate(mcmc.default_pargs(acc="kawasaki"))
+    with pytest.raises(pm.PolymcError, match="numeric-type 'float16' not understood"):
+        mcmc.validate(mcmc.default_pargs(numeric_type="float16"))
+    with pytest.raises(pm.PolymcError, match="not implemented for the HPC env"):
+        mcmc.validate(mcmc.default_pargs(profile=True))
+    with pytest.raises(pm.PolymcError, match="fixed-force only"):
+        mcmc.validate(mcmc.default_pargs(ensemble_type="end-to-end"))
+    with pytest.raises(pm.PolymcError, match="chain-type is not understood"):
+        mcmc.case_from_pargs(mcmc.default_pargs(chain_type="rubber"))
+    with pytest.raises(pm.PolymcError, match="energy-type is not understood"):
+        mcmc.case_from_pargs(mcmc.default_pargs(energy_type="cutoff"))
+    mcmc.validate(mcmc.default_pargs(numeric_type="big"))  # accepted: device sums are compensated
+
+
+def test_julia_float_formatting():
+    from polymc.output import julia_float as jf, julia_vector
+    assert jf(0.1) == "0.1" and jf(500.0) == "500.0" and jf(1e-5) == "1.0e-5" and jf(1e-4) == "0.0001"
+    assert jf(999999.0) == "999999.0" and jf(1e6) == "1.0e6" and jf(1234567.8) == "1.2345678e6"
+    assert jf(-3.5e-7) == "-3.5e-7" and jf(float("nan")) == "NaN" and jf(float("-inf")) == "-Inf"
+    assert jf(45944.166900017364) == "45944.166900017364"
+    rng = np.random.default_rng(0)
+    for x in np.concatenate([rng.normal(size=200) * 10.0 ** rng.integers(-12, 12, 200), [0.0, 1.0, -2.0]]):
+        assert float(jf(x)) == x          # round-trips, so Meta.parse/eval gives the same Float64
+    assert julia_vector([1.0, -2.5e-9, 3]) == "[1.0, -2.5e-9, 3.0]"
+
+
+def test_result_lines_are_the_aggregator_schema():
+    """scripts/aggregate_mcmc.jl:71-72 does split(line,"=")[2] |> Meta.parse |> eval per line, in
+    line order; scripts/plot_hermans.py:53-69 does the same with Python eval."""
+    from polymc.output import result_lines
+    avg = np.arange(1.0, 17.0) * 1.5e-3
+    lines = result_lines(avg, 0.3456, mlen=2.0, n=10)
+    keys = [ln.split("=")[0].strip() for ln in lines]
+    assert keys == ["<r>", "<r/nb>", "<rj2>", "<r2>", "<p>", "<pj2>", "<p2>", "<U>", "<U2>", "AR"]
+    vals = []
+    for ln in lines:
+        parts = ln.split("=")
+        assert len(parts) == 2                      # key text must not contain '='
+        vals.append(ast.literal_eval(parts[1].strip()))
+    assert vals[0] == list(avg[0:3]) and vals[2] == list(avg[3:6]) and vals[3] == avg[6]
+    assert vals[1] == [x / 20.0 for x in avg[0:3]]
+    assert vals[4] == list(avg[7:10]) and vals[5] == list(avg[10:13]) and vals[6] == avg[13]
+    assert vals[7] == avg[14] and vals[8] == avg[15] and vals[9] == 0.3456
+    assert lines[0].startswith("<r>    =   [") and lines[9].startswith("AR     =   ")
+
+
+def test_csv_headers_and_rows():
+    import io
+    from polymc.output import ROLL_HEADER, TRAJ_HEADER, write_rows
+    assert TRAJ_HEADER == "step,r1,r2,r3,p1,p2,p3,U"
+    assert ROLL_HEADER.split(",") == ["step", "r1", "r2", "r3", "r1sq", "r2sq", "r3sq", "rsq", "p1", "p2", "p3",
+                                      "p1sq", "p2sq", "p3sq", "psq", "U", "Usq"]
+    f = io.StringIO()
+    write_rows(f, np.array([[500.0, 1.5, -2.0, 1e-7, 0, 0, 0, -3.25]]))
+    assert f.getvalue() == "500.0,1.5,-2.0,1.0e-7,0.0,0.0,0.0,-3.25\n"
+
+
+def test_abi_exports_every_declared_symbol(pm):
+    """The shared library loads and exports exactly the entry points include/polymc.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "polymc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(pmc_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 24
+    L = ctypes.CDLL(pm.lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(pm.lib.EXPORTS) == declared
+    assert pm.load().pmc_abi_version() == 1
+    assert ctypes.sizeof(pm.PmcCase) == 13 * 8 + 2 * 8 + 6 * 4
+
+
+def test_no_cpu_fallback(pm):
+    """Without a CUDA device every compute entry point fails loudly (no oracle/CPU route)."""
+    if pm.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pm.PolymcError) as ei:
+        pm.Ensemble(pm.make_case(n=10))
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+    with pytest.raises(pm.PolymcError):
+        pm.fp64_peak_probe()
+    # the product package must not import, link or call the oracle
+    src_dir = os.path.join(ROOT, "polymer-stats_b200")
+    forbidden = re.compile(r"import\s+oracle|from\s+oracle|libpolymc_oracle|polymc_oracle\.h|\borc_\w+|closed_form")
+    for dirpath, _, files in os.walk(src_dir):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".jl", "Makefile")):
+                txt = open(os.path.join(dirpath, fn), encoding="utf-8").read()
+                assert not forbidden.search(txt), os.path.join(dirpath, fn)
+
+
+def test_create_argument_validation(pm):
+    L = pm.load()
+    h = ctypes.c_void_p()
+    c = pm.make_case(n=10)
+    arr = (pm.PmcCase * 1)(c)
+    assert L.pmc_create(arr, 0, 1, 0, 0, 0, ctypes.byref(h)) == -1
+    assert b"case" in L.pmc_last_error()
+    bad = pm.make_case(n=10)
+    bad.kT = 0.0
+    assert L.pmc_create((pm.PmcCase * 1)(bad), 1, 1, 0, 0, 0, ctypes.byref(h)) == -1
+    mixed = (pm.PmcCase * 2)(pm.make_case(n=10), pm.make_case(n=11))
+    assert L.pmc_create(mixed, 2, 1, 0, 0, 0, ctypes.byref(h)) == -1
+    assert b"bucket" in L.pmc_last_error()
+    assert L.pmc_create(arr, 1, 1, 0, 0, 0, None) == -1
+
+
+def test_bucket_and_shard(pm):
+    from polymc import sweep
+    cases = [pm.make_case(n=100), pm.make_case(n=512, energy_type="interacting"), pm.make_case(n=100, Fz=1.0)]
+    b = sweep.bucket_cases(cases)
+    assert list(b.values()) == [[0, 2], [1]]
+    for total in (0, 1, 7, 4096, 16384):
+        for world in (1, 2, 3, 8):
+            spans = [sweep.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b_ - a_ for a_, b_ in spans]
+            assert max(sizes) - min(sizes) <= 1
