@@ -136,73 +136,115 @@ __device__ double cta_pair_energy(const CtaView& S, int n, int energy_type) {
 //   (x_B, μ_B, eB = μ_B·D);  r = x_L − x_B,  r' = r − D;
 //   μ_L·r' = μ_L·r − μ_L·D and μ_B·r' = μ_B·r − eB save two dot products;
 //   g = y³(μ_L·μ_B + (−3μ_L·r)(μ_B·r) y²),  y = 1/|r|.
-template <int T>
+// Shared-memory loads are not free next to the FP64 pipe (≈1.7 issue cycles per LDS.64 against 2 per
+// DFMA, tools/fp64_mix.cu), so each lane keeps NL=2 lane items and every broadcast item loaded from
+// shared memory serves two pairs; an odd last group of 32 lane items runs with NL=1.
+struct LaneItem {
+  double x, y, z;     // position
+  double ax, ay, az;  // μ
+  double tx, ty, tz;  // −3μ
+  double c;           // −3μ·D
+};
+
+__device__ __forceinline__ LaneItem load_lane_item(const CtaView& S, int L, double Dx, double Dy, double Dz) {
+  LaneItem it;
+  it.x = S.sx[L]; it.y = S.sy[L]; it.z = S.sz[L];
+  it.ax = S.mx[L]; it.ay = S.my[L]; it.az = S.mz[L];
+  it.tx = -3.0 * it.ax; it.ty = -3.0 * it.ay; it.tz = -3.0 * it.az;
+  it.c = fma(it.tz, Dz, fma(it.ty, Dy, it.tx * Dx));
+  return it;
+}
+
+// new − old of one pair: lane item `it` against broadcast item (bx,by,bz; ux,uy,uz; e)
+__device__ __forceinline__ double rect_pair(const LaneItem& it, double bx, double by, double bz, double ux,
+                                            double uy, double uz, double e, double Dx, double Dy, double Dz,
+                                            double acc) {
+  const double rx = it.x - bx, ry = it.y - by, rz = it.z - bz;
+  const double mm = fma(it.az, uz, fma(it.ay, uy, it.ax * ux));
+  const double r2 = fma(rz, rz, fma(ry, ry, rx * rx));
+  const double a3 = fma(it.tz, rz, fma(it.ty, ry, it.tx * rx));
+  const double bb = fma(uz, rz, fma(uy, ry, ux * rx));
+  const double qx = rx - Dx, qy = ry - Dy, qz = rz - Dz;
+  const double q2 = fma(qz, qz, fma(qy, qy, qx * qx));
+  const double a3n = a3 - it.c;
+  const double bn = bb - e;
+  const double y = rsqrt_fast(r2);
+  const double yn = rsqrt_fast(q2);
+  const double y2 = y * y, yn2 = yn * yn;
+  const double t = fma(a3 * bb, y2, mm);
+  const double tn = fma(a3n * bn, yn2, mm);
+  acc = fma(tn, yn2 * yn, acc);
+  return fma(-t, y2 * y, acc);
+}
+
+template <int T, int UNROLL = 2>
 __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, int baseB, int B, double Dx,
                                            double Dy, double Dz) {
   constexpr int W = T / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = (A + 31) >> 5;
-  const int U = G * B;
-  int u = (int)(((long long)U * warp) / W);
-  const int u1 = (int)(((long long)U * (warp + 1)) / W);
+  const double* __restrict__ bxp = S.sx + baseB;
+  const double* __restrict__ byp = S.sy + baseB;
+  const double* __restrict__ bzp = S.sz + baseB;
+  const double* __restrict__ mxp = S.mx + baseB;
+  const double* __restrict__ myp = S.my + baseB;
+  const double* __restrict__ mzp = S.mz + baseB;
+  const double* __restrict__ ep = S.E + baseB;
   double acc = 0.0;
-  if (u >= u1) return acc;
-  int g = u / B;
-  int k = u - g * B;
-  while (u < u1) {
-    const int li = g * 32 + lane;
-    const bool valid = li < A;
-    const int L = baseA + min(li, A - 1);
-    const double xL = S.sx[L], yL = S.sy[L], zL = S.sz[L];
-    const double ax = S.mx[L], ay = S.my[L], az = S.mz[L];
-    const double tx = -3.0 * ax, ty = -3.0 * ay, tz = -3.0 * az;
-    const double cL = fma(tz, Dz, fma(ty, Dy, tx * Dx));
-    const int kend = min(B, k + (u1 - u));
-    u += kend - k;
-    double a0 = 0.0, a1 = 0.0;
-    const double* __restrict__ bxp = S.sx + baseB;
-    const double* __restrict__ byp = S.sy + baseB;
-    const double* __restrict__ bzp = S.sz + baseB;
-    const double* __restrict__ mxp = S.mx + baseB;
-    const double* __restrict__ myp = S.my + baseB;
-    const double* __restrict__ mzp = S.mz + baseB;
-    const double* __restrict__ ep = S.E + baseB;
-#define PMC_RECT_PAIR(KK, ACC)                                                      \
-  {                                                                                 \
-    const double rx = xL - bxp[KK], ry = yL - byp[KK], rz = zL - bzp[KK];           \
-    const double ux = mxp[KK], uy = myp[KK], uz = mzp[KK];                          \
-    const double mm = fma(az, uz, fma(ay, uy, ax * ux));                            \
-    const double r2 = fma(rz, rz, fma(ry, ry, rx * rx));                            \
-    const double a3 = fma(tz, rz, fma(ty, ry, tx * rx));                            \
-    const double bb = fma(uz, rz, fma(uy, ry, ux * rx));                            \
-    const double qx = rx - Dx, qy = ry - Dy, qz = rz - Dz;                          \
-    const double q2 = fma(qz, qz, fma(qy, qy, qx * qx));                            \
-    const double a3n = a3 - cL;                                                     \
-    const double bn = bb - ep[KK];                                                  \
-    const double y = rsqrt_fast(r2);                                                \
-    const double yn = rsqrt_fast(q2);                                               \
-    const double y2 = y * y, yn2 = yn * yn;                                         \
-    const double t = fma(a3 * bb, y2, mm);                                          \
-    const double tn = fma(a3n * bn, yn2, mm);                                       \
-    ACC = fma(tn, yn2 * yn, ACC);                                                   \
-    ACC = fma(-t, y2 * y, ACC);                                                     \
-  }
-    for (; k + 1 < kend; k += 2) {
-      PMC_RECT_PAIR(k, a0)
-      PMC_RECT_PAIR(k + 1, a1)
+  // phase 1: group pairs (64 lane items per warp pass), two pairs per broadcast load
+  const int G2 = G >> 1;
+  {
+    const int U = G2 * B;
+    int u = (int)(((long long)U * warp) / W);
+    const int u1 = (int)(((long long)U * (warp + 1)) / W);
+    if (u < u1) {
+      int g = u / B;
+      int k = u - g * B;
+      while (u < u1) {
+        const int l0 = g * 64 + lane, l1 = l0 + 32;
+        const bool v0 = l0 < A, v1 = l1 < A;
+        const LaneItem i0 = load_lane_item(S, baseA + min(l0, A - 1), Dx, Dy, Dz);
+        const LaneItem i1 = load_lane_item(S, baseA + min(l1, A - 1), Dx, Dy, Dz);
+        const int kend = min(B, k + (u1 - u));
+        u += kend - k;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll UNROLL
+        for (; k < kend; ++k) {
+          const double bx = bxp[k], by = byp[k], bz = bzp[k];
+          const double ux = mxp[k], uy = myp[k], uz = mzp[k], e = ep[k];
+          a0 = rect_pair(i0, bx, by, bz, ux, uy, uz, e, Dx, Dy, Dz, a0);
+          a1 = rect_pair(i1, bx, by, bz, ux, uy, uz, e, Dx, Dy, Dz, a1);
+        }
+        acc += (v0 ? a0 : 0.0) + (v1 ? a1 : 0.0);
+        k = 0;
+        ++g;
+      }
     }
-    if (k < kend) PMC_RECT_PAIR(k, a0)
-#undef PMC_RECT_PAIR
-    acc += valid ? (a0 + a1) : 0.0;
-    k = 0;
-    ++g;
+  }
+  // phase 2: the odd last group of 32 lane items
+  if (G & 1) {
+    int k = (int)(((long long)B * warp) / W);
+    const int kend = (int)(((long long)B * (warp + 1)) / W);
+    if (k < kend) {
+      const int li = (G - 1) * 32 + lane;
+      const bool valid = li < A;
+      const LaneItem it = load_lane_item(S, baseA + min(li, A - 1), Dx, Dy, Dz);
+      double a0 = 0.0, a1 = 0.0;
+      for (; k + 1 < kend; k += 2) {
+        a0 = rect_pair(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], ep[k], Dx, Dy, Dz, a0);
+        a1 = rect_pair(it, bxp[k + 1], byp[k + 1], bzp[k + 1], mxp[k + 1], myp[k + 1], mzp[k + 1], ep[k + 1], Dx,
+                       Dy, Dz, a1);
+      }
+      if (k < kend) a0 = rect_pair(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], ep[k], Dx, Dy, Dz, a0);
+      acc += valid ? (a0 + a1) : 0.0;
+    }
   }
   return acc;
 }
 
 // 4π × Σ over changed pairs of (new − old), summed over the CTA (result in every thread).
 // Contains two barriers (after E, and inside the reduction); no trailing barrier.
-template <int T>
+template <int T, int UNROLL = 2>
 __device__ __forceinline__ double cta_delta_pairs(const CtaView& S, int n, int energy_type, double b, int idx,
                                                   double npx, double npy, double npz,   // μ'
                                                   double dnx, double dny, double dnz) { // Δn̂
@@ -244,7 +286,7 @@ __device__ __forceinline__ double cta_delta_pairs(const CtaView& S, int n, int e
     }
   }
   __syncthreads();  // E visible
-  if (rect) acc += rect_sum<T>(S, baseA, A, baseB, B, ex, ey, ez);
+  if (rect) acc += rect_sum<T, UNROLL>(S, baseA, A, baseB, B, ex, ey, ez);
   return block_sum<T>(acc, S.part, /*trailing_sync=*/false);
 }
 
@@ -308,7 +350,7 @@ __device__ __forceinline__ void stage_row(const ChainDyn& D, long long step, dou
 }
 
 // The hot loop (mcmc_eap_chain.jl:276-350) for one interacting chain per CTA.
-template <int T, int MINB>
+template <int T, int MINB, int UNROLL = 2>
 __global__ void __launch_bounds__(T, MINB) k_run_cta(const RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const CtaView S = carve(smem_raw, a.n);
@@ -339,7 +381,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta(const RunArgs a) {
     double dsum = 0.0;
     bool accept = false;
     if (!skip) {
-      dsum = kInv4Pi * cta_delta_pairs<T>(S, n, 1, b, idx, q->mx, q->my, q->mz, dnx, dny, dnz);
+      dsum = kInv4Pi * cta_delta_pairs<T, UNROLL>(S, n, 1, b, idx, q->mx, q->my, q->mz, dnx, dny, dnz);
       accept = metropolis(q->single - dsum * inv_kT, q->eps);
     }
     if (accept) {  // apply move!: x_idx += (b/2)Δn̂, x_{j>idx} += bΔn̂, μ_idx = μ'

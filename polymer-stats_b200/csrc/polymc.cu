@@ -100,7 +100,9 @@ int check_chain(const pmc_handle* h, int64_t chain) {
 // (n²/6 pairs) without leaving most lanes idle on short chains.  PMC_CTA_THREADS overrides.
 int pick_cta_threads(int n) {
   int t = n <= 96 ? 64 : n <= 256 ? 128 : n <= 1536 ? 256 : 512;
-  const int o = env_int("PMC_CTA_THREADS", 0);
+  int o = env_int("PMC_CTA_THREADS", 0);
+  const int cfg = env_int("PMC_RUN_CFG", 0);
+  if (cfg > 0) o = cfg / 100;
   if (o == 64 || o == 128 || o == 256 || o == 512 || o == 1024) t = o;
   return t;
 }
@@ -134,19 +136,41 @@ int launch_energy(pmc_handle* h, const EnergyArgs& a, int nblocks) {
 int launch_run_cta(pmc_handle* h, const RunArgs& a) {
   const size_t smem = cta_smem_bytes(h->n);
   const int nblocks = (int)h->nchains;
-#define PMC_CASE(TT, MB)                                                    \
-  case TT: {                                                                \
-    int rc = set_smem(k_run_cta<TT, MB>, smem);                             \
+  // PMC_RUN_CFG = threads*100 + minblocks*10 + unroll selects a tuning variant (experiments only)
+  const int cfg = env_int("PMC_RUN_CFG", 0);
+#define PMC_LAUNCH(TT, MB, UR)                                              \
+  {                                                                         \
+    int rc = set_smem(k_run_cta<TT, MB, UR>, smem);                         \
     if (rc) return rc;                                                      \
-    k_run_cta<TT, MB><<<nblocks, TT, smem, h->stream>>>(a);             \
-    ++h->launches;                 \
-    break;                                                                  \
+    k_run_cta<TT, MB, UR><<<nblocks, TT, smem, h->stream>>>(a);             \
+    ++h->launches;                                                          \
   }
-  switch (h->cta_threads) {
-    PMC_CASE(64, 8) PMC_CASE(128, 6) PMC_CASE(256, 3) PMC_CASE(512, 1) PMC_CASE(1024, 1)
+  if (cfg == 12842) PMC_LAUNCH(128, 4, 2)
+  else if (cfg == 12841) PMC_LAUNCH(128, 4, 1)
+  else if (cfg == 25621) PMC_LAUNCH(256, 2, 1)
+  else if (cfg == 51211) PMC_LAUNCH(512, 1, 1)
+  else if (cfg == 12862) PMC_LAUNCH(128, 6, 2)
+  else if (cfg == 12861) PMC_LAUNCH(128, 6, 1)
+  else if (cfg == 12882) PMC_LAUNCH(128, 8, 2)
+  else if (cfg == 12881) PMC_LAUNCH(128, 8, 1)
+  else if (cfg == 25632) PMC_LAUNCH(256, 3, 2)
+  else if (cfg == 25631) PMC_LAUNCH(256, 3, 1)
+  else if (cfg == 25642) PMC_LAUNCH(256, 4, 2)
+  else if (cfg == 25641) PMC_LAUNCH(256, 4, 1)
+  else if (cfg == 25622) PMC_LAUNCH(256, 2, 2)
+  else if (cfg == 51212) PMC_LAUNCH(512, 1, 2)
+  else if (cfg == 51222) PMC_LAUNCH(512, 2, 2)
+  else if (cfg == 102412) PMC_LAUNCH(1024, 1, 2)
+  else if (cfg == 102411) PMC_LAUNCH(1024, 1, 1)
+  else switch (h->cta_threads) {
+    case 64: PMC_LAUNCH(64, 8, 2) break;
+    case 128: PMC_LAUNCH(128, 4, 2) break;
+    case 256: PMC_LAUNCH(256, 2, 2) break;
+    case 512: PMC_LAUNCH(512, 1, 2) break;
+    case 1024: PMC_LAUNCH(1024, 1, 2) break;
     default: return fail(PMC_ERR_INVALID, "bad cta_threads");
   }
-#undef PMC_CASE
+#undef PMC_LAUNCH
   PMC_CU(cudaGetLastError());
   return PMC_OK;
 }

@@ -168,6 +168,40 @@ def test_trajectory_matches_oracle(pm, O, et, n, steps, ct, flips, umb):
             np.testing.assert_allclose(th, oth, rtol=0, atol=1e-12)
 
 
+def test_trajectory_n512_matches_oracle(pm, O):
+    """Headline chain length: 16 lane groups, both rectangle orientations, odd/even group counts."""
+    pc, oc = both_cases(pm, O, n=512, E0=1.0, Fz=0.5, energy_type="interacting", steps_per_adjust=100)
+    with pm.Ensemble(pc, replicas=148 * 3 + 1, seed=20260101) as ens:
+        traj, roll = ens.run(600, 100)
+        diag = ens.diagnostics()
+        for c in (0, 7, 444):
+            run = O.Run(oc, 20260101, c, 1)
+            ot, orl = run.steps(600, 100)
+            assert diag[c, 4] == run.diag()["nacc_total"]
+            assert diag[c, 0] == pytest.approx(run.diag()["phi_step"], rel=1e-14)
+            scale = max(1.0, np.abs(ot).max(), run.chain().abs_pair_sum())
+            np.testing.assert_allclose(traj[c], ot, rtol=0, atol=1e-9 * scale)
+
+
+@pytest.mark.parametrize("n", [65, 97, 512, 1000, 2049])
+def test_delta_u_every_rectangle_shape(pm, O, n):
+    """ΔU over many monomer indices: every split of heads/tails, lane-side choice and partial group."""
+    pc, oc = both_cases(pm, O, n=n, E0=1.5, K1=1.0, K2=0.2, Fz=0.4, Fx=-0.3, b=0.9, energy_type="interacting")
+    rng = np.random.default_rng(n)
+    with pm.Ensemble(pc, replicas=1, seed=77) as ens:
+        phi, th = ens.get_state(0)
+        och = O.Chain(oc, phi, th)
+        idxs = sorted(set([0, 1, 2, 30, 31, 32, 33, 63, 64, 65, n // 2 - 1, n // 2, n // 2 + 1, n - 66, n - 65, n - 64,
+                           n - 34, n - 33, n - 32, n - 3, n - 2, n - 1] + list(rng.integers(0, n, 12))))
+        for idx in idxs:
+            if not 0 <= idx < n:
+                continue
+            dphi, dth = float(rng.uniform(-1.2, 1.2)), float(rng.uniform(-0.6, 0.6))
+            dg, do = ens.delta_u(0, int(idx), dphi, dth), och.delta_u(int(idx), dphi, dth)
+            sc = max(1.0, do["abs_sum"] + abs(do["du"]) + abs(do["drF"]))
+            assert abs(dg["dU"] - do["dU"]) <= TOL * sc, (n, idx, dg, do)
+
+
 def test_trajectory_matches_reference_algorithm(pm, O):
     """Against oracle algo 0 = the reference's own algorithm (deep copy + full U recompute, stateful
     logπ_prev, incrementally updated Ω): same decisions on weakly coupled chains."""
@@ -317,7 +351,14 @@ def test_full_size_c2_properties(pm, O):
             och = O.Chain(oc, phi[cidx], th[cidx])
             scale = 1.0 + och.abs_pair_sum() + abs(och.energy()["U"])
             assert abs(E[cidx, 0] - och.energy()["U"]) <= TOL * scale
-            assert abs(d[cidx, 6] - E[cidx, 0]) <= 1e-10 * scale
+            # conditioning: positions carry absolute rounding ≈ eps·|x| (cumulative sums, eap_chain.jl:49-51),
+            # so a pair at distance r_min moves its 1/r³ term by ≈ 3·eps·|x|/r_min relative — the running U
+            # (incrementally shifted x) and the recomputed U (fresh cumsum) may differ by that much.
+            xs = och.xs()
+            i, j = np.triu_indices(512, 1)
+            rmin = np.sqrt(((xs[i] - xs[j]) ** 2).sum(1)).min()
+            bound = 1e-10 * scale + 100 * 2.2e-16 * scale * np.abs(xs).max() / rmin
+            assert abs(d[cidx, 6] - E[cidx, 0]) <= bound, (cidx, d[cidx, 6], E[cidx, 0], scale, rmin)
         # trajectory rows report the running state: last row's U equals the running U
         np.testing.assert_array_equal(traj[:, -1, 7], d[:, 6])
         # state stays in its domain; r equals b·Σn̂ recomputed from the state
