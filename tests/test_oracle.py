@@ -70,6 +70,25 @@ def test_random_kat_energies_and_moves(O, kat):
                 assert abs((c2.energy()["U"] - u0) - d["dU"]) <= 1e-11 * mv["scale"]
 
 
+def test_full_recompute_conditioning(O):
+    """The reference's full recompute is ill-conditioned near contacts (no excluded volume, SURVEY
+    finding 8): U(move!(copy)) − U(chain) carries ≈3·eps·|x|/r_min·Σ|terms| of noise, while the
+    changed-pair ΔU does not.  This is why GPU-vs-recompute drift is judged against Σ|pair terms|."""
+    n = 512
+    oc = O.make_case(n=n, E0=1.0, Fz=0.5, energy_type="interacting")
+    seen_large = False
+    for c in range(40):
+        ch = O.Chain(oc, seed=20260101, chain_id=c)
+        S = ch.abs_pair_sum()
+        d = ch.delta_u(7, 0.3, 0.2)
+        c2 = ch.copy()
+        c2.move(7, 0.3, 0.2)
+        incons = abs((c2.energy()["U"] - ch.energy()["U"]) - d["dU"])
+        assert incons <= 1e-9 * (S + 1.0)            # bounded relative to Σ|terms| (with contact amplification)
+        seen_large |= incons > 1e-12 * max(1.0, d["abs_sum"])
+    assert seen_large                                # ...but far above the ΔU's own rounding level
+
+
 def test_changed_pair_count_formula(O):
     # SURVEY finding 2: (idx)(n-1-idx) + (n-1) changed pairs; mean (n-1)(n-2)/6 + (n-1)
     n = 512
