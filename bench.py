@@ -103,6 +103,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def make_config(workload, kw, per_gpu, S, stepout):
+    """The `config` object — identical for both arms."""
+    return {"workload": f"{workload}: {kw['energy_type']} {kw['chain_type']} chains n={kw['n']}, "
+                        f"{per_gpu} replicas per GPU, {S} trials per step, stepout={stepout}",
+            "chains_per_gpu": per_gpu, "trials_per_step": S, "seed": SEED,
+            "l2": "flushed between timed steps (256 MiB write)", **kw}
+
+
 def cpu_reference_run(kw, n_chains, trials, threads, algo=0):
     """The reference algorithm (deep-copy-free full energy recompute per trial, oracle algo 0) on
     host threads, one chain per thread at a time."""
@@ -131,6 +139,11 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return 0
     kw, per_gpu, S, stepout = WORKLOADS[args.workload]
+    if args.chains_per_gpu:
+        per_gpu = args.chains_per_gpu
+    if args.trials_per_step:
+        S = args.trials_per_step
+        stepout = min(stepout, S)
     threads = os.cpu_count() or 1
     trials = sized_cpu_sample(kw, threads, target_s=args.ref_step_seconds)
     for _ in range(args.warmup):
@@ -147,18 +160,35 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {kw['energy_type']} {kw['chain_type']} chains n={kw['n']}",
-                   **{k: v for k, v in kw.items()}},
+        "config": make_config(args.workload, kw, per_gpu, S, stepout),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference algorithm (oracle/polymc_oracle.c, algo 0); "
                                  "Julia is not installed in this image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Exactly one JSON line on the real stdout (libraries such as NCCL may print to fd 1; everything
+    else is redirected to stderr for the duration of the run)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -185,7 +215,7 @@ def main():
     import polymc as pm
 
     if not torch.cuda.is_available() or pm.device_count() < 1:
-        print(json.dumps({"error": "no CUDA device: libpolymc_b200 has no CPU fallback"}), flush=True)
+        emit({"error": "no CUDA device: libpolymc_b200 has no CPU fallback"})
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -317,15 +347,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {kw['energy_type']} {kw['chain_type']} chains n={n}, "
-                                   f"{per_gpu} replicas per GPU, {S} trials per step, stepout={stepout}",
-                       "chains_per_gpu": per_gpu, "trials_per_step": S, "seed": SEED,
-                       "l2": "flushed between timed steps (256 MiB write)", **kw},
+            "config": make_config(args.workload, kw, per_gpu, S, stepout),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ens.close()
     if world > 1:
         dist.destroy_process_group()

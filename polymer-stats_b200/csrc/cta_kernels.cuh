@@ -139,6 +139,21 @@ __device__ double cta_pair_energy(const CtaView& S, int n, int energy_type) {
 // Shared-memory loads are not free next to the FP64 pipe (≈1.7 issue cycles per LDS.64 against 2 per
 // DFMA, tools/fp64_mix.cu), so each lane keeps NL=2 lane items and every broadcast item loaded from
 // shared memory serves two pairs; an odd last group of 32 lane items runs with NL=1.
+// A team = the warps that share the pair work of one chain: the whole CTA (FIRST_WARP = 0, plain
+// __syncthreads) or the worker warps of the warp-specialised kernel (named barrier 1).
+template <int NW, int FIRST_WARP>
+struct Team {
+  static constexpr int kWarps = NW;
+  static constexpr int kThreads = NW * 32;
+  __device__ __forceinline__ static int tid() { return (int)threadIdx.x - FIRST_WARP * 32; }
+  __device__ __forceinline__ static int warp() { return (int)(threadIdx.x >> 5) - FIRST_WARP; }
+  __device__ __forceinline__ static int lane() { return (int)(threadIdx.x & 31); }
+  __device__ __forceinline__ static void sync() {
+    if (FIRST_WARP == 0) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+  }
+};
+
 struct LaneItem {
   double x, y, z;     // position
   double ax, ay, az;  // μ
@@ -177,11 +192,11 @@ __device__ __forceinline__ double rect_pair(const LaneItem& it, double bx, doubl
   return fma(-t, y2 * y, acc);
 }
 
-template <int T, int UNROLL = 2>
+template <class TEAM, int UNROLL = 2>
 __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, int baseB, int B, double Dx,
                                            double Dy, double Dz) {
-  constexpr int W = T / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int W = TEAM::kWarps;
+  const int lane = TEAM::lane(), warp = TEAM::warp();
   const int G = (A + 31) >> 5;
   const double* __restrict__ bxp = S.sx + baseB;
   const double* __restrict__ byp = S.sy + baseB;
@@ -242,13 +257,14 @@ __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, i
   return acc;
 }
 
-// 4π × Σ over changed pairs of (new − old), summed over the CTA (result in every thread).
-// Contains two barriers (after E, and inside the reduction); no trailing barrier.
-template <int T, int UNROLL = 2>
-__device__ __forceinline__ double cta_delta_pairs(const CtaView& S, int n, int energy_type, double b, int idx,
-                                                  double npx, double npy, double npz,   // μ'
-                                                  double dnx, double dny, double dnz) { // Δn̂
-  const int tid = threadIdx.x;
+// 4π × Σ over changed pairs of (new − old): this thread's share (row part + rectangle).  Contains one
+// team barrier (after E).
+template <class TEAM, int UNROLL = 2>
+__device__ __forceinline__ double delta_pairs_partial(const CtaView& S, int n, int energy_type, double b, int idx,
+                                                      double npx, double npy, double npz,   // μ'
+                                                      double dnx, double dny, double dnz) { // Δn̂
+  constexpr int T = TEAM::kThreads;
+  const int tid = TEAM::tid();
   const double Dx = b * dnx, Dy = b * dny, Dz = b * dnz;  // tail translation
   const double hx = 0.5 * Dx, hy = 0.5 * Dy, hz = 0.5 * Dz;
   const int H = idx, Tl = n - 1 - idx;
@@ -285,8 +301,17 @@ __device__ __forceinline__ double cta_delta_pairs(const CtaView& S, int n, int e
              pair_g(ox, oy, oz, ux, uy, uz, rx, ry, rz);
     }
   }
-  __syncthreads();  // E visible
-  if (rect) acc += rect_sum<T, UNROLL>(S, baseA, A, baseB, B, ex, ey, ez);
+  TEAM::sync();  // E visible
+  if (rect) acc += rect_sum<TEAM, UNROLL>(S, baseA, A, baseB, B, ex, ey, ez);
+  return acc;
+}
+
+// Whole-CTA version: summed over the CTA, result in every thread; no trailing barrier.
+template <int T, int UNROLL = 2>
+__device__ __forceinline__ double cta_delta_pairs(const CtaView& S, int n, int energy_type, double b, int idx,
+                                                  double npx, double npy, double npz, double dnx, double dny,
+                                                  double dnz) {
+  const double acc = delta_pairs_partial<Team<T / 32, 0>, UNROLL>(S, n, energy_type, b, idx, npx, npy, npz, dnx, dny, dnz);
   return block_sum<T>(acc, S.part, /*trailing_sync=*/false);
 }
 
@@ -318,9 +343,8 @@ __device__ __forceinline__ void make_proposal(const RunArgs& a, const ChainParam
   build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
 }
 
-// Thread 0 (lane kernel: every thread): bookkeeping after the accept/reject decision —
-// counters (mcmc_eap_chain.jl:288-292), adaptation (:301-322), averagers (:327-328).
-__device__ __forceinline__ void after_decision(const ChainParams& P, ChainDyn& D, const Proposal& q, bool accept,
+// State update of an accepted move and the trial counters (mcmc_eap_chain.jl:288-292).
+__device__ __forceinline__ void apply_decision(const ChainParams& P, ChainDyn& D, const Proposal& q, bool accept,
                                                double dU_pairs, long long step) {
   if (accept) {
     D.U += q.du + q.drF + dU_pairs;
@@ -334,8 +358,19 @@ __device__ __forceinline__ void after_decision(const ChainParams& P, ChainDyn& D
   D.natt += 1;
   D.steps_total += 1;
   D.step = step;
+}
+
+// Step adaptation (:301-322) then the 8 averagers (:327-328) on the post-decision state.
+__device__ __forceinline__ void bookkeep(const ChainParams& P, ChainDyn& D, long long step) {
   adapt_steps(P, step, D.phi_step, D.theta_step, D.nacc, D.natt);
   record_averages(P, D.acc, D.comp, D.r, D.p, D.U, D.su, D.log_gauge);
+}
+
+// Thread 0 (lane kernel: every thread): everything after the accept/reject decision.
+__device__ __forceinline__ void after_decision(const ChainParams& P, ChainDyn& D, const Proposal& q, bool accept,
+                                               double dU_pairs, long long step) {
+  apply_decision(P, D, q, accept, dU_pairs, step);
+  bookkeep(P, D, step);
 }
 
 __device__ __forceinline__ void stage_row(const ChainDyn& D, long long step, double* rowbuf) {
@@ -416,6 +451,181 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta(const RunArgs a) {
   }
   __syncthreads();
   if (tid == 0) a.dyn[c] = *S.dyn;
+}
+
+// The accept/reject decision from the summed pair partials; explicit rounding so that every call site
+// (control warp and workers) takes bit-identical decisions.
+__device__ __forceinline__ bool decide(double single, double tsum, double inv_kT, double eps, double& dsum) {
+  dsum = __dmul_rn(kInv4Pi, tsum);
+  return metropolis(__fma_rn(-dsum, inv_kT, single), eps);
+}
+
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// Warp-specialised variant of the hot loop: warp 0 is the control warp (RNG, proposal, bookkeeping,
+// output rows), warps 1..WK are the workers that own the pair sums.  The control warp prepares the
+// proposal of trial s+1 and does the bookkeeping of trial s−1 WHILE the workers evaluate trial s, so
+// the serial per-trial work leaves the critical path.  The proposal of trial s+1 depends on the
+// outcome of trial s only when both touch the same monomer, or when trial s ends an adaptation
+// window (step sizes may change): those cases are built after the decision instead.
+// Barriers per trial: two whole-CTA (proposal published / partial sums ready) + one workers-only.
+template <int WK, int MINB, int UNROLL = 2>
+__global__ void __launch_bounds__((WK + 1) * 32, MINB) k_run_cta_ws(const RunArgs a) {
+  using TEAM = Team<WK, 1>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = a.n;
+  const bool control = tid < 32;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  if (tid == 0) {
+    *S.par = a.par[c];
+    *S.dyn = a.dyn[c];
+  }
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<(WK + 1) * 32>(mono, P, n, S);
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const double b = P.b, inv_kT = P.inv_kT;
+  const long long step0 = S.dyn->step;
+  const bool adapt_on = P.adj_scale != 1.0 && P.steps_per_adjust > 0;
+  double* part = S.part;  // [2][WK] ping-pong by trial parity
+
+  if (control) {
+    ChainDyn& D = *S.dyn;
+    long long row = 0;
+    bool booked = true;  // bookkeeping of the previous trial done?
+    if (tid == 0) make_proposal(a, P, D, mono, chain_id, step0 + 1, S.prop[1]);
+    cta_sync();  // (A) of trial 1
+    for (long long s = 1; s <= a.nsteps; ++s) {
+      const long long step = step0 + s;
+      const Proposal* q = &S.prop[s & 1];
+      // ---- overlapped with the workers' pair sums of trial s -------------------------------------
+      if (!booked) {  // bookkeeping of trial s−1
+        const long long pstep = step - 1;
+        if (tid == 0) bookkeep(P, D, pstep);
+        const bool isrow = a.stepout > 0 && (pstep % a.stepout) == 0;
+        if (isrow) {
+          if (tid == 0) stage_row(D, pstep, S.rowbuf);
+          __syncwarp();
+          if (row < a.rows) {
+            if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = S.rowbuf[tid];
+            if (tid < 17) a.roll[((size_t)c * a.rows + row) * 17 + tid] = S.rowbuf[8 + tid];
+          }
+          __syncwarp();
+          ++row;
+        }
+        booked = true;
+      }
+      const bool last = (s == a.nsteps);
+      const bool adapt_step = adapt_on && (step % P.steps_per_adjust) == 0;
+      bool deferred = false;
+      if (!last && tid == 0) {
+        const Draws d = draw_step(a.seed, chain_id, (uint32_t)D.init, step + 1, n);
+        if (d.idx == q->idx || adapt_step) {
+          deferred = true;
+        } else {
+          const MonoRec rec = mono[d.idx];
+          double dphi, dtheta;
+          increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
+          build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, S.prop[(s + 1) & 1]);
+        }
+      }
+      cta_sync();  // (C) partial sums of trial s are in part[s&1]
+      // ---- decision (the workers take the same one) ----------------------------------------------
+      if (tid == 0) {
+        double dsum = 0.0;
+        bool accept = false;
+        if (!q->skip) {
+          const double* ps = part + (s & 1) * WK;
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < WK; ++w) t += ps[w];
+          accept = decide(q->single, t, inv_kT, q->eps, dsum);
+        }
+        if (accept) {
+          MonoRec rec;
+          rec.phi = q->phi; rec.theta = q->theta;
+          rec.nx = q->nx; rec.ny = q->ny; rec.nz = q->nz; rec.sth = q->sth;
+          mono[q->idx] = rec;
+        }
+        apply_decision(P, D, *q, accept, dsum, step);
+        if (deferred) {
+          bookkeep(P, D, step);  // adaptation must precede the next proposal
+          make_proposal(a, P, D, mono, chain_id, step + 1, S.prop[(s + 1) & 1]);
+        }
+      }
+      deferred = __shfl_sync(0xffffffffu, (int)deferred, 0) != 0;
+      booked = false;
+      if (deferred) {  // rows of a trial booked early
+        const bool isrow = a.stepout > 0 && (step % a.stepout) == 0;
+        if (isrow) {
+          if (tid == 0) stage_row(D, step, S.rowbuf);
+          __syncwarp();
+          if (row < a.rows) {
+            if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = S.rowbuf[tid];
+            if (tid < 17) a.roll[((size_t)c * a.rows + row) * 17 + tid] = S.rowbuf[8 + tid];
+          }
+          __syncwarp();
+          ++row;
+        }
+        booked = true;
+      }
+      cta_sync();  // (A) of trial s+1: proposal published
+    }
+    if (!booked) {  // bookkeeping of the last trial
+      const long long pstep = step0 + a.nsteps;
+      if (tid == 0) bookkeep(P, D, pstep);
+      const bool isrow = a.stepout > 0 && (pstep % a.stepout) == 0;
+      if (isrow) {
+        if (tid == 0) stage_row(D, pstep, S.rowbuf);
+        __syncwarp();
+        if (row < a.rows) {
+          if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = S.rowbuf[tid];
+          if (tid < 17) a.roll[((size_t)c * a.rows + row) * 17 + tid] = S.rowbuf[8 + tid];
+        }
+        __syncwarp();
+      }
+    }
+    if (tid == 0) a.dyn[c] = D;
+  } else {
+    // ---- workers ----------------------------------------------------------------------------------
+    const int wtid = TEAM::tid();
+    cta_sync();  // (A) of trial 1
+    for (long long s = 1; s <= a.nsteps; ++s) {
+      const Proposal* q = &S.prop[s & 1];
+      const int idx = q->idx;
+      const bool skip = q->skip;
+      const double dnx = q->dnx, dny = q->dny, dnz = q->dnz;
+      double* ps = part + (s & 1) * WK;
+      if (!skip) {
+        double acc = delta_pairs_partial<TEAM, UNROLL>(S, n, 1, b, idx, q->mx, q->my, q->mz, dnx, dny, dnz);
+        acc = warp_sum(acc);
+        if (TEAM::lane() == 0) ps[TEAM::warp()] = acc;
+      }
+      cta_sync();  // (C)
+      bool accept = false;
+      if (!skip) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < WK; ++w) t += ps[w];
+        double dsum;
+        accept = decide(q->single, t, inv_kT, q->eps, dsum);
+      }
+      if (accept) {  // apply move!: x_idx += (b/2)Δn̂, x_{j>idx} += bΔn̂, μ_idx = μ'
+        const double Dx = b * dnx, Dy = b * dny, Dz = b * dnz;
+        for (int j = idx + 1 + wtid; j < n; j += TEAM::kThreads) {
+          S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
+        }
+        if (wtid == 0) {
+          S.sx[idx] += 0.5 * Dx; S.sy[idx] += 0.5 * Dy; S.sz[idx] += 0.5 * Dz;
+          S.mx[idx] = q->mx; S.my[idx] = q->my; S.mz[idx] = q->mz;
+        }
+      }
+      cta_sync();  // (A) of trial s+1
+    }
+  }
 }
 
 // Recompute {U, Σu, U_dd, Ω, r, p} of chains from their records (EAPChain ctor tail,

@@ -69,6 +69,7 @@ struct pmc_handle {
   float last_ms = 0.f;
   int64_t launches = 0;
   int cta_threads = 256;      // block size of the CTA-per-chain kernels
+  int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
   std::vector<ChainDyn> host_dyn;
 };
 
@@ -99,7 +100,7 @@ int check_chain(const pmc_handle* h, int64_t chain) {
 // Block size for the CTA-per-chain kernels: enough threads to cover the mean rectangle
 // (n²/6 pairs) without leaving most lanes idle on short chains.  PMC_CTA_THREADS overrides.
 int pick_cta_threads(int n) {
-  int t = n <= 96 ? 64 : n <= 256 ? 128 : n <= 1536 ? 256 : 512;
+  int t = n <= 96 ? 64 : n <= 1024 ? 128 : n <= 1536 ? 256 : 512;
   int o = env_int("PMC_CTA_THREADS", 0);
   const int cfg = env_int("PMC_RUN_CFG", 0);
   if (cfg > 0) o = cfg / 100;
@@ -138,6 +139,28 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
   const int nblocks = (int)h->nchains;
   // PMC_RUN_CFG = threads*100 + minblocks*10 + unroll selects a tuning variant (experiments only)
   const int cfg = env_int("PMC_RUN_CFG", 0);
+  // PMC_RUN_WS = workers*10 + minblocks selects the warp-specialised kernel (control warp + workers)
+  const int ws = env_int("PMC_RUN_WS", h->ws_cfg);
+#define PMC_LAUNCH_WS(WK, MB)                                               \
+  {                                                                         \
+    int rc = set_smem(k_run_cta_ws<WK, MB, 2>, smem);                       \
+    if (rc) return rc;                                                      \
+    k_run_cta_ws<WK, MB, 2><<<nblocks, (WK + 1) * 32, smem, h->stream>>>(a); \
+    ++h->launches;                                                          \
+    PMC_CU(cudaGetLastError());                                             \
+    return PMC_OK;                                                          \
+  }
+  if (cfg == 0) {
+    if (ws == 34) PMC_LAUNCH_WS(3, 4)
+    if (ws == 43) PMC_LAUNCH_WS(4, 3)
+    if (ws == 72) PMC_LAUNCH_WS(7, 2)
+    if (ws == 52) PMC_LAUNCH_WS(5, 2)
+    if (ws == 71) PMC_LAUNCH_WS(7, 1)
+    if (ws == 151) PMC_LAUNCH_WS(15, 1)
+    if (ws == 14) PMC_LAUNCH_WS(1, 4)
+    if (ws == 18) PMC_LAUNCH_WS(1, 8)
+  }
+#undef PMC_LAUNCH_WS
 #define PMC_LAUNCH(TT, MB, UR)                                              \
   {                                                                         \
     int rc = set_smem(k_run_cta<TT, MB, UR>, smem);                         \

@@ -16,11 +16,13 @@ for _ in range(3):
 F = 2*34*((n-1)*(n-2)/6+(n-1))
 print("%%d %%d %%.3f %%.4f %%.2f" %% (n, R, best, R*steps/best/1e3, R*steps/best/1e3*1e6*F/1e12))
 ''' % ROOT
-for n, R, steps, cfgs in ((512, 4096, 300, [0, 12842, 12841, 25622, 25621, 51212, 51211, 25632]),
-                          (4096, 148, 20, [0, 51212, 51211, 102412]),
-                          (100, 8192, 2000, [0, 12842, 12841])):
+for n, R, steps, cfgs in ((512, 4096, 300, [0, 12842, "ws34", "ws43", "ws72", "ws52", "ws71"]),
+                          (4096, 148, 20, [0, "ws151", "ws71"]),
+                          (100, 8192, 2000, [0, "ws34", "ws14", "ws18"]),
+                          (256, 4096, 1000, [0, 12842, "ws34", "ws72"])):
     for cfg in cfgs:
         env = dict(os.environ)
-        if cfg: env["PMC_RUN_CFG"] = str(cfg)
+        if isinstance(cfg, str): env["PMC_RUN_WS"] = cfg[2:]
+        elif cfg: env["PMC_RUN_CFG"] = str(cfg)
         out = subprocess.run([sys.executable, "-c", child, str(n), str(R), str(steps)], env=env, capture_output=True, text=True)
         print("cfg", cfg, "->", out.stdout.strip() or out.stderr.strip()[-300:], "(n R ms Mupd/s TF)", flush=True)
