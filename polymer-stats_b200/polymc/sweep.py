@@ -69,28 +69,21 @@ def gather_rows(local: np.ndarray, total_rows: int, lo: int, device=None) -> np.
     return full
 
 
-def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
-              rank: int | None = None, world: int | None = None, torch_device=None):
-    """Run every (case, replica) chain of a sweep for nsteps trials, sharded over the ranks of the
-    current torch.distributed group (or a single process).  Returns dict of gathered arrays, chain
-    order = case-major: avg [ncases*replicas][16], acc_rate, normalizer, sums [..][17]."""
-    dist = _dist()
-    if rank is None:
-        rank = dist.get_rank() if dist else 0
-    if world is None:
-        world = dist.get_world_size() if dist else 1
+def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
+              rank: int = 0, world: int = 1):
+    """Run this rank's contiguous block of every (n, energy) bucket.  Returns a list of
+    (global chain ids of the bucket, lo, block [hi-lo][35]) with block columns = 16 averages,
+    acceptance rate, normaliser, 17 raw sums.  No communication."""
     cases = list(cases)
-    total = len(cases) * replicas
-    out = {"avg": np.full((total, 16), np.nan), "acc_rate": np.full(total, np.nan),
-           "normalizer": np.full(total, np.nan), "sums": np.full((total, 17), np.nan)}
+    out = []
     for (_, _), idxs in bucket_cases(cases).items():
         # global chain ids of this bucket, case-major
         gids = np.concatenate([np.arange(i * replicas, (i + 1) * replicas) for i in idxs])
         lo, hi = shard_range(len(gids), rank, world)
         mine = gids[lo:hi]
         block = np.zeros((hi - lo, 35))
-        # a rank's block may start/end inside a case: run one handle per contiguous run of chains
-        # that share a case, with chain_id_base = global id of the first chain.
+        # a rank's block may start/end inside a case: one handle per run of consecutive chains of
+        # one case, with chain_id_base = global id of its first chain.
         pos = 0
         while pos < len(mine):
             case_i = mine[pos] // replicas
@@ -106,9 +99,32 @@ def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
                 block[pos:end, 17] = nrm
                 block[pos:end, 18:35] = ens.accumulators()
             pos = end
-        full = gather_rows(block, len(gids), lo, device=torch_device)
-        out["avg"][gids] = full[:, :16]
-        out["acc_rate"][gids] = full[:, 16]
-        out["normalizer"][gids] = full[:, 17]
-        out["sums"][gids] = full[:, 18:35]
+        out.append((gids, lo, block))
     return out
+
+
+def assemble(total: int, parts):
+    """dict of result arrays from [(gids, full [len(gids)][35]), ...]."""
+    res = {"avg": np.full((total, 16), np.nan), "acc_rate": np.full(total, np.nan),
+           "normalizer": np.full(total, np.nan), "sums": np.full((total, 17), np.nan)}
+    for gids, full in parts:
+        res["avg"][gids] = full[:, :16]
+        res["acc_rate"][gids] = full[:, 16]
+        res["normalizer"][gids] = full[:, 17]
+        res["sums"][gids] = full[:, 18:35]
+    return res
+
+
+def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
+              torch_device=None):
+    """Run every (case, replica) chain of a sweep for nsteps trials, sharded over the ranks of the
+    current torch.distributed group (or a single process), then gather the final per-chain results on
+    every rank.  Chain order = case-major: avg [ncases*replicas][16], acc_rate, normalizer, sums [..][17]."""
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    cases = list(cases)
+    parts = []
+    for gids, lo, block in run_shard(cases, replicas, nsteps, stepout, seed, device, rank, world):
+        parts.append((gids, gather_rows(block, len(gids), lo, device=torch_device)))
+    return assemble(len(cases) * replicas, parts)
