@@ -321,13 +321,20 @@ def main():
     kavg_ms = sum(kernel_ms) / len(kernel_ms)
     achieved_tf = per_gpu * S * F / (kavg_ms * 1e-3) / 1e12
     derived_tf = 148 * 64 * 2 * 1.965e9 / 1e12
-    kernel = "k_run_cta" if kw["energy_type"] == "interacting" else "k_run_lane"
+    kernel = "k_run_cta_win" if kw["energy_type"] == "interacting" and n <= 3000 else (
+        "k_run_cta" if kw["energy_type"] == "interacting" else "k_run_lane")
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the C2 launch, from
+    # profiles/r01d_dram_traffic_k_run_cta_win_bench_launch.csv (ncu, same command): 105.3 MB read (the
+    # chain records, once per launch) + 2.8-6.3 MB written.  Other workloads: not captured.
+    traffic = 1.10e8 if (args.workload == "C2" and per_gpu == 4096 and S == 500) else None
     roofline = {
         "bound": "fp64", "kernel": kernel, "achieved": achieved_tf, "peak": probe_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / probe_tf, "traffic": None,
+        "frac": achieved_tf / probe_tf, "traffic": traffic,
         "peak_source": "measured in this run: DFMA-only microbenchmark pmc_fp64_peak_probe (MEASURED_PEAKS.json "
                        "holds no FP64 figure)",
         "peak_derived": derived_tf, "frac_of_derived": achieved_tf / derived_tf,
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum); the path is FP64-pipe "
+                        "bound, HBM traffic is ~0.02 % of peak",
         "flop_per_update": F, "updates_per_launch": per_gpu * S, "kernel_ms_avg": kavg_ms,
         "kernel_share_of_step": kavg_ms * len(kernel_ms) / sum(step_ms),
     }

@@ -462,6 +462,119 @@ __device__ __forceinline__ bool decide(double single, double tsum, double inv_kT
 
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
+// Windowed variant of the hot loop: the serial part of a trial (Philox, sincos, log, …) is taken off
+// the per-trial critical path by building the proposals of the next WIN trials at once, one trial
+// per lane of warp 0.  A proposal depends on the chain only through the record of its own monomer, so
+// it stays valid unless an earlier trial of the window moves the same monomer: accepted trials mark
+// later same-monomer proposals dirty and those are rebuilt (serially, rarely) when their turn comes.
+// A window never crosses a step-size adaptation boundary (mcmc_eap_chain.jl:301-322).
+constexpr int kWin = 32;
+
+__host__ __device__ inline size_t cta_smem_bytes_win(int n) {
+  return cta_smem_bytes(n) + kWin * sizeof(Proposal) + 16;
+}
+
+template <int T, int MINB, int UNROLL = 2>
+__global__ void __launch_bounds__(T, MINB) k_run_cta_win(const RunArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  Proposal* win = reinterpret_cast<Proposal*>(smem_raw + cta_smem_bytes(a.n));
+  unsigned* dirty = reinterpret_cast<unsigned*>(win + kWin);
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = a.n;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  if (tid == 0) {
+    *S.par = a.par[c];
+    *S.dyn = a.dyn[c];
+  }
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const double b = P.b, inv_kT = P.inv_kT;
+  const long long step0 = S.dyn->step;
+  const uint32_t init = (uint32_t)S.dyn->init;
+  const bool adapt_on = P.adj_scale != 1.0 && P.steps_per_adjust > 0;
+  long long row = 0;
+
+  long long s = 1;
+  while (s <= a.nsteps) {
+    // ---- window [s, s+wlen) ----------------------------------------------------------------------
+    long long wl = a.nsteps - s + 1;
+    if (wl > kWin) wl = kWin;
+    if (adapt_on) {
+      const long long to_boundary = P.steps_per_adjust - ((step0 + s - 1) % P.steps_per_adjust);  // ≥1
+      if (wl > to_boundary) wl = to_boundary;
+    }
+    const int wlen = (int)wl;
+    if (tid < 32) {
+      if (tid < wlen) {
+        const Draws d = draw_step(a.seed, chain_id, init, step0 + s + tid, n);
+        const MonoRec rec = mono[d.idx];
+        double dphi, dtheta;
+        increments(P, d, rec.theta, S.dyn->phi_step, S.dyn->theta_step, dphi, dtheta);
+        build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, win[tid]);
+      }
+      if (tid == 0) *dirty = 0u;
+    }
+    __syncthreads();  // window visible
+    for (int k = 0; k < wlen; ++k) {
+      const long long step = step0 + s + k;
+      if ((*dirty >> k) & 1u) {  // an earlier trial of this window moved the same monomer: rebuild
+        if (tid == 0) make_proposal(a, P, *S.dyn, mono, chain_id, step, win[k]);
+        __syncthreads();
+      }
+      const Proposal* q = &win[k];
+      const int idx = q->idx;
+      const bool skip = q->skip;
+      const double dnx = q->dnx, dny = q->dny, dnz = q->dnz;
+      double dsum = 0.0;
+      bool accept = false;
+      if (!skip) {
+        const double t = cta_delta_pairs<T, UNROLL>(S, n, 1, b, idx, q->mx, q->my, q->mz, dnx, dny, dnz);
+        accept = decide(q->single, t, inv_kT, q->eps, dsum);
+      }
+      if (accept) {  // apply move!: x_idx += (b/2)Δn̂, x_{j>idx} += bΔn̂, μ_idx = μ'
+        const double Dx = b * dnx, Dy = b * dny, Dz = b * dnz;
+        for (int j = idx + 1 + tid; j < n; j += T) {
+          S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
+        }
+        if (tid < 32) {  // later proposals of the window on the same monomer are stale now
+          const bool stale = tid > k && tid < wlen && win[tid].idx == idx;
+          const unsigned m = __ballot_sync(0xffffffffu, stale);
+          if (tid == 0 && m) *dirty |= m;
+        }
+      }
+      if (tid == 0) {
+        if (accept) {
+          S.sx[idx] += 0.5 * b * dnx; S.sy[idx] += 0.5 * b * dny; S.sz[idx] += 0.5 * b * dnz;
+          S.mx[idx] = q->mx; S.my[idx] = q->my; S.mz[idx] = q->mz;
+          MonoRec rec;
+          rec.phi = q->phi; rec.theta = q->theta;
+          rec.nx = q->nx; rec.ny = q->ny; rec.nz = q->nz; rec.sth = q->sth;
+          mono[idx] = rec;
+        }
+        after_decision(P, *S.dyn, *q, accept, dsum, step);
+      }
+      const bool isrow = a.stepout > 0 && (step % a.stepout) == 0;
+      if (isrow && tid < 32) {
+        if (tid == 0) stage_row(*S.dyn, step, S.rowbuf);
+        __syncwarp();
+        if (row < a.rows) {
+          if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = S.rowbuf[tid];
+          if (tid < 17) a.roll[((size_t)c * a.rows + row) * 17 + tid] = S.rowbuf[8 + tid];
+        }
+        __syncwarp();
+      }
+      if (isrow) ++row;
+      __syncthreads();  // state, records and dirty mask of this trial are visible
+    }
+    s += wlen;
+  }
+  if (tid == 0) a.dyn[c] = *S.dyn;
+}
+
 // Warp-specialised variant of the hot loop: warp 0 is the control warp (RNG, proposal, bookkeeping,
 // output rows), warps 1..WK are the workers that own the pair sums.  The control warp prepares the
 // proposal of trial s+1 and does the bookkeeping of trial s−1 WHILE the workers evaluate trial s, so

@@ -70,6 +70,7 @@ struct pmc_handle {
   int64_t launches = 0;
   int cta_threads = 256;      // block size of the CTA-per-chain kernels
   int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
+  int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;
 };
 
@@ -100,7 +101,7 @@ int check_chain(const pmc_handle* h, int64_t chain) {
 // Block size for the CTA-per-chain kernels: enough threads to cover the mean rectangle
 // (n²/6 pairs) without leaving most lanes idle on short chains.  PMC_CTA_THREADS overrides.
 int pick_cta_threads(int n) {
-  int t = n <= 96 ? 64 : n <= 1024 ? 128 : n <= 1536 ? 256 : 512;
+  int t = n <= 128 ? 64 : n <= 1024 ? 128 : n <= 1536 ? 256 : 512;
   int o = env_int("PMC_CTA_THREADS", 0);
   const int cfg = env_int("PMC_RUN_CFG", 0);
   if (cfg > 0) o = cfg / 100;
@@ -161,6 +162,31 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
     if (ws == 18) PMC_LAUNCH_WS(1, 8)
   }
 #undef PMC_LAUNCH_WS
+  // windowed kernel (32 proposals built at once by warp 0): needs 6.7 KB more shared memory
+  const int use_win = env_int("PMC_RUN_WIN", h->use_win);
+  const size_t smem_win = cta_smem_bytes_win(h->n);
+#define PMC_LAUNCH_WIN(TT, MB)                                              \
+  {                                                                         \
+    int rc = set_smem(k_run_cta_win<TT, MB, 2>, smem_win);                  \
+    if (rc) return rc;                                                      \
+    k_run_cta_win<TT, MB, 2><<<nblocks, TT, smem_win, h->stream>>>(a);      \
+    ++h->launches;                                                          \
+    PMC_CU(cudaGetLastError());                                             \
+    return PMC_OK;                                                          \
+  }
+  if (cfg == 0 && use_win && smem_win <= (size_t)kSmemMax) {
+    if (use_win == 648) PMC_LAUNCH_WIN(64, 8)
+    if (use_win == 1286) PMC_LAUNCH_WIN(128, 6)
+    if (use_win == 2563) PMC_LAUNCH_WIN(256, 3)
+    switch (h->cta_threads) {
+      case 64: PMC_LAUNCH_WIN(64, 8)
+      case 128: PMC_LAUNCH_WIN(128, 4)
+      case 256: PMC_LAUNCH_WIN(256, 2)
+      case 512: PMC_LAUNCH_WIN(512, 1)
+      default: break;
+    }
+  }
+#undef PMC_LAUNCH_WIN
 #define PMC_LAUNCH(TT, MB, UR)                                              \
   {                                                                         \
     int rc = set_smem(k_run_cta<TT, MB, UR>, smem);                         \

@@ -16,13 +16,16 @@ for _ in range(3):
 F = 2*34*((n-1)*(n-2)/6+(n-1))
 print("%%d %%d %%.3f %%.4f %%.2f" %% (n, R, best, R*steps/best/1e3, R*steps/best/1e3*1e6*F/1e12))
 ''' % ROOT
-for n, R, steps, cfgs in ((512, 4096, 300, [0, 12842, "ws34", "ws43", "ws72", "ws52", "ws71"]),
-                          (4096, 148, 20, [0, "ws151", "ws71"]),
-                          (100, 8192, 2000, [0, "ws34", "ws14", "ws18"]),
-                          (256, 4096, 1000, [0, 12842, "ws34", "ws72"])):
+for n, R, steps, cfgs in ((512, 4096, 300, [0, "win1", "win1286", "win2563"]),
+                          (100, 8192, 2000, [0, "win1", "win648", "win1286", "thr64", "thr64win"]),
+                          (256, 4096, 1000, [0, "win1", "win1286"]),
+                          (64, 8192, 4000, [0, "win1"]),
+                          (1024, 1184, 100, [0, "win1"])):
     for cfg in cfgs:
         env = dict(os.environ)
-        if isinstance(cfg, str): env["PMC_RUN_WS"] = cfg[2:]
+        if isinstance(cfg, str) and cfg.startswith("win"): env["PMC_RUN_WIN"] = cfg[3:]
+        elif cfg == "thr64": env["PMC_CTA_THREADS"] = "64"
+        elif cfg == "thr64win": env["PMC_CTA_THREADS"] = "64"; env["PMC_RUN_WIN"] = "1"
         elif cfg: env["PMC_RUN_CFG"] = str(cfg)
         out = subprocess.run([sys.executable, "-c", child, str(n), str(R), str(steps)], env=env, capture_output=True, text=True)
         print("cfg", cfg, "->", out.stdout.strip() or out.stderr.strip()[-300:], "(n R ms Mupd/s TF)", flush=True)
