@@ -58,7 +58,8 @@ typedef struct pmc_case {
   int32_t do_flips;                       /* --do-flips                                           */
   int32_t umbrella;                       /* --umbrella-sampling                                  */
   int32_t force_init;                     /* --force-init                                         */
-  int32_t reserved;                       /* must be 0                                            */
+  int32_t accum_mode;                     /* --numeric-type: 0 = float64 (plain sums, the reference default),
+                                             1 = float128|dec128|big → Neumaier-compensated FP64 sums      */
 } pmc_case;
 
 typedef struct pmc_handle pmc_handle;

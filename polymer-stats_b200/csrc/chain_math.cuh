@@ -223,6 +223,7 @@ __device__ __forceinline__ void adapt_steps(const ChainParams& P, long long step
 }
 
 // record! of the 8 averagers (average.jl:40-48; umbrella :63-73) on the current state.
+template <bool COMP = true>
 __device__ __forceinline__ void record_averages(const ChainParams& P, double* acc, double* comp,
                                                 const double* r, const double* p, double U, double su,
                                                 double log_gauge) {
@@ -234,7 +235,10 @@ __device__ __forceinline__ void record_averages(const ChainParams& P, double* ac
                              p[0] * p[0] + p[1] * p[1] + p[2] * p[2],
                              U, U * U, 1.0};
 #pragma unroll
-  for (int k = 0; k < kNumAcc; ++k) comp_add(acc[k], comp[k], v[k] * wgt);
+  for (int k = 0; k < kNumAcc; ++k) {
+    if (COMP) comp_add(acc[k], comp[k], v[k] * wgt);
+    else acc[k] += v[k] * wgt;  // plain Float64 sums, as the reference's default --numeric-type (average.jl:40-48)
+  }
 }
 
 }  // namespace pmc

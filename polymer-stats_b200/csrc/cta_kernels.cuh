@@ -361,16 +361,18 @@ __device__ __forceinline__ void apply_decision(const ChainParams& P, ChainDyn& D
 }
 
 // Step adaptation (:301-322) then the 8 averagers (:327-328) on the post-decision state.
+template <bool COMP = true>
 __device__ __forceinline__ void bookkeep(const ChainParams& P, ChainDyn& D, long long step) {
   adapt_steps(P, step, D.phi_step, D.theta_step, D.nacc, D.natt);
-  record_averages(P, D.acc, D.comp, D.r, D.p, D.U, D.su, D.log_gauge);
+  record_averages<COMP>(P, D.acc, D.comp, D.r, D.p, D.U, D.su, D.log_gauge);
 }
 
 // Thread 0 (lane kernel: every thread): everything after the accept/reject decision.
+template <bool COMP = true>
 __device__ __forceinline__ void after_decision(const ChainParams& P, ChainDyn& D, const Proposal& q, bool accept,
                                                double dU_pairs, long long step) {
   apply_decision(P, D, q, accept, dU_pairs, step);
-  bookkeep(P, D, step);
+  bookkeep<COMP>(P, D, step);
 }
 
 __device__ __forceinline__ void stage_row(const ChainDyn& D, long long step, double* rowbuf) {

@@ -34,8 +34,8 @@ __device__ __forceinline__ double lane_delta_pairs(const MonoRec* __restrict__ m
 }
 
 // The hot loop (mcmc_eap_chain.jl:276-350), one chain per thread.
-template <int T>
-__global__ void __launch_bounds__(T) k_run_lane(const RunArgs a) {
+template <int T, int MINB, bool COMP>
+__global__ void __launch_bounds__(T, MINB) k_run_lane(const RunArgs a) {
   const int c = blockIdx.x * T + threadIdx.x;
   if (c >= a.nchains) return;
   const int n = a.n;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(T) k_run_lane(const RunArgs a) {
       nr.nx = q.nx; nr.ny = q.ny; nr.nz = q.nz; nr.sth = q.sth;
       mono[d.idx] = nr;
     }
-    after_decision(P, D, q, accept, dsum, step);
+    after_decision<COMP>(P, D, q, accept, dsum, step);
     if (a.stepout > 0 && (step % a.stepout) == 0) {
       if (row < a.rows) {
         double rb[kRowDoubles];
@@ -81,6 +81,153 @@ __global__ void __launch_bounds__(T) k_run_lane(const RunArgs a) {
     }
   }
   a.dyn[c] = D;
+}
+
+// One chain per WARP, 32 trials per window: for few chains (a sweep of 16k points is only 512 warps
+// with one chain per lane) the machine is filled by giving every lane one TRIAL of the same chain.
+// The draws of a trial do not depend on the chain state, and its outcome depends on the chain only
+// through the record of its own monomer (and, for Ising, the two neighbours), so the trials of a
+// window commute unless they touch conflicting monomers.  A window is resolved in rounds: a trial is
+// ready when no EARLIER unresolved trial of the window conflicts with it; ready trials are mutually
+// independent and are proposed, decided and applied in parallel.  The running r, p, U, Σu after each
+// trial — needed by the averagers, which record every trial — are inclusive prefix sums of the
+// accepted increments.  Each lane keeps its own compensated accumulators; they are combined at output
+// rows and at the end.  Windows never cross an adaptation boundary or an output row.
+template <int ISING, int MINB, bool COMP>
+__global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int c = (int)((blockIdx.x * 128u + threadIdx.x) >> 5);
+  if (c >= a.nchains) return;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int n = a.n;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  const ChainParams P = a.par[c];
+  ChainDyn D = a.dyn[c];  // uniform scalars (every lane holds a copy); accumulators: lane 0 only
+  double acc[kNumAcc], comp[kNumAcc];
+#pragma unroll
+  for (int k = 0; k < kNumAcc; ++k) {
+    acc[k] = lane == 0 ? D.acc[k] : 0.0;
+    comp[k] = lane == 0 ? D.comp[k] : 0.0;
+  }
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const long long step0 = D.step;
+  const bool adapt_on = P.adj_scale != 1.0 && P.steps_per_adjust > 0;
+  long long row = 0;
+  long long s = 1;
+  while (s <= a.nsteps) {
+    long long wl = a.nsteps - s + 1;
+    if (wl > 32) wl = 32;
+    if (adapt_on) {
+      const long long tb = P.steps_per_adjust - ((step0 + s - 1) % P.steps_per_adjust);
+      if (wl > tb) wl = tb;
+    }
+    if (a.stepout > 0) {
+      const long long tr = a.stepout - ((step0 + s - 1) % a.stepout);
+      if (wl > tr) wl = tr;
+    }
+    const int wlen = (int)wl;
+    const bool active = lane < wlen;
+    const long long step = step0 + s + lane;
+    Draws d;
+    d.idx = 0; d.flipbit = 0; d.u_phi = d.u_theta = d.eps = 0.0;
+    if (active) d = draw_step(a.seed, chain_id, (uint32_t)D.init, step, n);
+    // earlier trials of the window that conflict with this one
+    unsigned cmask = 0;
+    for (int j = 0; j < wlen; ++j) {
+      const int ij = __shfl_sync(FULL, d.idx, j);
+      const int dist = ij > d.idx ? ij - d.idx : d.idx - ij;
+      if (j < lane && dist <= ISING) cmask |= 1u << j;
+    }
+    bool pending = active;
+    bool accept = false;
+    double drx = 0, dry = 0, drz = 0, dpx = 0, dpy = 0, dpz = 0, dU = 0, dsu = 0, dOm = 0;
+    unsigned pmask;
+    while ((pmask = __ballot_sync(FULL, pending)) != 0u) {
+      const bool ready = pending && (cmask & pmask) == 0u;
+      if (ready) {
+        const MonoRec rec = mono[d.idx];
+        double dphi, dtheta;
+        increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
+        Proposal q;
+        build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+        if (!q.skip) {
+          const double dsum = kInv4Pi * lane_delta_pairs(mono, n, ISING ? 2 : 0, P, rec, q);
+          accept = metropolis(q.single - dsum * P.inv_kT, q.eps);
+          if (accept) {
+            MonoRec nr;
+            nr.phi = q.phi; nr.theta = q.theta;
+            nr.nx = q.nx; nr.ny = q.ny; nr.nz = q.nz; nr.sth = q.sth;
+            mono[d.idx] = nr;
+            drx = P.b * q.dnx; dry = P.b * q.dny; drz = P.b * q.dnz;
+            dpx = q.dmx; dpy = q.dmy; dpz = q.dmz;
+            dU = q.du + q.drF + dsum;
+            dsu = q.du;
+            dOm = q.dOmega;
+          }
+        }
+        pending = false;
+      }
+      __syncwarp();  // record writes of this round are visible to the next
+    }
+    // running state after each trial of the window: inclusive prefix sums of the increments
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t0 = __shfl_up_sync(FULL, drx, o), t1 = __shfl_up_sync(FULL, dry, o), t2 = __shfl_up_sync(FULL, drz, o);
+      const double t3 = __shfl_up_sync(FULL, dpx, o), t4 = __shfl_up_sync(FULL, dpy, o), t5 = __shfl_up_sync(FULL, dpz, o);
+      const double t6 = __shfl_up_sync(FULL, dU, o), t7 = __shfl_up_sync(FULL, dsu, o), t8 = __shfl_up_sync(FULL, dOm, o);
+      if (lane >= o) { drx += t0; dry += t1; drz += t2; dpx += t3; dpy += t4; dpz += t5; dU += t6; dsu += t7; dOm += t8; }
+    }
+    if (active) {
+      const double r[3] = {D.r[0] + drx, D.r[1] + dry, D.r[2] + drz};
+      const double p[3] = {D.p[0] + dpx, D.p[1] + dpy, D.p[2] + dpz};
+      record_averages<COMP>(P, acc, comp, r, p, D.U + dU, D.su + dsu, D.log_gauge);
+    }
+    const int last = wlen - 1;
+    D.r[0] += __shfl_sync(FULL, drx, last); D.r[1] += __shfl_sync(FULL, dry, last); D.r[2] += __shfl_sync(FULL, drz, last);
+    D.p[0] += __shfl_sync(FULL, dpx, last); D.p[1] += __shfl_sync(FULL, dpy, last); D.p[2] += __shfl_sync(FULL, dpz, last);
+    D.U += __shfl_sync(FULL, dU, last);
+    D.su += __shfl_sync(FULL, dsu, last);
+    D.Omega += __shfl_sync(FULL, dOm, last);
+    const int nacc_w = __popc(__ballot_sync(FULL, accept));
+    D.nacc += nacc_w; D.nacc_total += nacc_w;
+    D.natt += wlen; D.steps_total += wlen;
+    const long long step_last = step0 + s + last;
+    D.step = step_last;
+    adapt_steps(P, step_last, D.phi_step, D.theta_step, D.nacc, D.natt);  // no-op unless a boundary
+    if (a.stepout > 0 && (step_last % a.stepout) == 0) {
+      double tot[kNumAcc];
+#pragma unroll
+      for (int k = 0; k < kNumAcc; ++k) {
+        double v = acc[k] + comp[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        tot[k] = v;
+      }
+      if (lane == 0 && row < a.rows) {
+        double* t = a.traj + ((size_t)c * a.rows + row) * 8;
+        double* rr = a.roll + ((size_t)c * a.rows + row) * 17;
+        t[0] = (double)step_last;
+        t[1] = D.r[0]; t[2] = D.r[1]; t[3] = D.r[2];
+        t[4] = D.p[0]; t[5] = D.p[1]; t[6] = D.p[2];
+        t[7] = D.U;
+        rr[0] = (double)step_last;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) rr[1 + k] = tot[k] / tot[16];
+      }
+      ++row;
+    }
+    s += wlen;
+  }
+  // combine the per-lane accumulators
+#pragma unroll
+  for (int k = 0; k < kNumAcc; ++k) {
+    double v = acc[k] + comp[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    D.acc[k] = v;
+    D.comp[k] = 0.0;
+  }
+  if (lane == 0) a.dyn[c] = D;
 }
 
 // Non-mutating ΔU of one scripted move through the lane path's device code.

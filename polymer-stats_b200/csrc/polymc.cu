@@ -70,6 +70,8 @@ struct pmc_handle {
   int64_t launches = 0;
   int cta_threads = 256;      // block size of the CTA-per-chain kernels
   int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
+  long long warp_mode_below = 20000;
+  int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
   int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;
 };
@@ -282,7 +284,7 @@ int validate_case(const pmc_case& c, const pmc_case& first) {
   if (c.energy_type < 0 || c.energy_type > 2)
     return fail(PMC_ERR_INVALID, "energy-type is not understood.");  // eap_chain.jl:104
   if (!(c.kT > 0.0)) return fail(PMC_ERR_INVALID, "kT must be positive");
-  if (c.reserved != 0) return fail(PMC_ERR_INVALID, "pmc_case.reserved must be 0");
+  if (c.accum_mode != 0 && c.accum_mode != 1) return fail(PMC_ERR_INVALID, "accum_mode must be 0 or 1");
   return PMC_OK;
 }
 
@@ -373,6 +375,9 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   h->seed = seed;
   h->chain_id_base = chain_id_base;
   h->cta_threads = pick_cta_threads(n);
+  h->compensated = 0;
+  for (int64_t i = 0; i < ncases; ++i)
+    if (cases[i].accum_mode || cases[i].umbrella) h->compensated = 1;  // umbrella weights span many decades
 
   std::vector<ChainParams> par((size_t)nchains);
   std::vector<ChainDyn> dyn((size_t)nchains);
@@ -623,8 +628,34 @@ int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, do
   if (h->energy_type == PMC_ENERGY_INTERACTING) {
     if ((rc = launch_run_cta(h, a))) return rc;
   } else {
-    constexpr int TB = 64;
-    k_run_lane<TB><<<(unsigned)((h->nchains + TB - 1) / TB), TB, 0, h->stream>>>(a);
+    // few chains: one chain per warp with 32-trial windows fills the machine; many chains: one per lane
+    const int mode = env_int("PMC_LANE_MODE", 0);  // 1 = lane, 2 = warp, 0 = by chain count
+    const bool use_warp = mode == 2 || (mode == 0 && h->nchains < h->warp_mode_below);
+    // PMC_LANE_CFG = minblocks*10 + compensated selects a tuning variant (experiments only)
+    const int lcfg = env_int("PMC_LANE_CFG", -1);
+    const bool comp = lcfg >= 0 ? (lcfg % 10) != 0 : h->compensated != 0;
+    const int mb = lcfg >= 0 ? lcfg / 10 : 0;
+    if (use_warp) {
+      const unsigned nb = (unsigned)((h->nchains + 3) / 4);
+      const bool ising = h->energy_type == PMC_ENERGY_ISING;
+#define PMC_W(IS, MB, CP) k_run_warp<IS, MB, CP><<<nb, 128, 0, h->stream>>>(a)
+#define PMC_WSEL(MB)                                                        \
+  {                                                                         \
+    if (ising) { if (comp) PMC_W(1, MB, true); else PMC_W(1, MB, false); }  \
+    else { if (comp) PMC_W(0, MB, true); else PMC_W(0, MB, false); }        \
+  }
+      if (mb == 3) PMC_WSEL(3) else if (mb == 2) PMC_WSEL(2) else PMC_WSEL(4)
+#undef PMC_WSEL
+#undef PMC_W
+    } else {
+      constexpr int TB = 64;
+      const unsigned nb = (unsigned)((h->nchains + TB - 1) / TB);
+#define PMC_L(MB, CP) k_run_lane<TB, MB, CP><<<nb, TB, 0, h->stream>>>(a)
+      if (mb == 6 || (mb == 0 && !comp)) { if (comp) PMC_L(6, true); else PMC_L(6, false); }
+      else if (mb == 8) { if (comp) PMC_L(8, true); else PMC_L(8, false); }
+      else { if (comp) PMC_L(4, true); else PMC_L(4, false); }
+#undef PMC_L
+    }
     ++h->launches;
     PMC_CU(cudaGetLastError());
   }

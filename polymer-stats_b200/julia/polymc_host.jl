@@ -17,7 +17,7 @@ struct PmcCase
   phi_step::Cdouble; theta_step::Cdouble
   adj_lb::Cdouble; adj_ub::Cdouble; adj_scale::Cdouble
   n::Int64; steps_per_adjust::Int64
-  chain_type::Int32; energy_type::Int32; do_flips::Int32; umbrella::Int32; force_init::Int32; reserved::Int32
+  chain_type::Int32; energy_type::Int32; do_flips::Int32; umbrella::Int32; force_init::Int32; accum_mode::Int32
 end
 
 pmc_error() = unsafe_string(ccall((:pmc_last_error, LIBPOLYMC), Cstring, ()))
@@ -61,7 +61,8 @@ function case_of(p)
   haskey(et, p["energy-type"]) || error("energy-type is not understood.")
   PmcCase(p["E0"], p["K1"], p["K2"], p["mu"], p["kT"], p["Fz"], p["Fx"], p["mlen"], p["phi-step"], p["theta-step"],
           p["step-adjust-lb"], p["step-adjust-ub"], p["step-adjust-scale"], p["num-monomers"], p["steps-per-adjust"],
-          ct[p["chain-type"]], et[p["energy-type"]], p["do-flips"], p["umbrella-sampling"], p["force-init"], 0)
+          ct[p["chain-type"]], et[p["energy-type"]], p["do-flips"], p["umbrella-sampling"], p["force-init"],
+          p["numeric-type"] == "float64" ? 0 : 1)
 end
 
 function mcmc(nsteps::Int, p)

@@ -51,7 +51,7 @@ class PmcCase(C.Structure):
         ("n", C.c_int64), ("steps_per_adjust", C.c_int64),
         ("chain_type", C.c_int32), ("energy_type", C.c_int32),
         ("do_flips", C.c_int32), ("umbrella", C.c_int32),
-        ("force_init", C.c_int32), ("reserved", C.c_int32),
+        ("force_init", C.c_int32), ("accum_mode", C.c_int32),
     ]
 
 
@@ -59,7 +59,7 @@ def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=
               chain_type="dielectric", energy_type="noninteracting",
               phi_step=3 * math.pi / 8, theta_step=3 * math.pi / 16,
               adj_lb=0.15, adj_ub=0.55, adj_scale=1.1, steps_per_adjust=2500,
-              do_flips=False, umbrella=False, force_init=False) -> PmcCase:
+              do_flips=False, umbrella=False, force_init=False, accum_mode=0) -> PmcCase:
     """Defaults are the ArgParse defaults of mcmc_eap_chain.jl:19-153."""
     if chain_type not in CHAIN_TYPES:
         raise PolymcError(-1, "chain-type is not understood.")      # eap_chain.jl:86
@@ -67,7 +67,7 @@ def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=
         raise PolymcError(-1, "energy-type is not understood.")     # eap_chain.jl:104
     return PmcCase(E0, K1, K2, mu, kT, Fz, Fx, b, phi_step, theta_step, adj_lb, adj_ub, adj_scale,
                    n, steps_per_adjust, CHAIN_TYPES[chain_type], ENERGY_TYPES[energy_type],
-                   int(do_flips), int(umbrella), int(force_init), 0)
+                   int(do_flips), int(umbrella), int(force_init), int(accum_mode))
 
 
 def build(force: bool = False) -> str:

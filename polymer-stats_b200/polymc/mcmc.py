@@ -97,7 +97,8 @@ def case_from_pargs(pargs: dict) -> lib.PmcCase:
         phi_step=pargs["phi-step"], theta_step=pargs["theta-step"],
         adj_lb=pargs["step-adjust-lb"], adj_ub=pargs["step-adjust-ub"], adj_scale=pargs["step-adjust-scale"],
         steps_per_adjust=pargs["steps-per-adjust"], do_flips=pargs["do-flips"],
-        umbrella=pargs["umbrella-sampling"], force_init=pargs["force-init"])
+        umbrella=pargs["umbrella-sampling"], force_init=pargs["force-init"],
+        accum_mode=0 if pargs.get("numeric-type", "float64") == "float64" else 1)
 
 
 def validate(pargs: dict):

@@ -45,5 +45,5 @@ def O():
 
 def both_cases(pm, O, **kw):
     """The same case for the CUDA library and for the oracle."""
-    okw = {k: v for k, v in kw.items() if k != "force_init"}
+    okw = {k: v for k, v in kw.items() if k not in ("force_init", "accum_mode")}
     return pm.make_case(**kw), O.make_case(**okw)

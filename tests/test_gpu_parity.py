@@ -168,6 +168,49 @@ def test_trajectory_matches_oracle(pm, O, et, n, steps, ct, flips, umb):
             np.testing.assert_allclose(th, oth, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("et", ["noninteracting", "Ising"])
+@pytest.mark.parametrize("mode,accum", [("1", 0), ("1", 1), ("2", 0), ("2", 1)])
+def test_lane_and_warp_kernels_match_oracle(pm, O, et, mode, accum, monkeypatch):
+    """Both O(1)-ΔU kernels (one chain per lane / one chain per warp with 32-trial windows), plain and
+    compensated accumulators, windows cut by adaptation (every 70) and output rows (every 45)."""
+    monkeypatch.setenv("PMC_LANE_MODE", mode)
+    pc, oc = both_cases(pm, O, n=37, E0=1.5, K2=0.2, Fz=0.6, Fx=-0.2, energy_type=et, do_flips=True,
+                        steps_per_adjust=70, accum_mode=accum)
+    with pm.Ensemble(pc, replicas=5, seed=31, chain_id_base=9) as ens:
+        t1, r1 = ens.run(900, 45)
+        t2, r2 = ens.run(1000, 45)           # continues: 1900 trials, rows at 945, 990, ...
+        avg, ar, nrm = ens.averages()
+        diag = ens.diagnostics()
+        for c in (0, 4):
+            run = O.Run(oc, 31, 9 + c, 1)
+            ot, orl = run.steps(1900, 45)
+            traj = np.concatenate([t1[c], t2[c]])
+            roll = np.concatenate([r1[c], r2[c]])
+            assert traj.shape == ot.shape
+            np.testing.assert_allclose(traj, ot, rtol=0, atol=1e-10 * max(1.0, np.abs(ot).max()))
+            np.testing.assert_allclose(roll, orl, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(orl).max()))
+            od = run.diag()
+            assert diag[c, 4] == od["nacc_total"] and diag[c, 2] == od["nacc"] and diag[c, 3] == od["natt"]
+            assert diag[c, 0] == pytest.approx(od["phi_step"], rel=1e-14)
+            assert ar[c] == run.averages()[1] and nrm[c] == 1900
+            phi, th = ens.get_state(c)
+            ophi, oth = run.chain().state()
+            np.testing.assert_allclose(phi, ophi, rtol=0, atol=1e-12)
+            np.testing.assert_allclose(th, oth, rtol=0, atol=1e-12)
+
+
+def test_many_chains_take_the_lane_kernel(pm, O):
+    """Above ~20k chains the library switches from chain-per-warp to chain-per-lane; same results."""
+    pc, oc = both_cases(pm, O, n=16, E0=1.0, Fz=0.5, energy_type="Ising")
+    R = 24576
+    with pm.Ensemble(pc, replicas=R, seed=6) as ens:
+        traj, _ = ens.run(300, 100)
+        for c in (0, 12345, R - 1):
+            run = O.Run(oc, 6, c, 1)
+            ot, _ = run.steps(300, 100)
+            np.testing.assert_allclose(traj[c], ot, rtol=0, atol=1e-10 * max(1.0, np.abs(ot).max()))
+
+
 def test_trajectory_n512_matches_oracle(pm, O):
     """Headline chain length: 16 lane groups, both rectangle orientations, odd/even group counts."""
     pc, oc = both_cases(pm, O, n=512, E0=1.0, Fz=0.5, energy_type="interacting", steps_per_adjust=100)
