@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libpolymc_oracle.so")
 
 CHAIN_TYPES = {"dielectric": 0, "polar": 1}
-ENERGY_TYPES = {"noninteracting": 0, "interacting": 1, "Ising": 2}
+ENERGY_TYPES = {"noninteracting": 0, "interacting": 1, "Ising": 2, "cutoff": 3}
 
 AVG_NAMES = ["r1", "r2", "r3", "r1sq", "r2sq", "r3sq", "rsq",
              "p1", "p2", "p3", "p1sq", "p2sq", "p3sq", "psq", "U", "Usq"]
@@ -36,6 +36,9 @@ class OrcCase(C.Structure):
         ("chain_type", C.c_int32), ("energy_type", C.c_int32),
         ("do_flips", C.c_int32), ("umbrella", C.c_int32),
         ("omega_compat", C.c_int32), ("_pad", C.c_int32),
+        # clustering driver (mcmc_clustering_eap_chain.jl:19-153)
+        ("kappa", C.c_double), ("psi0", C.c_double), ("cutoff_radius", C.c_double), ("cluster_prob", C.c_double),
+        ("clustering", C.c_int32), ("alpha_carry", C.c_int32), ("cutoff_full", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -43,11 +46,16 @@ def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=
               chain_type="dielectric", energy_type="noninteracting",
               phi_step=3 * math.pi / 8, theta_step=3 * math.pi / 16,
               adj_lb=0.15, adj_ub=0.55, adj_scale=1.1, steps_per_adjust=2500,
-              do_flips=False, umbrella=False, omega_compat=False) -> OrcCase:
-    """Defaults are the ArgParse defaults of mcmc_eap_chain.jl:19-153."""
+              do_flips=False, umbrella=False, omega_compat=False,
+              kappa=0.0, psi0=0.0, cutoff_radius=7.5, cluster_prob=0.5, clustering=False, alpha_carry=True,
+              cutoff_full=False) -> OrcCase:
+    """Defaults are the ArgParse defaults of mcmc_eap_chain.jl:19-153 (and, for the clustering fields,
+    of mcmc_clustering_eap_chain.jl:36-51,87-90; note that driver's own defaults for --energy-type (Ising)
+    and --step-adjust-ub (0.40) differ and are set by its host)."""
     return OrcCase(E0, K1, K2, mu, kT, Fz, Fx, b, phi_step, theta_step, adj_lb, adj_ub, adj_scale,
                    n, steps_per_adjust, CHAIN_TYPES[chain_type], ENERGY_TYPES[energy_type],
-                   int(do_flips), int(umbrella), int(omega_compat), 0)
+                   int(do_flips), int(umbrella), int(omega_compat), 0,
+                   kappa, psi0, cutoff_radius, cluster_prob, int(clustering), int(alpha_carry), int(cutoff_full), 0)
 
 
 def build(force: bool = False) -> str:
@@ -93,6 +101,22 @@ def lib():
     L.orc_chain_state.argtypes = [vp, dp, dp]
     L.orc_chain_move.argtypes = [vp, C.c_int64, C.c_double, C.c_double]
     L.orc_chain_delta_u.argtypes = [vp, C.c_int64, C.c_double, C.c_double, dp]
+    L.orc_chain_energy_ex.argtypes = [vp, dp]
+    L.orc_chain_new_x0.argtypes = [cp, C.c_uint64, C.c_uint32, C.c_uint32, dp, C.c_int64, dp]
+    L.orc_chain_new_x0.restype = vp
+    L.orc_draw_cluster.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_int32, C.c_int64]
+    L.orc_draw_cluster.restype = C.c_double
+    L.orc_draw_cluster_gate.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64]
+    L.orc_draw_cluster_gate.restype = C.c_double
+    L.orc_chain_delta_segment.argtypes = [vp, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_int64, dp]
+    L.orc_chain_move_segment.argtypes = [vp, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_int64]
+    L.orc_chain_link_prob.argtypes = [vp, C.c_int64]
+    L.orc_chain_link_prob.restype = C.c_double
+    L.orc_run_begin_stage.argtypes = [vp, C.c_double]
+    L.orc_run_init_x0.argtypes = [vp, dp, C.c_int64, dp]
+    L.orc_run_extra_averages.argtypes = [vp, dp]
+    L.orc_run_steps_ex.argtypes = [vp, C.c_int64, C.c_int64, dp, dp, dp]
+    L.orc_run_cluster_stats.argtypes = [vp, dp]
     L.orc_run_new.argtypes = [cp, C.c_uint64, C.c_uint32, C.c_int32]
     L.orc_run_new.restype = vp
     L.orc_run_set_state.argtypes = [vp, dp, dp]
@@ -175,6 +199,27 @@ class Chain:
     def abs_pair_sum(self):
         return lib().orc_chain_abs_pair_sum(self._p)
 
+    def energy_ex(self):
+        """-> dict(U, su (incl. bending), Udd, Omega, Ubend, psi, cos2, abs_pair_sum)."""
+        o = np.empty(8)
+        lib().orc_chain_energy_ex(self._p, _dp(o))
+        return dict(zip(["U", "su", "Udd", "Omega", "Ubend", "psi", "cos2", "abs_pair_sum"], o))
+
+    def link_prob(self, i0):
+        """pflip_linear(n̂_i·n̂_{i+1}) (eap_chain.jl:267,290)."""
+        return lib().orc_chain_link_prob(self._p, i0)
+
+    def delta_segment(self, idx0, dphi, dtheta, reflect, lo0, hi0):
+        """Changed-term ΔU of move!(idx) followed by refl_n! on [lo,hi]; non-mutating."""
+        o = np.empty(12)
+        lib().orc_chain_delta_segment(self._p, idx0, dphi, dtheta, int(reflect), lo0, hi0, _dp(o))
+        return dict(zip(["dU", "dOmega", "abs_sum", "du", "drF", "dpair", "dbend", "dpsi", "dcos2",
+                         "dp1", "dp2", "dp3"], o))
+
+    def move_segment(self, idx0, dphi, dtheta, reflect, lo0, hi0):
+        """The same composite trial done literally (move! + refl_n! per monomer, full recomputes); mutates."""
+        lib().orc_chain_move_segment(self._p, idx0, dphi, dtheta, int(reflect), lo0, hi0)
+
     def r(self):
         o = np.empty(3)
         lib().orc_chain_r(self._p, _dp(o))
@@ -243,6 +288,36 @@ class Run:
 
     def reinit(self, force=False):
         return bool(lib().orc_run_reinit(self._p, int(force)))
+
+    # ---- clustering driver (mcmc_clustering_eap_chain.jl) ----
+    def begin_stage(self, kT):
+        """A fresh mcmc(nsteps, pargs, chain) call on the current chain at temperature kT (:171-265)."""
+        lib().orc_run_begin_stage(self._p, float(kT))
+
+    def init_x0(self, x0, dx0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        dx0 = np.ascontiguousarray(dx0, dtype=np.float64)
+        lib().orc_run_init_x0(self._p, _dp(x0), x0.size, _dp(dx0))
+
+    def steps_ex(self, nsteps, stepout=0, want_state=False):
+        """-> traj [rows][8], roll [rows][19], state [rows][2n] (phi,theta interleaved) or None."""
+        rows = nsteps // stepout if stepout else 0
+        traj = np.zeros((rows, 8))
+        roll = np.zeros((rows, 19))
+        state = np.zeros((rows, 2 * int(self.case.n))) if want_state else None
+        lib().orc_run_steps_ex(self._p, nsteps, stepout, _dp(traj) if rows else None, _dp(roll) if rows else None,
+                               _dp(state) if (want_state and rows) else None)
+        return traj, roll, state
+
+    def extra_averages(self):
+        o = np.empty(2)
+        lib().orc_run_extra_averages(self._p, _dp(o))
+        return o
+
+    def cluster_stats(self):
+        o = np.empty(3)
+        lib().orc_run_cluster_stats(self._p, _dp(o))
+        return dict(zip(["ncluster", "cluster_sum", "cluster_max"], o))
 
     def averages(self):
         avg = np.empty(16)

@@ -48,7 +48,8 @@ static inline double u53(uint32_t lo, uint32_t hi) {
 }
 
 /* Stream tags (word 3 of the counter): (init << 8) | sub.                                      */
-enum { SUB_STEP_A = 0, SUB_STEP_B = 1, SUB_INIT = 2, SUB_REINIT = 3 };
+enum { SUB_STEP_A = 0, SUB_STEP_B = 1, SUB_INIT = 2, SUB_REINIT = 3, SUB_CLUSTER_UP = 4, SUB_CLUSTER_DOWN = 5,
+       SUB_CLUSTER_GATE = 6 };
 
 static void philox_at(uint64_t seed, uint32_t chain_id, uint32_t init, uint32_t sub, uint64_t pos,
                       uint32_t out[4]) {
@@ -79,6 +80,22 @@ void orc_draw_step(uint64_t seed, uint32_t chain_id, uint32_t init, int64_t step
   *eps = u53(b[2], b[3]);
 }
 
+/* cluster_flip! draws an unbounded number of uniforms per trial (eap_chain.jl:273,291,307).  Uniform #k
+ * of the upward (stream 0) / downward (stream 1) growth is word pair (k&1) of the Philox block at
+ * position step + ((k>>1) << 40); steps stay below 2^40. */
+double orc_draw_cluster(uint64_t seed, uint32_t chain_id, uint32_t init, int64_t step, int32_t stream, int64_t k) {
+  uint32_t w[4];
+  philox_at(seed, chain_id, init, stream ? SUB_CLUSTER_DOWN : SUB_CLUSTER_UP,
+            (uint64_t)step + (((uint64_t)k >> 1) << 40), w);
+  return (k & 1) ? u53(w[2], w[3]) : u53(w[0], w[1]);
+}
+
+double orc_draw_cluster_gate(uint64_t seed, uint32_t chain_id, uint32_t init, int64_t step) {
+  uint32_t w[4];
+  philox_at(seed, chain_id, init, SUB_CLUSTER_GATE, (uint64_t)step, w);
+  return u53(w[0], w[1]);
+}
+
 double orc_draw_reinit_eps(uint64_t seed, uint32_t chain_id, uint32_t init) {
   uint32_t w[4];
   philox_at(seed, chain_id, init, SUB_REINIT, 0, w);
@@ -86,14 +103,15 @@ double orc_draw_reinit_eps(uint64_t seed, uint32_t chain_id, uint32_t init) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* EAPChain (inc/eap_chain.jl:12-36).  kappa == 0 in this driver (no --bend-mod; :91), so the   */
-/* psi / ubend caches (:45-47,:54-58) carry no energy and are not stored.                       */
+/* EAPChain (inc/eap_chain.jl:12-36).  kappa == 0 in mcmc_eap_chain.jl (no --bend-mod; :91); the */
+/* clustering driver sets it, and averages psi (mcmc_clustering_eap_chain.jl:244).              */
 /* ------------------------------------------------------------------------------------------ */
 struct orc_chain {
   orc_case c;
   int64_t n;
   double *phi, *cphi, *sphi, *theta, *ctheta, *stheta;
   double *nhat, *mus, *us, *xs; /* 3n, 3n, n, 3n */
+  double *psis;                 /* n-1 bond angles (eap_chain.jl:29) */
   double r[3];
   double Omega;
   double U;
@@ -126,6 +144,19 @@ static inline void mu_of(const orc_case* c, double cphi, double sphi, double cth
 /* u(E0, mu) = -1/2 E0 mu_z  (eap_chain.jl:53); same 1/2 for polar chains. */
 static inline double u_self(double E0, const double mu[3]) { return -1.0 / 2 * E0 * mu[2]; }
 
+/* ψj (eap_chain.jl:45-47): acos(min(1, max(-1, n̂_i·n̂_{i+1}))) */
+static inline double psi_of(const double* na, const double* nb) {
+  double d = na[0] * nb[0] + na[1] * nb[1] + na[2] * nb[2];
+  return acos(fmin(1.0, fmax(-1.0, d)));
+}
+static inline double psi_j(const orc_chain* ch, int64_t i) { return psi_of(&ch->nhat[3 * i], &ch->nhat[3 * (i + 1)]); }
+
+/* ubend (eap_chain.jl:54-58): κ/2 (ψ_i − ψ0)² for every monomer but the last. */
+static inline double ubend_val(const orc_case* c, double psi) { return c->kappa / 2 * (psi - c->psi0) * (psi - c->psi0); }
+static inline double ubend(const orc_chain* ch, int64_t i) {
+  return (i != ch->n - 1) ? ubend_val(&ch->c, ch->psis[i]) : 0.0;
+}
+
 /* update_xs! (eap_chain.jl:49-51): xs = b (cumsum(n̂) - n̂/2) */
 static void update_xs(orc_chain* ch) {
   double s[3] = {0, 0, 0};
@@ -155,6 +186,37 @@ static inline double pair_term(const double* xi, const double* xj, const double*
   return (mm - 3 * a * b) / (4 * M_PI * r3);
 }
 
+/* One term of UCutoff (eap_chain.jl:176-187): zero beyond the cut-off radius. */
+static inline double pair_term_cut(const double* xi, const double* xj, const double* mi, const double* mj,
+                                   double crad2) {
+  double r0 = xi[0] - xj[0], r1 = xi[1] - xj[1], r2c = xi[2] - xj[2];
+  double r2 = r0 * r0 + r1 * r1 + r2c * r2c;
+  if (r2 > crad2) return 0.0;
+  return pair_term(xi, xj, mi, mj);
+}
+
+static inline double crad2_of(const orc_case* c) {
+  double cr = c->cutoff_radius * c->b; /* UCutoff(pargs["cutoff-radius"]*pargs["mlen"]), eap_chain.jl:102 */
+  return cr * cr;
+}
+
+/* The pair term the chain's energy type uses between two arbitrary sites. */
+static inline double pair_any(const orc_case* c, const double* xi, const double* xj, const double* mi,
+                              const double* mj) {
+  if (c->energy_type == ORC_ENERGY_CUTOFF) return pair_term_cut(xi, xj, mi, mj, crad2_of(c));
+  return pair_term(xi, xj, mi, mj);
+}
+
+/* UCutoff functor (eap_chain.jl:171-192). */
+static double U_cutoff(const orc_chain* ch) {
+  double crad2 = crad2_of(&ch->c);
+  double U = 0.0;
+  for (int64_t i = 0; i < ch->n; ++i)
+    for (int64_t j = i + 1; j < ch->n; ++j)
+      U += pair_term_cut(&ch->xs[3 * i], &ch->xs[3 * j], &ch->mus[3 * i], &ch->mus[3 * j], crad2);
+  return U;
+}
+
 /* U_interaction (eap_chain.jl:196-211): all pairs, i outer, j inner. */
 static double U_interaction(const orc_chain* ch) {
   double U = 0.0;
@@ -181,15 +243,18 @@ static double sum_us(const orc_chain* ch) {
 static double U_pairs(const orc_chain* ch) {
   if (ch->c.energy_type == ORC_ENERGY_INTERACTING) return U_interaction(ch);
   if (ch->c.energy_type == ORC_ENERGY_ISING) return U_Ising(ch);
+  if (ch->c.energy_type == ORC_ENERGY_CUTOFF) return U_cutoff(ch);
   return 0.0;
 }
 
-/* Energy functors (inc/energy.jl:7-9, :13-16, :20-23). */
+/* Energy functors (inc/energy.jl:7-9, :13-16, :20-23) and UCutoff (eap_chain.jl:171-192), which is the
+ * bare pair sum: it adds neither Σu nor −r·F (unlike InteractingEnergy). */
 static double U_total(const orc_chain* ch) {
   double r[3];
   end_to_end(ch, r);
   double rf = r[0] * ch->c.Fx + r[1] * 0.0 + r[2] * ch->c.Fz;
   if (ch->c.energy_type == ORC_ENERGY_NONINTERACTING) return sum_us(ch) - rf;
+  if (ch->c.energy_type == ORC_ENERGY_CUTOFF && !ch->c.cutoff_full) return U_cutoff(ch);
   return sum_us(ch) + U_pairs(ch) - rf;
 }
 
@@ -208,6 +273,7 @@ static orc_chain* chain_alloc(const orc_case* c) {
   ch->mus = (double*)calloc(3 * n, sizeof(double));
   ch->us = (double*)calloc(n, sizeof(double));
   ch->xs = (double*)calloc(3 * n, sizeof(double));
+  ch->psis = (double*)calloc(n ? n : 1, sizeof(double));
   return ch;
 }
 
@@ -226,8 +292,9 @@ orc_chain* orc_chain_new(const orc_case* c, const double* phi, const double* the
     slog += log(ch->stheta[i]);
     nhat_of(ch->cphi[i], ch->sphi[i], ch->ctheta[i], ch->stheta[i], &ch->nhat[3 * i]);
     mu_of(c, ch->cphi[i], ch->sphi[i], ch->ctheta[i], ch->stheta[i], &ch->mus[3 * i]);
-    ch->us[i] = u_self(c->E0, &ch->mus[3 * i]);
   }
+  for (int64_t i = 0; i + 1 < ch->n; ++i) ch->psis[i] = psi_j(ch, i);                           /* :125 */
+  for (int64_t i = 0; i < ch->n; ++i) ch->us[i] = u_self(c->E0, &ch->mus[3 * i]) + ubend(ch, i); /* :130 */
   /* eap_chain.jl:117 stores log(prod(sin θ)), which underflows to -Inf for n >~ 1100 and then
    * accepts every move (SURVEY finding 7).  The intended Σ log sin θ is the default here.     */
   ch->Omega = c->omega_compat ? log(prod) : slog;
@@ -241,6 +308,26 @@ orc_chain* orc_chain_new_random(const orc_case* c, uint64_t seed, uint32_t chain
   double* phi = (double*)malloc(sizeof(double) * (size_t)c->n);
   double* theta = (double*)malloc(sizeof(double) * (size_t)c->n);
   for (int64_t k = 0; k < c->n; ++k) orc_draw_init(seed, chain_id, init, k, &phi[k], &theta[k]);
+  orc_chain* ch = orc_chain_new(c, phi, theta);
+  free(phi);
+  free(theta);
+  return ch;
+}
+
+/* EAPChain(pargs) with --x0/--dx0 (eap_chain.jl:63-78): ϕ = ϕ0 + rand(Uniform(0,dx0[1])), θ = θ0 +
+ * rand(Uniform(0,dx0[2])); x0 = [ϕ;θ] for all monomers or 2n interleaved values. */
+orc_chain* orc_chain_new_x0(const orc_case* c, uint64_t seed, uint32_t chain_id, uint32_t init, const double* x0,
+                            int64_t x0_len, const double dx0[2]) {
+  if (x0_len != 2 && x0_len != 2 * c->n) return NULL;
+  double* phi = (double*)malloc(sizeof(double) * (size_t)c->n);
+  double* theta = (double*)malloc(sizeof(double) * (size_t)c->n);
+  for (int64_t k = 0; k < c->n; ++k) {
+    uint32_t w[4];
+    philox_at(seed, chain_id, init, SUB_INIT, (uint64_t)k, w);
+    double p0 = x0_len == 2 ? x0[0] : x0[2 * k], t0 = x0_len == 2 ? x0[1] : x0[2 * k + 1];
+    phi[k] = p0 + (0.0 + (dx0[0] - 0.0) * u53(w[0], w[1]));
+    theta[k] = t0 + (0.0 + (dx0[1] - 0.0) * u53(w[2], w[3]));
+  }
   orc_chain* ch = orc_chain_new(c, phi, theta);
   free(phi);
   free(theta);
@@ -261,6 +348,7 @@ orc_chain* orc_chain_copy(const orc_chain* s) {
   memcpy(ch->mus, s->mus, 3 * n * sizeof(double));
   memcpy(ch->us, s->us, n * sizeof(double));
   memcpy(ch->xs, s->xs, 3 * n * sizeof(double));
+  memcpy(ch->psis, s->psis, n * sizeof(double));
   memcpy(ch->r, s->r, sizeof(ch->r));
   ch->Omega = s->Omega;
   ch->U = s->U;
@@ -279,6 +367,7 @@ static void chain_assign(orc_chain* d, const orc_chain* s) {
   memcpy(d->mus, s->mus, 3 * n * sizeof(double));
   memcpy(d->us, s->us, n * sizeof(double));
   memcpy(d->xs, s->xs, 3 * n * sizeof(double));
+  memcpy(d->psis, s->psis, n * sizeof(double));
   memcpy(d->r, s->r, sizeof(d->r));
   d->Omega = s->Omega;
   d->U = s->U;
@@ -288,7 +377,7 @@ void orc_chain_free(orc_chain* ch) {
   if (!ch) return;
   free(ch->phi); free(ch->cphi); free(ch->sphi);
   free(ch->theta); free(ch->ctheta); free(ch->stheta);
-  free(ch->nhat); free(ch->mus); free(ch->us); free(ch->xs);
+  free(ch->nhat); free(ch->mus); free(ch->us); free(ch->xs); free(ch->psis);
   free(ch);
 }
 
@@ -301,15 +390,49 @@ void orc_chain_energy(const orc_chain* ch, double out4[4]) {
 
 double orc_chain_abs_pair_sum(const orc_chain* ch) {
   double s = 0.0;
-  if (ch->c.energy_type == ORC_ENERGY_INTERACTING) {
+  if (ch->c.energy_type == ORC_ENERGY_INTERACTING || ch->c.energy_type == ORC_ENERGY_CUTOFF) {
     for (int64_t i = 0; i < ch->n; ++i)
       for (int64_t j = i + 1; j < ch->n; ++j)
-        s += fabs(pair_term(&ch->xs[3 * i], &ch->xs[3 * j], &ch->mus[3 * i], &ch->mus[3 * j]));
+        s += fabs(pair_any(&ch->c, &ch->xs[3 * i], &ch->xs[3 * j], &ch->mus[3 * i], &ch->mus[3 * j]));
   } else if (ch->c.energy_type == ORC_ENERGY_ISING) {
     for (int64_t i = 0; i + 1 < ch->n; ++i)
       s += fabs(pair_term(&ch->xs[3 * i], &ch->xs[3 * (i + 1)], &ch->mus[3 * i], &ch->mus[3 * (i + 1)]));
   }
   return s;
+}
+
+static double sum_ubend(const orc_chain* ch) {
+  double s = 0.0;
+  for (int64_t i = 0; i + 1 < ch->n; ++i) s += ubend(ch, i);
+  return s;
+}
+
+/* accessors of the two extra averagers, mcmc_clustering_eap_chain.jl:243-244 */
+static double sum_cos2(const orc_chain* ch) {
+  double s = 0.0;
+  for (int64_t i = 0; i < ch->n; ++i) s += ch->ctheta[i] * ch->ctheta[i];
+  return s;
+}
+static double sum_psi(const orc_chain* ch) {
+  double s = 0.0;
+  for (int64_t i = 0; i + 1 < ch->n; ++i) s += ch->psis[i];
+  return s;
+}
+
+void orc_chain_energy_ex(const orc_chain* ch, double out8[8]) {
+  out8[0] = U_total(ch);
+  out8[1] = sum_us(ch);
+  out8[2] = U_pairs(ch);
+  out8[3] = ch->Omega;
+  out8[4] = sum_ubend(ch);
+  out8[5] = sum_psi(ch) / (double)(ch->n - 1);
+  out8[6] = sum_cos2(ch);
+  out8[7] = orc_chain_abs_pair_sum(ch);
+}
+
+double orc_chain_link_prob(const orc_chain* ch, int64_t i) {
+  const double *a = &ch->nhat[3 * i], *b = &ch->nhat[3 * (i + 1)];
+  return (1 + (a[0] * b[0] + a[1] * b[1] + a[2] * b[2])) / 2;
 }
 
 void orc_chain_r(const orc_chain* ch, double r[3]) { end_to_end(ch, r); }
@@ -341,8 +464,12 @@ static void chain_move_caches(orc_chain* ch, int64_t idx, double dphi, double dt
   ch->stheta[idx] = sth;
   nhat_of(ch->cphi[idx], ch->sphi[idx], ch->ctheta[idx], ch->stheta[idx], &ch->nhat[3 * idx]);
   mu_of(&ch->c, ch->cphi[idx], ch->sphi[idx], ch->ctheta[idx], ch->stheta[idx], &ch->mus[3 * idx]);
-  if (idx > 0) ch->us[idx - 1] = u_self(ch->c.E0, &ch->mus[3 * (idx - 1)]);
-  ch->us[idx] = u_self(ch->c.E0, &ch->mus[3 * idx]);
+  if (idx < ch->n - 1) ch->psis[idx] = psi_j(ch, idx);                                      /* :246 */
+  if (idx > 0) {                                                                            /* :247-250 */
+    ch->psis[idx - 1] = psi_j(ch, idx - 1);
+    ch->us[idx - 1] = u_self(ch->c.E0, &ch->mus[3 * (idx - 1)]) + ubend(ch, idx - 1);
+  }
+  ch->us[idx] = u_self(ch->c.E0, &ch->mus[3 * idx]) + ubend(ch, idx);                       /* :251 */
   update_xs(ch);
   end_to_end(ch, ch->r);
 }
@@ -370,7 +497,7 @@ void orc_chain_delta_u(const orc_chain* ch, int64_t idx, double dphi, double dth
     xi_new[k] = ch->xs[3 * idx + k] + 0.5 * c->b * dn[k];  /* x'_idx = x_idx + (b/2)Δn̂   */
   }
   double dOmega = log(sth / ch->stheta[idx]);
-  double du = u_self(c->E0, mu1) - ch->us[idx];
+  double du = u_self(c->E0, mu1) - u_self(c->E0, &ch->mus[3 * idx]);
   double drF = -(D[0] * c->Fx + D[2] * c->Fz);
   double dpair = 0.0, abs_sum = 0.0;
   const double* xi_old = &ch->xs[3 * idx];
@@ -412,6 +539,121 @@ void orc_chain_delta_u(const orc_chain* ch, int64_t idx, double dphi, double dth
   out[5] = dpair;
 }
 
+/* refl_n! (eap_chain.jl:263-265): move!(chain, idx, 0, π − 2θ_idx). */
+static void chain_refl_caches(orc_chain* ch, int64_t i) { chain_move_caches(ch, i, 0.0, M_PI - 2 * ch->theta[i]); }
+
+/* The composite trial of the clustering driver done literally (mcmc_clustering_eap_chain.jl:272-273 →
+ * eap_chain.jl:230-257, :311-315): move!, then refl_n! for every monomer of the cluster, each with its
+ * own full energy recompute. */
+void orc_chain_move_segment(orc_chain* ch, int64_t idx, double dphi, double dtheta, int32_t reflect, int64_t lo,
+                            int64_t hi) {
+  orc_chain_move(ch, idx, dphi, dtheta);
+  if (reflect)
+    for (int64_t i = lo; i <= hi; ++i) {
+      chain_refl_caches(ch, i);
+      ch->U = U_total(ch);
+    }
+}
+
+/* The same composite trial in changed-term form (ours; equal to the literal form in real arithmetic).
+ * Monomers lo..hi get new directions and dipoles, the tail j > hi is translated rigidly by D = bΣΔn̂, so
+ * the changed pair terms are segment×everything and heads(i<lo)×tails(j>hi); bond angles ψ change on the
+ * bonds lo−1..hi. */
+void orc_chain_delta_segment(const orc_chain* ch, int64_t idx, double dphi, double dtheta, int32_t reflect,
+                             int64_t lo, int64_t hi, double out[12]) {
+  const orc_case* c = &ch->c;
+  const int64_t n = ch->n;
+  if (!reflect) lo = hi = idx;
+  const int64_t m = hi - lo + 1;
+  double* nn = (double*)malloc(sizeof(double) * 3 * (size_t)m);  /* n̂' */
+  double* mn = (double*)malloc(sizeof(double) * 3 * (size_t)m);  /* μ' */
+  double* xn = (double*)malloc(sizeof(double) * 3 * (size_t)m);  /* x' */
+  double dOmega = 0.0, du = 0.0, dcos2 = 0.0, dp[3] = {0, 0, 0};
+  double S[3] = {0, 0, 0};  /* running Σ Δn̂ over the segment */
+  for (int64_t k = 0; k < m; ++k) {
+    const int64_t i = lo + k;
+    double phi1 = ch->phi[i], th1 = ch->theta[i], sprev = ch->stheta[i];
+    if (i == idx) {  /* move! (:232-238) */
+      phi1 += dphi;
+      th1 = fmin(M_PI, fmax(0.0, th1 + dtheta));
+      double s1 = sin(th1);
+      dOmega += log(s1 / sprev);
+      sprev = s1;
+    }
+    if (reflect) {   /* refl_n!: dϕ = 0, dθ = π − 2θ (:263-265) */
+      phi1 += 0.0;
+      th1 = fmin(M_PI, fmax(0.0, th1 + (M_PI - 2 * th1)));
+      double s2 = sin(th1);
+      dOmega += log(s2 / sprev);
+      sprev = s2;
+    }
+    double cph = cos(phi1), sph = sin(phi1), cth = cos(th1), sth = sin(th1);
+    nhat_of(cph, sph, cth, sth, &nn[3 * k]);
+    mu_of(c, cph, sph, cth, sth, &mn[3 * k]);
+    du += u_self(c->E0, &mn[3 * k]) - u_self(c->E0, &ch->mus[3 * i]);
+    dcos2 += cth * cth - ch->ctheta[i] * ch->ctheta[i];
+    for (int q = 0; q < 3; ++q) {
+      const double dn = nn[3 * k + q] - ch->nhat[3 * i + q];
+      xn[3 * k + q] = ch->xs[3 * i + q] + c->b * (S[q] + 0.5 * dn);  /* update_xs! restricted to the segment */
+      S[q] += dn;
+      dp[q] += mn[3 * k + q] - ch->mus[3 * i + q];
+    }
+  }
+  const double D[3] = {c->b * S[0], c->b * S[1], c->b * S[2]};
+  const double drF = -(D[0] * c->Fx + D[2] * c->Fz);
+  /* bonds lo−1 .. hi */
+  double dbend = 0.0, dpsi = 0.0;
+  for (int64_t i = (lo > 0 ? lo - 1 : 0); i <= hi && i + 1 < n; ++i) {
+    const double* a = (i >= lo) ? &nn[3 * (i - lo)] : &ch->nhat[3 * i];
+    const double* b2 = (i + 1 <= hi) ? &nn[3 * (i + 1 - lo)] : &ch->nhat[3 * (i + 1)];
+    const double psi_new = psi_of(a, b2);
+    dpsi += psi_new - ch->psis[i];
+    dbend += ubend_val(c, psi_new) - ubend_val(c, ch->psis[i]);
+  }
+  /* pair terms */
+  double dpair = 0.0, abs_sum = 0.0;
+#define NEW_X(j, buf)                                                                     \
+  const double* buf##p;                                                                   \
+  double buf[3];                                                                          \
+  if ((j) >= lo && (j) <= hi) buf##p = &xn[3 * ((j) - lo)];                               \
+  else if ((j) > hi) { for (int q = 0; q < 3; ++q) buf[q] = ch->xs[3 * (j) + q] + D[q]; buf##p = buf; } \
+  else buf##p = &ch->xs[3 * (j)];
+#define NEW_MU(j) (((j) >= lo && (j) <= hi) ? &mn[3 * ((j) - lo)] : &ch->mus[3 * (j)])
+#define ADD_PAIR(i, j)                                                                     \
+  do {                                                                                     \
+    NEW_X(i, xi) NEW_X(j, xj)                                                              \
+    const double e_old = pair_any(c, &ch->xs[3 * (i)], &ch->xs[3 * (j)], &ch->mus[3 * (i)], &ch->mus[3 * (j)]); \
+    const double e_new = pair_any(c, xip, xjp, NEW_MU(i), NEW_MU(j));                      \
+    dpair += e_new - e_old;                                                                \
+    abs_sum += fabs(e_new) + fabs(e_old);                                                  \
+  } while (0)
+  if (c->energy_type == ORC_ENERGY_ISING) {
+    for (int64_t i = (lo > 0 ? lo - 1 : 0); i <= hi && i + 1 < n; ++i) ADD_PAIR(i, i + 1);
+  } else if (c->energy_type == ORC_ENERGY_INTERACTING || c->energy_type == ORC_ENERGY_CUTOFF) {
+    for (int64_t s2 = lo; s2 <= hi; ++s2) {  /* segment × everything (each pair once) */
+      for (int64_t j = 0; j < lo; ++j) ADD_PAIR(j, s2);
+      for (int64_t j = s2 + 1; j < n; ++j) ADD_PAIR(s2, j);
+    }
+    for (int64_t i = 0; i < lo; ++i)         /* heads × tails */
+      for (int64_t j = hi + 1; j < n; ++j) ADD_PAIR(i, j);
+  }
+#undef ADD_PAIR
+#undef NEW_MU
+#undef NEW_X
+  const int bare = (c->energy_type == ORC_ENERGY_CUTOFF && !c->cutoff_full);
+  out[0] = bare ? dpair : (du + dbend) + drF + dpair;
+  out[1] = dOmega;
+  out[2] = abs_sum;
+  out[3] = du;
+  out[4] = drF;
+  out[5] = dpair;
+  out[6] = dbend;
+  out[7] = dpsi;
+  out[8] = dcos2;
+  out[9] = dp[0]; out[10] = dp[1]; out[11] = dp[2];
+  free(nn); free(mn); free(xn);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* The sampler: Metropolis (inc/acceptance.jl:13-39), adaptation (mcmc_eap_chain.jl:301-322),   */
 /* averagers (inc/average.jl:8-48, :52-97), re-init (mcmc_eap_chain.jl:352-361).               */
@@ -433,7 +675,15 @@ struct orc_run {
   double normalizer;
   /* running quantities of the ΔU formulation (algo 1) */
   double p[3], su;
+  /* clustering driver */
+  double carry;          /* algo 1: logπ_prev − logπ(chain) = log α of the last accepted trial (acceptance.jl:30-33) */
+  double acc_x[2];       /* Σ of the two extra averagers (mcmc_clustering_eap_chain.jl:243-244) */
+  double spsi, scos2;    /* algo 1: running Σψ and Σcos²θ */
+  double ncluster, cluster_sum, cluster_max;
 };
+
+static void orc_run_steps_impl(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, double* roll, int roll_cols,
+                               double* state);
 
 /* AntiDipoleWeightFunction (average.jl:109-124) or WeightlessFunction (=1.0, average.jl:102). */
 static double weight_of(const orc_run* r, double su) {
@@ -444,7 +694,20 @@ static double weight_of(const orc_run* r, double su) {
 static void run_bind_chain(orc_run* r) {
   r->su = sum_us(r->chain);
   orc_chain_p(r->chain, r->p);
+  r->spsi = sum_psi(r->chain);
+  r->scos2 = sum_cos2(r->chain);
+  r->carry = 0.0;
   r->logpi_prev = -r->chain->U / r->c.kT + r->chain->Omega + weight_of(r, r->su);
+}
+
+/* AntiDipoleWeightFunction(chain) (average.jl:109-118): the gauge is fixed when it is constructed. */
+static void run_bind_gauge(orc_run* r) {
+  const orc_case* c = &r->c;
+  r->cF = 0.2 + 0.8 * exp(-(c->Fx * c->Fx + c->Fz * c->Fz) / c->kT);
+  if (c->chain_type == ORC_CHAIN_DIELECTRIC)
+    r->log_gauge = -(c->K1 + 2 * c->K2) * c->E0 * c->E0 * (double)c->n / (3 * c->kT) + r->chain->Omega;
+  else /* eigvals(mu*I)[end] = mu */
+    r->log_gauge = -c->mu * c->E0 * (double)c->n / (3 * c->kT) + r->chain->Omega;
 }
 
 orc_run* orc_run_new(const orc_case* c, uint64_t seed, uint32_t chain_id, int32_t algo) {
@@ -457,13 +720,40 @@ orc_run* orc_run_new(const orc_case* c, uint64_t seed, uint32_t chain_id, int32_
   r->theta_step = c->theta_step;
   r->chain = orc_chain_new_random(c, seed, chain_id, 0);
   r->trial = orc_chain_copy(r->chain);
-  r->cF = 0.2 + 0.8 * exp(-(c->Fx * c->Fx + c->Fz * c->Fz) / c->kT);
-  if (c->chain_type == ORC_CHAIN_DIELECTRIC)
-    r->log_gauge = -(c->K1 + 2 * c->K2) * c->E0 * c->E0 * (double)c->n / (3 * c->kT) + r->chain->Omega;
-  else /* eigvals(mu*I)[end] = mu */
-    r->log_gauge = -c->mu * c->E0 * (double)c->n / (3 * c->kT) + r->chain->Omega;
+  run_bind_gauge(r);
   run_bind_chain(r);
   return r;
+}
+
+/* A fresh `mcmc(nsteps, pargs, chain)` call of the clustering driver on the current chain
+ * (mcmc_clustering_eap_chain.jl:171-265): chain.kT = kT (:172), chain.U = U(chain) (:176), new weight
+ * function (:177) and acceptor (:178-181), new averagers (:196-251), counters and step sizes (:173,:262-264).
+ * burnargs is a *copy* of pargs (:368,:378), so the adapted step sizes saved at :348-349 never reach the
+ * next stage: every stage starts from --phi-step/--theta-step. */
+void orc_run_begin_stage(orc_run* r, double kT) {
+  r->c.kT = kT;
+  r->chain->c.kT = kT;
+  r->trial->c.kT = kT;
+  r->chain->U = U_total(r->chain);
+  r->init += 1; /* fresh random numbers for the new stage */
+  r->phi_step = r->c.phi_step;
+  r->theta_step = r->c.theta_step;
+  r->nacc = r->natt = r->nacc_total = r->steps_total = 0;
+  memset(r->acc, 0, sizeof(r->acc));
+  memset(r->acc_x, 0, sizeof(r->acc_x));
+  r->normalizer = 0.0;
+  r->ncluster = r->cluster_sum = r->cluster_max = 0.0;
+  run_bind_gauge(r);
+  run_bind_chain(r);
+}
+
+void orc_run_init_x0(orc_run* r, const double* x0, int64_t x0_len, const double dx0[2]) {
+  orc_chain* ch = orc_chain_new_x0(&r->c, r->seed, r->chain_id, 0, x0, x0_len, dx0);
+  if (!ch) return;
+  chain_assign(r->chain, ch);
+  orc_chain_free(ch);
+  run_bind_gauge(r);
+  run_bind_chain(r);
 }
 
 void orc_run_set_state(orc_run* r, const double* phi, const double* theta) {
@@ -490,18 +780,24 @@ static void record(orc_run* r) {
                   p[0], p[1], p[2], p[0] * p[0], p[1] * p[1], p[2] * p[2],
                   p[0] * p[0] + p[1] * p[1] + p[2] * p[2],
                   ch->U, ch->U * ch->U};
+  /* mcmc_clustering_eap_chain.jl:243-244: Σcos²θ and Σψ/(n−1) */
+  double x[2] = {(r->algo == 0) ? sum_cos2(ch) : r->scos2,
+                 ((r->algo == 0) ? sum_psi(ch) : r->spsi) / (double)(ch->n - 1)};
   if (r->c.umbrella) {
     double su = (r->algo == 0) ? sum_us(ch) : r->su;
     double expw = exp(weight_of(r, su));
     for (int k = 0; k < 16; ++k) r->acc[k] += v[k] / expw;
+    for (int k = 0; k < 2; ++k) r->acc_x[k] += x[k] / expw;
     r->normalizer += 1.0 / expw;
   } else {
     for (int k = 0; k < 16; ++k) r->acc[k] += v[k];
+    for (int k = 0; k < 2; ++k) r->acc_x[k] += x[k];
     r->normalizer += 1;
   }
 }
 
-static void emit_rows(const orc_run* r, int64_t step, double* traj_row, double* roll_row) {
+static void emit_rows(const orc_run* r, int64_t step, double* traj_row, double* roll_row, int roll_cols,
+                      double* state_row) {
   const orc_chain* ch = r->chain;
   if (traj_row) { /* mcmc_eap_chain.jl:330-333 */
     double p[3];
@@ -514,13 +810,146 @@ static void emit_rows(const orc_run* r, int64_t step, double* traj_row, double* 
   if (roll_row) { /* mcmc_eap_chain.jl:334-346 */
     roll_row[0] = (double)step;
     for (int k = 0; k < 16; ++k) roll_row[1 + k] = r->acc[k] / r->normalizer;
+    if (roll_cols == 19) /* mcmc_clustering_eap_chain.jl:344-345 */
+      for (int k = 0; k < 2; ++k) roll_row[17 + k] = r->acc_x[k] / r->normalizer;
   }
+  if (state_row) /* :317: phi1,theta1,phi2,theta2,… (the μ columns :318 are a function of these) */
+    for (int64_t i = 0; i < ch->n; ++i) {
+      state_row[2 * i] = ch->phi[i];
+      state_row[2 * i + 1] = ch->theta[i];
+    }
+}
+
+/* cluster_flip! (eap_chain.jl:269-333) on the chain `t` that already carries the single-monomer move:
+ * decides the cluster [lo,hi] and the link probabilities at its ends.  Returns 0 if the gate draw says
+ * "no cluster" (rand() <= ϵflip → α = 1, :273). */
+static int cluster_grow(const orc_run* r, const orc_chain* t, int64_t step, int64_t idx, int64_t* lo, int64_t* hi,
+                        double* upper_p, double* lower_p) {
+  const orc_case* c = &r->c;
+  if (orc_draw_cluster_gate(r->seed, r->chain_id, r->init, step) <= c->cluster_prob) return 0;
+  int64_t u = idx, k = 0;
+  double up;
+  for (;;) { /* :276-289 */
+    if (u >= t->n - 1) { up = 0.0; break; }
+    up = orc_chain_link_prob(t, u);
+    if (orc_draw_cluster(r->seed, r->chain_id, r->init, step, 0, k++) <= up) u += 1; else break;
+  }
+  int64_t l = idx;
+  double lp;
+  k = 0;
+  for (;;) { /* :292-305 */
+    if (l <= 0) { lp = 0.0; break; }
+    lp = orc_chain_link_prob(t, l - 1);
+    if (orc_draw_cluster(r->seed, r->chain_id, r->init, step, 1, k++) <= lp) l -= 1; else break;
+  }
+  *lo = l; *hi = u; *upper_p = up; *lower_p = lp;
+  return 1;
 }
 
 void orc_run_steps(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, double* roll) {
+  orc_run_steps_impl(r, nsteps, stepout, traj, roll, 17, NULL);
+}
+
+void orc_run_steps_ex(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, double* roll19, double* state) {
+  orc_run_steps_impl(r, nsteps, stepout, traj, roll19, 19, state);
+}
+
+/* One trial of mcmc_clustering_eap_chain.jl:267-279: move!, cluster_flip!, acceptor with α. */
+static int cluster_trial(orc_run* r, int64_t step) {
+  const orc_case* c = &r->c;
+  int64_t idx;
+  double uphi, uth, eps;
+  int32_t flipbit;
+  orc_draw_step(r->seed, r->chain_id, r->init, step, c->n, &idx, &uphi, &flipbit, &uth, &eps);
+  const double dphi = -r->phi_step + (2 * r->phi_step) * uphi;   /* :268-270 */
+  const double dth = -r->theta_step + (2 * r->theta_step) * uth;
+  int64_t lo = idx, hi = idx;
+  double up = 0.0, lp = 0.0, alpha = 1.0;
+  int reflect = 0, accepted = 0;
+  if (r->algo == 0) {
+    chain_assign(r->trial, r->chain);                 /* :271 */
+    orc_chain_move(r->trial, idx, dphi, dth);         /* :272 */
+    reflect = cluster_grow(r, r->trial, step, idx, &lo, &hi, &up, &lp);
+    if (reflect) {
+      for (int64_t i = lo; i <= hi; ++i) {            /* eap_chain.jl:311-315 */
+        chain_refl_caches(r->trial, i);
+        r->trial->U = U_total(r->trial);
+      }
+      const double nup = hi < c->n - 1 ? orc_chain_link_prob(r->trial, hi) : 0.0;      /* :317-321 */
+      const double nlp = lo > 0 ? orc_chain_link_prob(r->trial, lo - 1) : 0.0;         /* :322-326 */
+      alpha = ((1 - nup) * (1 - nlp)) / ((1 - up) * (1 - lp));                         /* :327-330 */
+    }
+    /* acceptance.jl:29-37 */
+    const double logpi_chain = -r->trial->U / c->kT + r->trial->Omega + weight_of(r, c->umbrella ? sum_us(r->trial) : 0.0);
+    const double logpi = logpi_chain + log(alpha);
+    if ((logpi >= r->logpi_prev) || (eps < exp(logpi - r->logpi_prev))) {
+      r->logpi_prev = c->alpha_carry ? logpi : logpi_chain;
+      orc_chain* t = r->chain; r->chain = r->trial; r->trial = t;
+      accepted = 1;
+    }
+  } else {
+    /* link probabilities are read from the chain carrying the single-monomer move: build only n̂'_idx */
+    orc_chain* t = r->trial; /* scratch view: copy n̂ of idx's neighbourhood lazily = copy all n̂ (cheap, O(n)) */
+    memcpy(t->nhat, r->chain->nhat, sizeof(double) * 3 * (size_t)c->n);
+    {
+      const double phi1 = r->chain->phi[idx] + dphi;
+      const double th1 = fmin(M_PI, fmax(0.0, r->chain->theta[idx] + dth));
+      nhat_of(cos(phi1), sin(phi1), cos(th1), sin(th1), &t->nhat[3 * idx]);
+    }
+    reflect = cluster_grow(r, t, step, idx, &lo, &hi, &up, &lp);
+    double d[12];
+    orc_chain_delta_segment(r->chain, idx, dphi, dth, reflect, lo, hi, d);
+    if (reflect) {
+      /* n̂ after the reflections at the two ends of the cluster: refl_n! maps θ → π−θ */
+      for (int64_t i = lo; i <= hi; i += (hi > lo ? hi - lo : 1)) {
+        double phi1 = r->chain->phi[i], th1 = r->chain->theta[i];
+        if (i == idx) { phi1 += dphi; th1 = fmin(M_PI, fmax(0.0, th1 + dth)); }
+        th1 = fmin(M_PI, fmax(0.0, th1 + (M_PI - 2 * th1)));
+        nhat_of(cos(phi1), sin(phi1), cos(th1), sin(th1), &t->nhat[3 * i]);
+      }
+      const double nup = hi < c->n - 1 ? orc_chain_link_prob(t, hi) : 0.0;
+      const double nlp = lo > 0 ? orc_chain_link_prob(t, lo - 1) : 0.0;
+      alpha = ((1 - nup) * (1 - nlp)) / ((1 - up) * (1 - lp));
+    }
+    const double dsu = d[3] + d[6];
+    const double dw = c->umbrella ? dsu / c->kT * r->cF : 0.0;
+    const double la = log(alpha);
+    const double dlogpi = -d[0] / c->kT + d[1] + dw + la - r->carry;
+    if ((dlogpi >= 0.0) || (eps < exp(dlogpi))) {
+      orc_chain* ch = r->chain;
+      const double Unew = ch->U + d[0], Onew = ch->Omega + d[1];
+      chain_move_caches(ch, idx, dphi, dth);
+      if (reflect)
+        for (int64_t i = lo; i <= hi; ++i) chain_refl_caches(ch, i);
+      ch->U = Unew;
+      ch->Omega = Onew;
+      for (int k = 0; k < 3; ++k) r->p[k] += d[9 + k];
+      r->su += dsu;
+      r->spsi += d[7];
+      r->scos2 += d[8];
+      r->carry = c->alpha_carry ? la : 0.0;
+      accepted = 1;
+    }
+  }
+  if (reflect) {
+    const double sz = (double)(hi - lo + 1);
+    r->ncluster += 1; r->cluster_sum += sz;
+    if (sz > r->cluster_max) r->cluster_max = sz;
+  }
+  return accepted;
+}
+
+static void orc_run_steps_impl(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, double* roll, int roll_cols,
+                               double* state) {
   const orc_case* c = &r->c;
   int64_t row = 0;
   for (int64_t step = 1; step <= nsteps; ++step) {
+    if (c->clustering) {
+      const int acc = cluster_trial(r, step);
+      if (acc) { r->nacc += 1; r->nacc_total += 1; }
+      goto counted;
+    }
+    {
     int64_t idx;
     double uphi, uth, eps;
     int32_t flipbit;
@@ -558,6 +987,8 @@ void orc_run_steps(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, do
       }
     }
     if (accepted) { r->nacc += 1; r->nacc_total += 1; }
+    }
+  counted:
     r->natt += 1;
     r->steps_total += 1;
     /* step-size adaptation (mcmc_eap_chain.jl:301-322) */
@@ -575,7 +1006,8 @@ void orc_run_steps(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, do
     }
     record(r);
     if (stepout > 0 && step % stepout == 0) {
-      emit_rows(r, step, traj ? traj + 8 * row : NULL, roll ? roll + 17 * row : NULL);
+      emit_rows(r, step, traj ? traj + 8 * row : NULL, roll ? roll + roll_cols * row : NULL, roll_cols,
+                state ? state + 2 * c->n * row : NULL);
       ++row;
     }
   }
@@ -595,6 +1027,14 @@ int32_t orc_run_reinit(orc_run* r, int32_t force_init) {
   }
   orc_chain_free(nc);
   return take;
+}
+
+void orc_run_extra_averages(const orc_run* r, double ex[2]) {
+  for (int k = 0; k < 2; ++k) ex[k] = r->acc_x[k] / r->normalizer;
+}
+
+void orc_run_cluster_stats(const orc_run* r, double out[3]) {
+  out[0] = r->ncluster; out[1] = r->cluster_sum; out[2] = r->cluster_max;
 }
 
 void orc_run_averages(const orc_run* r, double avg[16], double* acc_rate, double* normalizer) {

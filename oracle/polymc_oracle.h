@@ -3,7 +3,8 @@
  *
  * A plain-C restatement of the fixed-force MCMC hot path of grasingerm/polymer-stats
  * (mcmc_eap_chain.jl + inc/eap_chain.jl, energy.jl, dipole_response.jl, acceptance.jl,
- * average.jl).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * average.jl) and of its clustering twin mcmc_clustering_eap_chain.jl (cluster_flip!, bending
+ * energy, UCutoff, burn-in stages).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * `--impl reference` leg may load this library; the shipped CUDA library never does.
  *
  * PARITY UNPINNED by the reference: the reference ships no tests, no golden vectors and no
@@ -26,7 +27,7 @@ extern "C" {
 #endif
 
 enum { ORC_CHAIN_DIELECTRIC = 0, ORC_CHAIN_POLAR = 1 };
-enum { ORC_ENERGY_NONINTERACTING = 0, ORC_ENERGY_INTERACTING = 1, ORC_ENERGY_ISING = 2 };
+enum { ORC_ENERGY_NONINTERACTING = 0, ORC_ENERGY_INTERACTING = 1, ORC_ENERGY_ISING = 2, ORC_ENERGY_CUTOFF = 3 };
 
 /* One case = one command line of mcmc_eap_chain.jl (mcmc_eap_chain.jl:19-153). */
 typedef struct orc_case {
@@ -41,6 +42,17 @@ typedef struct orc_case {
   int32_t umbrella;
   int32_t omega_compat; /* 1: Omega0 = log(prod(sin theta)) exactly as eap_chain.jl:117 (underflows n>~1100) */
   int32_t _pad;
+  /* ---- clustering driver, mcmc_clustering_eap_chain.jl:19-153 ---- */
+  double kappa, psi0;      /* --bend-mod, --bend-angle (eap_chain.jl:54-58,91-92)                    */
+  double cutoff_radius;    /* --cutoff-radius in monomer lengths (UCutoff, eap_chain.jl:102,165-192) */
+  double cluster_prob;     /* --cluster-prob: cluster_flip! returns early iff rand() <= it (:273)    */
+  int32_t clustering;      /* 1: the trial of mcmc_clustering_eap_chain.jl:267-279 (move! + cluster_flip!,
+                              alpha in the acceptor, two extra averagers)                           */
+  int32_t alpha_carry;     /* 1 (reference): the acceptor stores logπ+log(alpha) as logπ_prev
+                              (acceptance.jl:30-33); 0: stores logπ only (plain Metropolis-Hastings)  */
+  int32_t cutoff_full;     /* 0 (reference): the UCutoff functor is the bare pair sum — no Σu, no −r·F
+                              (eap_chain.jl:171-192 vs energy.jl:13-16); 1: Σu + U_cut − r·F          */
+  int32_t _pad2;
 } orc_case;
 
 typedef struct orc_chain orc_chain;
@@ -76,6 +88,29 @@ void orc_chain_move(orc_chain* ch, int64_t idx0, double dphi, double dtheta);
  * out = {dU, dOmega, sum|changed pair terms| (old and new), du_self, dr·F part, dU_pairs}. */
 void orc_chain_delta_u(const orc_chain* ch, int64_t idx0, double dphi, double dtheta, double out[6]);
 
+/* out8 = {U, sum(us) incl. bending, U_dd, Omega, U_bend, sum(psi)/(n-1), sum(cos^2 theta), sum|pair terms|}. */
+void orc_chain_energy_ex(const orc_chain* ch, double out8[8]);
+/* EAPChain(pargs) with --x0/--dx0 (eap_chain.jl:63-78): x0 has 2 or 2n entries (phi,theta interleaved);
+ * the perturbations rand(Uniform(0,dx0[k])) reuse the uniforms of the random-init stream. */
+orc_chain* orc_chain_new_x0(const orc_case* c, uint64_t seed, uint32_t chain_id, uint32_t init,
+                            const double* x0, int64_t x0_len, const double dx0[2]);
+/* Uniform #k of the cluster-growth streams (stream 0 = up, 1 = down) and the gate uniform of
+ * cluster_flip! (eap_chain.jl:280,291,307). */
+double orc_draw_cluster(uint64_t seed, uint32_t chain_id, uint32_t init, int64_t step, int32_t stream, int64_t k);
+double orc_draw_cluster_gate(uint64_t seed, uint32_t chain_id, uint32_t init, int64_t step);
+/* The composite trial of the clustering driver in changed-term form, non-mutating: move!(idx0,dphi,dtheta)
+ * followed (if reflect) by refl_n! of every monomer in [lo0,hi0] (lo0 <= idx0 <= hi0).
+ * out[12] = {dU, dOmega, sum|changed pair terms|, du_self, drF, dU_pairs, dU_bend, d sum(psi),
+ *            d sum(cos^2 theta), dp1, dp2, dp3}. */
+void orc_chain_delta_segment(const orc_chain* ch, int64_t idx0, double dphi, double dtheta, int32_t reflect,
+                             int64_t lo0, int64_t hi0, double out[12]);
+/* The same composite trial done literally as the reference does (move! then refl_n! per monomer, each a
+ * full recompute); mutates. */
+void orc_chain_move_segment(orc_chain* ch, int64_t idx0, double dphi, double dtheta, int32_t reflect,
+                            int64_t lo0, int64_t hi0);
+/* (1 + n̂_i·n̂_{i+1})/2, pflip_linear (eap_chain.jl:267,290). */
+double orc_chain_link_prob(const orc_chain* ch, int64_t i0);
+
 /* Whole MCMC loop, mcmc_eap_chain.jl:266-363 for ONE init segment of an existing run state. */
 typedef struct orc_run orc_run;
 orc_run* orc_run_new(const orc_case* c, uint64_t seed, uint32_t chain_id, int32_t algo /*0 full recompute, 1 ΔU*/);
@@ -88,6 +123,18 @@ int32_t orc_run_reinit(orc_run* r, int32_t force_init);
 void orc_run_averages(const orc_run* r, double avg[16], double* acc_rate, double* normalizer);
 void orc_run_diag(const orc_run* r, double out[8]); /* phi_step, theta_step, nacc, natt, nacc_total, steps_total, U, Omega */
 const orc_chain* orc_run_chain(const orc_run* r);
+/* Clustering driver: a fresh `mcmc(nsteps, pargs, chain)` call on the current chain at temperature kT
+ * (mcmc_clustering_eap_chain.jl:171-265: kT, U, weight function, acceptor, averagers, counters and step
+ * sizes are rebuilt; the chain is kept).  Advances the RNG stream tag. */
+void orc_run_begin_stage(orc_run* r, double kT);
+/* Replace the chain by one built from --x0/--dx0. */
+void orc_run_init_x0(orc_run* r, const double* x0, int64_t x0_len, const double dx0[2]);
+/* The two extra averagers of the clustering driver (:243-244): <sum cos^2 theta>, <sum(psi)/(n-1)>. */
+void orc_run_extra_averages(const orc_run* r, double ex[2]);
+/* Clustering rows: roll19 = step + 16 + {Ealign, psi} (:334-346); state = [rows][2n] (phi,theta interleaved, :317). */
+void orc_run_steps_ex(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, double* roll19, double* state);
+/* Cluster statistics of the run so far: {trials with a cluster flip, sum of cluster sizes, largest}. */
+void orc_run_cluster_stats(const orc_run* r, double out[3]);
 void orc_run_free(orc_run* r);
 
 /* Multi-threaded throughput probe for bench.py's cpu_baseline / --impl reference leg:
