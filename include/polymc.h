@@ -1,7 +1,9 @@
 /*
  * polymc.h — C ABI of libpolymc_b200.so: the B200 (sm_100a) fixed-force-ensemble MCMC hot path
  * of grasingerm/polymer-stats, i.e. everything inside `mcmc(nsteps, pargs)` of
- * mcmc_eap_chain.jl:171-376 for thousands of independent chains at once.
+ * mcmc_eap_chain.jl:171-376 for thousands of independent chains at once — and, since ABI version 2,
+ * inside `mcmc(nsteps, pargs, chain)` of its clustering twin mcmc_clustering_eap_chain.jl:171-352
+ * (cluster_flip!, bending energy, cut-off pair sum, burn-in stages).
  *
  * The reference has no FFI of its own (pure Julia).  The seams this ABI replaces are ordinary
  * Julia functions; each entry point below cites the one it stands in for.  A Julia host binds
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PMC_ABI_VERSION 1
+#define PMC_ABI_VERSION 2
 
 typedef enum pmc_status {
   PMC_OK = 0,
@@ -44,7 +46,8 @@ typedef enum pmc_status {
 /* --chain-type (mcmc_eap_chain.jl:25-28; inc/eap_chain.jl:81-87) */
 enum { PMC_CHAIN_DIELECTRIC = 0, PMC_CHAIN_POLAR = 1 };
 /* --energy-type (mcmc_eap_chain.jl:41-44; inc/eap_chain.jl:95-105; "Ising" is accepted by the ctor) */
-enum { PMC_ENERGY_NONINTERACTING = 0, PMC_ENERGY_INTERACTING = 1, PMC_ENERGY_ISING = 2 };
+enum { PMC_ENERGY_NONINTERACTING = 0, PMC_ENERGY_INTERACTING = 1, PMC_ENERGY_ISING = 2,
+       PMC_ENERGY_CUTOFF = 3 /* UCutoff, inc/eap_chain.jl:102,165-192; mcmc_clustering_eap_chain.jl:44-51 */ };
 
 /* One case = one command line of mcmc_eap_chain.jl (ArgParse table :19-153). */
 typedef struct pmc_case {
@@ -60,6 +63,20 @@ typedef struct pmc_case {
   int32_t force_init;                     /* --force-init                                         */
   int32_t accum_mode;                     /* --numeric-type: 0 = float64 (plain sums, the reference default),
                                              1 = float128|dec128|big → Neumaier-compensated FP64 sums      */
+  /* ---- mcmc_clustering_eap_chain.jl (ABI v2); all zero = the plain driver ---------------------- */
+  double kappa, psi0;                     /* --bend-mod --bend-angle (:36-43; inc/eap_chain.jl:54-58,91-92)  */
+  double cutoff_radius;                   /* --cutoff-radius, monomer lengths (:48-51; inc/eap_chain.jl:102)  */
+  double cluster_prob;                    /* --cluster-prob (:87-90): cluster_flip! returns early (no flip)
+                                             iff rand() <= cluster_prob (inc/eap_chain.jl:273)               */
+  int32_t clustering;                     /* 1: the trial is move! + cluster_flip! with α in the acceptor
+                                             (mcmc_clustering_eap_chain.jl:267-279) and the two extra
+                                             averagers <Σcos²θ>, <Σψ/(n-1)> (:243-244) are recorded           */
+  int32_t alpha_carry;                    /* 1 = reference: the acceptor stores logπ+log α as logπ_prev
+                                             (inc/acceptance.jl:30-33); 0 = stores logπ (plain M-H)           */
+  int32_t cutoff_full;                    /* 0 = reference: the UCutoff functor is the bare pair sum, without
+                                             Σu and −r·F (inc/eap_chain.jl:171-192 vs inc/energy.jl:13-16);
+                                             1 = Σu + U_cut − r·F                                             */
+  int32_t reserved;
 } pmc_case;
 
 typedef struct pmc_handle pmc_handle;
@@ -102,6 +119,18 @@ int32_t pmc_observables(pmc_handle* h, int64_t chain, double out[6]);
  * WITHOUT mutating the chain: out[3] = {dU, dOmega, theta_was_clamped}.  Same device code as pmc_run. */
 int32_t pmc_delta_u(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, double dtheta, double out[3]);
 
+/* out[8] = {U, sum(us) incl. bending, U_dipole_dipole, Omega, U_bend, sum(psi)/(n-1), sum(cos^2 theta), 0}:
+ * the pieces of `U(chain)` with `ubend` (inc/eap_chain.jl:54-58,130) and UCutoff (:171-192), and the
+ * accessors of the two extra averagers (mcmc_clustering_eap_chain.jl:243-244). */
+int32_t pmc_energy_ex(pmc_handle* h, int64_t chain, double out[8]);
+/* The composite trial of the clustering driver WITHOUT mutating the chain — `move!(trial, idx, dphi,
+ * dtheta)` followed, if reflect, by `refl_n!(trial, i)` for i in [lo0,hi0] (inc/eap_chain.jl:263-265,
+ * 311-315; lo0 <= idx0 <= hi0, 0-based): out[12] = {dU, dOmega, dU_pairs, du_self, -dr·F, dU_bend,
+ * d sum(psi), d sum(cos^2 theta), dp1, dp2, dp3, log(alpha)} with alpha of inc/eap_chain.jl:317-330.
+ * Same device code as pmc_run on a clustering handle. */
+int32_t pmc_delta_segment(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, double dtheta, int32_t reflect,
+                          int64_t lo0, int64_t hi0, double out[12]);
+
 /* ---- the hot loop ------------------------------------------------------------------------ */
 /* Runs `nsteps` Metropolis trials on every chain — the `for step=1:nsteps` loop,
  * mcmc_eap_chain.jl:276-350: proposal :277-280, ΔU (replacing the deep copy + full recompute
@@ -113,6 +142,20 @@ int32_t pmc_delta_u(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, dou
  * The step counter continues across calls within one init. */
 int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll);
 int64_t pmc_rows_for(const pmc_handle* h, int64_t nsteps, int64_t stepout);
+/* The loop of the clustering driver, mcmc_clustering_eap_chain.jl:267-336 (handles whose cases set
+ * clustering, kappa or PMC_ENERGY_CUTOFF): roll19 [chains][rows][19] = step + 16 averages + Ealign + psi
+ * (:259,:334-346); state [chains][rows][2n] = phi1,theta1,phi2,theta2,… of each trajectory row (:317; the
+ * mu columns :318 are a function of these and are filled in by the host).  Any pointer may be NULL.
+ * pmc_run on such a handle runs the same loop and returns the first 17 rolling columns. */
+int32_t pmc_run_ex(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll19, double* state);
+/* A fresh `mcmc(nsteps, pargs, chain)` call on the chains as they are (mcmc_clustering_eap_chain.jl:171-265,
+ * the burn-in ladder :365-386): kT = kT_case * kT_scale, chain.U = U(chain), new weight function, acceptor,
+ * averagers, counters; step sizes restart from --phi-step/--theta-step (burnargs is a copy of pargs, :368);
+ * the step counter restarts and a fresh random stream is used. */
+int32_t pmc_begin_stage(pmc_handle* h, double kT_scale);
+/* `EAPChain(pargs)` with --x0/--dx0 (inc/eap_chain.jl:63-78): phi = phi0 + U(0,dx0[0]), theta = theta0 +
+ * U(0,dx0[1]); x0 holds {phi0, theta0} (x0_len 2) or 2n interleaved values. */
+int32_t pmc_init_x0(pmc_handle* h, const double* x0, int64_t x0_len, const double dx0[2]);
 /* Device time of the last pmc_run's MCMC kernel, CUDA events on the handle's stream. */
 int32_t pmc_last_run_ms(const pmc_handle* h, float* ms);
 /* Number of CUDA kernels this handle has launched so far (bench.py's `gpu_launches`). */
@@ -132,6 +175,12 @@ int32_t pmc_reinit(pmc_handle* h, int32_t* replaced);
 int32_t pmc_averages(pmc_handle* h, double* avg, double* acc_rate, double* normalizer);
 /* Raw accumulators for pooling replicas exactly: sums [chains][17] (16 sums + normaliser). */
 int32_t pmc_accumulators(pmc_handle* h, double* sums);
+/* The two extra averagers of the clustering driver (mcmc_clustering_eap_chain.jl:243-244, printed :398-399):
+ * ex [chains][2] = {<sum cos^2 theta>, <sum(psi)/(n-1)>}; raw sums for pooling: sums [chains][2]. */
+int32_t pmc_extra_averages(pmc_handle* h, double* ex);
+int32_t pmc_extra_accumulators(pmc_handle* h, double* sums);
+/* out [chains][3] = {trials with a cluster flip, sum of cluster sizes, largest cluster} of the current stage. */
+int32_t pmc_cluster_stats(pmc_handle* h, double* out);
 /* diag [chains][8] = {phi_step, theta_step, nacc, natt, nacc_total, trials, U_running, max |U_running -
  * U_recomputed| seen at re-synchronisation}. */
 int32_t pmc_diagnostics(pmc_handle* h, double* diag);

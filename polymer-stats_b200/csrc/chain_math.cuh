@@ -1,8 +1,9 @@
 // chain_math.cuh — device-side chain physics shared by every kernel of libpolymc_b200.
 //
 // Restates, for one monomer / one pair at a time, the arithmetic of
-//   inc/eap_chain.jl:40-58 (n̂, u), :200-207 (pair term), :230-257 (move!),
-//   inc/dipole_response.jl:7-29, inc/acceptance.jl:29-37, mcmc_eap_chain.jl:277-280
+//   inc/eap_chain.jl:40-58 (n̂, ψ, u, ubend), :176-187 and :200-207 (pair terms), :230-257 (move!),
+//   :263-333 (refl_n!, cluster_flip!), inc/dipole_response.jl:7-29, inc/acceptance.jl:29-37,
+//   mcmc_eap_chain.jl:277-280
 // in the changed-pair ΔU form of SURVEY.md §8a.  All arithmetic is FP64.
 #pragma once
 
@@ -18,7 +19,8 @@ constexpr double kInv4Pi = 0.07957747154594767;  // 1/(4π), hoisted out of the 
 // Philox4x32-10 (Salmon et al. SC'11).  Stream definition (DESIGN.md "RNG streams"):
 //   key = (seed_lo, seed_hi), counter = (pos_lo, pos_hi, chain_id, (init << 8) | sub)
 // ---------------------------------------------------------------------------------------------
-enum : uint32_t { SUB_STEP_A = 0, SUB_STEP_B = 1, SUB_INIT = 2, SUB_REINIT = 3 };
+enum : uint32_t { SUB_STEP_A = 0, SUB_STEP_B = 1, SUB_INIT = 2, SUB_REINIT = 3, SUB_CLUSTER_UP = 4,
+                  SUB_CLUSTER_DOWN = 5, SUB_CLUSTER_GATE = 6 };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -43,6 +45,21 @@ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
   return (double)(v >> 11) * 0x1.0p-53;
 }
 
+// cluster_flip! draws an unbounded number of uniforms per trial (eap_chain.jl:273,291,307): uniform #k
+// of the upward / downward growth is word pair (k&1) of the Philox block at position
+// step + ((k>>1) << 40) of stream SUB_CLUSTER_UP / _DOWN (steps stay below 2^40).
+__device__ __forceinline__ double draw_cluster(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
+                                               uint32_t sub, int k) {
+  const uint4 w = philox_at(seed, chain_id, init, sub, (uint64_t)step + (((uint64_t)k >> 1) << 40));
+  return (k & 1) ? u53(w.z, w.w) : u53(w.x, w.y);
+}
+
+__device__ __forceinline__ double draw_cluster_gate(uint64_t seed, uint32_t chain_id, uint32_t init,
+                                                    long long step) {
+  const uint4 w = philox_at(seed, chain_id, init, SUB_CLUSTER_GATE, (uint64_t)step);
+  return u53(w.x, w.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Per-monomer record in HBM.  (phi, theta) is the independent state (EAPChain.ϕs/θs,
 // eap_chain.jl:22,25); n̂ and sinθ are the caches a proposal needs (n̂s, sθs, :27,:28).
@@ -63,6 +80,11 @@ struct ChainParams {
   double phi_step0, theta_step0;
   long long steps_per_adjust;
   int do_flips, umbrella, force_init, pad;
+  // clustering driver (mcmc_clustering_eap_chain.jl): bending energy, cut-off pair sum, cluster flips
+  double kappa, psi0;     // --bend-mod, --bend-angle (eap_chain.jl:54-58)
+  double crad2;           // (cutoff-radius · mlen)², eap_chain.jl:102,172
+  double cluster_prob;    // cluster_flip! returns early iff rand() <= cluster_prob (eap_chain.jl:273)
+  int clustering, alpha_carry, cutoff_full, pad2;
 };
 
 constexpr int kNumAcc = 17;  // 16 sums (rolling.csv order) + normaliser
@@ -77,6 +99,15 @@ struct ChainDyn {
   double acc[kNumAcc], comp[kNumAcc];  // Neumaier-compensated sums
   long long nacc, natt, nacc_total, steps_total, step;
   int init, valid;
+};
+
+// Extra per-chain scalars of the clustering driver (kept apart from ChainDyn so that the tuned kernels
+// of mcmc_eap_chain.jl are untouched).
+struct ChainDynX {
+  double spsi, scos2;           // running Σψ_i and Σcos²θ_i (mcmc_clustering_eap_chain.jl:243-244)
+  double carry;                 // logπ_prev − logπ(chain) = log α of the last accepted trial (acceptance.jl:30-33)
+  double acc[2], comp[2];       // Σ of the two extra averagers (Neumaier-compensated)
+  double ncluster, cluster_sum, cluster_max;  // trials with a cluster flip, Σ cluster sizes, largest cluster
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -103,6 +134,36 @@ __device__ __forceinline__ double pair_g(double ax, double ay, double az, double
   const double y2 = y * y;
   const double t = fma(-3.0 * a * b, y2, mm);
   return t * (y2 * y);
+}
+
+// One term of UCutoff (eap_chain.jl:176-187): zero when r² > crad².
+__device__ __forceinline__ double pair_g_cut(double ax, double ay, double az, double bx, double by, double bz,
+                                             double rx, double ry, double rz, double crad2) {
+  const double r2 = fma(rz, rz, fma(ry, ry, rx * rx));
+  const double g = pair_g(ax, ay, az, bx, by, bz, rx, ry, rz);
+  return (r2 > crad2) ? 0.0 : g;
+}
+
+// ψ (eap_chain.jl:45-47): acos(min(1, max(-1, n̂_a·n̂_b)))
+__device__ __forceinline__ double psi_of(double ax, double ay, double az, double bx, double by, double bz) {
+  const double d = fma(az, bz, fma(ay, by, ax * bx));
+  return acos(fmin(1.0, fmax(-1.0, d)));
+}
+
+// ubend (eap_chain.jl:54-58)
+__device__ __forceinline__ double ubend_of(const ChainParams& P, double psi) {
+  const double t = psi - P.psi0;
+  return 0.5 * P.kappa * t * t;
+}
+
+// pflip_linear of a bond (eap_chain.jl:267,290): (1 + n̂_a·n̂_b)/2
+__device__ __forceinline__ double link_prob(double ax, double ay, double az, double bx, double by, double bz) {
+  return (1.0 + (ax * bx + ay * by + az * bz)) / 2.0;
+}
+
+// refl_n! (eap_chain.jl:263-265) = move!(chain, i, 0, π − 2θ_i): θ ← clamp(θ + (π − 2θ)).
+__device__ __forceinline__ double reflect_theta(double theta) {
+  return fmin(kPi, fmax(0.0, theta + (kPi - 2.0 * theta)));
 }
 
 __device__ __forceinline__ void mu_of(const ChainParams& P, double nx, double ny, double nz, double& mx,

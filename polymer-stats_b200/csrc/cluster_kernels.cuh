@@ -1,0 +1,788 @@
+// cluster_kernels.cuh — the trial of the clustering driver (mcmc_clustering_eap_chain.jl:267-279):
+//   move!(trial, idx, dϕ, dθ)  →  α = cluster_flip!(trial, idx)  →  acceptor(trial, ϵ; α)
+// with bending energy (--bend-mod/--bend-angle, eap_chain.jl:54-58), the cut-off pair sum (UCutoff,
+// eap_chain.jl:165-192) and the two extra averagers ⟨Σcos²θ⟩, ⟨Σψ/(n−1)⟩ (:243-244).
+//
+// The reference deep-copies the chain, calls move! and then refl_n! (= move!(i, 0, π−2θ_i)) for every
+// monomer of the cluster, each with a full O(n²) energy recompute (eap_chain.jl:311-315).  Here the whole
+// composite trial is ONE segment update: monomers lo..hi get new directions and dipoles, the tail j>hi is
+// translated rigidly by D = bΣΔn̂, so the changed pair terms are segment×everything plus the rectangle
+// heads(i<lo)×tails(j>hi) (same rectangle code as the single-monomer kernels), the changed bond angles
+// are lo−1..hi.  A trial without a cluster is the segment lo = hi = idx.
+//
+// Two packings, as for mcmc_eap_chain.jl: one CTA per chain (all-pairs and cut-off energies), one chain
+// per lane (non-interacting and Ising energies).
+#pragma once
+
+#include "lane_kernels.cuh"
+
+namespace pmc {
+
+// Sums reduced over the CTA for one composite trial.
+enum { R_PAIR = 0, R_BEND, R_PSI, R_USELF, R_OMEGA, R_COS2, R_PX, R_PY, R_PZ, kNumRed };
+
+struct ClusterCtl {
+  int idx, lo, hi, reflect;
+  double up, lp;  // link probabilities at the two ends of the cluster before the flip (eap_chain.jl:276-305)
+};
+
+struct ClView {
+  double *nhx, *nhy, *nhz;  // n̂_i of the current state (eap_chain.jl:27)
+  double *nnx, *nny, *nnz;  // n̂'_i of the trial, valid on the segment
+  double *xnx, *xny, *xnz;  // x'_i of the trial, valid on the segment
+  double* red;              // [kNumRed][32] warp partials
+  ClusterCtl* ctl;
+  ChainDynX* dx;
+};
+
+__host__ __device__ inline size_t cluster_smem_bytes(int n) {
+  size_t b = cta_smem_bytes(n);
+  b += (size_t)9 * n * sizeof(double) + (size_t)kNumRed * 32 * sizeof(double);
+  b += sizeof(ClusterCtl) + sizeof(ChainDynX);
+  return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ ClView carve_cluster(unsigned char* base, int n) {
+  ClView X;
+  double* d = reinterpret_cast<double*>(base + cta_smem_bytes(n));
+  X.nhx = d; X.nhy = d + n; X.nhz = d + 2 * n;
+  X.nnx = d + 3 * n; X.nny = d + 4 * n; X.nnz = d + 5 * n;
+  X.xnx = d + 6 * n; X.xny = d + 7 * n; X.xnz = d + 8 * n;
+  X.red = d + 9 * n;
+  X.ctl = reinterpret_cast<ClusterCtl*>(X.red + kNumRed * 32);
+  X.dx = reinterpret_cast<ChainDynX*>(X.ctl + 1);
+  return X;
+}
+
+template <int T>
+__device__ __forceinline__ void load_nhat(const MonoRec* __restrict__ mono, int n, const ClView& X) {
+  for (int i = threadIdx.x; i < n; i += T) {
+    const MonoRec r = mono[i];
+    X.nhx[i] = r.nx; X.nhy[i] = r.ny; X.nhz[i] = r.nz;
+  }
+}
+
+// n̂ of monomer i on the chain that carries the single-monomer move (cluster_flip! runs on the trial
+// chain AFTER move!, mcmc_clustering_eap_chain.jl:272-273).
+__device__ __forceinline__ void nhat_trial(const ClView& X, const Proposal& q, int i, double& x, double& y,
+                                           double& z) {
+  if (i == q.idx) { x = q.nx; y = q.ny; z = q.nz; }
+  else { x = X.nhx[i]; y = X.nhy[i]; z = X.nhz[i]; }
+}
+
+// cluster_flip! up to the flips (eap_chain.jl:273-309), by one warp: the growth draws are counter-based,
+// so 32 bonds are tested per round and the first failing one ends the growth — same result as the
+// reference's sequential loop on the same uniforms.
+__device__ __forceinline__ void warp_cluster_grow(const ClView& X, const Proposal& q, const ChainParams& P, int n,
+                                                  uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
+                                                  ClusterCtl& out) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int idx = q.idx;
+  int lo = idx, hi = idx, reflect = 0;
+  double up = 0.0, lp = 0.0;
+  if (P.clustering) {
+    double gate = 0.0;
+    if (lane == 0) gate = draw_cluster_gate(seed, chain_id, init, step);
+    gate = __shfl_sync(FULL, gate, 0);
+    reflect = !(gate <= P.cluster_prob);  // `if rand() <= ϵflip; return 1.0; end`, eap_chain.jl:273
+  }
+  if (reflect) {
+    // upward: bond (u,u+1), eap_chain.jl:276-289
+    for (int k0 = 0;; k0 += 32) {
+      const int bnd = hi + lane;
+      bool stop = true;
+      double pr = 0.0;
+      if (bnd < n - 1) {
+        double ax, ay, az, bx, by, bz;
+        nhat_trial(X, q, bnd, ax, ay, az);
+        nhat_trial(X, q, bnd + 1, bx, by, bz);
+        pr = link_prob(ax, ay, az, bx, by, bz);
+        stop = !(draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_UP, k0 + lane) <= pr);
+      }
+      const unsigned m = __ballot_sync(FULL, stop);
+      if (m) {
+        const int f = __ffs(m) - 1;
+        up = __shfl_sync(FULL, pr, f);  // 0 when the chain end stopped the growth (:277-279)
+        hi += f;
+        break;
+      }
+      hi += 32;
+    }
+    // downward: bond (l−1,l), eap_chain.jl:292-305
+    for (int k0 = 0;; k0 += 32) {
+      const int l = lo - lane;
+      bool stop = true;
+      double pr = 0.0;
+      if (l > 0) {
+        double ax, ay, az, bx, by, bz;
+        nhat_trial(X, q, l, ax, ay, az);
+        nhat_trial(X, q, l - 1, bx, by, bz);
+        pr = link_prob(ax, ay, az, bx, by, bz);
+        stop = !(draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k0 + lane) <= pr);
+      }
+      const unsigned m = __ballot_sync(FULL, stop);
+      if (m) {
+        const int f = __ffs(m) - 1;
+        lp = __shfl_sync(FULL, pr, f);
+        lo -= f;
+        break;
+      }
+      lo -= 32;
+    }
+  }
+  if (lane == 0) {
+    out.idx = idx; out.lo = lo; out.hi = hi; out.reflect = reflect;
+    out.up = up; out.lp = lp;
+  }
+}
+
+// New angles of segment monomer c: move! for idx (already in the proposal), then refl_n! if the cluster
+// is flipped.  Returns ϕ', θ'.
+__device__ __forceinline__ void segment_angles(const MonoRec* __restrict__ mono, const Proposal& q, int c,
+                                               bool reflect, double& phi, double& theta, double& sth_before) {
+  if (c == q.idx) {
+    phi = q.phi; theta = q.theta; sth_before = q.sth;
+  } else {
+    const MonoRec r = mono[c];
+    phi = r.phi; theta = r.theta; sth_before = r.sth;
+  }
+  if (reflect) theta = reflect_theta(theta);
+}
+
+// Everything between the cluster selection and the decision: n̂', x' of the segment into X.nn / X.xn,
+// sinθ' into S.E[c], the kNumRed changed-term sums (in every thread) and the tail translation D.
+// Contains CTA barriers; all threads must call it.
+template <int T, bool CUT, int UNROLL = 2>
+__device__ void segment_trial_sums(const CtaView& S, const ClView& X, const MonoRec* __restrict__ mono,
+                                   const ChainParams& P, int n, int energy_type, const Proposal& q, int lo, int hi,
+                                   bool reflect, double* sums, double& Dx, double& Dy, double& Dz) {
+  constexpr int W = T / 32;
+  using TEAM = Team<W, 0>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = hi - lo + 1;
+  const int C = (m + T - 1) / T;
+  const int c0 = min(hi + 1, lo + tid * C), c1 = min(hi + 1, c0 + C);
+  double acc[kNumRed];
+#pragma unroll
+  for (int k = 0; k < kNumRed; ++k) acc[k] = 0.0;
+  // ---- pass 1: new directions of this thread's chunk, chunk total of Δn̂ -------------------------------
+  double lx = 0, ly = 0, lz = 0;
+  for (int c = c0; c < c1; ++c) {
+    double nx, ny, nz, sth;
+    if (!reflect) {  // the segment is idx alone
+      nx = q.nx; ny = q.ny; nz = q.nz; sth = q.sth;
+      acc[R_OMEGA] += q.dOmega;
+    } else {
+      double phi, theta, sb;
+      segment_angles(mono, q, c, true, phi, theta, sb);
+      double sph, cph, cth;
+      sincos(phi, &sph, &cph);
+      sincos(theta, &sth, &cth);
+      nx = cph * sth; ny = sph * sth; nz = cth;
+      acc[R_OMEGA] += (c == q.idx ? q.dOmega : 0.0) + log(sth / sb);  // Ω += log(sθ'/sθ), eap_chain.jl:238
+    }
+    X.nnx[c] = nx; X.nny[c] = ny; X.nnz[c] = nz;
+    S.E[c] = sth;
+    double ux, uy, uz;
+    mu_of(P, nx, ny, nz, ux, uy, uz);
+    const double ox = S.mx[c], oy = S.my[c], oz = S.mz[c];
+    acc[R_USELF] += -0.5 * P.E0 * uz - (-0.5 * P.E0 * oz);
+    acc[R_PX] += ux - ox; acc[R_PY] += uy - oy; acc[R_PZ] += uz - oz;
+    const double onz = X.nhz[c];
+    acc[R_COS2] += nz * nz - onz * onz;
+    lx += nx - X.nhx[c]; ly += ny - X.nhy[c]; lz += nz - onz;
+  }
+  // ---- block scan of the chunk totals (update_xs! restricted to the segment, eap_chain.jl:49-51) --------
+  double ix = lx, iy = ly, iz = lz;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double tx = __shfl_up_sync(0xffffffffu, ix, o);
+    const double ty = __shfl_up_sync(0xffffffffu, iy, o);
+    const double tz = __shfl_up_sync(0xffffffffu, iz, o);
+    if (lane >= o) { ix += tx; iy += ty; iz += tz; }
+  }
+  if (lane == 31) { S.part[warp] = ix; S.part[32 + warp] = iy; S.part[64 + warp] = iz; }
+  __syncthreads();
+  double ox = 0, oy = 0, oz = 0, tx = 0, ty = 0, tz = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const double px = S.part[w], py = S.part[32 + w], pz = S.part[64 + w];
+    if (w < warp) { ox += px; oy += py; oz += pz; }
+    tx += px; ty += py; tz += pz;
+  }
+  double sxx = ox + (ix - lx), syy = oy + (iy - ly), szz = oz + (iz - lz);  // exclusive prefix of the chunk
+  for (int c = c0; c < c1; ++c) {
+    const double dx = X.nnx[c] - X.nhx[c], dy = X.nny[c] - X.nhy[c], dz = X.nnz[c] - X.nhz[c];
+    X.xnx[c] = S.sx[c] + P.b * (sxx + 0.5 * dx);
+    X.xny[c] = S.sy[c] + P.b * (syy + 0.5 * dy);
+    X.xnz[c] = S.sz[c] + P.b * (szz + 0.5 * dz);
+    sxx += dx; syy += dy; szz += dz;
+  }
+  Dx = P.b * tx; Dy = P.b * ty; Dz = P.b * tz;
+  // ---- rectangle set-up: heads [0,lo) × tails (hi,n) ----------------------------------------------------
+  const int H = lo, Tl = n - 1 - hi;
+  const bool pairs_all = (energy_type == 1 || energy_type == 3);
+  const bool rect = pairs_all && H > 0 && Tl > 0;
+  bool lanes_are_heads = true;
+  if (rect) {
+    const long long costH = (long long)((H + 31) >> 5) * Tl;
+    const long long costT = (long long)((Tl + 31) >> 5) * H;
+    lanes_are_heads = costH <= costT;
+  }
+  const double sgn = lanes_are_heads ? 1.0 : -1.0;
+  const double ex = sgn * Dx, ey = sgn * Dy, ez = sgn * Dz;
+  const int baseA = lanes_are_heads ? 0 : hi + 1, A = lanes_are_heads ? H : Tl;
+  const int baseB = lanes_are_heads ? hi + 1 : 0, B = lanes_are_heads ? Tl : H;
+  if (rect)
+    for (int k = tid; k < B; k += T)
+      S.E[baseB + k] = fma(S.mz[baseB + k], ez, fma(S.my[baseB + k], ey, S.mx[baseB + k] * ex));
+  __syncthreads();  // X.nn, X.xn, S.E visible
+  // ---- bonds lo−1..hi: ψ and bending energy (eap_chain.jl:45-47,54-58,246-251) ---------------------------
+  {
+    const int b0 = max(lo - 1, 0), b1 = min(hi, n - 2);
+    for (int i = b0 + tid; i <= b1; i += T) {
+      const bool an = i >= lo, bn = i + 1 <= hi;
+      const double ax = X.nhx[i], ay = X.nhy[i], az = X.nhz[i];
+      const double bx = X.nhx[i + 1], by = X.nhy[i + 1], bz = X.nhz[i + 1];
+      const double psi_old = psi_of(ax, ay, az, bx, by, bz);
+      const double psi_new = psi_of(an ? X.nnx[i] : ax, an ? X.nny[i] : ay, an ? X.nnz[i] : az,
+                                    bn ? X.nnx[i + 1] : bx, bn ? X.nny[i + 1] : by, bn ? X.nnz[i + 1] : bz);
+      acc[R_PSI] += psi_new - psi_old;
+      acc[R_BEND] += ubend_of(P, psi_new) - ubend_of(P, psi_old);
+      if (energy_type == 2) {  // U_Ising (eap_chain.jl:215-228): the same bonds
+        double ux, uy, uz, vx, vy, vz;
+        if (an) mu_of(P, X.nnx[i], X.nny[i], X.nnz[i], ux, uy, uz); else { ux = S.mx[i]; uy = S.my[i]; uz = S.mz[i]; }
+        if (bn) mu_of(P, X.nnx[i + 1], X.nny[i + 1], X.nnz[i + 1], vx, vy, vz);
+        else { vx = S.mx[i + 1]; vy = S.my[i + 1]; vz = S.mz[i + 1]; }
+        const double pxn = an ? X.xnx[i] : S.sx[i], pyn = an ? X.xny[i] : S.sy[i], pzn = an ? X.xnz[i] : S.sz[i];
+        const double qxn = bn ? X.xnx[i + 1] : S.sx[i + 1] + Dx, qyn = bn ? X.xny[i + 1] : S.sy[i + 1] + Dy,
+                     qzn = bn ? X.xnz[i + 1] : S.sz[i + 1] + Dz;
+        acc[R_PAIR] += pair_g(ux, uy, uz, vx, vy, vz, pxn - qxn, pyn - qyn, pzn - qzn) -
+                       pair_g(S.mx[i], S.my[i], S.mz[i], S.mx[i + 1], S.my[i + 1], S.mz[i + 1], S.sx[i] - S.sx[i + 1],
+                              S.sy[i] - S.sy[i + 1], S.sz[i] - S.sz[i + 1]);
+      }
+    }
+  }
+  // ---- segment × everything (each pair once) -----------------------------------------------------------
+  if (pairs_all) {
+    double a = 0.0;
+    for (int c = lo; c <= hi; ++c) {
+      const double xi = S.sx[c], yi = S.sy[c], zi = S.sz[c];
+      const double oxm = S.mx[c], oym = S.my[c], ozm = S.mz[c];
+      const double xni = X.xnx[c], yni = X.xny[c], zni = X.xnz[c];
+      double nmx, nmy, nmz;
+      mu_of(P, X.nnx[c], X.nny[c], X.nnz[c], nmx, nmy, nmz);
+      for (int j = tid; j < n; j += T) {
+        if (j >= lo && j <= c) continue;
+        const double jx = S.sx[j], jy = S.sy[j], jz = S.sz[j];
+        const double ux = S.mx[j], uy = S.my[j], uz = S.mz[j];
+        double njx, njy, njz, vx, vy, vz;
+        if (j < lo) { njx = jx; njy = jy; njz = jz; vx = ux; vy = uy; vz = uz; }
+        else if (j > hi) { njx = jx + Dx; njy = jy + Dy; njz = jz + Dz; vx = ux; vy = uy; vz = uz; }
+        else {
+          njx = X.xnx[j]; njy = X.xny[j]; njz = X.xnz[j];
+          mu_of(P, X.nnx[j], X.nny[j], X.nnz[j], vx, vy, vz);
+        }
+        if (CUT)
+          a += pair_g_cut(nmx, nmy, nmz, vx, vy, vz, xni - njx, yni - njy, zni - njz, P.crad2) -
+               pair_g_cut(oxm, oym, ozm, ux, uy, uz, xi - jx, yi - jy, zi - jz, P.crad2);
+        else
+          a += pair_g(nmx, nmy, nmz, vx, vy, vz, xni - njx, yni - njy, zni - njz) -
+               pair_g(oxm, oym, ozm, ux, uy, uz, xi - jx, yi - jy, zi - jz);
+      }
+    }
+    if (rect) a += rect_sum<TEAM, UNROLL, CUT>(S, baseA, A, baseB, B, ex, ey, ez, P.crad2);
+    acc[R_PAIR] += a;
+  }
+  // ---- reduce ------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < kNumRed; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) X.red[k * 32 + warp] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kNumRed; ++k) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) s += X.red[k * 32 + w];
+    sums[k] = s;
+  }
+  sums[R_PAIR] *= kInv4Pi;
+}
+
+// α of cluster_flip! (eap_chain.jl:317-330) from the link probabilities before and after the flip.
+__device__ __forceinline__ double cluster_log_alpha(const ClView& X, int n, int lo, int hi, double up, double lp) {
+  const double nup = (hi < n - 1) ? link_prob(X.nnx[hi], X.nny[hi], X.nnz[hi], X.nhx[hi + 1], X.nhy[hi + 1], X.nhz[hi + 1]) : 0.0;
+  const double nlp = (lo > 0) ? link_prob(X.nnx[lo], X.nny[lo], X.nnz[lo], X.nhx[lo - 1], X.nhy[lo - 1], X.nhz[lo - 1]) : 0.0;
+  return log(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
+}
+
+// record! of the two extra averagers (mcmc_clustering_eap_chain.jl:243-244), same weight as the others.
+__device__ __forceinline__ void record_extras(const ChainParams& P, ChainDynX& DX, double su, double log_gauge,
+                                              int n) {
+  double wgt = 1.0;
+  if (P.umbrella) wgt = 1.0 / exp(su * P.inv_kT * P.cF - log_gauge);
+  comp_add(DX.acc[0], DX.comp[0], DX.scos2 * wgt);
+  comp_add(DX.acc[1], DX.comp[1], DX.spsi / (double)(n - 1) * wgt);
+}
+
+// Decision quantities of one composite trial from the reduced sums (identical in every thread).
+struct SegDecision {
+  double dU, dsu, dlogpi, la;
+};
+
+__device__ __forceinline__ SegDecision segment_decision(const ChainParams& P, int energy_type, const double* sums,
+                                                        double Dx, double Dz, double la, double carry) {
+  SegDecision d;
+  const bool bare = (energy_type == 3) && !P.cutoff_full;  // the UCutoff functor is the bare pair sum
+  const double drF = -(Dx * P.Fx + Dz * P.Fz);             // −Δr·F, energy.jl:8
+  d.dsu = sums[R_USELF] + sums[R_BEND];                    // Δ sum(chain.us)
+  d.dU = bare ? sums[R_PAIR] : d.dsu + drF + sums[R_PAIR];
+  const double dw = P.umbrella ? d.dsu * P.inv_kT * P.cF : 0.0;  // average.jl:120-124
+  d.la = la;
+  d.dlogpi = -d.dU * P.inv_kT + sums[R_OMEGA] + dw + la - carry;  // acceptance.jl:30-31
+  return d;
+}
+
+__device__ __forceinline__ void stage_row_cluster(const ChainDyn& D, const ChainDynX& DX, long long step,
+                                                  double* rowbuf /* 8 + 19 */) {
+  stage_row(D, step, rowbuf);
+  const double nrm = D.acc[16] + D.comp[16];
+  rowbuf[25] = (DX.acc[0] + DX.comp[0]) / nrm;
+  rowbuf[26] = (DX.acc[1] + DX.comp[1]) / nrm;
+}
+
+constexpr int kRowDoublesCluster = 28;
+
+// The hot loop of mcmc_clustering_eap_chain.jl:267-336 for one chain per CTA.
+template <int T, int MINB, bool CUT>
+__global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  const ClView X = carve_cluster(smem_raw, a.n);
+  __shared__ double rowbuf[kRowDoublesCluster];
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = a.n;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  if (tid == 0) {
+    *S.par = a.par[c];
+    *S.dyn = a.dyn[c];
+    *X.dx = a.dynx[c];
+  }
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  load_nhat<T>(mono, n, X);
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const long long step0 = S.dyn->step;
+  const uint32_t init = (uint32_t)S.dyn->init;
+  long long row = 0;
+  Proposal* q = &S.prop[0];
+
+  for (long long s = 1; s <= a.nsteps; ++s) {
+    const long long step = step0 + s;
+    __syncthreads();  // state of the previous trial (records, n̂, x, μ) is visible
+    if (tid < 32) {
+      if (tid == 0) make_proposal(a, P, *S.dyn, mono, chain_id, step, *q);
+      __syncwarp();
+      warp_cluster_grow(X, *q, P, n, a.seed, chain_id, init, step, *X.ctl);
+    }
+    __syncthreads();  // proposal and cluster are visible
+    const int idx = X.ctl->idx, lo = X.ctl->lo, hi = X.ctl->hi;
+    const bool reflect = X.ctl->reflect != 0;
+    const double carry = X.dx->carry;
+    double sums[kNumRed], Dx, Dy, Dz;
+    segment_trial_sums<T, CUT>(S, X, mono, P, n, a.energy_type, *q, lo, hi, reflect, sums, Dx, Dy, Dz);
+    const double la = reflect ? cluster_log_alpha(X, n, lo, hi, X.ctl->up, X.ctl->lp) : 0.0;
+    const SegDecision dec = segment_decision(P, a.energy_type, sums, Dx, Dz, la, carry);
+    const bool accept = metropolis(dec.dlogpi, q->eps);
+    if (accept) {  // the trial chain becomes the chain (mcmc_clustering_eap_chain.jl:274-275)
+      for (int k = lo + tid; k <= hi; k += T) {
+        double phi, theta, sb;
+        segment_angles(mono, *q, k, reflect, phi, theta, sb);
+        MonoRec rec;
+        rec.phi = phi; rec.theta = theta;
+        rec.nx = X.nnx[k]; rec.ny = X.nny[k]; rec.nz = X.nnz[k]; rec.sth = S.E[k];
+        mono[k] = rec;
+        X.nhx[k] = rec.nx; X.nhy[k] = rec.ny; X.nhz[k] = rec.nz;
+        S.sx[k] = X.xnx[k]; S.sy[k] = X.xny[k]; S.sz[k] = X.xnz[k];
+        double ux, uy, uz;
+        mu_of(P, rec.nx, rec.ny, rec.nz, ux, uy, uz);
+        S.mx[k] = ux; S.my[k] = uy; S.mz[k] = uz;
+      }
+      for (int j = hi + 1 + tid; j < n; j += T) {
+        S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
+      }
+    }
+    if (tid == 0) {
+      ChainDyn& D = *S.dyn;
+      ChainDynX& DX = *X.dx;
+      if (accept) {
+        D.U += dec.dU;
+        D.Omega += sums[R_OMEGA];
+        D.su += dec.dsu;
+        D.r[0] += Dx; D.r[1] += Dy; D.r[2] += Dz;
+        D.p[0] += sums[R_PX]; D.p[1] += sums[R_PY]; D.p[2] += sums[R_PZ];
+        DX.spsi += sums[R_PSI];
+        DX.scos2 += sums[R_COS2];
+        DX.carry = P.alpha_carry ? dec.la : 0.0;  // logπ_prev = logπ + log α (acceptance.jl:32-33)
+        D.nacc += 1;
+        D.nacc_total += 1;
+      }
+      D.natt += 1;
+      D.steps_total += 1;
+      D.step = step;
+      if (reflect) {
+        const double sz = (double)(hi - lo + 1);
+        DX.ncluster += 1.0; DX.cluster_sum += sz; DX.cluster_max = fmax(DX.cluster_max, sz);
+      }
+      bookkeep(P, D, step);
+      record_extras(P, DX, D.su, D.log_gauge, n);
+    }
+    const bool isrow = a.stepout > 0 && (step % a.stepout) == 0;
+    if (isrow) {
+      __syncthreads();  // records of this trial are visible
+      if (row < a.rows) {
+        if (tid == 0) stage_row_cluster(*S.dyn, *X.dx, step, rowbuf);
+        if (a.state) {
+          double* st = a.state + ((size_t)c * a.rows + row) * 2 * (size_t)n;
+          for (int k = tid; k < n; k += T) {
+            const MonoRec r = mono[k];
+            st[2 * k] = r.phi; st[2 * k + 1] = r.theta;
+          }
+        }
+        __syncthreads();
+        if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = rowbuf[tid];
+        if (tid < a.roll_cols) a.roll[((size_t)c * a.rows + row) * a.roll_cols + tid] = rowbuf[8 + tid];
+      }
+      ++row;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    a.dyn[c] = *S.dyn;
+    a.dynx[c] = *X.dx;
+  }
+}
+
+// Non-mutating changed-term sums of one scripted composite trial (same device code as the run kernel).
+struct SegDeltaArgs {
+  const MonoRec* mono;
+  const ChainParams* par;
+  double* out;  // {dU, dOmega, dU_pairs, du_self, drF, dU_bend, dΣψ, dΣcos²θ, dp1, dp2, dp3, log α}
+  int n, energy_type, chain, idx, lo, hi, reflect;
+  double dphi, dtheta;
+};
+
+template <int T, bool CUT>
+__global__ void __launch_bounds__(T) k_delta_segment_cta(const SegDeltaArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  const ClView X = carve_cluster(smem_raw, a.n);
+  const int tid = threadIdx.x, n = a.n;
+  const MonoRec* mono = a.mono + (size_t)a.chain * n;
+  if (tid == 0) *S.par = a.par[a.chain];
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  load_nhat<T>(mono, n, X);
+  if (tid == 0) build_proposal(P, mono[a.idx], a.idx, a.dphi, a.dtheta, 0.0, S.prop[0]);
+  __syncthreads();
+  const Proposal& q = S.prop[0];
+  const bool reflect = a.reflect != 0;
+  const int lo = reflect ? a.lo : a.idx, hi = reflect ? a.hi : a.idx;
+  double sums[kNumRed], Dx, Dy, Dz;
+  segment_trial_sums<T, CUT>(S, X, mono, P, n, a.energy_type, q, lo, hi, reflect, sums, Dx, Dy, Dz);
+  if (tid == 0) {
+    double up = 0.0, lp = 0.0;  // link probabilities before the flip, on the chain carrying the move
+    if (reflect) {
+      double ax, ay, az, bx, by, bz;
+      if (hi < n - 1) { nhat_trial(X, q, hi, ax, ay, az); nhat_trial(X, q, hi + 1, bx, by, bz); up = link_prob(ax, ay, az, bx, by, bz); }
+      if (lo > 0) { nhat_trial(X, q, lo, ax, ay, az); nhat_trial(X, q, lo - 1, bx, by, bz); lp = link_prob(ax, ay, az, bx, by, bz); }
+    }
+    const double la = reflect ? cluster_log_alpha(X, n, lo, hi, up, lp) : 0.0;
+    const SegDecision d = segment_decision(P, a.energy_type, sums, Dx, Dz, la, 0.0);
+    a.out[0] = d.dU; a.out[1] = sums[R_OMEGA]; a.out[2] = sums[R_PAIR]; a.out[3] = sums[R_USELF];
+    a.out[4] = -(Dx * P.Fx + Dz * P.Fz); a.out[5] = sums[R_BEND]; a.out[6] = sums[R_PSI]; a.out[7] = sums[R_COS2];
+    a.out[8] = sums[R_PX]; a.out[9] = sums[R_PY]; a.out[10] = sums[R_PZ]; a.out[11] = la;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One chain per lane: non-interacting and Ising energies (+ bending), O(|cluster|) per trial.
+// ---------------------------------------------------------------------------------------------
+struct LaneSeg {
+  double dOmega, du_self, dbend, dpsi, dcos2, dpair;  // dpair: 4π × Σ(new − old) of U_Ising terms
+  double dpx, dpy, dpz, sx, sy, sz;                   // Δp, ΣΔn̂
+};
+
+// n̂', μ', sinθ' of segment monomer c (and its old record).
+struct LaneMono {
+  double nx, ny, nz, mx, my, mz;
+};
+
+__device__ __forceinline__ void lane_new_mono(const ChainParams& P, const MonoRec* __restrict__ mono, const Proposal& q,
+                                              int c, bool reflect, MonoRec& nrec, double& dOmega) {
+  if (!reflect) {  // c == idx
+    nrec.phi = q.phi; nrec.theta = q.theta; nrec.nx = q.nx; nrec.ny = q.ny; nrec.nz = q.nz; nrec.sth = q.sth;
+    dOmega = q.dOmega;
+    return;
+  }
+  double phi, theta, sb;
+  segment_angles(mono, q, c, true, phi, theta, sb);
+  double sph, cph, sth, cth;
+  sincos(phi, &sph, &cph);
+  sincos(theta, &sth, &cth);
+  nrec.phi = phi; nrec.theta = theta;
+  nrec.nx = cph * sth; nrec.ny = sph * sth; nrec.nz = cth; nrec.sth = sth;
+  dOmega = (c == q.idx ? q.dOmega : 0.0) + log(sth / sb);
+}
+
+// Changed-term sums of the composite trial on segment [lo,hi] for O(1)-per-bond energies: one sweep over
+// the bonds lo−1..hi, carrying the old and new state of the left monomer of the bond in registers.
+template <bool ISING>
+__device__ __forceinline__ void lane_segment_sums(const MonoRec* __restrict__ mono, int n, const ChainParams& P,
+                                                  const MonoRec& rec_idx, const Proposal& q, int lo, int hi,
+                                                  bool reflect, LaneSeg& o, double& nlo_x, double& nlo_y,
+                                                  double& nlo_z, double& nhi_x, double& nhi_y, double& nhi_z) {
+  o.dOmega = o.du_self = o.dbend = o.dpsi = o.dcos2 = o.dpair = 0.0;
+  o.dpx = o.dpy = o.dpz = o.sx = o.sy = o.sz = 0.0;
+  const double hb = -0.5 * P.b;
+  // left neighbour of the segment (unchanged)
+  bool have_left = lo > 0;
+  double lox = 0, loy = 0, loz = 0, lnx = 0, lny = 0, lnz = 0;  // old / new n̂ of the left monomer of the bond
+  if (have_left) {
+    const MonoRec l = mono[lo - 1];
+    lox = lnx = l.nx; loy = lny = l.ny; loz = lnz = l.nz;
+  }
+  for (int c = lo; c <= hi + 1; ++c) {
+    if (c >= n) break;
+    double cox, coy, coz, cnx, cny, cnz;  // old / new n̂ of monomer c
+    if (c <= hi) {
+      const MonoRec orec = (c == q.idx) ? rec_idx : mono[c];
+      MonoRec nrec;
+      double dOm;
+      lane_new_mono(P, mono, q, c, reflect, nrec, dOm);
+      cox = orec.nx; coy = orec.ny; coz = orec.nz;
+      cnx = nrec.nx; cny = nrec.ny; cnz = nrec.nz;
+      double ux, uy, uz, vx, vy, vz;
+      mu_of(P, cox, coy, coz, ux, uy, uz);
+      mu_of(P, cnx, cny, cnz, vx, vy, vz);
+      o.dOmega += dOm;
+      o.du_self += -0.5 * P.E0 * vz - (-0.5 * P.E0 * uz);
+      o.dpx += vx - ux; o.dpy += vy - uy; o.dpz += vz - uz;
+      o.dcos2 += cnz * cnz - coz * coz;
+      o.sx += cnx - cox; o.sy += cny - coy; o.sz += cnz - coz;
+      if (c == lo) { nlo_x = cnx; nlo_y = cny; nlo_z = cnz; }
+      if (c == hi) { nhi_x = cnx; nhi_y = cny; nhi_z = cnz; }
+    } else {  // right neighbour of the segment (unchanged)
+      const MonoRec r = mono[c];
+      cox = cnx = r.nx; coy = cny = r.ny; coz = cnz = r.nz;
+    }
+    if (have_left) {  // bond (c−1, c)
+      const double psi_old = psi_of(lox, loy, loz, cox, coy, coz);
+      const double psi_new = psi_of(lnx, lny, lnz, cnx, cny, cnz);
+      o.dpsi += psi_new - psi_old;
+      o.dbend += ubend_of(P, psi_new) - ubend_of(P, psi_old);
+      if (ISING) {  // separation x_i − x_{i+1} = −(b/2)(n̂_i + n̂_{i+1})
+        double aox, aoy, aoz, anx, any_, anz, box, boy, boz, bnx, bny, bnz;
+        mu_of(P, lox, loy, loz, aox, aoy, aoz);
+        mu_of(P, lnx, lny, lnz, anx, any_, anz);
+        mu_of(P, cox, coy, coz, box, boy, boz);
+        mu_of(P, cnx, cny, cnz, bnx, bny, bnz);
+        o.dpair += pair_g(anx, any_, anz, bnx, bny, bnz, hb * (lnx + cnx), hb * (lny + cny), hb * (lnz + cnz)) -
+                   pair_g(aox, aoy, aoz, box, boy, boz, hb * (lox + cox), hb * (loy + coy), hb * (loz + coz));
+      }
+    }
+    lox = cox; loy = coy; loz = coz; lnx = cnx; lny = cny; lnz = cnz;
+    have_left = true;
+  }
+}
+
+// Sequential cluster growth for one lane (eap_chain.jl:276-305).
+__device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mono, const Proposal& q, int n,
+                                                  uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
+                                                  int& lo, int& hi, double& up, double& lp) {
+  const int idx = q.idx;
+  hi = idx;
+  double ax = q.nx, ay = q.ny, az = q.nz;
+  for (int k = 0;; ++k) {
+    if (hi >= n - 1) { up = 0.0; break; }
+    const MonoRec b = mono[hi + 1];
+    up = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
+    if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_UP, k) <= up) { hi += 1; ax = b.nx; ay = b.ny; az = b.nz; }
+    else break;
+  }
+  lo = idx;
+  ax = q.nx; ay = q.ny; az = q.nz;
+  for (int k = 0;; ++k) {
+    if (lo <= 0) { lp = 0.0; break; }
+    const MonoRec b = mono[lo - 1];
+    lp = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
+    if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k) <= lp) { lo -= 1; ax = b.nx; ay = b.ny; az = b.nz; }
+    else break;
+  }
+}
+
+template <int T, int MINB, bool ISING>
+__global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
+  const int c = blockIdx.x * T + threadIdx.x;
+  if (c >= a.nchains) return;
+  const int n = a.n;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  const ChainParams P = a.par[c];
+  ChainDyn D = a.dyn[c];
+  ChainDynX DX = a.dynx[c];
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const long long step0 = D.step;
+  long long row = 0;
+  for (long long s = 1; s <= a.nsteps; ++s) {
+    const long long step = step0 + s;
+    const Draws d = draw_step(a.seed, chain_id, (uint32_t)D.init, step, n);
+    const MonoRec rec = mono[d.idx];
+    double dphi, dtheta;
+    increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
+    Proposal q;
+    build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+    int lo = d.idx, hi = d.idx;
+    double up = 0.0, lp = 0.0;
+    bool reflect = false;
+    if (P.clustering) reflect = !(draw_cluster_gate(a.seed, chain_id, (uint32_t)D.init, step) <= P.cluster_prob);
+    if (reflect) lane_cluster_grow(mono, q, n, a.seed, chain_id, (uint32_t)D.init, step, lo, hi, up, lp);
+    LaneSeg g;
+    double nlx = 0, nly = 0, nlz = 0, nhx = 0, nhy = 0, nhz = 0;
+    lane_segment_sums<ISING>(mono, n, P, rec, q, lo, hi, reflect, g, nlx, nly, nlz, nhx, nhy, nhz);
+    double la = 0.0;
+    if (reflect) {  // eap_chain.jl:317-330
+      double nup = 0.0, nlp = 0.0;
+      if (hi < n - 1) { const MonoRec b = mono[hi + 1]; nup = link_prob(nhx, nhy, nhz, b.nx, b.ny, b.nz); }
+      if (lo > 0) { const MonoRec b = mono[lo - 1]; nlp = link_prob(nlx, nly, nlz, b.nx, b.ny, b.nz); }
+      la = log(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
+    }
+    const double Dx = P.b * g.sx, Dy = P.b * g.sy, Dz = P.b * g.sz;
+    const double dpairs = kInv4Pi * g.dpair;
+    const double dsu = g.du_self + g.dbend;
+    const double dU = dsu - (Dx * P.Fx + Dz * P.Fz) + dpairs;
+    const double dw = P.umbrella ? dsu * P.inv_kT * P.cF : 0.0;
+    const double dlogpi = -dU * P.inv_kT + g.dOmega + dw + la - DX.carry;
+    const bool accept = metropolis(dlogpi, q.eps);
+    if (accept) {
+      for (int k = lo; k <= hi; ++k) {
+        MonoRec nrec;
+        double dOm;
+        lane_new_mono(P, mono, q, k, reflect, nrec, dOm);
+        mono[k] = nrec;
+      }
+      D.U += dU; D.Omega += g.dOmega; D.su += dsu;
+      D.r[0] += Dx; D.r[1] += Dy; D.r[2] += Dz;
+      D.p[0] += g.dpx; D.p[1] += g.dpy; D.p[2] += g.dpz;
+      DX.spsi += g.dpsi; DX.scos2 += g.dcos2;
+      DX.carry = P.alpha_carry ? la : 0.0;
+      D.nacc += 1; D.nacc_total += 1;
+    }
+    D.natt += 1; D.steps_total += 1; D.step = step;
+    if (reflect) {
+      const double sz = (double)(hi - lo + 1);
+      DX.ncluster += 1.0; DX.cluster_sum += sz; DX.cluster_max = fmax(DX.cluster_max, sz);
+    }
+    bookkeep(P, D, step);
+    record_extras(P, DX, D.su, D.log_gauge, n);
+    if (a.stepout > 0 && (step % a.stepout) == 0) {
+      if (row < a.rows) {
+        double rb[kRowDoublesCluster];
+        stage_row_cluster(D, DX, step, rb);
+        double* t = a.traj + ((size_t)c * a.rows + row) * 8;
+        double* r = a.roll + ((size_t)c * a.rows + row) * a.roll_cols;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = rb[k];
+        for (int k = 0; k < a.roll_cols; ++k) r[k] = rb[8 + k];
+        if (a.state) {
+          double* st = a.state + ((size_t)c * a.rows + row) * 2 * (size_t)n;
+          for (int k = 0; k < n; ++k) { st[2 * k] = mono[k].phi; st[2 * k + 1] = mono[k].theta; }
+        }
+      }
+      ++row;
+    }
+  }
+  a.dyn[c] = D;
+  a.dynx[c] = DX;
+}
+
+// Non-mutating sums of one scripted composite trial through the lane path's device code.
+template <bool ISING>
+__global__ void k_delta_segment_lane(const SegDeltaArgs a) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int n = a.n;
+  const MonoRec* mono = a.mono + (size_t)a.chain * n;
+  const ChainParams P = a.par[a.chain];
+  const MonoRec rec = mono[a.idx];
+  Proposal q;
+  build_proposal(P, rec, a.idx, a.dphi, a.dtheta, 0.0, q);
+  const bool reflect = a.reflect != 0;
+  const int lo = reflect ? a.lo : a.idx, hi = reflect ? a.hi : a.idx;
+  LaneSeg g;
+  double nlx = 0, nly = 0, nlz = 0, nhx = 0, nhy = 0, nhz = 0;
+  lane_segment_sums<ISING>(mono, n, P, rec, q, lo, hi, reflect, g, nlx, nly, nlz, nhx, nhy, nhz);
+  double la = 0.0;
+  if (reflect) {
+    double up = 0.0, lp = 0.0, nup = 0.0, nlp = 0.0;
+    if (hi < n - 1) {
+      const MonoRec b = mono[hi + 1];
+      const MonoRec t = mono[hi];
+      const bool m = hi == a.idx;
+      up = link_prob(m ? q.nx : t.nx, m ? q.ny : t.ny, m ? q.nz : t.nz, b.nx, b.ny, b.nz);
+      nup = link_prob(nhx, nhy, nhz, b.nx, b.ny, b.nz);
+    }
+    if (lo > 0) {
+      const MonoRec b = mono[lo - 1];
+      const MonoRec t = mono[lo];
+      const bool m = lo == a.idx;
+      lp = link_prob(m ? q.nx : t.nx, m ? q.ny : t.ny, m ? q.nz : t.nz, b.nx, b.ny, b.nz);
+      nlp = link_prob(nlx, nly, nlz, b.nx, b.ny, b.nz);
+    }
+    la = log(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
+  }
+  const double Dx = P.b * g.sx, Dz = P.b * g.sz;
+  const double dpairs = kInv4Pi * g.dpair;
+  a.out[0] = g.du_self + g.dbend - (Dx * P.Fx + Dz * P.Fz) + dpairs;
+  a.out[1] = g.dOmega; a.out[2] = dpairs; a.out[3] = g.du_self;
+  a.out[4] = -(Dx * P.Fx + Dz * P.Fz); a.out[5] = g.dbend; a.out[6] = g.dpsi; a.out[7] = g.dcos2;
+  a.out[8] = g.dpx; a.out[9] = g.dpy; a.out[10] = g.dpz; a.out[11] = la;
+}
+
+// A fresh `mcmc(nsteps, pargs, chain)` call on the current chains (mcmc_clustering_eap_chain.jl:171-265):
+// new averagers, counters, step sizes and acceptor; the RNG stream tag advances.  The running scalars and
+// the weight function are re-synchronised by k_energy_cta afterwards (rebind_gauge).
+__global__ void k_begin_stage(ChainDyn* dyn, ChainDynX* dynx, const ChainParams* par, int nchains, int new_init) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchains) return;
+  ChainDyn& D = dyn[c];
+  ChainDynX& X = dynx[c];
+  D.phi_step = par[c].phi_step0;
+  D.theta_step = par[c].theta_step0;
+  D.nacc = D.natt = D.nacc_total = D.steps_total = D.step = 0;
+  D.init = new_init;
+  D.drift_max = 0.0;
+  for (int k = 0; k < kNumAcc; ++k) { D.acc[k] = 0.0; D.comp[k] = 0.0; }
+  X.carry = 0.0;
+  X.acc[0] = X.acc[1] = X.comp[0] = X.comp[1] = 0.0;
+  X.ncluster = X.cluster_sum = X.cluster_max = 0.0;
+}
+
+// --x0/--dx0 initial chains (eap_chain.jl:63-78): ϕ = ϕ0 + U(0,dx0[1]), θ = θ0 + U(0,dx0[2]); the uniforms
+// are those of the random-init stream.
+__global__ void k_fill_x0(MonoRec* mono, long long total, int n, uint64_t seed, uint32_t chain_id_base,
+                          uint32_t init, const double* x0, int x0_len, double dx0_phi, double dx0_theta) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const long long c = g / n;
+  const int k = (int)(g - c * n);
+  const uint4 w = philox_at(seed, chain_id_base + (uint32_t)c, init, SUB_INIT, (uint64_t)k);
+  const double p0 = x0_len == 2 ? x0[0] : x0[2 * k], t0 = x0_len == 2 ? x0[1] : x0[2 * k + 1];
+  mono[g] = make_record(p0 + (0.0 + (dx0_phi - 0.0) * u53(w.x, w.y)), t0 + (0.0 + (dx0_theta - 0.0) * u53(w.z, w.w)));
+}
+
+}  // namespace pmc

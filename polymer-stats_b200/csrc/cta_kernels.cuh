@@ -112,11 +112,18 @@ __device__ void load_chain(const MonoRec* __restrict__ mono, const ChainParams& 
 // 4π × dipole-dipole energy of the staged chain: U_interaction (eap_chain.jl:196-211) or
 // U_Ising (:215-228).  Result in every thread.
 template <int T>
-__device__ double cta_pair_energy(const CtaView& S, int n, int energy_type) {
+__device__ double cta_pair_energy(const CtaView& S, int n, int energy_type, double crad2 = 0.0) {
   constexpr int W = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double acc = 0.0;
-  if (energy_type == 1) {
+  if (energy_type == 3) {  // UCutoff, eap_chain.jl:171-192
+    for (int i = warp; i < n - 1; i += W) {
+      const double xi = S.sx[i], yi = S.sy[i], zi = S.sz[i];
+      const double ax = S.mx[i], ay = S.my[i], az = S.mz[i];
+      for (int j = i + 1 + lane; j < n; j += 32)
+        acc += pair_g_cut(ax, ay, az, S.mx[j], S.my[j], S.mz[j], xi - S.sx[j], yi - S.sy[j], zi - S.sz[j], crad2);
+    }
+  } else if (energy_type == 1) {
     for (int i = warp; i < n - 1; i += W) {
       const double xi = S.sx[i], yi = S.sy[i], zi = S.sz[i];
       const double ax = S.mx[i], ay = S.my[i], az = S.mz[i];
@@ -170,10 +177,12 @@ __device__ __forceinline__ LaneItem load_lane_item(const CtaView& S, int L, doub
   return it;
 }
 
-// new − old of one pair: lane item `it` against broadcast item (bx,by,bz; ux,uy,uz; e)
+// new − old of one pair: lane item `it` against broadcast item (bx,by,bz; ux,uy,uz; e).
+// CUT: UCutoff (eap_chain.jl:176-187) — a term is zero when its own r² exceeds crad².
+template <bool CUT = false>
 __device__ __forceinline__ double rect_pair(const LaneItem& it, double bx, double by, double bz, double ux,
                                             double uy, double uz, double e, double Dx, double Dy, double Dz,
-                                            double acc) {
+                                            double acc, double crad2 = 0.0) {
   const double rx = it.x - bx, ry = it.y - by, rz = it.z - bz;
   const double mm = fma(it.az, uz, fma(it.ay, uy, it.ax * ux));
   const double r2 = fma(rz, rz, fma(ry, ry, rx * rx));
@@ -188,13 +197,18 @@ __device__ __forceinline__ double rect_pair(const LaneItem& it, double bx, doubl
   const double y2 = y * y, yn2 = yn * yn;
   const double t = fma(a3 * bb, y2, mm);
   const double tn = fma(a3n * bn, yn2, mm);
-  acc = fma(tn, yn2 * yn, acc);
-  return fma(-t, y2 * y, acc);
+  if constexpr (CUT) {
+    const double gn = tn * (yn2 * yn), go = t * (y2 * y);
+    return acc + ((q2 > crad2 ? 0.0 : gn) - (r2 > crad2 ? 0.0 : go));
+  } else {
+    acc = fma(tn, yn2 * yn, acc);
+    return fma(-t, y2 * y, acc);
+  }
 }
 
-template <class TEAM, int UNROLL = 2>
+template <class TEAM, int UNROLL = 2, bool CUT = false>
 __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, int baseB, int B, double Dx,
-                                           double Dy, double Dz) {
+                                           double Dy, double Dz, double crad2 = 0.0) {
   constexpr int W = TEAM::kWarps;
   const int lane = TEAM::lane(), warp = TEAM::warp();
   const int G = (A + 31) >> 5;
@@ -227,8 +241,8 @@ __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, i
         for (; k < kend; ++k) {
           const double bx = bxp[k], by = byp[k], bz = bzp[k];
           const double ux = mxp[k], uy = myp[k], uz = mzp[k], e = ep[k];
-          a0 = rect_pair(i0, bx, by, bz, ux, uy, uz, e, Dx, Dy, Dz, a0);
-          a1 = rect_pair(i1, bx, by, bz, ux, uy, uz, e, Dx, Dy, Dz, a1);
+          a0 = rect_pair<CUT>(i0, bx, by, bz, ux, uy, uz, e, Dx, Dy, Dz, a0, crad2);
+          a1 = rect_pair<CUT>(i1, bx, by, bz, ux, uy, uz, e, Dx, Dy, Dz, a1, crad2);
         }
         acc += (v0 ? a0 : 0.0) + (v1 ? a1 : 0.0);
         k = 0;
@@ -246,11 +260,12 @@ __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, i
       const LaneItem it = load_lane_item(S, baseA + min(li, A - 1), Dx, Dy, Dz);
       double a0 = 0.0, a1 = 0.0;
       for (; k + 1 < kend; k += 2) {
-        a0 = rect_pair(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], ep[k], Dx, Dy, Dz, a0);
-        a1 = rect_pair(it, bxp[k + 1], byp[k + 1], bzp[k + 1], mxp[k + 1], myp[k + 1], mzp[k + 1], ep[k + 1], Dx,
-                       Dy, Dz, a1);
+        a0 = rect_pair<CUT>(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], ep[k], Dx, Dy, Dz, a0, crad2);
+        a1 = rect_pair<CUT>(it, bxp[k + 1], byp[k + 1], bzp[k + 1], mxp[k + 1], myp[k + 1], mzp[k + 1], ep[k + 1],
+                            Dx, Dy, Dz, a1, crad2);
       }
-      if (k < kend) a0 = rect_pair(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], ep[k], Dx, Dy, Dz, a0);
+      if (k < kend)
+        a0 = rect_pair<CUT>(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], ep[k], Dx, Dy, Dz, a0, crad2);
       acc += valid ? (a0 + a1) : 0.0;
     }
   }
@@ -330,6 +345,10 @@ struct RunArgs {
   int n;
   int nchains;
   int energy_type;
+  // clustering driver only (cluster_kernels.cuh)
+  ChainDynX* dynx;
+  double* state;   // [chains][rows][2n] (phi,theta interleaved) or null
+  int roll_cols;   // 17, or 19 with the two extra averagers
 };
 
 // Thread 0: draw and build the proposal of trial `step`.
@@ -753,7 +772,26 @@ struct EnergyArgs {
   double* obs6;  // [nchains][6] or null
   int n, energy_type, first_chain;
   int update_dyn, rebind_gauge;
+  ChainDynX* dynx;  // re-synchronised together with dyn
+  double* out8;     // [nchains][8] = {U, Σu (incl. bending), U_dd, Ω, U_bend, Σψ/(n−1), Σcos²θ, 0} or null
 };
+
+// Σ over bonds of ubend (eap_chain.jl:54-58) and ψ (:45-47), Σ over monomers of cos²θ: this thread's share.
+template <int T>
+__device__ __forceinline__ void bond_sums_partial(const MonoRec* __restrict__ mono, const ChainParams& P, int n,
+                                                  double& ub, double& sp, double& c2) {
+  ub = 0.0; sp = 0.0; c2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += T) {
+    const MonoRec a = mono[i];
+    c2 += a.nz * a.nz;
+    if (i + 1 < n) {
+      const MonoRec b = mono[i + 1];
+      const double psi = psi_of(a.nx, a.ny, a.nz, b.nx, b.ny, b.nz);
+      sp += psi;
+      ub += ubend_of(P, psi);
+    }
+  }
+}
 
 template <int T>
 __global__ void __launch_bounds__(T) k_energy_cta(const EnergyArgs a) {
@@ -772,21 +810,34 @@ __global__ void __launch_bounds__(T) k_energy_cta(const EnergyArgs a) {
     om += log(mono[i].sth);
     px += S.mx[i]; py += S.my[i]; pz += S.mz[i];
   }
+  double ub, sp, c2;
+  bond_sums_partial<T>(mono, P, n, ub, sp, c2);
   su = block_sum<T>(su, S.part);
   om = block_sum<T>(om, S.part);
   px = block_sum<T>(px, S.part);
   py = block_sum<T>(py, S.part);
   pz = block_sum<T>(pz, S.part);
-  const double udd = kInv4Pi * cta_pair_energy<T>(S, n, a.energy_type);
+  ub = block_sum<T>(ub, S.part);
+  sp = block_sum<T>(sp, S.part);
+  c2 = block_sum<T>(c2, S.part);
+  su += ub;  // us[i] = u + ubend (eap_chain.jl:130)
+  const double udd = kInv4Pi * cta_pair_energy<T>(S, n, a.energy_type, P.crad2);
   if (tid == 0) {
     // end_to_end (eap_chain.jl:405): x_n + (b/2) n̂_n
     const double rx = S.sx[n - 1] + 0.5 * P.b * mono[n - 1].nx;
     const double ry = S.sy[n - 1] + 0.5 * P.b * mono[n - 1].ny;
     const double rz = S.sz[n - 1] + 0.5 * P.b * mono[n - 1].nz;
-    const double U = su + udd - (rx * P.Fx + rz * P.Fz);  // energy.jl:7-23
+    // energy.jl:7-23; the UCutoff functor (eap_chain.jl:171-192) is the bare pair sum unless cutoff_full
+    const bool bare = (a.energy_type == 3) && !P.cutoff_full;
+    const double U = bare ? udd : su + udd - (rx * P.Fx + rz * P.Fz);
     if (a.out4) {
       double* o = a.out4 + (size_t)blockIdx.x * 4;
       o[0] = U; o[1] = su; o[2] = udd; o[3] = om;
+    }
+    if (a.out8) {
+      double* o = a.out8 + (size_t)blockIdx.x * 8;
+      o[0] = U; o[1] = su; o[2] = udd; o[3] = om;
+      o[4] = ub; o[5] = sp / (double)(n - 1); o[6] = c2; o[7] = 0.0;
     }
     if (a.obs6) {
       double* o = a.obs6 + (size_t)blockIdx.x * 6;
@@ -800,6 +851,10 @@ __global__ void __launch_bounds__(T) k_energy_cta(const EnergyArgs a) {
       D.p[0] = px; D.p[1] = py; D.p[2] = pz;
       if (a.rebind_gauge || !D.valid) D.log_gauge = P.gauge0 + om;
       D.valid = 1;
+      if (a.dynx) {
+        a.dynx[c].spsi = sp;
+        a.dynx[c].scos2 = c2;
+      }
     }
   }
 }
@@ -865,16 +920,21 @@ __global__ void __launch_bounds__(T) k_reinit_cta(const ReinitArgs a) {
     om += log(cand[i].sth);
     px += S.mx[i]; py += S.my[i]; pz += S.mz[i];
   }
+  double ub, sp, c2;
+  bond_sums_partial<T>(cand, P, n, ub, sp, c2);
   su = block_sum<T>(su, S.part);
   om = block_sum<T>(om, S.part);
   px = block_sum<T>(px, S.part);
   py = block_sum<T>(py, S.part);
   pz = block_sum<T>(pz, S.part);
-  const double udd = kInv4Pi * cta_pair_energy<T>(S, n, a.energy_type);
+  ub = block_sum<T>(ub, S.part);
+  su += ub;
+  const double udd = kInv4Pi * cta_pair_energy<T>(S, n, a.energy_type, P.crad2);
   const double rx = S.sx[n - 1] + 0.5 * P.b * cand[n - 1].nx;
   const double ry = S.sy[n - 1] + 0.5 * P.b * cand[n - 1].ny;
   const double rz = S.sz[n - 1] + 0.5 * P.b * cand[n - 1].nz;
-  const double U = su + udd - (rx * P.Fx + rz * P.Fz);
+  const bool bare = (a.energy_type == 3) && !P.cutoff_full;
+  const double U = bare ? udd : su + udd - (rx * P.Fx + rz * P.Fz);
   const ChainDyn& D0 = a.dyn[c];
   const uint4 w = philox_at(a.seed, a.chain_id_base + (uint32_t)c, (uint32_t)a.new_init, SUB_REINIT, 0);
   const double eps = u53(w.x, w.y);

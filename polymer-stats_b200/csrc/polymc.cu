@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "lane_kernels.cuh"
+#include "cluster_kernels.cuh"
 
 using namespace pmc;
 
@@ -74,6 +74,16 @@ struct pmc_handle {
   int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
   int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;
+  // clustering driver (mcmc_clustering_eap_chain.jl)
+  int cluster_mode = 0;       // 1: the composite-trial kernels of cluster_kernels.cuh run this handle
+  ChainDynX* dynx = nullptr;
+  double* state = nullptr;    // [chains][rows][2n] state rows of the last pmc_run_ex
+  size_t state_cap = 0;
+  double* x0buf = nullptr;
+  std::vector<pmc_case> cases;
+  int replicas = 1;
+  double kT_scale = 1.0;
+  std::vector<ChainDynX> host_dynx;
 };
 
 namespace {
@@ -272,6 +282,7 @@ int refresh(pmc_handle* h, bool rebind_gauge, int first = 0, int count = -1) {
   a.out4 = nullptr; a.obs6 = nullptr;
   a.n = h->n; a.energy_type = h->energy_type; a.first_chain = first;
   a.update_dyn = 1; a.rebind_gauge = rebind_gauge ? 1 : 0;
+  a.dynx = h->dynx; a.out8 = nullptr;
   return launch_energy(h, a, count < 0 ? (int)h->nchains : count);
 }
 
@@ -281,14 +292,24 @@ int validate_case(const pmc_case& c, const pmc_case& first) {
     return fail(PMC_ERR_INVALID, "all cases of one handle must share num-monomers and energy-type; bucket the sweep");
   if (c.chain_type != PMC_CHAIN_DIELECTRIC && c.chain_type != PMC_CHAIN_POLAR)
     return fail(PMC_ERR_INVALID, "chain-type is not understood.");  // eap_chain.jl:86
-  if (c.energy_type < 0 || c.energy_type > 2)
+  if (c.energy_type < 0 || c.energy_type > 3)
     return fail(PMC_ERR_INVALID, "energy-type is not understood.");  // eap_chain.jl:104
   if (!(c.kT > 0.0)) return fail(PMC_ERR_INVALID, "kT must be positive");
   if (c.accum_mode != 0 && c.accum_mode != 1) return fail(PMC_ERR_INVALID, "accum_mode must be 0 or 1");
+  if (c.clustering && c.n < 2) return fail(PMC_ERR_INVALID, "the clustering driver needs num-monomers >= 2");
+  if (!(c.cluster_prob >= 0.0 && c.cluster_prob <= 1.0) && c.clustering)
+    return fail(PMC_ERR_INVALID, "cluster-prob must be in [0,1]");
   return PMC_OK;
 }
 
-ChainParams params_of(const pmc_case& c) {
+// Does this case need the composite-trial kernels (cluster flips, bending energy, cut-off pair sum)?
+bool needs_cluster_path(const pmc_case& c) {
+  return c.clustering != 0 || c.kappa != 0.0 || c.energy_type == PMC_ENERGY_CUTOFF;
+}
+
+ChainParams params_of(const pmc_case& c0, double kT_scale = 1.0) {
+  pmc_case c = c0;
+  c.kT = c0.kT * kT_scale;  // burn-in stage temperature (mcmc_clustering_eap_chain.jl:367-381)
   ChainParams P{};
   if (c.chain_type == PMC_CHAIN_DIELECTRIC) {  // dipole_response.jl:7-11
     P.alpha = (c.K1 - c.K2) * c.E0;
@@ -308,8 +329,15 @@ ChainParams params_of(const pmc_case& c) {
   P.phi_step0 = c.phi_step; P.theta_step0 = c.theta_step;
   P.steps_per_adjust = c.steps_per_adjust;
   P.do_flips = c.do_flips; P.umbrella = c.umbrella; P.force_init = c.force_init;
+  P.kappa = c.kappa; P.psi0 = c.psi0;
+  P.crad2 = (c.cutoff_radius * c.b) * (c.cutoff_radius * c.b);  // UCutoff(cutoff-radius·mlen), eap_chain.jl:102
+  P.cluster_prob = c.cluster_prob;
+  P.clustering = c.clustering; P.alpha_carry = c.alpha_carry; P.cutoff_full = c.cutoff_full;
   return P;
 }
+
+// Block size of the composite-trial CTA kernels.
+int pick_cluster_threads(int n) { return n <= 160 ? 64 : n <= 1024 ? 128 : 256; }
 
 int fetch_dyn(pmc_handle* h) {
   h->host_dyn.resize((size_t)h->nchains);
@@ -378,6 +406,19 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   h->compensated = 0;
   for (int64_t i = 0; i < ncases; ++i)
     if (cases[i].accum_mode || cases[i].umbrella) h->compensated = 1;  // umbrella weights span many decades
+  h->cases.assign(cases, cases + ncases);
+  h->replicas = replicas_per_case;
+  for (int64_t i = 0; i < ncases; ++i)
+    if (needs_cluster_path(cases[i])) h->cluster_mode = 1;
+  const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
+  if (h->cluster_mode && cta_pairs) {
+    h->cta_threads = pick_cluster_threads(n);
+    if (cluster_smem_bytes(n) > (size_t)kSmemMax) {
+      delete h;
+      return fail(PMC_ERR_UNSUPPORTED, "chain too long for the clustering / bending / cut-off kernels: 16 n doubles "
+                                       "must fit one CTA's 227 KB shared memory (num-monomers <= ~1750)");
+    }
+  }
 
   std::vector<ChainParams> par((size_t)nchains);
   std::vector<ChainDyn> dyn((size_t)nchains);
@@ -405,6 +446,8 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   PMC_TRY(PMC_CU(cudaMalloc(&h->mono, total * sizeof(MonoRec))));
   PMC_TRY(PMC_CU(cudaMalloc(&h->par, (size_t)nchains * sizeof(ChainParams))));
   PMC_TRY(PMC_CU(cudaMalloc(&h->dyn, (size_t)nchains * sizeof(ChainDyn))));
+  PMC_TRY(PMC_CU(cudaMalloc(&h->dynx, (size_t)nchains * sizeof(ChainDynX))));
+  PMC_TRY(PMC_CU(cudaMemset(h->dynx, 0, (size_t)nchains * sizeof(ChainDynX))));
   PMC_TRY(PMC_CU(cudaMalloc(&h->flags, (size_t)nchains * sizeof(int))));
   PMC_TRY(PMC_CU(cudaEventCreate(&h->ev0)));
   PMC_TRY(PMC_CU(cudaEventCreate(&h->ev1)));
@@ -434,6 +477,9 @@ void pmc_destroy(pmc_handle* h) {
   if (h->cand) cudaFree(h->cand);
   if (h->par) cudaFree(h->par);
   if (h->dyn) cudaFree(h->dyn);
+  if (h->dynx) cudaFree(h->dynx);
+  if (h->state) cudaFree(h->state);
+  if (h->x0buf) cudaFree(h->x0buf);
   if (h->traj) cudaFree(h->traj);
   if (h->roll) cudaFree(h->roll);
   if (h->scratch) cudaFree(h->scratch);
@@ -515,13 +561,16 @@ int32_t pmc_get_state_all(pmc_handle* h, double* phi, double* theta) {
   return get_state_range(h, 0, h->nchains, phi, theta);
 }
 
-static int energy_range(pmc_handle* h, int64_t first, int64_t count, double* out4, double* obs6) {
-  int rc = ensure_scratch(h, (size_t)count * 10);
+static int energy_range(pmc_handle* h, int64_t first, int64_t count, double* out4, double* obs6,
+                        double* out8 = nullptr) {
+  int rc = ensure_scratch(h, (size_t)count * 18);
   if (rc) return rc;
   EnergyArgs a{};
   a.mono = h->mono; a.par = h->par; a.dyn = h->dyn;
   a.out4 = h->scratch;
   a.obs6 = h->scratch + (size_t)count * 4;
+  a.out8 = h->scratch + (size_t)count * 10;
+  a.dynx = nullptr;
   a.n = h->n; a.energy_type = h->energy_type; a.first_chain = (int)first;
   a.update_dyn = 0; a.rebind_gauge = 0;
   rc = launch_energy(h, a, (int)count);
@@ -530,6 +579,83 @@ static int energy_range(pmc_handle* h, int64_t first, int64_t count, double* out
     PMC_CU(cudaMemcpyAsync(out4, a.out4, (size_t)count * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (obs6)
     PMC_CU(cudaMemcpyAsync(obs6, a.obs6, (size_t)count * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (out8)
+    PMC_CU(cudaMemcpyAsync(out8, a.out8, (size_t)count * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  return PMC_OK;
+}
+
+// Launch helpers of the composite-trial kernels.
+static int launch_run_cluster(pmc_handle* h, const RunArgs& a) {
+  const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
+  if (cta_pairs) {
+    const size_t smem = cluster_smem_bytes(h->n);
+    const int nblocks = (int)h->nchains;
+    const bool cut = h->energy_type == PMC_ENERGY_CUTOFF;
+#define PMC_CL(TT, MB)                                                                    \
+  {                                                                                       \
+    if (cut) {                                                                            \
+      int rc = set_smem(k_run_cta_cluster<TT, MB, true>, smem);                           \
+      if (rc) return rc;                                                                  \
+      k_run_cta_cluster<TT, MB, true><<<nblocks, TT, smem, h->stream>>>(a);               \
+    } else {                                                                              \
+      int rc = set_smem(k_run_cta_cluster<TT, MB, false>, smem);                          \
+      if (rc) return rc;                                                                  \
+      k_run_cta_cluster<TT, MB, false><<<nblocks, TT, smem, h->stream>>>(a);              \
+    }                                                                                     \
+  }
+    switch (h->cta_threads) {
+      case 64: PMC_CL(64, 6) break;
+      case 128: PMC_CL(128, 3) break;
+      case 256: PMC_CL(256, 1) break;
+      default: return fail(PMC_ERR_INVALID, "bad cta_threads");
+    }
+#undef PMC_CL
+  } else {
+    constexpr int TB = 64;
+    const unsigned nb = (unsigned)((h->nchains + TB - 1) / TB);
+    if (h->energy_type == PMC_ENERGY_ISING) k_run_lane_cluster<TB, 4, true><<<nb, TB, 0, h->stream>>>(a);
+    else k_run_lane_cluster<TB, 4, false><<<nb, TB, 0, h->stream>>>(a);
+  }
+  ++h->launches;
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+
+static int launch_delta_segment(pmc_handle* h, const SegDeltaArgs& a) {
+  const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
+  if (cta_pairs) {
+    const size_t smem = cluster_smem_bytes(h->n);
+    if (smem > (size_t)kSmemMax) return fail(PMC_ERR_UNSUPPORTED, "chain too long for the composite-trial kernel");
+    const bool cut = h->energy_type == PMC_ENERGY_CUTOFF;
+    const int tt = pick_cluster_threads(h->n);
+#define PMC_DS(TT)                                                                        \
+  {                                                                                       \
+    if (cut) {                                                                            \
+      int rc = set_smem(k_delta_segment_cta<TT, true>, smem);                             \
+      if (rc) return rc;                                                                  \
+      k_delta_segment_cta<TT, true><<<1, TT, smem, h->stream>>>(a);                       \
+    } else {                                                                              \
+      int rc = set_smem(k_delta_segment_cta<TT, false>, smem);                            \
+      if (rc) return rc;                                                                  \
+      k_delta_segment_cta<TT, false><<<1, TT, smem, h->stream>>>(a);                      \
+    }                                                                                     \
+  }
+    if (tt == 64) PMC_DS(64) else if (tt == 128) PMC_DS(128) else PMC_DS(256)
+#undef PMC_DS
+  } else {
+    if (h->energy_type == PMC_ENERGY_ISING) k_delta_segment_lane<true><<<1, 32, 0, h->stream>>>(a);
+    else k_delta_segment_lane<false><<<1, 32, 0, h->stream>>>(a);
+  }
+  ++h->launches;
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+
+static int fetch_dynx(pmc_handle* h) {
+  h->host_dynx.resize((size_t)h->nchains);
+  PMC_CU(cudaMemcpyAsync(h->host_dynx.data(), h->dynx, sizeof(ChainDynX) * (size_t)h->nchains, cudaMemcpyDeviceToHost,
+                         h->stream));
   PMC_CU(cudaStreamSynchronize(h->stream));
   return PMC_OK;
 }
@@ -563,6 +689,16 @@ int32_t pmc_delta_u(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, dou
   if ((rc = check_chain(h, chain))) return rc;
   if (!out) return fail(PMC_ERR_INVALID, "null out");
   if (idx0 < 0 || idx0 >= h->n) return fail(PMC_ERR_INVALID, "monomer index out of range");
+  if (h->cluster_mode) {  // bending energy / cut-off pair sum live in the composite-trial code
+    double o[12];
+    rc = pmc_delta_segment(h, chain, idx0, dphi, dtheta, 0, idx0, idx0, o);
+    if (rc) return rc;
+    MonoRec rec;
+    PMC_CU(cudaMemcpy(&rec, h->mono + (size_t)chain * h->n + idx0, sizeof(rec), cudaMemcpyDeviceToHost));
+    const double traw = rec.theta + dtheta;
+    out[0] = o[0]; out[1] = o[1]; out[2] = (traw < 0.0 || traw > kPi) ? 1.0 : 0.0;
+    return PMC_OK;
+  }
   if ((rc = ensure_scratch(h, 8))) return rc;
   DeltaArgs a{};
   a.mono = h->mono; a.par = h->par; a.out = h->scratch;
@@ -589,11 +725,26 @@ int64_t pmc_rows_for(const pmc_handle* h, int64_t nsteps, int64_t stepout) {
   return (step0 + nsteps) / stepout - step0 / stepout;
 }
 
+static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll, int roll_cols,
+                    double* state);
+
 int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll) {
+  return run_impl(h, nsteps, stepout, traj, roll, 17, nullptr);
+}
+
+int32_t pmc_run_ex(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll19, double* state) {
+  if (h && !h->cluster_mode)
+    return fail(PMC_ERR_INVALID, "pmc_run_ex needs a clustering-driver handle (clustering, bend-mod or cutoff case)");
+  return run_impl(h, nsteps, stepout, traj, roll19, 19, state);
+}
+
+static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll, int roll_cols,
+                    double* state) {
   int rc = check_handle(h);
   if (rc) return rc;
   if (nsteps < 0) return fail(PMC_ERR_INVALID, "nsteps must be >= 0");
   if (nsteps == 0) return PMC_OK;
+  if (nsteps >= (1LL << 40)) return fail(PMC_ERR_INVALID, "nsteps must stay below 2^40");
   // re-synchronise running scalars against a full recompute (records drift, SURVEY §7 "hard parts")
   if ((rc = refresh(h, false))) return rc;
   // step0 (shared by all chains) decides the row count
@@ -605,7 +756,14 @@ int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, do
     h->host_dyn[0] = d0;
   }
   const int64_t rows = pmc_rows_for(h, nsteps, stepout);
-  const size_t ntraj = (size_t)h->nchains * (size_t)rows * 8, nroll = (size_t)h->nchains * (size_t)rows * 17;
+  const size_t ntraj = (size_t)h->nchains * (size_t)rows * 8, nroll = (size_t)h->nchains * (size_t)rows * roll_cols;
+  const size_t nstate = state ? (size_t)h->nchains * (size_t)rows * 2 * (size_t)h->n : 0;
+  if (nstate > h->state_cap) {
+    if (h->state) cudaFree(h->state);
+    h->state = nullptr; h->state_cap = 0;
+    PMC_CU(cudaMalloc(&h->state, nstate * sizeof(double)));
+    h->state_cap = nstate;
+  }
   if (ntraj > h->traj_cap) {
     if (h->traj) cudaFree(h->traj);
     h->traj = nullptr; h->traj_cap = 0;
@@ -624,8 +782,11 @@ int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, do
   a.nsteps = nsteps; a.stepout = stepout; a.rows = rows;
   a.seed = h->seed; a.chain_id_base = h->chain_id_base;
   a.n = h->n; a.nchains = (int)h->nchains; a.energy_type = h->energy_type;
+  a.dynx = h->dynx; a.state = nstate ? h->state : nullptr; a.roll_cols = roll_cols;
   PMC_CU(cudaEventRecord(h->ev0, h->stream));
-  if (h->energy_type == PMC_ENERGY_INTERACTING) {
+  if (h->cluster_mode) {
+    if ((rc = launch_run_cluster(h, a))) return rc;
+  } else if (h->energy_type == PMC_ENERGY_INTERACTING) {
     if ((rc = launch_run_cta(h, a))) return rc;
   } else {
     // few chains: one chain per warp with 32-trial windows fills the machine; many chains: one per lane
@@ -664,6 +825,8 @@ int32_t pmc_run(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, do
     PMC_CU(cudaMemcpyAsync(traj, h->traj, ntraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (roll && rows > 0)
     PMC_CU(cudaMemcpyAsync(roll, h->roll, nroll * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (state && rows > 0)
+    PMC_CU(cudaMemcpyAsync(state, h->state, nstate * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   PMC_CU(cudaStreamSynchronize(h->stream));
   PMC_CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   h->host_dyn[0].step += nsteps;
@@ -695,6 +858,7 @@ int32_t pmc_reinit(pmc_handle* h, int32_t* replaced) {
   a.seed = h->seed; a.chain_id_base = h->chain_id_base;
   a.n = h->n; a.energy_type = h->energy_type; a.new_init = h->init;
   if ((rc = launch_reinit(h, a))) return rc;
+  if (h->cluster_mode && (rc = refresh(h, false))) return rc;  // Σψ, Σcos²θ of the new chains
   if (replaced)
     PMC_CU(cudaMemcpyAsync(replaced, h->flags, (size_t)h->nchains * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   PMC_CU(cudaStreamSynchronize(h->stream));
@@ -741,6 +905,116 @@ int32_t pmc_diagnostics(pmc_handle* h, double* diag) {
     o[2] = (double)d.nacc; o[3] = (double)d.natt;
     o[4] = (double)d.nacc_total; o[5] = (double)d.steps_total;
     o[6] = d.U; o[7] = d.drift_max;
+  }
+  return PMC_OK;
+}
+
+int32_t pmc_energy_ex(pmc_handle* h, int64_t chain, double out[8]) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = check_chain(h, chain))) return rc;
+  if (!out) return fail(PMC_ERR_INVALID, "null out");
+  return energy_range(h, chain, 1, nullptr, nullptr, out);
+}
+
+int32_t pmc_delta_segment(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, double dtheta, int32_t reflect,
+                          int64_t lo0, int64_t hi0, double out[12]) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if ((rc = check_chain(h, chain))) return rc;
+  if (!out) return fail(PMC_ERR_INVALID, "null out");
+  if (idx0 < 0 || idx0 >= h->n) return fail(PMC_ERR_INVALID, "monomer index out of range");
+  if (reflect && !(0 <= lo0 && lo0 <= idx0 && idx0 <= hi0 && hi0 < h->n))
+    return fail(PMC_ERR_INVALID, "cluster bounds must satisfy 0 <= lo <= idx <= hi < n");
+  if ((rc = ensure_scratch(h, 16))) return rc;
+  SegDeltaArgs a{};
+  a.mono = h->mono; a.par = h->par; a.out = h->scratch;
+  a.n = h->n; a.energy_type = h->energy_type; a.chain = (int)chain; a.idx = (int)idx0;
+  a.lo = (int)lo0; a.hi = (int)hi0; a.reflect = reflect ? 1 : 0;
+  a.dphi = dphi; a.dtheta = dtheta;
+  if ((rc = launch_delta_segment(h, a))) return rc;
+  PMC_CU(cudaMemcpyAsync(out, h->scratch, 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  return PMC_OK;
+}
+
+int32_t pmc_begin_stage(pmc_handle* h, double kT_scale) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!(kT_scale > 0.0)) return fail(PMC_ERR_INVALID, "kT_scale must be positive");
+  h->kT_scale = kT_scale;
+  std::vector<ChainParams> par((size_t)h->nchains);
+  for (int64_t c = 0; c < h->nchains; ++c) par[(size_t)c] = params_of(h->cases[(size_t)(c / h->replicas)], kT_scale);
+  PMC_CU(cudaMemcpyAsync(h->par, par.data(), par.size() * sizeof(ChainParams), cudaMemcpyHostToDevice, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));  // `par` is pageable host memory
+  h->init += 1;
+  const int tb = 128;
+  k_begin_stage<<<(unsigned)((h->nchains + tb - 1) / tb), tb, 0, h->stream>>>(h->dyn, h->dynx, h->par, (int)h->nchains,
+                                                                             h->init);
+  ++h->launches;
+  PMC_CU(cudaGetLastError());
+  if ((rc = refresh(h, /*rebind_gauge=*/true))) return rc;  // chain.U = U(chain); wf = AntiDipoleWeightFunction(chain)
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  if (!h->host_dyn.empty()) h->host_dyn[0].step = 0;
+  return PMC_OK;
+}
+
+int32_t pmc_init_x0(pmc_handle* h, const double* x0, int64_t x0_len, const double dx0[2]) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!x0 || !dx0) return fail(PMC_ERR_INVALID, "null x0/dx0");
+  if (x0_len != 2 && x0_len != 2 * (int64_t)h->n) return fail(PMC_ERR_INVALID, "Invalid input for 'x0'");  // eap_chain.jl:76
+  if (!h->x0buf) PMC_CU(cudaMalloc(&h->x0buf, 2 * (size_t)h->n * sizeof(double)));
+  PMC_CU(cudaMemcpyAsync(h->x0buf, x0, (size_t)x0_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const size_t total = (size_t)h->nchains * (size_t)h->n;
+  const int tb = 256;
+  k_fill_x0<<<(unsigned)((total + tb - 1) / tb), tb, 0, h->stream>>>(h->mono, (long long)total, h->n, h->seed,
+                                                                    h->chain_id_base, 0u, h->x0buf, (int)x0_len, dx0[0],
+                                                                    dx0[1]);
+  ++h->launches;
+  PMC_CU(cudaGetLastError());
+  if ((rc = refresh(h, /*rebind_gauge=*/true))) return rc;
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  return PMC_OK;
+}
+
+int32_t pmc_extra_accumulators(pmc_handle* h, double* sums) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!sums) return fail(PMC_ERR_INVALID, "null sums");
+  if ((rc = fetch_dynx(h))) return rc;
+  for (int64_t c = 0; c < h->nchains; ++c) {
+    const ChainDynX& d = h->host_dynx[(size_t)c];
+    sums[c * 2 + 0] = d.acc[0] + d.comp[0];
+    sums[c * 2 + 1] = d.acc[1] + d.comp[1];
+  }
+  return PMC_OK;
+}
+
+int32_t pmc_extra_averages(pmc_handle* h, double* ex) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!ex) return fail(PMC_ERR_INVALID, "null ex");
+  if ((rc = fetch_dyn(h))) return rc;
+  if ((rc = fetch_dynx(h))) return rc;
+  for (int64_t c = 0; c < h->nchains; ++c) {
+    const ChainDynX& d = h->host_dynx[(size_t)c];
+    const ChainDyn& D = h->host_dyn[(size_t)c];
+    const double nrm = D.acc[16] + D.comp[16];
+    ex[c * 2 + 0] = (d.acc[0] + d.comp[0]) / nrm;
+    ex[c * 2 + 1] = (d.acc[1] + d.comp[1]) / nrm;
+  }
+  return PMC_OK;
+}
+
+int32_t pmc_cluster_stats(pmc_handle* h, double* out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!out) return fail(PMC_ERR_INVALID, "null out");
+  if ((rc = fetch_dynx(h))) return rc;
+  for (int64_t c = 0; c < h->nchains; ++c) {
+    const ChainDynX& d = h->host_dynx[(size_t)c];
+    out[c * 3 + 0] = d.ncluster; out[c * 3 + 1] = d.cluster_sum; out[c * 3 + 2] = d.cluster_max;
   }
   return PMC_OK;
 }

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_ROOT, "libpolymc_b200.so")
 CSRC_DIR = os.path.join(_ROOT, "csrc")
 
 CHAIN_TYPES = {"dielectric": 0, "polar": 1}
-ENERGY_TYPES = {"noninteracting": 0, "interacting": 1, "Ising": 2}
+ENERGY_TYPES = {"noninteracting": 0, "interacting": 1, "Ising": 2, "cutoff": 3}
 
 AVG_NAMES = ["r1", "r2", "r3", "r1sq", "r2sq", "r3sq", "rsq",
              "p1", "p2", "p3", "p1sq", "p2sq", "p3sq", "psq", "U", "Usq"]
@@ -29,6 +29,9 @@ EXPORTS = [
     "pmc_set_state_all", "pmc_get_state_all", "pmc_energy", "pmc_energy_all", "pmc_observables",
     "pmc_delta_u", "pmc_run", "pmc_rows_for", "pmc_last_run_ms", "pmc_reinit", "pmc_averages",
     "pmc_accumulators", "pmc_diagnostics", "pmc_fp64_peak_probe", "pmc_launch_count",
+    # ABI v2: the clustering driver (mcmc_clustering_eap_chain.jl)
+    "pmc_energy_ex", "pmc_delta_segment", "pmc_run_ex", "pmc_begin_stage", "pmc_init_x0",
+    "pmc_extra_averages", "pmc_extra_accumulators", "pmc_cluster_stats",
 ]
 
 
@@ -52,6 +55,9 @@ class PmcCase(C.Structure):
         ("chain_type", C.c_int32), ("energy_type", C.c_int32),
         ("do_flips", C.c_int32), ("umbrella", C.c_int32),
         ("force_init", C.c_int32), ("accum_mode", C.c_int32),
+        # mcmc_clustering_eap_chain.jl:36-51,87-90
+        ("kappa", C.c_double), ("psi0", C.c_double), ("cutoff_radius", C.c_double), ("cluster_prob", C.c_double),
+        ("clustering", C.c_int32), ("alpha_carry", C.c_int32), ("cutoff_full", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -59,15 +65,19 @@ def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=
               chain_type="dielectric", energy_type="noninteracting",
               phi_step=3 * math.pi / 8, theta_step=3 * math.pi / 16,
               adj_lb=0.15, adj_ub=0.55, adj_scale=1.1, steps_per_adjust=2500,
-              do_flips=False, umbrella=False, force_init=False, accum_mode=0) -> PmcCase:
-    """Defaults are the ArgParse defaults of mcmc_eap_chain.jl:19-153."""
+              do_flips=False, umbrella=False, force_init=False, accum_mode=0,
+              kappa=0.0, psi0=0.0, cutoff_radius=7.5, cluster_prob=0.5, clustering=False, alpha_carry=True,
+              cutoff_full=False) -> PmcCase:
+    """Defaults are the ArgParse defaults of mcmc_eap_chain.jl:19-153; the clustering fields default to
+    "off" (kappa 0, clustering False) with the option defaults of mcmc_clustering_eap_chain.jl:48-51,87-90."""
     if chain_type not in CHAIN_TYPES:
         raise PolymcError(-1, "chain-type is not understood.")      # eap_chain.jl:86
     if energy_type not in ENERGY_TYPES:
         raise PolymcError(-1, "energy-type is not understood.")     # eap_chain.jl:104
     return PmcCase(E0, K1, K2, mu, kT, Fz, Fx, b, phi_step, theta_step, adj_lb, adj_ub, adj_scale,
                    n, steps_per_adjust, CHAIN_TYPES[chain_type], ENERGY_TYPES[energy_type],
-                   int(do_flips), int(umbrella), int(force_init), int(accum_mode))
+                   int(do_flips), int(umbrella), int(force_init), int(accum_mode),
+                   kappa, psi0, cutoff_radius, cluster_prob, int(clustering), int(alpha_carry), int(cutoff_full), 0)
 
 
 def build(force: bool = False) -> str:
@@ -126,11 +136,20 @@ def load():
     L.pmc_accumulators.argtypes = [hp, dp]
     L.pmc_diagnostics.argtypes = [hp, dp]
     L.pmc_fp64_peak_probe.argtypes = [C.c_int32, C.c_int32, dp, C.POINTER(C.c_float)]
+    L.pmc_energy_ex.argtypes = [hp, C.c_int64, dp]
+    L.pmc_delta_segment.argtypes = [hp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_int64,
+                                    C.c_int64, dp]
+    L.pmc_run_ex.argtypes = [hp, C.c_int64, C.c_int64, dp, dp, dp]
+    L.pmc_begin_stage.argtypes = [hp, C.c_double]
+    L.pmc_init_x0.argtypes = [hp, dp, C.c_int64, dp]
+    L.pmc_extra_averages.argtypes = [hp, dp]
+    L.pmc_extra_accumulators.argtypes = [hp, dp]
+    L.pmc_cluster_stats.argtypes = [hp, dp]
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int:  # default restype: every status-returning entry point
             f.restype = C.c_int32
-    if L.pmc_abi_version() != 1:
+    if L.pmc_abi_version() != 2:
         raise PolymcError(-1, "ABI version mismatch")
     _lib = L
     return L
@@ -288,3 +307,53 @@ class Ensemble:
         d = np.empty((self.nchains, 8))
         _check(load().pmc_diagnostics(self._h, _dp(d)))
         return d
+
+    # ---- clustering driver (mcmc_clustering_eap_chain.jl), ABI v2 ----
+    def energy_ex(self, chain):
+        o = np.empty(8)
+        _check(load().pmc_energy_ex(self._h, chain, _dp(o)))
+        return {"U": o[0], "su": o[1], "Udd": o[2], "Omega": o[3], "Ubend": o[4], "psi": o[5], "cos2": o[6]}
+
+    def delta_segment(self, chain, idx0, dphi, dtheta, reflect, lo0, hi0):
+        o = np.empty(12)
+        _check(load().pmc_delta_segment(self._h, chain, idx0, dphi, dtheta, int(reflect), lo0, hi0, _dp(o)))
+        return dict(zip(["dU", "dOmega", "dpair", "du", "drF", "dbend", "dpsi", "dcos2", "dp1", "dp2", "dp3",
+                         "log_alpha"], o))
+
+    def run_ex(self, nsteps, stepout=0, fetch_rows=True, want_state=False):
+        """The clustering driver's loop.  Returns (traj [chains][rows][8], roll [chains][rows][19],
+        state [chains][rows][2n] or None)."""
+        rows = self.rows_for(nsteps, stepout)
+        traj = roll = state = None
+        if fetch_rows and rows > 0:
+            traj = np.empty((self.nchains, rows, 8))
+            roll = np.empty((self.nchains, rows, 19))
+            if want_state:
+                state = np.empty((self.nchains, rows, 2 * self.n))
+        _check(load().pmc_run_ex(self._h, nsteps, stepout, _dp(traj), _dp(roll), _dp(state)))
+        return traj, roll, state
+
+    def begin_stage(self, kT_scale=1.0):
+        _check(load().pmc_begin_stage(self._h, float(kT_scale)))
+
+    def init_x0(self, x0, dx0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).ravel()
+        dx0 = np.ascontiguousarray(dx0, dtype=np.float64).ravel()
+        if dx0.size != 2:
+            raise PolymcError(-1, "Invalid input for 'dx0'")
+        _check(load().pmc_init_x0(self._h, _dp(x0), x0.size, _dp(dx0)))
+
+    def extra_averages(self):
+        o = np.empty((self.nchains, 2))
+        _check(load().pmc_extra_averages(self._h, _dp(o)))
+        return o
+
+    def extra_accumulators(self):
+        o = np.empty((self.nchains, 2))
+        _check(load().pmc_extra_accumulators(self._h, _dp(o)))
+        return o
+
+    def cluster_stats(self):
+        o = np.empty((self.nchains, 3))
+        _check(load().pmc_cluster_stats(self._h, _dp(o)))
+        return o

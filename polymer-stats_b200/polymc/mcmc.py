@@ -90,6 +90,11 @@ def _log(pargs, level, msg):
 
 def case_from_pargs(pargs: dict) -> lib.PmcCase:
     """EAPChain(pargs) argument mapping (inc/eap_chain.jl:60-135)."""
+    if pargs["energy-type"] == "cutoff":
+        # this driver has no --cutoff-radius, so the reference dies on pargs["cutoff-radius"]
+        # (inc/eap_chain.jl:102); the cut-off energy belongs to mcmc_clustering_eap_chain
+        raise lib.PolymcError(-1, "energy-type is not understood. ('cutoff' needs --cutoff-radius: use "
+                                  "mcmc_clustering_eap_chain)")
     return lib.make_case(
         n=pargs["num-monomers"], E0=pargs["E0"], K1=pargs["K1"], K2=pargs["K2"], mu=pargs["mu"],
         kT=pargs["kT"], Fz=pargs["Fz"], Fx=pargs["Fx"], b=pargs["mlen"],

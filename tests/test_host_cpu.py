@@ -129,8 +129,8 @@ def test_abi_exports_every_declared_symbol(pm):
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(pm.lib.EXPORTS) == declared
-    assert pm.load().pmc_abi_version() == 1
-    assert ctypes.sizeof(pm.PmcCase) == 13 * 8 + 2 * 8 + 6 * 4
+    assert pm.load().pmc_abi_version() == 2
+    assert ctypes.sizeof(pm.PmcCase) == 13 * 8 + 2 * 8 + 6 * 4 + 4 * 8 + 4 * 4
 
 
 def test_no_cpu_fallback(pm):
