@@ -40,13 +40,21 @@ WORKLOADS = {
                 energy_type="noninteracting"), 16384, 20000, 500),
     "C5": (dict(n=4096, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.5, Fx=0.0, chain_type="dielectric",
                 energy_type="interacting"), 148, 50, 50),
+    # the clustering driver (mcmc_clustering_eap_chain.jl), shapes of its launchers:
+    # run/phases-kT-small-n_2023-09-09.jl (all-pairs, bending), run/Ising_2025-12-17.jl, run/phases-big_2023-05-18.jl
+    "K1": (dict(n=100, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.25, Fx=0.0, chain_type="dielectric",
+                energy_type="interacting", kappa=0.5, clustering=True, adj_ub=0.40), 4096, 500, 250),
+    "K2": (dict(n=100, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.25, Fx=0.0, chain_type="dielectric",
+                energy_type="Ising", kappa=0.5, clustering=True, adj_ub=0.40), 65536, 2000, 250),
+    "K3": (dict(n=400, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.25, Fx=0.0, chain_type="dielectric",
+                energy_type="cutoff", cutoff_radius=7.5, kappa=0.5, clustering=True, adj_ub=0.40), 2368, 200, 100),
 }
 SEED = 20260101
 
 
 def flops_per_update(n: int, energy_type: str) -> float:
     """Algorithmic FP64 flop per update (SURVEY.md §8d / BASELINE.md §3)."""
-    if energy_type == "interacting":
+    if energy_type in ("interacting", "cutoff"):
         return 2.0 * 34.0 * ((n - 1) * (n - 2) / 6.0 + (n - 1))
     return 210.0 if energy_type == "Ising" else 66.0
 
@@ -103,9 +111,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def metric_of(workload, kw):
+    if workload == "C2":
+        return METRIC
+    drv = "clustering driver, " if kw.get("clustering") else ""
+    return f"monomer MC updates/sec (whole box), {drv}{kw['energy_type']} n={kw['n']} {kw['chain_type']} chains"
+
+
 def make_config(workload, kw, per_gpu, S, stepout):
     """The `config` object — identical for both arms."""
-    return {"workload": f"{workload}: {kw['energy_type']} {kw['chain_type']} chains n={kw['n']}, "
+    drv = "clustering driver (move! + cluster_flip!), " if kw.get("clustering") else ""
+    return {"workload": f"{workload}: {drv}{kw['energy_type']} {kw['chain_type']} chains n={kw['n']}, "
                         f"{per_gpu} replicas per GPU, {S} trials per step, stepout={stepout}",
             "chains_per_gpu": per_gpu, "trials_per_step": S, "seed": SEED,
             "l2": "flushed between timed steps (256 MiB write)", **kw}
@@ -157,7 +173,7 @@ def run_reference_arm(args, rank, world):
     sample = (f"{threads} chains x {trials} trials per step (one chain per thread), n={kw['n']} "
               f"{kw['energy_type']} {kw['chain_type']}, same parameters as the GPU arm")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_of(args.workload, kw), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": make_config(args.workload, kw, per_gpu, S, stepout),
@@ -247,9 +263,19 @@ def main():
     # ---- measured FP64 roofline denominator (DFMA microbenchmark, before the clocks heat up) ----
     probe_tf = max(pm.fp64_peak_probe(local_rank, 1 << 16)[0] for _ in range(3))
 
+    clustering = bool(kw.get("clustering"))
+    if clustering:
+        ens.begin_stage(1.0)   # a fresh mcmc(nsteps, pargs, chain) call (mcmc_clustering_eap_chain.jl:171-265)
+
+    def run_resident():
+        if clustering:
+            ens.run_ex(S, stepout, fetch_rows=False)
+        else:
+            ens.run(S, stepout, fetch_rows=False)
+
     # ---- warm-up -------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 0)):
-        ens.run(S, stepout, fetch_rows=False)
+        run_resident()
 
     # ---- value: state resident in HBM, device-timed -----------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -262,7 +288,7 @@ def main():
         flush.fill_(1.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        ens.run(S, stepout, fetch_rows=False)
+        run_resident()
         e1.record(stream)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
@@ -292,7 +318,7 @@ def main():
         # keep the step counter aligned with stepout so that every e2e step emits `rows` rows
         def e2e_step():
             ens.set_state_all(phi_h.numpy(), th_h.numpy())                 # H2D + cache rebuild
-            ens.run(S, stepout, traj=traj_h.numpy(), roll=roll_h.numpy())  # hot loop + D2H rows
+            ens.run(S, stepout, traj=traj_h.numpy(), roll=roll_h.numpy())  # hot loop + D2H rows (17 columns)
             avg, ar, nrm = ens.averages()                                  # D2H results
             if world > 1:                                                  # final gather of averages (NCCL)
                 t = torch.from_numpy(np.concatenate([avg, ar[:, None], nrm[:, None]], axis=1)).to(dev)
@@ -318,11 +344,21 @@ def main():
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     F = flops_per_update(n, kw["energy_type"])
+    if clustering:
+        # changed pair terms of a composite trial: segment×everything + heads×tails, from the measured cluster
+        # sizes (the single-monomer formula with the segment in place of idx): informational
+        cs = ens.cluster_stats()
+        trials = ens.diagnostics()[:, 5].sum()
+        mean_seg = 1.0 + (cs[:, 1].sum() - cs[:, 0].sum()) / max(1.0, trials)
+        if kw["energy_type"] in ("interacting", "cutoff"):
+            F = 2.0 * 34.0 * ((n - mean_seg) * (n - mean_seg - 1) / 6.0 + mean_seg * (n - 1))
     kavg_ms = sum(kernel_ms) / len(kernel_ms)
     achieved_tf = per_gpu * S * F / (kavg_ms * 1e-3) / 1e12
     derived_tf = 148 * 64 * 2 * 1.965e9 / 1e12
     kernel = "k_run_cta_win" if kw["energy_type"] == "interacting" and n <= 3000 else (
         "k_run_cta" if kw["energy_type"] == "interacting" else "k_run_lane")
+    if clustering:
+        kernel = "k_run_cta_cluster" if kw["energy_type"] in ("interacting", "cutoff") else "k_run_lane_cluster"
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the C2 launch, from
     # profiles/r01d_dram_traffic_k_run_cta_win_bench_launch.csv (ncu, same command): 105.3 MB read (the
     # chain records, once per launch) + 2.8-6.3 MB written.  Other workloads: not captured.
@@ -351,7 +387,7 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_of(args.workload, kw), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": make_config(args.workload, kw, per_gpu, S, stepout),

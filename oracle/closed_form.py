@@ -76,3 +76,19 @@ def langevin(f):
     small = np.abs(f) < 1e-4
     fs = np.where(small, 1.0, f)
     return np.where(small, f / 3 - f ** 3 / 45, 1 / np.tanh(fs) - 1 / fs)
+
+
+def bond_angle_mean(kappa, psi0=0.0, kT=1.0, nquad=2000):
+    """⟨ψ⟩ of a chain whose ONLY energy is bending, ubend = κ/2 (ψ−ψ0)² (inc/eap_chain.jl:54-58; E0 = 0,
+    F = 0): the bond angles are independent with density ∝ sinψ · exp(−κ(ψ−ψ0)²/(2kT)) on [0,π]
+    (each direction is uniform on the sphere given its predecessor).  The clustering driver averages
+    Σψ/(n−1) (mcmc_clustering_eap_chain.jl:244)."""
+    xs, w = np.polynomial.legendre.leggauss(nquad)
+    psi = 0.5 * np.pi * (xs + 1.0)
+    dens = np.sin(psi) * np.exp(-kappa * (psi - psi0) ** 2 / (2 * kT)) * w
+    return float((psi * dens).sum() / dens.sum())
+
+
+def cos2_sum(n, **kw):
+    """⟨Σcos²θ⟩ of n independent monomers (mcmc_clustering_eap_chain.jl:243)."""
+    return n * float(single_monomer_moments(**kw)["n2"][2])

@@ -826,6 +826,7 @@ static void emit_rows(const orc_run* r, int64_t step, double* traj_row, double* 
 static int cluster_grow(const orc_run* r, const orc_chain* t, int64_t step, int64_t idx, int64_t* lo, int64_t* hi,
                         double* upper_p, double* lower_p) {
   const orc_case* c = &r->c;
+  if (!c->clustering) return 0; /* mcmc_eap_chain.jl has no cluster_flip! */
   if (orc_draw_cluster_gate(r->seed, r->chain_id, r->init, step) <= c->cluster_prob) return 0;
   int64_t u = idx, k = 0;
   double up;
@@ -862,7 +863,9 @@ static int cluster_trial(orc_run* r, int64_t step) {
   int32_t flipbit;
   orc_draw_step(r->seed, r->chain_id, r->init, step, c->n, &idx, &uphi, &flipbit, &uth, &eps);
   const double dphi = -r->phi_step + (2 * r->phi_step) * uphi;   /* :268-270 */
-  const double dth = -r->theta_step + (2 * r->theta_step) * uth;
+  /* (--do-flips exists only in mcmc_eap_chain.jl:279, which reaches this path when it carries bending energy) */
+  const double dth = ((c->do_flips && flipbit) ? M_PI - 2 * r->chain->theta[idx] : 0.0) +
+                     (-r->theta_step + (2 * r->theta_step) * uth);
   int64_t lo = idx, hi = idx;
   double up = 0.0, lp = 0.0, alpha = 1.0;
   int reflect = 0, accepted = 0;
@@ -944,7 +947,7 @@ static void orc_run_steps_impl(orc_run* r, int64_t nsteps, int64_t stepout, doub
   const orc_case* c = &r->c;
   int64_t row = 0;
   for (int64_t step = 1; step <= nsteps; ++step) {
-    if (c->clustering) {
+    if (c->clustering || c->kappa != 0.0 || c->energy_type == ORC_ENERGY_CUTOFF) {
       const int acc = cluster_trial(r, step);
       if (acc) { r->nacc += 1; r->nacc_total += 1; }
       goto counted;

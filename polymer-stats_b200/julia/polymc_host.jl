@@ -18,6 +18,9 @@ struct PmcCase
   adj_lb::Cdouble; adj_ub::Cdouble; adj_scale::Cdouble
   n::Int64; steps_per_adjust::Int64
   chain_type::Int32; energy_type::Int32; do_flips::Int32; umbrella::Int32; force_init::Int32; accum_mode::Int32
+  # ABI v2 — mcmc_clustering_eap_chain.jl; all zero for this driver
+  kappa::Cdouble; psi0::Cdouble; cutoff_radius::Cdouble; cluster_prob::Cdouble
+  clustering::Int32; alpha_carry::Int32; cutoff_full::Int32; reserved::Int32
 end
 
 pmc_error() = unsafe_string(ccall((:pmc_last_error, LIBPOLYMC), Cstring, ()))
@@ -62,7 +65,8 @@ function case_of(p)
   PmcCase(p["E0"], p["K1"], p["K2"], p["mu"], p["kT"], p["Fz"], p["Fx"], p["mlen"], p["phi-step"], p["theta-step"],
           p["step-adjust-lb"], p["step-adjust-ub"], p["step-adjust-scale"], p["num-monomers"], p["steps-per-adjust"],
           ct[p["chain-type"]], et[p["energy-type"]], p["do-flips"], p["umbrella-sampling"], p["force-init"],
-          p["numeric-type"] == "float64" ? 0 : 1)
+          p["numeric-type"] == "float64" ? 0 : 1,
+          0.0, 0.0, 7.5, 0.5, 0, 1, 0, 0)
 end
 
 function mcmc(nsteps::Int, p)

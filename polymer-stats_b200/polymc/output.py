@@ -68,3 +68,26 @@ def write_rows(fh, rows):
     for row in rows:
         fh.write(",".join(julia_float(x) for x in row))
         fh.write("\n")
+
+
+# ---- mcmc_clustering_eap_chain.jl: 12 stdout lines (:389-400), wider CSVs (:254-259) -------------------
+ROLL_HEADER_CLUSTERING = ROLL_HEADER + ",Ealign,psi"                                       # :259
+
+
+def traj_header_clustering(n: int) -> str:
+    """step,r1..3,p1..3,U, phi1,theta1,…,phin,thetan, mux1,muy1,muz1,…,muzn (:254-257)."""
+    cols = [TRAJ_HEADER]
+    cols += [f"phi{i},theta{i}" for i in range(1, n + 1)]
+    cols += [f"mux{i},muy{i},muz{i}" for i in range(1, n + 1)]
+    return ",".join(cols)
+
+
+def result_lines_clustering(avg16, cos2, psi, acc_rate, mlen, n):
+    """The 12 stdout lines, mcmc_clustering_eap_chain.jl:389-400: the 9 averages of the plain driver, then
+    `<cos2(θ)>`, `<ψ>` and AR last.  scripts/aggregate_mcmc.jl:54 names these 22 output columns."""
+    base = result_lines(avg16, acc_rate, mlen, n)
+    return base[:9] + [
+        f"<cos2(θ)>   =   {julia_float(cos2)}",
+        f"<ψ>    =   {julia_float(psi)}",
+        base[9],
+    ]
