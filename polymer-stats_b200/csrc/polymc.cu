@@ -39,6 +39,9 @@ int fail(int code, const std::string& msg) {
 
 constexpr int kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
+// the FFI mirrors of pmc_case (ctypes in polymc/lib.py, the Julia struct in julia/polymc_host.jl) rely on it
+static_assert(sizeof(pmc_case) == 13 * 8 + 2 * 8 + 6 * 4 + 4 * 8 + 4 * 4, "pmc_case layout changed: bump PMC_ABI_VERSION");
+
 int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return (v && *v) ? std::atoi(v) : dflt;

@@ -46,6 +46,58 @@ def test_cli_table_matches_reference(pm, cli_table):
             assert a.type is {"Float64": float, "Int": int, "String": str}[e["arg_type"]]
 
 
+def test_clustering_cli_table_matches_reference(pm):
+    """Every option of mcmc_clustering_eap_chain.jl:19-153: same long/short names, types and defaults."""
+    import json
+    from polymc import mcmc_clustering as mc
+    table = json.load(open(os.path.join(ROOT, "tests", "golden", "cli_table_clustering.json")))
+    by_long = {o: a for a in mc.build_parser()._actions for o in a.option_strings if o.startswith("--")}
+    assert len(table) == 34
+    for e in table:
+        assert e["long"] in by_long, e["long"]
+        a = by_long[e["long"]]
+        if e["short"]:
+            assert e["short"] in a.option_strings, (e["long"], e["short"])
+        if e["action"] == ":store_true":
+            assert a.default is False and a.nargs == 0
+        elif e["default"] is None:           # --x0 has no default
+            assert a.default is None
+        else:
+            want = _julia_default(e["default"])
+            assert a.default == pytest.approx(want) if isinstance(want, float) else a.default == want, e["long"]
+            assert a.type is {"Float64": float, "Int": int, "String": str}[e["arg_type"]]
+
+
+def test_clustering_cli_parses_launcher_style_argv(pm):
+    """argv exactly as run/phases-kT-small-n_2023-09-09.jl:44 builds it; the Julia vector options."""
+    from polymc import mcmc_clustering as mc
+    argv = ['--chain-type', 'dielectric', '--energy-type', 'interacting', '--x0', '[0.0; pi/2]', '-b', '1.0',
+            '--bend-mod', '0.25', '--E0', '0.5', '--K1', '1.0', '--K2', '0.0', '--kT', '0.1', '--Fz', '0.0', '--Fx', '0.0',
+            '-n', '24', '--num-steps', '2500000', '--burn-in', '200000', '-v', '2', '--prefix', 'out/x', '--stepout', '250']
+    p = mc.parse_args(argv)
+    assert p["energy-type"] == "interacting" and p["bend-mod"] == 0.25 and p["burn-in"] == 200000 and p["stepout"] == 250
+    assert p["step-adjust-ub"] == 0.40 and p["cluster-prob"] == 0.5 and p["num-steps"] == 2500000
+    c = mc.case_from_pargs(p)
+    assert c.clustering == 1 and c.alpha_carry == 1 and c.cutoff_full == 0 and c.kappa == 0.25 and c.energy_type == 1
+    assert mc.parse_julia_vector(p["burn-schedule"], "burn-schedule") == [1000.0, 100.0, 10.0, 2.0, 1.0]
+    assert mc.parse_julia_vector(p["x0"], "x0") == [0.0, pytest.approx(math.pi / 2)]
+    assert mc.parse_julia_vector("[0.0; π/2]", "x0")[1] == pytest.approx(math.pi / 2)
+    assert mc.parse_julia_vector(p["dx0"], "dx0") == [pytest.approx(2 * math.pi), 0.1]
+    assert mc.parse_julia_vector("[]", "burn-schedule") == []
+    for bad in ("run(`rm -rf /`)", "[1; exit()]", "1000"):
+        with pytest.raises(pm.PolymcError):
+            mc.parse_julia_vector(bad, "burn-schedule")
+    assert mc.case_from_pargs(mc.parse_args(["--energy-type", "cutoff", "--cutoff-radius", "5"])).energy_type == 3
+    with pytest.raises(pm.PolymcError, match="Not currently implemented"):
+        mc.validate(mc.default_pargs(profile=True))
+    # the 12 result lines keep the reference's keys and order (mcmc_clustering_eap_chain.jl:389-400)
+    from polymc.output import result_lines_clustering, traj_header_clustering, ROLL_HEADER_CLUSTERING
+    keys = [ln.split("=")[0].strip() for ln in result_lines_clustering(list(range(16)), 0.3, 1.2, 0.25, 1.0, 10)]
+    assert keys == ["<r>", "<r/nb>", "<rj2>", "<r2>", "<p>", "<pj2>", "<p2>", "<U>", "<U2>", "<cos2(θ)>", "<ψ>", "AR"]
+    assert traj_header_clustering(2) == "step,r1,r2,r3,p1,p2,p3,U,phi1,theta1,phi2,theta2,mux1,muy1,muz1,mux2,muy2,muz2"
+    assert ROLL_HEADER_CLUSTERING.endswith("U,Usq,Ealign,psi") and len(ROLL_HEADER_CLUSTERING.split(",")) == 19
+
+
 def test_cli_parses_launcher_style_argv(pm):
     """argv exactly as run/interacting_dielectric_study.jl:41 builds it."""
     from polymc import mcmc
