@@ -23,13 +23,15 @@ enum { R_PAIR = 0, R_BEND, R_PSI, R_USELF, R_OMEGA, R_COS2, R_PX, R_PY, R_PZ, kN
 
 struct ClusterCtl {
   int idx, lo, hi, reflect;
-  double up, lp;  // link probabilities at the two ends of the cluster before the flip (eap_chain.jl:276-305)
+  double up, lp;      // link probabilities at the two ends of the cluster before the flip (eap_chain.jl:276-305)
+  double Dx, Dy, Dz;  // tail translation bΣΔn̂ of a segment built by warp 0
 };
 
 struct ClView {
   double *nhx, *nhy, *nhz;  // n̂_i of the current state (eap_chain.jl:27)
   double *nnx, *nny, *nnz;  // n̂'_i of the trial, valid on the segment
   double *xnx, *xny, *xnz;  // x'_i of the trial, valid on the segment
+  double *psi, *psn;        // bond angles ψ_i of the current state (eap_chain.jl:29) and of the trial (bonds lo−1..hi)
   double* red;              // [kNumRed][32] warp partials
   ClusterCtl* ctl;
   ChainDynX* dx;
@@ -37,7 +39,7 @@ struct ClView {
 
 __host__ __device__ inline size_t cluster_smem_bytes(int n) {
   size_t b = cta_smem_bytes(n);
-  b += (size_t)9 * n * sizeof(double) + (size_t)kNumRed * 32 * sizeof(double);
+  b += (size_t)11 * n * sizeof(double) + (size_t)kNumRed * 32 * sizeof(double);
   b += sizeof(ClusterCtl) + sizeof(ChainDynX);
   return (b + 15) & ~(size_t)15;
 }
@@ -48,18 +50,24 @@ __device__ __forceinline__ ClView carve_cluster(unsigned char* base, int n) {
   X.nhx = d; X.nhy = d + n; X.nhz = d + 2 * n;
   X.nnx = d + 3 * n; X.nny = d + 4 * n; X.nnz = d + 5 * n;
   X.xnx = d + 6 * n; X.xny = d + 7 * n; X.xnz = d + 8 * n;
-  X.red = d + 9 * n;
+  X.psi = d + 9 * n; X.psn = d + 10 * n;
+  X.red = d + 11 * n;
   X.ctl = reinterpret_cast<ClusterCtl*>(X.red + kNumRed * 32);
   X.dx = reinterpret_cast<ChainDynX*>(X.ctl + 1);
   return X;
 }
 
+// n̂ and the bond angles ψ of the staged chain.  Ends with a barrier.
 template <int T>
 __device__ __forceinline__ void load_nhat(const MonoRec* __restrict__ mono, int n, const ClView& X) {
   for (int i = threadIdx.x; i < n; i += T) {
     const MonoRec r = mono[i];
     X.nhx[i] = r.nx; X.nhy[i] = r.ny; X.nhz[i] = r.nz;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i + 1 < n; i += T)
+    X.psi[i] = psi_of(X.nhx[i], X.nhy[i], X.nhz[i], X.nhx[i + 1], X.nhy[i + 1], X.nhz[i + 1]);
+  __syncthreads();
 }
 
 // n̂ of monomer i on the chain that carries the single-monomer move (cluster_flip! runs on the trial
@@ -150,50 +158,79 @@ __device__ __forceinline__ void segment_angles(const MonoRec* __restrict__ mono,
   if (reflect) theta = reflect_theta(theta);
 }
 
-// Everything between the cluster selection and the decision: n̂', x' of the segment into X.nn / X.xn,
-// sinθ' into S.E[c], the kNumRed changed-term sums (in every thread) and the tail translation D.
-// Contains CTA barriers; all threads must call it.
-template <int T, bool CUT, int UNROLL = 2>
-__device__ void segment_trial_sums(const CtaView& S, const ClView& X, const MonoRec* __restrict__ mono,
-                                   const ChainParams& P, int n, int energy_type, const Proposal& q, int lo, int hi,
-                                   bool reflect, double* sums, double& Dx, double& Dy, double& Dz) {
+// New direction of segment monomer c: n̂', sinθ' and this monomer's share of the changed single-monomer sums.
+__device__ __forceinline__ void segment_monomer(const CtaView& S, const ClView& X, const MonoRec* __restrict__ mono,
+                                                const ChainParams& P, const Proposal& q, int c, bool reflect,
+                                                double* acc, double& dnx, double& dny, double& dnz) {
+  double nx, ny, nz, sth;
+  if (!reflect) {  // the segment is idx alone
+    nx = q.nx; ny = q.ny; nz = q.nz; sth = q.sth;
+    acc[R_OMEGA] += q.dOmega;
+  } else {
+    double phi, theta, sb;
+    segment_angles(mono, q, c, true, phi, theta, sb);
+    double sph, cph, cth;
+    sincos(phi, &sph, &cph);
+    sincos(theta, &sth, &cth);
+    nx = cph * sth; ny = sph * sth; nz = cth;
+    acc[R_OMEGA] += (c == q.idx ? q.dOmega : 0.0) + log(sth / sb);  // Ω += log(sθ'/sθ), eap_chain.jl:238
+  }
+  X.nnx[c] = nx; X.nny[c] = ny; X.nnz[c] = nz;
+  S.E[c] = sth;
+  double ux, uy, uz;
+  mu_of(P, nx, ny, nz, ux, uy, uz);
+  const double ox = S.mx[c], oy = S.my[c], oz = S.mz[c];
+  acc[R_USELF] += -0.5 * P.E0 * uz - (-0.5 * P.E0 * oz);
+  acc[R_PX] += ux - ox; acc[R_PY] += uy - oy; acc[R_PZ] += uz - oz;
+  const double onz = X.nhz[c];
+  acc[R_COS2] += nz * nz - onz * onz;
+  dnx = nx - X.nhx[c]; dny = ny - X.nhy[c]; dnz = nz - onz;
+}
+
+// Segments of at most 32 monomers (nearly all of them) are built by the warp that selected the cluster:
+// one monomer per lane, positions by a warp scan (update_xs! restricted to the segment, eap_chain.jl:49-51).
+// Leaves n̂', x' in X.nn / X.xn, sinθ' in S.E, D = bΣΔn̂ in ctl; the lanes keep their partial sums in acc.
+__device__ __forceinline__ void warp_segment_build(const CtaView& S, const ClView& X, const MonoRec* __restrict__ mono,
+                                                   const ChainParams& P, const Proposal& q, int lo, int hi,
+                                                   bool reflect, double* acc, ClusterCtl& ctl) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int c = lo + lane;
+  double dx = 0, dy = 0, dz = 0;
+  if (c <= hi) segment_monomer(S, X, mono, P, q, c, reflect, acc, dx, dy, dz);
+  double ix = dx, iy = dy, iz = dz;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double tx = __shfl_up_sync(FULL, ix, o);
+    const double ty = __shfl_up_sync(FULL, iy, o);
+    const double tz = __shfl_up_sync(FULL, iz, o);
+    if (lane >= o) { ix += tx; iy += ty; iz += tz; }
+  }
+  if (c <= hi) {
+    X.xnx[c] = S.sx[c] + P.b * ((ix - dx) + 0.5 * dx);
+    X.xny[c] = S.sy[c] + P.b * ((iy - dy) + 0.5 * dy);
+    X.xnz[c] = S.sz[c] + P.b * ((iz - dz) + 0.5 * dz);
+  }
+  if (lane == 31) { ctl.Dx = P.b * ix; ctl.Dy = P.b * iy; ctl.Dz = P.b * iz; }
+}
+
+// The same for longer segments, by the whole CTA: contiguous chunks per thread and a block scan.
+// Contains two CTA barriers.
+template <int T>
+__device__ __forceinline__ void cta_segment_build(const CtaView& S, const ClView& X, const MonoRec* __restrict__ mono,
+                                                  const ChainParams& P, const Proposal& q, int lo, int hi,
+                                                  bool reflect, double* acc, double& Dx, double& Dy, double& Dz) {
   constexpr int W = T / 32;
-  using TEAM = Team<W, 0>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = hi - lo + 1;
   const int C = (m + T - 1) / T;
   const int c0 = min(hi + 1, lo + tid * C), c1 = min(hi + 1, c0 + C);
-  double acc[kNumRed];
-#pragma unroll
-  for (int k = 0; k < kNumRed; ++k) acc[k] = 0.0;
-  // ---- pass 1: new directions of this thread's chunk, chunk total of Δn̂ -------------------------------
   double lx = 0, ly = 0, lz = 0;
   for (int c = c0; c < c1; ++c) {
-    double nx, ny, nz, sth;
-    if (!reflect) {  // the segment is idx alone
-      nx = q.nx; ny = q.ny; nz = q.nz; sth = q.sth;
-      acc[R_OMEGA] += q.dOmega;
-    } else {
-      double phi, theta, sb;
-      segment_angles(mono, q, c, true, phi, theta, sb);
-      double sph, cph, cth;
-      sincos(phi, &sph, &cph);
-      sincos(theta, &sth, &cth);
-      nx = cph * sth; ny = sph * sth; nz = cth;
-      acc[R_OMEGA] += (c == q.idx ? q.dOmega : 0.0) + log(sth / sb);  // Ω += log(sθ'/sθ), eap_chain.jl:238
-    }
-    X.nnx[c] = nx; X.nny[c] = ny; X.nnz[c] = nz;
-    S.E[c] = sth;
-    double ux, uy, uz;
-    mu_of(P, nx, ny, nz, ux, uy, uz);
-    const double ox = S.mx[c], oy = S.my[c], oz = S.mz[c];
-    acc[R_USELF] += -0.5 * P.E0 * uz - (-0.5 * P.E0 * oz);
-    acc[R_PX] += ux - ox; acc[R_PY] += uy - oy; acc[R_PZ] += uz - oz;
-    const double onz = X.nhz[c];
-    acc[R_COS2] += nz * nz - onz * onz;
-    lx += nx - X.nhx[c]; ly += ny - X.nhy[c]; lz += nz - onz;
+    double dx, dy, dz;
+    segment_monomer(S, X, mono, P, q, c, reflect, acc, dx, dy, dz);
+    lx += dx; ly += dy; lz += dz;
   }
-  // ---- block scan of the chunk totals (update_xs! restricted to the segment, eap_chain.jl:49-51) --------
   double ix = lx, iy = ly, iz = lz;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -220,24 +257,18 @@ __device__ void segment_trial_sums(const CtaView& S, const ClView& X, const Mono
     sxx += dx; syy += dy; szz += dz;
   }
   Dx = P.b * tx; Dy = P.b * ty; Dz = P.b * tz;
-  // ---- rectangle set-up: heads [0,lo) × tails (hi,n) ----------------------------------------------------
-  const int H = lo, Tl = n - 1 - hi;
-  const bool pairs_all = (energy_type == 1 || energy_type == 3);
-  const bool rect = pairs_all && H > 0 && Tl > 0;
-  bool lanes_are_heads = true;
-  if (rect) {
-    const long long costH = (long long)((H + 31) >> 5) * Tl;
-    const long long costT = (long long)((Tl + 31) >> 5) * H;
-    lanes_are_heads = costH <= costT;
-  }
-  const double sgn = lanes_are_heads ? 1.0 : -1.0;
-  const double ex = sgn * Dx, ey = sgn * Dy, ez = sgn * Dz;
-  const int baseA = lanes_are_heads ? 0 : hi + 1, A = lanes_are_heads ? H : Tl;
-  const int baseB = lanes_are_heads ? hi + 1 : 0, B = lanes_are_heads ? Tl : H;
-  if (rect)
-    for (int k = tid; k < B; k += T)
-      S.E[baseB + k] = fma(S.mz[baseB + k], ez, fma(S.my[baseB + k], ey, S.mx[baseB + k] * ex));
   __syncthreads();  // X.nn, X.xn, S.E visible
+}
+
+// The changed-term sums over bonds and pairs for a built segment, added to this thread's acc and reduced
+// over the CTA: the kNumRed sums end up in every thread.  One CTA barrier.
+template <int T, bool CUT, int UNROLL = 1>
+__device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, const ChainParams& P, int n,
+                                             int energy_type, int lo, int hi, double Dx, double Dy, double Dz,
+                                             double* acc, double* sums) {
+  constexpr int W = T / 32;
+  using TEAM = Team<W, 0>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- bonds lo−1..hi: ψ and bending energy (eap_chain.jl:45-47,54-58,246-251) ---------------------------
   {
     const int b0 = max(lo - 1, 0), b1 = min(hi, n - 2);
@@ -245,27 +276,16 @@ __device__ void segment_trial_sums(const CtaView& S, const ClView& X, const Mono
       const bool an = i >= lo, bn = i + 1 <= hi;
       const double ax = X.nhx[i], ay = X.nhy[i], az = X.nhz[i];
       const double bx = X.nhx[i + 1], by = X.nhy[i + 1], bz = X.nhz[i + 1];
-      const double psi_old = psi_of(ax, ay, az, bx, by, bz);
+      const double psi_old = X.psi[i];
       const double psi_new = psi_of(an ? X.nnx[i] : ax, an ? X.nny[i] : ay, an ? X.nnz[i] : az,
                                     bn ? X.nnx[i + 1] : bx, bn ? X.nny[i + 1] : by, bn ? X.nnz[i + 1] : bz);
+      X.psn[i] = psi_new;
       acc[R_PSI] += psi_new - psi_old;
       acc[R_BEND] += ubend_of(P, psi_new) - ubend_of(P, psi_old);
-      if (energy_type == 2) {  // U_Ising (eap_chain.jl:215-228): the same bonds
-        double ux, uy, uz, vx, vy, vz;
-        if (an) mu_of(P, X.nnx[i], X.nny[i], X.nnz[i], ux, uy, uz); else { ux = S.mx[i]; uy = S.my[i]; uz = S.mz[i]; }
-        if (bn) mu_of(P, X.nnx[i + 1], X.nny[i + 1], X.nnz[i + 1], vx, vy, vz);
-        else { vx = S.mx[i + 1]; vy = S.my[i + 1]; vz = S.mz[i + 1]; }
-        const double pxn = an ? X.xnx[i] : S.sx[i], pyn = an ? X.xny[i] : S.sy[i], pzn = an ? X.xnz[i] : S.sz[i];
-        const double qxn = bn ? X.xnx[i + 1] : S.sx[i + 1] + Dx, qyn = bn ? X.xny[i + 1] : S.sy[i + 1] + Dy,
-                     qzn = bn ? X.xnz[i + 1] : S.sz[i + 1] + Dz;
-        acc[R_PAIR] += pair_g(ux, uy, uz, vx, vy, vz, pxn - qxn, pyn - qyn, pzn - qzn) -
-                       pair_g(S.mx[i], S.my[i], S.mz[i], S.mx[i + 1], S.my[i + 1], S.mz[i + 1], S.sx[i] - S.sx[i + 1],
-                              S.sy[i] - S.sy[i + 1], S.sz[i] - S.sz[i + 1]);
-      }
     }
   }
-  // ---- segment × everything (each pair once) -----------------------------------------------------------
-  if (pairs_all) {
+  // ---- pair terms: segment × everything (each pair once) and heads [0,lo) × tails (hi,n) ---------------
+  if (energy_type == 1 || energy_type == 3) {
     double a = 0.0;
     for (int c = lo; c <= hi; ++c) {
       const double xi = S.sx[c], yi = S.sy[c], zi = S.sz[c];
@@ -277,10 +297,9 @@ __device__ void segment_trial_sums(const CtaView& S, const ClView& X, const Mono
         if (j >= lo && j <= c) continue;
         const double jx = S.sx[j], jy = S.sy[j], jz = S.sz[j];
         const double ux = S.mx[j], uy = S.my[j], uz = S.mz[j];
-        double njx, njy, njz, vx, vy, vz;
-        if (j < lo) { njx = jx; njy = jy; njz = jz; vx = ux; vy = uy; vz = uz; }
-        else if (j > hi) { njx = jx + Dx; njy = jy + Dy; njz = jz + Dz; vx = ux; vy = uy; vz = uz; }
-        else {
+        double njx = jx, njy = jy, njz = jz, vx = ux, vy = uy, vz = uz;
+        if (j > hi) { njx += Dx; njy += Dy; njz += Dz; }
+        else if (j >= lo) {
           njx = X.xnx[j]; njy = X.xny[j]; njz = X.xnz[j];
           mu_of(P, X.nnx[j], X.nny[j], X.nnz[j], vx, vy, vz);
         }
@@ -292,7 +311,17 @@ __device__ void segment_trial_sums(const CtaView& S, const ClView& X, const Mono
                pair_g(oxm, oym, ozm, ux, uy, uz, xi - jx, yi - jy, zi - jz);
       }
     }
-    if (rect) a += rect_sum<TEAM, UNROLL, CUT>(S, baseA, A, baseB, B, ex, ey, ez, P.crad2);
+    const int H = lo, Tl = n - 1 - hi;
+    if (H > 0 && Tl > 0) {
+      // lane side = the one that wastes fewer lanes; r = x_L − x_B, so r' = r − D (L = head) or r + D (L = tail)
+      const long long costH = (long long)((H + 31) >> 5) * Tl;
+      const long long costT = (long long)((Tl + 31) >> 5) * H;
+      const bool lanes_are_heads = costH <= costT;
+      const double sgn = lanes_are_heads ? 1.0 : -1.0;
+      a += rect_sum<TEAM, UNROLL, CUT, true>(S, lanes_are_heads ? 0 : hi + 1, lanes_are_heads ? H : Tl,
+                                             lanes_are_heads ? hi + 1 : 0, lanes_are_heads ? Tl : H, sgn * Dx, sgn * Dy,
+                                             sgn * Dz, P.crad2);
+    }
     acc[R_PAIR] += a;
   }
   // ---- reduce ------------------------------------------------------------------------------------------
@@ -320,12 +349,30 @@ __device__ __forceinline__ double cluster_log_alpha(const ClView& X, int n, int 
 }
 
 // record! of the two extra averagers (mcmc_clustering_eap_chain.jl:243-244), same weight as the others.
+template <bool COMP>
 __device__ __forceinline__ void record_extras(const ChainParams& P, ChainDynX& DX, double su, double log_gauge,
                                               int n) {
   double wgt = 1.0;
   if (P.umbrella) wgt = 1.0 / exp(su * P.inv_kT * P.cF - log_gauge);
-  comp_add(DX.acc[0], DX.comp[0], DX.scos2 * wgt);
-  comp_add(DX.acc[1], DX.comp[1], DX.spsi / (double)(n - 1) * wgt);
+  if (COMP) {
+    comp_add(DX.acc[0], DX.comp[0], DX.scos2 * wgt);
+    comp_add(DX.acc[1], DX.comp[1], DX.spsi / (double)(n - 1) * wgt);
+  } else {  // plain Float64 sums, the reference's default --numeric-type (average.jl:40-48)
+    DX.acc[0] += DX.scos2 * wgt;
+    DX.acc[1] += DX.spsi / (double)(n - 1) * wgt;
+  }
+}
+
+// Step adaptation, the 8 + 2 averagers: everything after the decision (mcmc_clustering_eap_chain.jl:287-311).
+__device__ __forceinline__ void bookkeep_cluster(const ChainParams& P, ChainDyn& D, ChainDynX& DX, long long step, int n,
+                                                 bool compensated) {
+  if (compensated) {
+    bookkeep<true>(P, D, step);
+    record_extras<true>(P, DX, D.su, D.log_gauge, n);
+  } else {
+    bookkeep<false>(P, D, step);
+    record_extras<false>(P, DX, D.su, D.log_gauge, n);
+  }
 }
 
 // Decision quantities of one composite trial from the reduced sums (identical in every thread).
@@ -385,17 +432,24 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
   for (long long s = 1; s <= a.nsteps; ++s) {
     const long long step = step0 + s;
     __syncthreads();  // state of the previous trial (records, n̂, x, μ) is visible
+    double acc[kNumRed];
+#pragma unroll
+    for (int k = 0; k < kNumRed; ++k) acc[k] = 0.0;
     if (tid < 32) {
       if (tid == 0) make_proposal(a, P, *S.dyn, mono, chain_id, step, *q);
       __syncwarp();
       warp_cluster_grow(X, *q, P, n, a.seed, chain_id, init, step, *X.ctl);
+      __syncwarp();
+      if (X.ctl->hi - X.ctl->lo < 32)
+        warp_segment_build(S, X, mono, P, *q, X.ctl->lo, X.ctl->hi, X.ctl->reflect != 0, acc, *X.ctl);
     }
-    __syncthreads();  // proposal and cluster are visible
+    __syncthreads();  // proposal, cluster and (short) segment are visible
     const int idx = X.ctl->idx, lo = X.ctl->lo, hi = X.ctl->hi;
     const bool reflect = X.ctl->reflect != 0;
     const double carry = X.dx->carry;
-    double sums[kNumRed], Dx, Dy, Dz;
-    segment_trial_sums<T, CUT>(S, X, mono, P, n, a.energy_type, *q, lo, hi, reflect, sums, Dx, Dy, Dz);
+    double sums[kNumRed], Dx = X.ctl->Dx, Dy = X.ctl->Dy, Dz = X.ctl->Dz;
+    if (hi - lo >= 32) cta_segment_build<T>(S, X, mono, P, *q, lo, hi, reflect, acc, Dx, Dy, Dz);
+    segment_sums<T, CUT>(S, X, P, n, a.energy_type, lo, hi, Dx, Dy, Dz, acc, sums);
     const double la = reflect ? cluster_log_alpha(X, n, lo, hi, X.ctl->up, X.ctl->lp) : 0.0;
     const SegDecision dec = segment_decision(P, a.energy_type, sums, Dx, Dz, la, carry);
     const bool accept = metropolis(dec.dlogpi, q->eps);
@@ -416,6 +470,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
       for (int j = hi + 1 + tid; j < n; j += T) {
         S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
       }
+      for (int i = max(lo - 1, 0) + tid; i <= min(hi, n - 2); i += T) X.psi[i] = X.psn[i];
     }
     if (tid == 0) {
       ChainDyn& D = *S.dyn;
@@ -439,8 +494,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
         const double sz = (double)(hi - lo + 1);
         DX.ncluster += 1.0; DX.cluster_sum += sz; DX.cluster_max = fmax(DX.cluster_max, sz);
       }
-      bookkeep(P, D, step);
-      record_extras(P, DX, D.su, D.log_gauge, n);
+      bookkeep_cluster(P, D, DX, step, n, a.compensated != 0);
     }
     const bool isrow = a.stepout > 0 && (step % a.stepout) == 0;
     if (isrow) {
@@ -494,8 +548,18 @@ __global__ void __launch_bounds__(T) k_delta_segment_cta(const SegDeltaArgs a) {
   const Proposal& q = S.prop[0];
   const bool reflect = a.reflect != 0;
   const int lo = reflect ? a.lo : a.idx, hi = reflect ? a.hi : a.idx;
-  double sums[kNumRed], Dx, Dy, Dz;
-  segment_trial_sums<T, CUT>(S, X, mono, P, n, a.energy_type, q, lo, hi, reflect, sums, Dx, Dy, Dz);
+  __shared__ ClusterCtl dctl;
+  double acc[kNumRed], sums[kNumRed], Dx, Dy, Dz;
+#pragma unroll
+  for (int k = 0; k < kNumRed; ++k) acc[k] = 0.0;
+  if (hi - lo < 32) {  // the two build paths of the run kernel
+    if (tid < 32) warp_segment_build(S, X, mono, P, q, lo, hi, reflect, acc, dctl);
+    __syncthreads();
+    Dx = dctl.Dx; Dy = dctl.Dy; Dz = dctl.Dz;
+  } else {
+    cta_segment_build<T>(S, X, mono, P, q, lo, hi, reflect, acc, Dx, Dy, Dz);
+  }
+  segment_sums<T, CUT>(S, X, P, n, a.energy_type, lo, hi, Dx, Dy, Dz, acc, sums);
   if (tid == 0) {
     double up = 0.0, lp = 0.0;  // link probabilities before the flip, on the chain carrying the move
     if (reflect) {
@@ -627,7 +691,7 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
   }
 }
 
-template <int T, int MINB, bool ISING>
+template <int T, int MINB, bool ISING, bool COMP>
 __global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
   const int c = blockIdx.x * T + threadIdx.x;
   if (c >= a.nchains) return;
@@ -688,8 +752,8 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
       const double sz = (double)(hi - lo + 1);
       DX.ncluster += 1.0; DX.cluster_sum += sz; DX.cluster_max = fmax(DX.cluster_max, sz);
     }
-    bookkeep(P, D, step);
-    record_extras(P, DX, D.su, D.log_gauge, n);
+    bookkeep<COMP>(P, D, step);
+    record_extras<COMP>(P, DX, D.su, D.log_gauge, n);
     if (a.stepout > 0 && (step % a.stepout) == 0) {
       if (row < a.rows) {
         double rb[kRowDoublesCluster];

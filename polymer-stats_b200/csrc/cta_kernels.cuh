@@ -206,7 +206,9 @@ __device__ __forceinline__ double rect_pair(const LaneItem& it, double bx, doubl
   }
 }
 
-template <class TEAM, int UNROLL = 2, bool CUT = false>
+// EFLY: eB = μ_B·D is computed in the loop (3 DFMA per broadcast item) instead of being read from S.E —
+// saves the pre-pass and its barrier where barriers cost more than FP64 issue slots (short chains).
+template <class TEAM, int UNROLL = 2, bool CUT = false, bool EFLY = false>
 __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, int baseB, int B, double Dx,
                                            double Dy, double Dz, double crad2 = 0.0) {
   constexpr int W = TEAM::kWarps;
@@ -240,7 +242,8 @@ __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, i
 #pragma unroll UNROLL
         for (; k < kend; ++k) {
           const double bx = bxp[k], by = byp[k], bz = bzp[k];
-          const double ux = mxp[k], uy = myp[k], uz = mzp[k], e = ep[k];
+          const double ux = mxp[k], uy = myp[k], uz = mzp[k];
+          const double e = EFLY ? fma(uz, Dz, fma(uy, Dy, ux * Dx)) : ep[k];
           a0 = rect_pair<CUT>(i0, bx, by, bz, ux, uy, uz, e, Dx, Dy, Dz, a0, crad2);
           a1 = rect_pair<CUT>(i1, bx, by, bz, ux, uy, uz, e, Dx, Dy, Dz, a1, crad2);
         }
@@ -259,13 +262,16 @@ __device__ __forceinline__ double rect_sum(const CtaView& S, int baseA, int A, i
       const bool valid = li < A;
       const LaneItem it = load_lane_item(S, baseA + min(li, A - 1), Dx, Dy, Dz);
       double a0 = 0.0, a1 = 0.0;
+      auto eb = [&](int kk) {
+        return EFLY ? fma(mzp[kk], Dz, fma(myp[kk], Dy, mxp[kk] * Dx)) : ep[kk];
+      };
       for (; k + 1 < kend; k += 2) {
-        a0 = rect_pair<CUT>(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], ep[k], Dx, Dy, Dz, a0, crad2);
-        a1 = rect_pair<CUT>(it, bxp[k + 1], byp[k + 1], bzp[k + 1], mxp[k + 1], myp[k + 1], mzp[k + 1], ep[k + 1],
+        a0 = rect_pair<CUT>(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], eb(k), Dx, Dy, Dz, a0, crad2);
+        a1 = rect_pair<CUT>(it, bxp[k + 1], byp[k + 1], bzp[k + 1], mxp[k + 1], myp[k + 1], mzp[k + 1], eb(k + 1),
                             Dx, Dy, Dz, a1, crad2);
       }
       if (k < kend)
-        a0 = rect_pair<CUT>(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], ep[k], Dx, Dy, Dz, a0, crad2);
+        a0 = rect_pair<CUT>(it, bxp[k], byp[k], bzp[k], mxp[k], myp[k], mzp[k], eb(k), Dx, Dy, Dz, a0, crad2);
       acc += valid ? (a0 + a1) : 0.0;
     }
   }
@@ -349,6 +355,7 @@ struct RunArgs {
   ChainDynX* dynx;
   double* state;   // [chains][rows][2n] (phi,theta interleaved) or null
   int roll_cols;   // 17, or 19 with the two extra averagers
+  int compensated; // Neumaier-compensated accumulators (accum_mode 1 or umbrella weights), else plain sums
 };
 
 // Thread 0: draw and build the proposal of trial `step`.

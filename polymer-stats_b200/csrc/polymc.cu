@@ -142,7 +142,7 @@ int launch_energy(pmc_handle* h, const EnergyArgs& a, int nblocks) {
     break;                                                                  \
   }
   switch (h->cta_threads) {
-    PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
+    PMC_CASE(32) PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
     default: return fail(PMC_ERR_INVALID, "bad cta_threads");
   }
 #undef PMC_CASE
@@ -250,7 +250,7 @@ int launch_delta_cta(pmc_handle* h, const DeltaArgs& a) {
     break;                                                                  \
   }
   switch (h->cta_threads) {
-    PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
+    PMC_CASE(32) PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
     default: return fail(PMC_ERR_INVALID, "bad cta_threads");
   }
 #undef PMC_CASE
@@ -270,7 +270,7 @@ int launch_reinit(pmc_handle* h, const ReinitArgs& a) {
     break;                                                                  \
   }
   switch (h->cta_threads) {
-    PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
+    PMC_CASE(32) PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512) PMC_CASE(1024)
     default: return fail(PMC_ERR_INVALID, "bad cta_threads");
   }
 #undef PMC_CASE
@@ -340,7 +340,9 @@ ChainParams params_of(const pmc_case& c0, double kT_scale = 1.0) {
 }
 
 // Block size of the composite-trial CTA kernels.
-int pick_cluster_threads(int n) { return n <= 160 ? 64 : n <= 1024 ? 128 : 256; }
+// Short chains are latency bound (one serial proposal/cluster/decision chain per trial), so one warp per
+// chain and many chains per SM; measured crossovers in profiles/r01e_tune_cluster.txt.
+int pick_cluster_threads(int n) { return n <= 160 ? 32 : n <= 256 ? 64 : n <= 1024 ? 128 : 256; }
 
 int fetch_dyn(pmc_handle* h) {
   h->host_dyn.resize((size_t)h->nchains);
@@ -418,8 +420,8 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
     h->cta_threads = pick_cluster_threads(n);
     if (cluster_smem_bytes(n) > (size_t)kSmemMax) {
       delete h;
-      return fail(PMC_ERR_UNSUPPORTED, "chain too long for the clustering / bending / cut-off kernels: 16 n doubles "
-                                       "must fit one CTA's 227 KB shared memory (num-monomers <= ~1750)");
+      return fail(PMC_ERR_UNSUPPORTED, "chain too long for the clustering / bending / cut-off kernels: 18 n doubles "
+                                       "must fit one CTA's 227 KB shared memory (num-monomers <= ~1570)");
     }
   }
 
@@ -607,9 +609,21 @@ static int launch_run_cluster(pmc_handle* h, const RunArgs& a) {
       k_run_cta_cluster<TT, MB, false><<<nblocks, TT, smem, h->stream>>>(a);              \
     }                                                                                     \
   }
-    switch (h->cta_threads) {
+    // PMC_CLUSTER_CFG = threads*100 + minblocks selects a tuning variant (experiments only)
+    const int ccfg = env_int("PMC_CLUSTER_CFG", 0);
+    if (ccfg == 3216) PMC_CL(32, 16)
+    else if (ccfg == 3212) PMC_CL(32, 12)
+    else if (ccfg == 6408) PMC_CL(64, 8)
+    else if (ccfg == 6410) PMC_CL(64, 10)
+    else if (ccfg == 6406) PMC_CL(64, 6)
+    else if (ccfg == 12804) PMC_CL(128, 4)
+    else if (ccfg == 12803) PMC_CL(128, 3)
+    else if (ccfg == 12805) PMC_CL(128, 5)
+    else if (ccfg == 25602) PMC_CL(256, 2)
+    else switch (h->cta_threads) {
+      case 32: PMC_CL(32, 12) break;
       case 64: PMC_CL(64, 6) break;
-      case 128: PMC_CL(128, 3) break;
+      case 128: PMC_CL(128, 4) break;
       case 256: PMC_CL(256, 1) break;
       default: return fail(PMC_ERR_INVALID, "bad cta_threads");
     }
@@ -617,8 +631,29 @@ static int launch_run_cluster(pmc_handle* h, const RunArgs& a) {
   } else {
     constexpr int TB = 64;
     const unsigned nb = (unsigned)((h->nchains + TB - 1) / TB);
-    if (h->energy_type == PMC_ENERGY_ISING) k_run_lane_cluster<TB, 4, true><<<nb, TB, 0, h->stream>>>(a);
-    else k_run_lane_cluster<TB, 4, false><<<nb, TB, 0, h->stream>>>(a);
+    const bool ising = h->energy_type == PMC_ENERGY_ISING;
+    if (h->compensated) {
+      if (ising) k_run_lane_cluster<TB, 4, true, true><<<nb, TB, 0, h->stream>>>(a);
+      else k_run_lane_cluster<TB, 4, false, true><<<nb, TB, 0, h->stream>>>(a);
+    } else {
+      // PMC_LANE_CLUSTER_CFG = threads*100 + minblocks selects a tuning variant (experiments only)
+      const int lcfg = env_int("PMC_LANE_CLUSTER_CFG", 0);
+#define PMC_LC(TT, MB)                                                                                         \
+  {                                                                                                            \
+    const unsigned nbb = (unsigned)((h->nchains + TT - 1) / TT);                                               \
+    if (ising) k_run_lane_cluster<TT, MB, true, false><<<nbb, TT, 0, h->stream>>>(a);                          \
+    else k_run_lane_cluster<TT, MB, false, false><<<nbb, TT, 0, h->stream>>>(a);                               \
+  }
+      if (lcfg == 6403) PMC_LC(64, 3)
+      else if (lcfg == 6404) PMC_LC(64, 4)
+      else if (lcfg == 6408) PMC_LC(64, 8)
+      else if (lcfg == 3208) PMC_LC(32, 8)
+      else if (lcfg == 3212) PMC_LC(32, 12)
+      else if (lcfg == 3216) PMC_LC(32, 16)
+      else if (h->nchains >= 32768) PMC_LC(64, 8)  // many chains: occupancy beats the spills of the 128-register build
+      else PMC_LC(64, 4)
+#undef PMC_LC
+    }
   }
   ++h->launches;
   PMC_CU(cudaGetLastError());
@@ -644,7 +679,7 @@ static int launch_delta_segment(pmc_handle* h, const SegDeltaArgs& a) {
       k_delta_segment_cta<TT, false><<<1, TT, smem, h->stream>>>(a);                      \
     }                                                                                     \
   }
-    if (tt == 64) PMC_DS(64) else if (tt == 128) PMC_DS(128) else PMC_DS(256)
+    if (tt == 32) PMC_DS(32) else if (tt == 64) PMC_DS(64) else if (tt == 128) PMC_DS(128) else PMC_DS(256)
 #undef PMC_DS
   } else {
     if (h->energy_type == PMC_ENERGY_ISING) k_delta_segment_lane<true><<<1, 32, 0, h->stream>>>(a);
@@ -786,6 +821,7 @@ static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj
   a.seed = h->seed; a.chain_id_base = h->chain_id_base;
   a.n = h->n; a.nchains = (int)h->nchains; a.energy_type = h->energy_type;
   a.dynx = h->dynx; a.state = nstate ? h->state : nullptr; a.roll_cols = roll_cols;
+  a.compensated = h->compensated;
   PMC_CU(cudaEventRecord(h->ev0, h->stream));
   if (h->cluster_mode) {
     if ((rc = launch_run_cluster(h, a))) return rc;
