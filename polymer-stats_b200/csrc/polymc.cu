@@ -192,6 +192,9 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
   if (cfg == 0 && use_win && smem_win <= (size_t)kSmemMax) {
     if (use_win == 648) PMC_LAUNCH_WIN(64, 8)
     if (use_win == 1286) PMC_LAUNCH_WIN(128, 6)
+    if (use_win == 1285) PMC_LAUNCH_WIN(128, 5)
+    if (use_win == 2562) PMC_LAUNCH_WIN(256, 2)
+    if (use_win == 643) PMC_LAUNCH_WIN(64, 10)
     if (use_win == 2563) PMC_LAUNCH_WIN(256, 3)
     switch (h->cta_threads) {
       case 64: PMC_LAUNCH_WIN(64, 8)
