@@ -1,0 +1,60 @@
+"""Restatement of scripts/aggregate_mcmc.jl and scripts/reduce_tabular_data.jl working on `.out` FILES, the
+way the reference does (TEST INFRASTRUCTURE ONLY — the checker for polymc.aggregate, which builds the same
+tables in memory).  Each step cites the script line it follows."""
+from __future__ import annotations
+
+import ast
+import fnmatch
+import os
+
+INPUT_HEADERS = {"dielectric": ["E0", "K1", "K2", "kT", "Fz", "Fx", "n", "b"],     # aggregate_mcmc.jl:40-41
+                 "polar": ["E0", "mu", "kT", "Fz", "Fx", "n", "b"]}               # :42-43
+OUTPUT_HEADERS_3D = ["r1", "r2", "r3", "lambda1", "lambda2", "lambda3", "r1sq", "r2sq", "r3sq", "rsquared",
+                     "p1", "p2", "p3", "p1sq", "p2sq", "p3sq", "psquared", "U", "Usquared", "Ealign", "psi", "AR"]  # :54-55
+
+
+def _julia_eval(text: str):
+    """eval(Meta.parse(...)) of a result value: a Float64 literal or a `[a, b, c]` vector (:71)."""
+    t = text.strip().replace("NaN", "float('nan')").replace("Inf", "float('inf')")
+    v = eval(t, {"__builtins__": {}, "float": float})  # noqa: S307 - test infrastructure, our own files
+    return list(v) if isinstance(v, (list, tuple)) else [v]
+
+
+def aggregate_mcmc(indir: str, pattern: str, chain_type: str, kappaflag=False, runflag=False):
+    """aggregate_mcmc.jl:36-77 → (header, rows)."""
+    header = list(INPUT_HEADERS[chain_type])
+    if kappaflag:
+        header.append("kappa")                                                  # :50-52
+    header += OUTPUT_HEADERS_3D
+    rows = []
+    for name in sorted(os.listdir(indir)):                                      # readdir(pattern, indir), :61
+        if not fnmatch.fnmatchcase(name, pattern):
+            continue
+        fields = name.split(".")[0].split("_")                                   # :63
+        if runflag:
+            fields.pop()                                                        # :64-66
+        params = [ast.literal_eval(f.split("-", 1)[1].lstrip("0") or "0") * 1e-3 for f in fields]   # :69-70
+        vals = []
+        with open(os.path.join(indir, name), encoding="utf-8") as fh:
+            for line in fh.read().splitlines():                                  # readlines(infile), :72
+                vals += _julia_eval(line.split("=")[1])                          # :71
+        rows.append(params + vals)
+    return header, rows
+
+
+def reduce_tabular_data(header, rows, chain_type: str, kappaflag=False):
+    """reduce_tabular_data.jl:31-59 on one table."""
+    nparams = len(INPUT_HEADERS[chain_type]) + (1 if kappaflag else 0)          # :16-27
+    pooled = {}
+    for row in rows:                                                            # :38-50
+        k = tuple(row[:nparams])
+        data = [x for x in row[nparams:] if x != ""]
+        if k in pooled:
+            pooled[k] = ([a + b for a, b in zip(pooled[k][0], data)], pooled[k][1] + 1)
+        else:
+            pooled[k] = (data, 1)
+    out = []
+    for k in sorted(pooled):                                                    # :52-56
+        v, cnt = pooled[k]
+        out.append(list(k) + [x / cnt for x in v])
+    return header, out

@@ -69,11 +69,39 @@ def gather_rows(local: np.ndarray, total_rows: int, lo: int, device=None) -> np.
     return full
 
 
+NCOL = 37  # 16 averages, acceptance rate, normaliser, 17 raw sums, 2 raw sums of the clustering driver's extras
+
+
+def _segments(mine: np.ndarray, replicas: int):
+    """Split a rank's sorted global chain ids into runs that one handle can serve: a handle holds
+    `ncases` consecutive cases × `replicas` chains with ids chain_id_base + local index
+    (include/polymc.h), or a part of a single case.  Yields (pos, end, first_case, ncases, nrep)."""
+    pos, m = 0, len(mine)
+    while pos < m:
+        g0 = int(mine[pos])
+        case0, off = divmod(g0, replicas)
+        end = pos
+        while end < m and mine[end] == g0 + (end - pos):
+            end += 1
+        run = end - pos
+        if off != 0 or run < replicas:          # a partial case at a shard boundary
+            take = min(run, replicas - off)
+            yield pos, pos + take, case0, 1, take
+            pos += take
+        else:                                   # whole consecutive cases in one handle
+            ncases = run // replicas
+            yield pos, pos + ncases * replicas, case0, ncases, replicas
+            pos += ncases * replicas
+
+
 def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
-              rank: int = 0, world: int = 1):
+              rank: int = 0, world: int = 1, protocol=None):
     """Run this rank's contiguous block of every (n, energy) bucket.  Returns a list of
-    (global chain ids of the bucket, lo, block [hi-lo][35]) with block columns = 16 averages,
-    acceptance rate, normaliser, 17 raw sums.  No communication."""
+    (global chain ids of the bucket, lo, block [hi-lo][NCOL]).  No communication.
+
+    protocol None: `nsteps` trials of mcmc_eap_chain.jl's loop.  protocol = dict(burn_in=…, schedule=[…]):
+    the clustering driver's ladder (mcmc_clustering_eap_chain.jl:365-386) — a burn-in stage per kT
+    multiplier, then `nsteps` production trials at kT."""
     cases = list(cases)
     out = []
     for (_, _), idxs in bucket_cases(cases).items():
@@ -81,42 +109,44 @@ def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
         gids = np.concatenate([np.arange(i * replicas, (i + 1) * replicas) for i in idxs])
         lo, hi = shard_range(len(gids), rank, world)
         mine = gids[lo:hi]
-        block = np.zeros((hi - lo, 35))
-        # a rank's block may start/end inside a case: one handle per run of consecutive chains of
-        # one case, with chain_id_base = global id of its first chain.
-        pos = 0
-        while pos < len(mine):
-            case_i = mine[pos] // replicas
-            end = pos
-            while end < len(mine) and mine[end] // replicas == case_i and mine[end] == mine[pos] + (end - pos):
-                end += 1
-            with lib.Ensemble(cases[case_i], replicas=end - pos, seed=seed, device=device,
+        block = np.zeros((hi - lo, NCOL))
+        for pos, end, case0, ncases, nrep in _segments(mine, replicas):
+            with lib.Ensemble(cases[case0:case0 + ncases], replicas=nrep, seed=seed, device=device,
                               chain_id_base=int(mine[pos])) as ens:
-                ens.run(nsteps, stepout, fetch_rows=False)
+                if protocol is None:
+                    ens.run(nsteps, stepout, fetch_rows=False)
+                else:
+                    for mult in protocol.get("schedule", []):
+                        ens.begin_stage(float(mult))
+                        ens.run_ex(int(protocol.get("burn_in", 0)), 0, fetch_rows=False)
+                    ens.begin_stage(1.0)
+                    ens.run_ex(nsteps, 0, fetch_rows=False)
+                    block[pos:end, 35:37] = ens.extra_accumulators()
                 avg, ar, nrm = ens.averages()
                 block[pos:end, :16] = avg
                 block[pos:end, 16] = ar
                 block[pos:end, 17] = nrm
                 block[pos:end, 18:35] = ens.accumulators()
-            pos = end
         out.append((gids, lo, block))
     return out
 
 
 def assemble(total: int, parts):
-    """dict of result arrays from [(gids, full [len(gids)][35]), ...]."""
+    """dict of result arrays from [(gids, full [len(gids)][NCOL]), ...]."""
     res = {"avg": np.full((total, 16), np.nan), "acc_rate": np.full(total, np.nan),
-           "normalizer": np.full(total, np.nan), "sums": np.full((total, 17), np.nan)}
+           "normalizer": np.full(total, np.nan), "sums": np.full((total, 17), np.nan),
+           "extra_sums": np.full((total, 2), np.nan)}
     for gids, full in parts:
         res["avg"][gids] = full[:, :16]
         res["acc_rate"][gids] = full[:, 16]
         res["normalizer"][gids] = full[:, 17]
         res["sums"][gids] = full[:, 18:35]
+        res["extra_sums"][gids] = full[:, 35:37]
     return res
 
 
 def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
-              torch_device=None):
+              torch_device=None, protocol=None):
     """Run every (case, replica) chain of a sweep for nsteps trials, sharded over the ranks of the
     current torch.distributed group (or a single process), then gather the final per-chain results on
     every rank.  Chain order = case-major: avg [ncases*replicas][16], acc_rate, normalizer, sums [..][17]."""
@@ -125,6 +155,46 @@ def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
     world = dist.get_world_size() if dist else 1
     cases = list(cases)
     parts = []
-    for gids, lo, block in run_shard(cases, replicas, nsteps, stepout, seed, device, rank, world):
+    for gids, lo, block in run_shard(cases, replicas, nsteps, stepout, seed, device, rank, world, protocol):
         parts.append((gids, gather_rows(block, len(gids), lo, device=torch_device)))
     return assemble(len(cases) * replicas, parts)
+
+
+def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0, device: int = 0, torch_device=None,
+                kappaflag: bool = False, pooled: bool = False):
+    """A whole launcher + aggregate_mcmc.jl (+ reduce_tabular_data.jl) pipeline in one call (SURVEY §8f
+    rank 3): every pargs dict of `pargs_list` is one case (one launcher command line), run `runs` times as
+    independent replica chains (the launchers' `run-NNN` cases); the result is the aggregated table the
+    reference's scripts would build from the `.out` files.  Returns (header, rows, entries) with entries =
+    [(prefix, stdout text)] for optional `.out` emission."""
+    from . import aggregate as agg
+    from . import mcmc as plain_host
+    from . import mcmc_clustering as cl_host
+    if not pargs_list:
+        raise lib.PolymcError(-1, "empty sweep")
+    host = cl_host if driver == "clustering" else plain_host
+    chain_type = pargs_list[0]["chain-type"]
+    for p in pargs_list:
+        host.validate({**p, "replicas": 1})
+        if p["chain-type"] != chain_type:
+            raise lib.PolymcError(-1, "one aggregated table holds one chain type (aggregate_mcmc.jl:40-47)")
+    cases = [host.case_from_pargs(p) for p in pargs_list]
+    p0 = pargs_list[0]
+    protocol = None
+    if driver == "clustering":
+        protocol = dict(burn_in=p0["burn-in"], schedule=cl_host.parse_julia_vector(p0["burn-schedule"], "burn-schedule"))
+    res = run_sweep(cases, runs, p0["num-steps"], 0, seed, device, torch_device, protocol)
+    runflag = runs > 1
+    entries, texts = [], []
+    for i, p in enumerate(pargs_list):
+        for r in range(runs):
+            g = i * runs + r
+            prefix = agg.prefix_of(p, chain_type, kappaflag, run=(r + 1) if runflag else None)
+            avg = res["avg"][g]
+            ex = (res["extra_sums"][g] / res["normalizer"][g]) if driver == "clustering" else None
+            entries.append((prefix, agg.output_values(avg, res["acc_rate"][g], p["mlen"], p["num-monomers"], ex)))
+            texts.append((prefix, agg.out_text(avg, res["acc_rate"][g], p["mlen"], p["num-monomers"], ex)))
+    header, rows = agg.aggregate_table(entries, chain_type, kappaflag, runflag)
+    if pooled:
+        header, rows = agg.reduce_table(header, rows, len(agg.input_headers(chain_type, kappaflag)))
+    return header, rows, texts

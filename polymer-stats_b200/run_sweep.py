@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""A whole parameter study in one process: replaces `julia -p N run/<study>.jl` +
+`julia scripts/aggregate_mcmc.jl` (+ `scripts/reduce_tabular_data.jl`).
+
+    python polymer-stats_b200/run_sweep.py --driver clustering --out study.csv [--pooled-out pooled.csv] \
+        [--outdir outs/] --runs 5 --grid E0=0.1,1,10 --grid Fz=0,0.5,1 --kappaflag -- \
+        --energy-type interacting --bend-mod 0.5 -n 100 --num-steps 200000 --burn-in 20000
+
+Everything after `--` is the common command line of the driver (same options as mcmc_eap_chain.jl /
+mcmc_clustering_eap_chain.jl); every `--grid NAME=v1,v2,…` multiplies the case list (NAME is the long option
+name without dashes).  All chains of the study run concurrently on the GPU (sharded over ranks under torchrun);
+the aggregated table is the one aggregate_mcmc.jl would build from the per-case `.out` files, which are only
+written when --outdir is given."""
+import argparse
+import itertools
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from polymc import aggregate, mcmc, mcmc_clustering, sweep  # noqa: E402
+
+
+def main(argv=None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    common = []
+    if "--" in argv:
+        k = argv.index("--")
+        argv, common = argv[:k], argv[k + 1:]
+    ap = argparse.ArgumentParser(prog="run_sweep")
+    ap.add_argument("--driver", choices=["plain", "clustering"], default="plain")
+    ap.add_argument("--grid", action="append", default=[], help="NAME=v1,v2,... (long option name of the driver)")
+    ap.add_argument("--runs", type=int, default=1, help="independent runs per case (the launchers' run-NNN)")
+    ap.add_argument("--out", required=True, help="aggregated CSV (aggregate_mcmc.jl format)")
+    ap.add_argument("--pooled-out", default=None, help="pooled CSV (reduce_tabular_data.jl format)")
+    ap.add_argument("--outdir", default=None, help="also write the per-case <prefix>.out files here")
+    ap.add_argument("--kappaflag", action="store_true", help="file names / table carry the kappa column")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--device", type=int, default=0)
+    a = ap.parse_args(argv)
+    host = mcmc_clustering if a.driver == "clustering" else mcmc
+    axes = []
+    for g in a.grid:
+        name, vals = g.split("=", 1)
+        axes.append((name, vals.split(",")))
+    pargs_list = []
+    for combo in itertools.product(*[v for _, v in axes]):
+        extra = []
+        for (name, _), v in zip(axes, combo):
+            extra += [f"--{name}", v]
+        pargs_list.append(host.parse_args(common + extra))
+    header, rows, texts = sweep.sweep_table(pargs_list, driver=a.driver, runs=a.runs, seed=a.seed, device=a.device,
+                                            kappaflag=a.kappaflag)
+    aggregate.write_table(a.out, header, rows)
+    if a.pooled_out:
+        ct = pargs_list[0]["chain-type"]
+        h2, r2 = aggregate.reduce_table(header, rows, len(aggregate.input_headers(ct, a.kappaflag)))
+        aggregate.write_table(a.pooled_out, h2, r2)
+    if a.outdir:
+        aggregate.write_out_files(a.outdir, texts)
+    print(f"{len(pargs_list)} cases x {a.runs} runs -> {a.out}", file=sys.stderr)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
