@@ -76,7 +76,12 @@ typedef struct pmc_case {
   int32_t cutoff_full;                    /* 0 = reference: the UCutoff functor is the bare pair sum, without
                                              Σu and −r·F (inc/eap_chain.jl:171-192 vs inc/energy.jl:13-16);
                                              1 = Σu + U_cut − r·F                                             */
-  int32_t reserved;
+  int32_t planar;                         /* 1: the 2-D tree (2D/mcmc_clustering_eap_chain.jl, 2D/inc/eap_chain.jl): the state
+                                             is phi only, n = (cos phi, sin phi) in the x-z plane (field along z),
+                                             no solid-angle term, flip_n! = phi + pi, the cluster gate flips WITH
+                                             probability cluster_prob (2D/inc/eap_chain.jl:233), and every stage starts
+                                             from a NEW random chain (2D/mcmc_clustering_eap_chain.jl:151).  theta arrays
+                                             at this boundary are ignored (read back as 0).  Requires clustering = 1.   */
 } pmc_case;
 
 typedef struct pmc_handle pmc_handle;

@@ -92,3 +92,36 @@ def bond_angle_mean(kappa, psi0=0.0, kT=1.0, nquad=2000):
 def cos2_sum(n, **kw):
     """⟨Σcos²θ⟩ of n independent monomers (mcmc_clustering_eap_chain.jl:243)."""
     return n * float(single_monomer_moments(**kw)["n2"][2])
+
+
+def planar_chain_averages(n, *, chain_type="dielectric", E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0,
+                          b=1.0, nquad=4096):
+    """The 16 averages (3-D rolling.csv order, y components zero) of n independent PLANAR monomers
+    (2D/inc/eap_chain.jl): n̂ = (cosϕ, sinϕ), field along the second axis, flat measure dϕ — density
+    ∝ exp(−e(ϕ)/kT), e = −½E0μ₂ − b(Fx cosϕ + Fz sinϕ) (2D/inc/energy.jl:7-9, 2D/inc/eap_chain.jl:64)."""
+    ph = np.arange(nquad) * (2 * np.pi / nquad)   # periodic trapezoid: spectrally accurate
+    c, s = np.cos(ph), np.sin(ph)
+    if chain_type == "dielectric":                # 2D/inc/dipole_response.jl:7-10
+        f = (K1 - K2) * E0 * s
+        mx, mz = f * c, f * s + K2 * E0
+    else:                                         # :25-27
+        mx, mz = mu * c, mu * s
+    e = -0.5 * E0 * mz - b * (Fx * c + Fz * s)
+    w = np.exp(-(e - e.min()) / kT)
+    w /= w.sum()
+
+    def avg(fv):
+        return float((fv * w).sum())
+
+    nbar = np.array([avg(c), 0.0, avg(s)])
+    n2 = np.array([avg(c * c), 0.0, avg(s * s)])
+    mbar = np.array([avg(mx), 0.0, avg(mz)])
+    m2 = np.array([avg(mx * mx), 0.0, avg(mz * mz)])
+    eb, e2 = avg(e), avg(e * e)
+    r = n * b * nbar
+    rj2 = b * b * (n * n2 + n * (n - 1) * nbar ** 2)
+    p = n * mbar
+    pj2 = n * m2 + n * (n - 1) * mbar ** 2
+    U = n * eb
+    U2 = n * (e2 - eb ** 2) + (n * eb) ** 2
+    return np.concatenate([r, rj2, [rj2.sum()], p, pj2, [pj2.sum()], [U, U2]])

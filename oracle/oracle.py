@@ -38,7 +38,7 @@ class OrcCase(C.Structure):
         ("omega_compat", C.c_int32), ("_pad", C.c_int32),
         # clustering driver (mcmc_clustering_eap_chain.jl:19-153)
         ("kappa", C.c_double), ("psi0", C.c_double), ("cutoff_radius", C.c_double), ("cluster_prob", C.c_double),
-        ("clustering", C.c_int32), ("alpha_carry", C.c_int32), ("cutoff_full", C.c_int32), ("_pad2", C.c_int32),
+        ("clustering", C.c_int32), ("alpha_carry", C.c_int32), ("cutoff_full", C.c_int32), ("planar", C.c_int32),
     ]
 
 
@@ -48,14 +48,15 @@ def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=
               adj_lb=0.15, adj_ub=0.55, adj_scale=1.1, steps_per_adjust=2500,
               do_flips=False, umbrella=False, omega_compat=False,
               kappa=0.0, psi0=0.0, cutoff_radius=7.5, cluster_prob=0.5, clustering=False, alpha_carry=True,
-              cutoff_full=False) -> OrcCase:
+              cutoff_full=False, planar=False) -> OrcCase:
     """Defaults are the ArgParse defaults of mcmc_eap_chain.jl:19-153 (and, for the clustering fields,
     of mcmc_clustering_eap_chain.jl:36-51,87-90; note that driver's own defaults for --energy-type (Ising)
     and --step-adjust-ub (0.40) differ and are set by its host)."""
     return OrcCase(E0, K1, K2, mu, kT, Fz, Fx, b, phi_step, theta_step, adj_lb, adj_ub, adj_scale,
                    n, steps_per_adjust, CHAIN_TYPES[chain_type], ENERGY_TYPES[energy_type],
                    int(do_flips), int(umbrella), int(omega_compat), 0,
-                   kappa, psi0, cutoff_radius, cluster_prob, int(clustering), int(alpha_carry), int(cutoff_full), 0)
+                   kappa, psi0, cutoff_radius, cluster_prob, int(clustering), int(alpha_carry), int(cutoff_full),
+                   int(planar))
 
 
 def build(force: bool = False) -> str:

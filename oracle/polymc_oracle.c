@@ -141,6 +141,39 @@ static inline void mu_of(const orc_case* c, double cphi, double sphi, double cth
   }
 }
 
+/* The 2-D tree: n̂ = (cosϕ, sinϕ) (2D/inc/eap_chain.jl:33) with the field along the SECOND axis
+ * (μ_dielectric = (K1−K2)·E0·sinϕ·n̂ + K2·[0;E0], 2D/inc/dipole_response.jl:7-10; polar M·n̂, :25-27;
+ * u = −½E0μ[2], 2D/inc/eap_chain.jl:64).  Stored here in the x–z plane of the 3-vectors, y ≡ 0. */
+static inline void nhat_planar(double cphi, double sphi, double out[3]) {
+  out[0] = cphi;
+  out[1] = 0.0;
+  out[2] = sphi;
+}
+static inline void mu_planar(const orc_case* c, double cphi, double sphi, double out[3]) {
+  double nh[3];
+  nhat_planar(cphi, sphi, nh);
+  if (c->chain_type == ORC_CHAIN_DIELECTRIC) {
+    double f = (c->K1 - c->K2) * c->E0 * sphi;
+    out[0] = f * nh[0] + c->K2 * 0.0;
+    out[1] = 0.0;
+    out[2] = f * nh[2] + c->K2 * c->E0;
+  } else {
+    out[0] = c->mu * nh[0];
+    out[1] = 0.0;
+    out[2] = c->mu * nh[2];
+  }
+}
+/* direction and dipole of one monomer in either tree */
+static inline void dir_c(const orc_case* c, double cphi, double sphi, double cth, double sth, double nh[3], double mu[3]) {
+  if (c->planar) {
+    nhat_planar(cphi, sphi, nh);
+    mu_planar(c, cphi, sphi, mu);
+  } else {
+    nhat_of(cphi, sphi, cth, sth, nh);
+    mu_of(c, cphi, sphi, cth, sth, mu);
+  }
+}
+
 /* u(E0, mu) = -1/2 E0 mu_z  (eap_chain.jl:53); same 1/2 for polar chains. */
 static inline double u_self(double E0, const double mu[3]) { return -1.0 / 2 * E0 * mu[2]; }
 
@@ -288,10 +321,14 @@ orc_chain* orc_chain_new(const orc_case* c, const double* phi, const double* the
     ch->sphi[i] = sin(phi[i]);
     ch->ctheta[i] = cos(theta[i]);
     ch->stheta[i] = sin(theta[i]);
+    if (c->planar) { /* no θ in the 2-D tree: sinθ ≡ 1 makes every solid-angle term exactly 0 */
+      ch->theta[i] = 0.0;
+      ch->ctheta[i] = ch->sphi[i];
+      ch->stheta[i] = 1.0;
+    }
     prod *= ch->stheta[i];
     slog += log(ch->stheta[i]);
-    nhat_of(ch->cphi[i], ch->sphi[i], ch->ctheta[i], ch->stheta[i], &ch->nhat[3 * i]);
-    mu_of(c, ch->cphi[i], ch->sphi[i], ch->ctheta[i], ch->stheta[i], &ch->mus[3 * i]);
+    dir_c(c, ch->cphi[i], ch->sphi[i], ch->ctheta[i], ch->stheta[i], &ch->nhat[3 * i], &ch->mus[3 * i]);
   }
   for (int64_t i = 0; i + 1 < ch->n; ++i) ch->psis[i] = psi_j(ch, i);                           /* :125 */
   for (int64_t i = 0; i < ch->n; ++i) ch->us[i] = u_self(c->E0, &ch->mus[3 * i]) + ubend(ch, i); /* :130 */
@@ -457,13 +494,16 @@ static void chain_move_caches(orc_chain* ch, int64_t idx, double dphi, double dt
   ch->phi[idx] += dphi;
   ch->cphi[idx] = cos(ch->phi[idx]);
   ch->sphi[idx] = sin(ch->phi[idx]);
-  ch->theta[idx] = fmin(M_PI, fmax(0.0, ch->theta[idx] + dtheta));
-  double sth = sin(ch->theta[idx]);
-  ch->Omega += log(sth / ch->stheta[idx]);
-  ch->ctheta[idx] = cos(ch->theta[idx]);
-  ch->stheta[idx] = sth;
-  nhat_of(ch->cphi[idx], ch->sphi[idx], ch->ctheta[idx], ch->stheta[idx], &ch->nhat[3 * idx]);
-  mu_of(&ch->c, ch->cphi[idx], ch->sphi[idx], ch->ctheta[idx], ch->stheta[idx], &ch->mus[3 * idx]);
+  if (ch->c.planar) { /* move!(chain, idx, dϕ), 2D/inc/eap_chain.jl:171-187 */
+    ch->ctheta[idx] = ch->sphi[idx];
+  } else {
+    ch->theta[idx] = fmin(M_PI, fmax(0.0, ch->theta[idx] + dtheta));
+    double sth = sin(ch->theta[idx]);
+    ch->Omega += log(sth / ch->stheta[idx]);
+    ch->ctheta[idx] = cos(ch->theta[idx]);
+    ch->stheta[idx] = sth;
+  }
+  dir_c(&ch->c, ch->cphi[idx], ch->sphi[idx], ch->ctheta[idx], ch->stheta[idx], &ch->nhat[3 * idx], &ch->mus[3 * idx]);
   if (idx < ch->n - 1) ch->psis[idx] = psi_j(ch, idx);                                      /* :246 */
   if (idx > 0) {                                                                            /* :247-250 */
     ch->psis[idx - 1] = psi_j(ch, idx - 1);
@@ -540,7 +580,10 @@ void orc_chain_delta_u(const orc_chain* ch, int64_t idx, double dphi, double dth
 }
 
 /* refl_n! (eap_chain.jl:263-265): move!(chain, idx, 0, π − 2θ_idx). */
-static void chain_refl_caches(orc_chain* ch, int64_t i) { chain_move_caches(ch, i, 0.0, M_PI - 2 * ch->theta[i]); }
+static void chain_refl_caches(orc_chain* ch, int64_t i) {
+  if (ch->c.planar) chain_move_caches(ch, i, M_PI, 0.0); /* flip_n! = move!(chain, idx, π), 2D/inc/eap_chain.jl:189-191 */
+  else chain_move_caches(ch, i, 0.0, M_PI - 2 * ch->theta[i]);
+}
 
 /* The composite trial of the clustering driver done literally (mcmc_clustering_eap_chain.jl:272-273 →
  * eap_chain.jl:230-257, :311-315): move!, then refl_n! for every monomer of the cluster, each with its
@@ -573,23 +616,28 @@ void orc_chain_delta_segment(const orc_chain* ch, int64_t idx, double dphi, doub
   for (int64_t k = 0; k < m; ++k) {
     const int64_t i = lo + k;
     double phi1 = ch->phi[i], th1 = ch->theta[i], sprev = ch->stheta[i];
-    if (i == idx) {  /* move! (:232-238) */
-      phi1 += dphi;
-      th1 = fmin(M_PI, fmax(0.0, th1 + dtheta));
-      double s1 = sin(th1);
-      dOmega += log(s1 / sprev);
-      sprev = s1;
-    }
-    if (reflect) {   /* refl_n!: dϕ = 0, dθ = π − 2θ (:263-265) */
-      phi1 += 0.0;
-      th1 = fmin(M_PI, fmax(0.0, th1 + (M_PI - 2 * th1)));
-      double s2 = sin(th1);
-      dOmega += log(s2 / sprev);
-      sprev = s2;
+    if (c->planar) { /* 2-D: move! adds dϕ, flip_n! adds π; no θ, no solid angle */
+      if (i == idx) phi1 += dphi;
+      if (reflect) phi1 += M_PI;
+    } else {
+      if (i == idx) {  /* move! (:232-238) */
+        phi1 += dphi;
+        th1 = fmin(M_PI, fmax(0.0, th1 + dtheta));
+        double s1 = sin(th1);
+        dOmega += log(s1 / sprev);
+        sprev = s1;
+      }
+      if (reflect) {   /* refl_n!: dϕ = 0, dθ = π − 2θ (:263-265) */
+        phi1 += 0.0;
+        th1 = fmin(M_PI, fmax(0.0, th1 + (M_PI - 2 * th1)));
+        double s2 = sin(th1);
+        dOmega += log(s2 / sprev);
+        sprev = s2;
+      }
     }
     double cph = cos(phi1), sph = sin(phi1), cth = cos(th1), sth = sin(th1);
-    nhat_of(cph, sph, cth, sth, &nn[3 * k]);
-    mu_of(c, cph, sph, cth, sth, &mn[3 * k]);
+    if (c->planar) { cth = sph; sth = 1.0; }
+    dir_c(c, cph, sph, cth, sth, &nn[3 * k], &mn[3 * k]);
     du += u_self(c->E0, &mn[3 * k]) - u_self(c->E0, &ch->mus[3 * i]);
     dcos2 += cth * cth - ch->ctheta[i] * ch->ctheta[i];
     for (int q = 0; q < 3; ++q) {
@@ -736,6 +784,11 @@ void orc_run_begin_stage(orc_run* r, double kT) {
   r->trial->c.kT = kT;
   r->chain->U = U_total(r->chain);
   r->init += 1; /* fresh random numbers for the new stage */
+  if (r->c.planar) { /* 2D/mcmc_clustering_eap_chain.jl:151 `chain = EAPChain(pargs)`: every stage builds a NEW chain */
+    orc_chain* nc = orc_chain_new_random(&r->c, r->seed, r->chain_id, r->init);
+    chain_assign(r->chain, nc);
+    orc_chain_free(nc);
+  }
   r->phi_step = r->c.phi_step;
   r->theta_step = r->c.theta_step;
   r->nacc = r->natt = r->nacc_total = r->steps_total = 0;
@@ -827,7 +880,13 @@ static int cluster_grow(const orc_run* r, const orc_chain* t, int64_t step, int6
                         double* upper_p, double* lower_p) {
   const orc_case* c = &r->c;
   if (!c->clustering) return 0; /* mcmc_eap_chain.jl has no cluster_flip! */
-  if (orc_draw_cluster_gate(r->seed, r->chain_id, r->init, step) <= c->cluster_prob) return 0;
+  /* 3-D: the gate comes first and a hit means "no cluster" (eap_chain.jl:273).  2-D: the cluster is grown
+   * first and a hit means "flip it" (2D/inc/eap_chain.jl:233).  The growth uniforms are counter-based, so
+   * growing after the gate changes nothing. */
+  {
+    const int hit = orc_draw_cluster_gate(r->seed, r->chain_id, r->init, step) <= c->cluster_prob;
+    if (c->planar ? !hit : hit) return 0;
+  }
   int64_t u = idx, k = 0;
   double up;
   for (;;) { /* :276-289 */
@@ -864,8 +923,9 @@ static int cluster_trial(orc_run* r, int64_t step) {
   orc_draw_step(r->seed, r->chain_id, r->init, step, c->n, &idx, &uphi, &flipbit, &uth, &eps);
   const double dphi = -r->phi_step + (2 * r->phi_step) * uphi;   /* :268-270 */
   /* (--do-flips exists only in mcmc_eap_chain.jl:279, which reaches this path when it carries bending energy) */
-  const double dth = ((c->do_flips && flipbit) ? M_PI - 2 * r->chain->theta[idx] : 0.0) +
-                     (-r->theta_step + (2 * r->theta_step) * uth);
+  const double dth = c->planar ? 0.0 /* no dθ draw in 2D/mcmc_clustering_eap_chain.jl:238-241 */
+                               : ((c->do_flips && flipbit) ? M_PI - 2 * r->chain->theta[idx] : 0.0) +
+                                     (-r->theta_step + (2 * r->theta_step) * uth);
   int64_t lo = idx, hi = idx;
   double up = 0.0, lp = 0.0, alpha = 1.0;
   int reflect = 0, accepted = 0;
@@ -897,7 +957,8 @@ static int cluster_trial(orc_run* r, int64_t step) {
     {
       const double phi1 = r->chain->phi[idx] + dphi;
       const double th1 = fmin(M_PI, fmax(0.0, r->chain->theta[idx] + dth));
-      nhat_of(cos(phi1), sin(phi1), cos(th1), sin(th1), &t->nhat[3 * idx]);
+      if (c->planar) nhat_planar(cos(phi1), sin(phi1), &t->nhat[3 * idx]);
+      else nhat_of(cos(phi1), sin(phi1), cos(th1), sin(th1), &t->nhat[3 * idx]);
     }
     reflect = cluster_grow(r, t, step, idx, &lo, &hi, &up, &lp);
     double d[12];
@@ -907,6 +968,11 @@ static int cluster_trial(orc_run* r, int64_t step) {
       for (int64_t i = lo; i <= hi; i += (hi > lo ? hi - lo : 1)) {
         double phi1 = r->chain->phi[i], th1 = r->chain->theta[i];
         if (i == idx) { phi1 += dphi; th1 = fmin(M_PI, fmax(0.0, th1 + dth)); }
+        if (c->planar) {
+          phi1 += M_PI;
+          nhat_planar(cos(phi1), sin(phi1), &t->nhat[3 * i]);
+          continue;
+        }
         th1 = fmin(M_PI, fmax(0.0, th1 + (M_PI - 2 * th1)));
         nhat_of(cos(phi1), sin(phi1), cos(th1), sin(th1), &t->nhat[3 * i]);
       }

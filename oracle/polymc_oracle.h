@@ -52,7 +52,9 @@ typedef struct orc_case {
                               (acceptance.jl:30-33); 0: stores logπ only (plain Metropolis-Hastings)  */
   int32_t cutoff_full;     /* 0 (reference): the UCutoff functor is the bare pair sum — no Σu, no −r·F
                               (eap_chain.jl:171-192 vs energy.jl:13-16); 1: Σu + U_cut − r·F          */
-  int32_t _pad2;
+  int32_t planar;          /* 1: the 2-D tree (2D/inc/eap_chain.jl, 2D/mcmc_clustering_eap_chain.jl): phi-only state,
+                              n = (cos phi, sin phi) in the x-z plane, no solid angle, flip_n! = phi + pi, the cluster
+                              gate flips WITH probability cluster_prob, every stage starts from a new random chain   */
 } orc_case;
 
 typedef struct orc_chain orc_chain;

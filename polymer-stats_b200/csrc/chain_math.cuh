@@ -84,7 +84,8 @@ struct ChainParams {
   double kappa, psi0;     // --bend-mod, --bend-angle (eap_chain.jl:54-58)
   double crad2;           // (cutoff-radius · mlen)², eap_chain.jl:102,172
   double cluster_prob;    // cluster_flip! returns early iff rand() <= cluster_prob (eap_chain.jl:273)
-  int clustering, alpha_carry, cutoff_full, pad2;
+  int clustering, alpha_carry, cutoff_full;
+  int planar;             // 2-D tree (2D/inc/eap_chain.jl): state is ϕ only, n̂ = (cosϕ, 0, sinϕ), no solid angle
 };
 
 constexpr int kNumAcc = 17;  // 16 sums (rolling.csv order) + normaliser
@@ -250,6 +251,33 @@ __device__ __forceinline__ void build_proposal(const ChainParams& P, const MonoR
   const double dw = P.umbrella ? q.du * P.inv_kT * P.cF : 0.0;  // average.jl:120-124
   q.single = -(q.du + q.drF) * P.inv_kT + q.dOmega + dw;
   q.skip = (sth == 0.0);
+}
+
+// move! of the planar chain (2D/inc/eap_chain.jl:171-187): ϕ += dϕ, n̂ = (cosϕ, sinϕ) in the x–z plane
+// (the field is along the second axis, 2D/inc/dipole_response.jl:7-10), no θ and no solid-angle term.
+// In the record: n̂y = 0, sinθ ≡ 1 (so every log(sinθ'/sinθ) is exactly 0), θ ≡ 0.
+__device__ __forceinline__ void build_proposal_planar(const ChainParams& P, const MonoRec& rec, int idx, double dphi,
+                                                      double eps, Proposal& q) {
+  q.idx = idx;
+  q.eps = eps;
+  q.phi = rec.phi + dphi;
+  q.theta = 0.0;
+  q.clamped = 0;
+  double sph, cph;
+  sincos(q.phi, &sph, &cph);
+  q.sth = 1.0;
+  q.nx = cph; q.ny = 0.0; q.nz = sph;
+  mu_of(P, q.nx, q.ny, q.nz, q.mx, q.my, q.mz);
+  double omx, omy, omz;
+  mu_of(P, rec.nx, rec.ny, rec.nz, omx, omy, omz);
+  q.dnx = q.nx - rec.nx; q.dny = 0.0; q.dnz = q.nz - rec.nz;
+  q.dmx = q.mx - omx; q.dmy = q.my - omy; q.dmz = q.mz - omz;
+  q.dOmega = 0.0;
+  q.du = -0.5 * P.E0 * q.mz - (-0.5 * P.E0 * omz);   // u = −½E0μ[2], 2D/inc/eap_chain.jl:64
+  q.drF = -P.b * (q.dnx * P.Fx + q.dnz * P.Fz);      // −Δr·[Fx;Fz], 2D/inc/energy.jl:8
+  const double dw = P.umbrella ? q.du * P.inv_kT * P.cF : 0.0;
+  q.single = -(q.du + q.drF) * P.inv_kT + dw;
+  q.skip = 0;
 }
 
 // Proposal increments from raw draws: rand(Uniform(-s,s)) = -s + 2s·u (mcmc_eap_chain.jl:278-280).

@@ -78,6 +78,18 @@ __device__ __forceinline__ void nhat_trial(const ClView& X, const Proposal& q, i
   else { x = X.nhx[i]; y = X.nhy[i]; z = X.nhz[i]; }
 }
 
+// Draw and build the single-monomer part of trial `step` (mcmc_clustering_eap_chain.jl:267-270; the 2-D driver
+// draws no dθ, 2D/mcmc_clustering_eap_chain.jl:238-241).
+__device__ __forceinline__ void make_proposal_cl(const RunArgs& a, const ChainParams& P, const ChainDyn& D,
+                                                 const MonoRec* mono, uint32_t chain_id, long long step, Proposal& q) {
+  const Draws d = draw_step(a.seed, chain_id, (uint32_t)D.init, step, a.n);
+  const MonoRec rec = mono[d.idx];
+  double dphi, dtheta;
+  increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
+  if (P.planar) build_proposal_planar(P, rec, d.idx, dphi, d.eps, q);
+  else build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+}
+
 // cluster_flip! up to the flips (eap_chain.jl:273-309), by one warp: the growth draws are counter-based,
 // so 32 bonds are tested per round and the first failing one ends the growth — same result as the
 // reference's sequential loop on the same uniforms.
@@ -93,7 +105,9 @@ __device__ __forceinline__ void warp_cluster_grow(const ClView& X, const Proposa
     double gate = 0.0;
     if (lane == 0) gate = draw_cluster_gate(seed, chain_id, init, step);
     gate = __shfl_sync(FULL, gate, 0);
-    reflect = !(gate <= P.cluster_prob);  // `if rand() <= ϵflip; return 1.0; end`, eap_chain.jl:273
+    // 3-D: `if rand() <= ϵflip; return 1.0; end` BEFORE the growth (eap_chain.jl:273): flips with 1 − ϵflip;
+    // 2-D: `if rand() <= ϵflip … flip` AFTER the growth (2D/inc/eap_chain.jl:233): flips with ϵflip
+    reflect = P.planar ? (gate <= P.cluster_prob) : !(gate <= P.cluster_prob);
   }
   if (reflect) {
     // upward: bond (u,u+1), eap_chain.jl:276-289
@@ -148,14 +162,32 @@ __device__ __forceinline__ void warp_cluster_grow(const ClView& X, const Proposa
 // New angles of segment monomer c: move! for idx (already in the proposal), then refl_n! if the cluster
 // is flipped.  Returns ϕ', θ'.
 __device__ __forceinline__ void segment_angles(const MonoRec* __restrict__ mono, const Proposal& q, int c,
-                                               bool reflect, double& phi, double& theta, double& sth_before) {
+                                               bool reflect, int planar, double& phi, double& theta,
+                                               double& sth_before) {
   if (c == q.idx) {
     phi = q.phi; theta = q.theta; sth_before = q.sth;
   } else {
     const MonoRec r = mono[c];
     phi = r.phi; theta = r.theta; sth_before = r.sth;
   }
-  if (reflect) theta = reflect_theta(theta);
+  if (reflect) {
+    if (planar) phi += kPi;  // flip_n! = move!(chain, i, π), 2D/inc/eap_chain.jl:189-191
+    else theta = reflect_theta(theta);
+  }
+}
+
+// n̂ and sinθ from the angles: (cosϕ sinθ, sinϕ sinθ, cosθ) (eap_chain.jl:40) or the planar (cosϕ, 0, sinϕ).
+__device__ __forceinline__ void direction_of(int planar, double phi, double theta, double& nx, double& ny, double& nz,
+                                             double& sth) {
+  double sph, cph;
+  sincos(phi, &sph, &cph);
+  if (planar) {
+    nx = cph; ny = 0.0; nz = sph; sth = 1.0;
+  } else {
+    double cth;
+    sincos(theta, &sth, &cth);
+    nx = cph * sth; ny = sph * sth; nz = cth;
+  }
 }
 
 // New direction of segment monomer c: n̂', sinθ' and this monomer's share of the changed single-monomer sums.
@@ -168,12 +200,9 @@ __device__ __forceinline__ void segment_monomer(const CtaView& S, const ClView& 
     acc[R_OMEGA] += q.dOmega;
   } else {
     double phi, theta, sb;
-    segment_angles(mono, q, c, true, phi, theta, sb);
-    double sph, cph, cth;
-    sincos(phi, &sph, &cph);
-    sincos(theta, &sth, &cth);
-    nx = cph * sth; ny = sph * sth; nz = cth;
-    acc[R_OMEGA] += (c == q.idx ? q.dOmega : 0.0) + log(sth / sb);  // Ω += log(sθ'/sθ), eap_chain.jl:238
+    segment_angles(mono, q, c, true, P.planar, phi, theta, sb);
+    direction_of(P.planar, phi, theta, nx, ny, nz, sth);
+    if (!P.planar) acc[R_OMEGA] += (c == q.idx ? q.dOmega : 0.0) + log(sth / sb);  // Ω += log(sθ'/sθ), eap_chain.jl:238
   }
   X.nnx[c] = nx; X.nny[c] = ny; X.nnz[c] = nz;
   S.E[c] = sth;
@@ -436,7 +465,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
 #pragma unroll
     for (int k = 0; k < kNumRed; ++k) acc[k] = 0.0;
     if (tid < 32) {
-      if (tid == 0) make_proposal(a, P, *S.dyn, mono, chain_id, step, *q);
+      if (tid == 0) make_proposal_cl(a, P, *S.dyn, mono, chain_id, step, *q);
       __syncwarp();
       warp_cluster_grow(X, *q, P, n, a.seed, chain_id, init, step, *X.ctl);
       __syncwarp();
@@ -456,7 +485,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
     if (accept) {  // the trial chain becomes the chain (mcmc_clustering_eap_chain.jl:274-275)
       for (int k = lo + tid; k <= hi; k += T) {
         double phi, theta, sb;
-        segment_angles(mono, *q, k, reflect, phi, theta, sb);
+        segment_angles(mono, *q, k, reflect, P.planar, phi, theta, sb);
         MonoRec rec;
         rec.phi = phi; rec.theta = theta;
         rec.nx = X.nnx[k]; rec.ny = X.nny[k]; rec.nz = X.nnz[k]; rec.sth = S.E[k];
@@ -543,7 +572,10 @@ __global__ void __launch_bounds__(T) k_delta_segment_cta(const SegDeltaArgs a) {
   const ChainParams& P = *S.par;
   load_chain<T>(mono, P, n, S);
   load_nhat<T>(mono, n, X);
-  if (tid == 0) build_proposal(P, mono[a.idx], a.idx, a.dphi, a.dtheta, 0.0, S.prop[0]);
+  if (tid == 0) {
+    if (P.planar) build_proposal_planar(P, mono[a.idx], a.idx, a.dphi, 0.0, S.prop[0]);
+    else build_proposal(P, mono[a.idx], a.idx, a.dphi, a.dtheta, 0.0, S.prop[0]);
+  }
   __syncthreads();
   const Proposal& q = S.prop[0];
   const bool reflect = a.reflect != 0;
@@ -596,13 +628,10 @@ __device__ __forceinline__ void lane_new_mono(const ChainParams& P, const MonoRe
     return;
   }
   double phi, theta, sb;
-  segment_angles(mono, q, c, true, phi, theta, sb);
-  double sph, cph, sth, cth;
-  sincos(phi, &sph, &cph);
-  sincos(theta, &sth, &cth);
+  segment_angles(mono, q, c, true, P.planar, phi, theta, sb);
   nrec.phi = phi; nrec.theta = theta;
-  nrec.nx = cph * sth; nrec.ny = sph * sth; nrec.nz = cth; nrec.sth = sth;
-  dOmega = (c == q.idx ? q.dOmega : 0.0) + log(sth / sb);
+  direction_of(P.planar, phi, theta, nrec.nx, nrec.ny, nrec.nz, nrec.sth);
+  dOmega = P.planar ? 0.0 : (c == q.idx ? q.dOmega : 0.0) + log(nrec.sth / sb);
 }
 
 // Changed-term sums of the composite trial on segment [lo,hi] for O(1)-per-bond energies: one sweep over
@@ -710,11 +739,15 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
     double dphi, dtheta;
     increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
     Proposal q;
-    build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+    if (P.planar) build_proposal_planar(P, rec, d.idx, dphi, d.eps, q);
+    else build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
     int lo = d.idx, hi = d.idx;
     double up = 0.0, lp = 0.0;
     bool reflect = false;
-    if (P.clustering) reflect = !(draw_cluster_gate(a.seed, chain_id, (uint32_t)D.init, step) <= P.cluster_prob);
+    if (P.clustering) {
+      const bool g = draw_cluster_gate(a.seed, chain_id, (uint32_t)D.init, step) <= P.cluster_prob;
+      reflect = P.planar ? g : !g;  // the gate has opposite senses in the two trees (see warp_cluster_grow)
+    }
     if (reflect) lane_cluster_grow(mono, q, n, a.seed, chain_id, (uint32_t)D.init, step, lo, hi, up, lp);
     LaneSeg g;
     double nlx = 0, nly = 0, nlz = 0, nhx = 0, nhy = 0, nhz = 0;
@@ -784,7 +817,8 @@ __global__ void k_delta_segment_lane(const SegDeltaArgs a) {
   const ChainParams P = a.par[a.chain];
   const MonoRec rec = mono[a.idx];
   Proposal q;
-  build_proposal(P, rec, a.idx, a.dphi, a.dtheta, 0.0, q);
+  if (P.planar) build_proposal_planar(P, rec, a.idx, a.dphi, 0.0, q);
+  else build_proposal(P, rec, a.idx, a.dphi, a.dtheta, 0.0, q);
   const bool reflect = a.reflect != 0;
   const int lo = reflect ? a.lo : a.idx, hi = reflect ? a.hi : a.idx;
   LaneSeg g;

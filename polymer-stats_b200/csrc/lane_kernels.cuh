@@ -246,10 +246,15 @@ __global__ void k_delta_lane(const DeltaArgs a) {
 }
 
 // Records from angles: n̂ (eap_chain.jl:40) and sinθ caches.
-__device__ __forceinline__ MonoRec make_record(double phi, double theta) {
+__device__ __forceinline__ MonoRec make_record(double phi, double theta, int planar = 0) {
   MonoRec r;
   double sph, cph, sth, cth;
   sincos(phi, &sph, &cph);
+  if (planar) {  // 2D/inc/eap_chain.jl:33: n̂ = (cosϕ, sinϕ), kept in the x–z plane; no θ
+    r.phi = phi; r.theta = 0.0;
+    r.nx = cph; r.ny = 0.0; r.nz = sph; r.sth = 1.0;
+    return r;
+  }
   sincos(theta, &sth, &cth);
   r.phi = phi; r.theta = theta;
   r.nx = cph * sth; r.ny = sph * sth; r.nz = cth; r.sth = sth;
@@ -258,19 +263,20 @@ __device__ __forceinline__ MonoRec make_record(double phi, double theta) {
 
 // Random initial chains: ϕ~U(0,2π), θ~U(0,π) (eap_chain.jl:6-7,62).
 __global__ void k_fill_random(MonoRec* mono, long long total, int n, uint64_t seed, uint32_t chain_id_base,
-                              uint32_t init) {
+                              uint32_t init, int planar = 0) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
   const long long c = g / n;
   const int k = (int)(g - c * n);
   const uint4 w = philox_at(seed, chain_id_base + (uint32_t)c, init, SUB_INIT, (uint64_t)k);
-  mono[g] = make_record(0.0 + (2.0 * kPi - 0.0) * u53(w.x, w.y), 0.0 + (kPi - 0.0) * u53(w.z, w.w));
+  mono[g] = make_record(0.0 + (2.0 * kPi - 0.0) * u53(w.x, w.y), 0.0 + (kPi - 0.0) * u53(w.z, w.w), planar);
 }
 
-__global__ void k_build_records(MonoRec* mono, const double* phi, const double* theta, long long total) {
+__global__ void k_build_records(MonoRec* mono, const double* phi, const double* theta, long long total,
+                                int planar = 0) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
-  mono[g] = make_record(phi[g], theta[g]);
+  mono[g] = make_record(phi[g], theta[g], planar);
 }
 
 __global__ void k_extract_state(const MonoRec* mono, double* phi, double* theta, long long total) {

@@ -87,6 +87,7 @@ struct pmc_handle {
   int replicas = 1;
   double kT_scale = 1.0;
   std::vector<ChainDynX> host_dynx;
+  int planar = 0;             // 2-D tree
 };
 
 namespace {
@@ -303,6 +304,9 @@ int validate_case(const pmc_case& c, const pmc_case& first) {
   if (!(c.kT > 0.0)) return fail(PMC_ERR_INVALID, "kT must be positive");
   if (c.accum_mode != 0 && c.accum_mode != 1) return fail(PMC_ERR_INVALID, "accum_mode must be 0 or 1");
   if (c.clustering && c.n < 2) return fail(PMC_ERR_INVALID, "the clustering driver needs num-monomers >= 2");
+  if (c.planar != first.planar) return fail(PMC_ERR_INVALID, "all cases of one handle must be planar or none");
+  if (c.planar && (!c.clustering || c.kappa != 0.0 || c.energy_type == PMC_ENERGY_CUTOFF || c.do_flips))
+    return fail(PMC_ERR_INVALID, "the 2-D tree has only the clustering driver, without bending, cut-off or --do-flips");
   if (!(c.cluster_prob >= 0.0 && c.cluster_prob <= 1.0) && c.clustering)
     return fail(PMC_ERR_INVALID, "cluster-prob must be in [0,1]");
   return PMC_OK;
@@ -339,6 +343,7 @@ ChainParams params_of(const pmc_case& c0, double kT_scale = 1.0) {
   P.crad2 = (c.cutoff_radius * c.b) * (c.cutoff_radius * c.b);  // UCutoff(cutoff-radius·mlen), eap_chain.jl:102
   P.cluster_prob = c.cluster_prob;
   P.clustering = c.clustering; P.alpha_carry = c.alpha_carry; P.cutoff_full = c.cutoff_full;
+  P.planar = c.planar;
   return P;
 }
 
@@ -416,6 +421,7 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
     if (cases[i].accum_mode || cases[i].umbrella) h->compensated = 1;  // umbrella weights span many decades
   h->cases.assign(cases, cases + ncases);
   h->replicas = replicas_per_case;
+  h->planar = cases[0].planar;
   for (int64_t i = 0; i < ncases; ++i)
     if (needs_cluster_path(cases[i])) h->cluster_mode = 1;
   const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
@@ -464,7 +470,8 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   {
     const int tb = 256;
     const long long blocks = ((long long)total + tb - 1) / tb;
-    k_fill_random<<<(unsigned)blocks, tb, 0, h->stream>>>(h->mono, (long long)total, n, seed, chain_id_base, 0u);
+    k_fill_random<<<(unsigned)blocks, tb, 0, h->stream>>>(h->mono, (long long)total, n, seed, chain_id_base, 0u,
+                                                          h->planar);
     ++h->launches;
     PMC_TRY(PMC_CU(cudaGetLastError()));
   }
@@ -517,7 +524,7 @@ static int set_state_range(pmc_handle* h, int64_t first, int64_t count, const do
   PMC_CU(cudaMemcpyAsync(h->scratch + m, theta, m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   const int tb = 256;
   k_build_records<<<(unsigned)((m + tb - 1) / tb), tb, 0, h->stream>>>(h->mono + (size_t)first * h->n, h->scratch,
-                                                                         h->scratch + m, (long long)m);
+                                                                         h->scratch + m, (long long)m, h->planar);
   ++h->launches;
   PMC_CU(cudaGetLastError());
   // a new state replaces the chain the weight function was built from (mcmc_eap_chain.jl:175-177)
@@ -891,7 +898,7 @@ int32_t pmc_reinit(pmc_handle* h, int32_t* replaced) {
   h->init += 1;
   const int tb = 256;
   k_fill_random<<<(unsigned)((total + tb - 1) / tb), tb, 0, h->stream>>>(h->cand, (long long)total, h->n, h->seed,
-                                                                        h->chain_id_base, (uint32_t)h->init);
+                                                                        h->chain_id_base, (uint32_t)h->init, h->planar);
   ++h->launches;
   PMC_CU(cudaGetLastError());
   if ((rc = refresh(h, false))) return rc;  // current U, Ω exact before comparing
@@ -990,6 +997,13 @@ int32_t pmc_begin_stage(pmc_handle* h, double kT_scale) {
   PMC_CU(cudaMemcpyAsync(h->par, par.data(), par.size() * sizeof(ChainParams), cudaMemcpyHostToDevice, h->stream));
   PMC_CU(cudaStreamSynchronize(h->stream));  // `par` is pageable host memory
   h->init += 1;
+  if (h->planar) {  // 2D/mcmc_clustering_eap_chain.jl:151: `chain = EAPChain(pargs)` — every stage builds a new chain
+    const size_t total = (size_t)h->nchains * (size_t)h->n;
+    k_fill_random<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->mono, (long long)total, h->n, h->seed,
+                                                                          h->chain_id_base, (uint32_t)h->init, 1);
+    ++h->launches;
+    PMC_CU(cudaGetLastError());
+  }
   const int tb = 128;
   k_begin_stage<<<(unsigned)((h->nchains + tb - 1) / tb), tb, 0, h->stream>>>(h->dyn, h->dynx, h->par, (int)h->nchains,
                                                                              h->init);
@@ -1005,6 +1019,7 @@ int32_t pmc_init_x0(pmc_handle* h, const double* x0, int64_t x0_len, const doubl
   int rc = check_handle(h);
   if (rc) return rc;
   if (!x0 || !dx0) return fail(PMC_ERR_INVALID, "null x0/dx0");
+  if (h->planar) return fail(PMC_ERR_UNSUPPORTED, "the 2-D tree has no --x0 (2D/inc/eap_chain.jl:66-67)");
   if (x0_len != 2 && x0_len != 2 * (int64_t)h->n) return fail(PMC_ERR_INVALID, "Invalid input for 'x0'");  // eap_chain.jl:76
   if (!h->x0buf) PMC_CU(cudaMalloc(&h->x0buf, 2 * (size_t)h->n * sizeof(double)));
   PMC_CU(cudaMemcpyAsync(h->x0buf, x0, (size_t)x0_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));

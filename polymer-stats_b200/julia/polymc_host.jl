@@ -20,7 +20,7 @@ struct PmcCase
   chain_type::Int32; energy_type::Int32; do_flips::Int32; umbrella::Int32; force_init::Int32; accum_mode::Int32
   # ABI v2 — mcmc_clustering_eap_chain.jl; all zero for this driver
   kappa::Cdouble; psi0::Cdouble; cutoff_radius::Cdouble; cluster_prob::Cdouble
-  clustering::Int32; alpha_carry::Int32; cutoff_full::Int32; reserved::Int32
+  clustering::Int32; alpha_carry::Int32; cutoff_full::Int32; planar::Int32
 end
 
 pmc_error() = unsafe_string(ccall((:pmc_last_error, LIBPOLYMC), Cstring, ()))

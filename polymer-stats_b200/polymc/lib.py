@@ -57,7 +57,7 @@ class PmcCase(C.Structure):
         ("force_init", C.c_int32), ("accum_mode", C.c_int32),
         # mcmc_clustering_eap_chain.jl:36-51,87-90
         ("kappa", C.c_double), ("psi0", C.c_double), ("cutoff_radius", C.c_double), ("cluster_prob", C.c_double),
-        ("clustering", C.c_int32), ("alpha_carry", C.c_int32), ("cutoff_full", C.c_int32), ("reserved", C.c_int32),
+        ("clustering", C.c_int32), ("alpha_carry", C.c_int32), ("cutoff_full", C.c_int32), ("planar", C.c_int32),
     ]
 
 
@@ -67,7 +67,7 @@ def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=
               adj_lb=0.15, adj_ub=0.55, adj_scale=1.1, steps_per_adjust=2500,
               do_flips=False, umbrella=False, force_init=False, accum_mode=0,
               kappa=0.0, psi0=0.0, cutoff_radius=7.5, cluster_prob=0.5, clustering=False, alpha_carry=True,
-              cutoff_full=False) -> PmcCase:
+              cutoff_full=False, planar=False) -> PmcCase:
     """Defaults are the ArgParse defaults of mcmc_eap_chain.jl:19-153; the clustering fields default to
     "off" (kappa 0, clustering False) with the option defaults of mcmc_clustering_eap_chain.jl:48-51,87-90."""
     if chain_type not in CHAIN_TYPES:
@@ -77,7 +77,8 @@ def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=
     return PmcCase(E0, K1, K2, mu, kT, Fz, Fx, b, phi_step, theta_step, adj_lb, adj_ub, adj_scale,
                    n, steps_per_adjust, CHAIN_TYPES[chain_type], ENERGY_TYPES[energy_type],
                    int(do_flips), int(umbrella), int(force_init), int(accum_mode),
-                   kappa, psi0, cutoff_radius, cluster_prob, int(clustering), int(alpha_carry), int(cutoff_full), 0)
+                   kappa, psi0, cutoff_radius, cluster_prob, int(clustering), int(alpha_carry), int(cutoff_full),
+                   int(planar))
 
 
 def build(force: bool = False) -> str:

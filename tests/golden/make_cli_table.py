@@ -9,7 +9,9 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 JOBS = [("/root/reference/mcmc_eap_chain.jl", os.path.join(HERE, "cli_table.json")),
         # the clustering driver's table, mcmc_clustering_eap_chain.jl:19-153
-        ("/root/reference/mcmc_clustering_eap_chain.jl", os.path.join(HERE, "cli_table_clustering.json"))]
+        ("/root/reference/mcmc_clustering_eap_chain.jl", os.path.join(HERE, "cli_table_clustering.json")),
+        # the 2-D tree's only driver, 2D/mcmc_clustering_eap_chain.jl:19-133
+        ("/root/reference/2D/mcmc_clustering_eap_chain.jl", os.path.join(HERE, "cli_table_clustering_2d.json"))]
 
 # each entry: one or two quoted option strings followed by indented key = value lines
 pat = re.compile(r'^\s*((?:"-[^"]+"\s*,?\s*)+)\n((?:\s+\w+\s*=.*\n)+)', re.M)

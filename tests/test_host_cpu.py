@@ -232,3 +232,28 @@ def test_bucket_and_shard(pm):
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b_ - a_ for a_, b_ in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_planar_cli_table_matches_reference(pm):
+    """Every option of 2D/mcmc_clustering_eap_chain.jl:19-133: same long/short names, types and defaults."""
+    import json
+    from polymc import mcmc_clustering_2d as m2
+    table = json.load(open(os.path.join(ROOT, "tests", "golden", "cli_table_clustering_2d.json")))
+    by_long = {o: a for a in m2.build_parser()._actions for o in a.option_strings if o.startswith("--")}
+    assert len(table) == 28
+    for e in table:
+        assert e["long"] in by_long, e["long"]
+        a = by_long[e["long"]]
+        if e["short"]:
+            assert e["short"] in a.option_strings, (e["long"], e["short"])
+        if e["action"] == ":store_true":
+            assert a.default is False and a.nargs == 0
+        else:
+            want = _julia_default(e["default"])
+            assert a.default == pytest.approx(want) if isinstance(want, float) else a.default == want, e["long"]
+            assert a.type is {"Float64": float, "Int": int, "String": str}[e["arg_type"]]
+    assert "--theta-step" not in by_long and "--bend-mod" not in by_long and "--x0" not in by_long
+    c = m2.case_from_pargs(m2.default_pargs())
+    assert c.planar == 1 and c.clustering == 1 and c.energy_type == 0 and c.theta_step == c.phi_step / 2
+    lines = m2.result_lines_2d([m2.Average(1.0, 2.0)] * 4, [m2.Average(np.array([1.0, 3.0]), 2.0)] * 4, 0.25, 1.0, 10)
+    assert lines[0] == "<r>    =   [0.5, 1.5]" and lines[-1] == "AR     =   0.25" and len(lines) == 10
