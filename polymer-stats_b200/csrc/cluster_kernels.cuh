@@ -316,6 +316,22 @@ __device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, 
   // ---- pair terms: segment × everything (each pair once) and heads [0,lo) × tails (hi,n) ---------------
   if (energy_type == 1 || energy_type == 3) {
     double a = 0.0;
+    const int H = lo, Tl = n - 1 - hi;
+    // short chains (≤ 2 warps): eB = μ_B·D on the fly — a barrier costs more than 3 DFMA per broadcast item;
+    // longer chains: the pre-pass into S.E and its barrier are amortised, and the rectangle loop is unrolled
+    constexpr bool EFLY = (T <= 64);
+    constexpr int UR = (T <= 64) ? 1 : 2;
+    const bool rect = H > 0 && Tl > 0;
+    // lane side = the one that wastes fewer lanes; r = x_L − x_B, so r' = r − D (L = head) or r + D (L = tail)
+    const long long costH = (long long)((H + 31) >> 5) * Tl;
+    const long long costT = (long long)((Tl + 31) >> 5) * H;
+    const bool lanes_are_heads = costH <= costT;
+    const double sgn = lanes_are_heads ? 1.0 : -1.0;
+    const int baseA = lanes_are_heads ? 0 : hi + 1, A = lanes_are_heads ? H : Tl;
+    const int baseB = lanes_are_heads ? hi + 1 : 0, B = lanes_are_heads ? Tl : H;
+    if (!EFLY && rect)
+      for (int k = tid; k < B; k += T)
+        S.E[baseB + k] = sgn * fma(S.mz[baseB + k], Dz, fma(S.my[baseB + k], Dy, S.mx[baseB + k] * Dx));
     for (int c = lo; c <= hi; ++c) {
       const double xi = S.sx[c], yi = S.sy[c], zi = S.sz[c];
       const double oxm = S.mx[c], oym = S.my[c], ozm = S.mz[c];
@@ -340,17 +356,8 @@ __device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, 
                pair_g(oxm, oym, ozm, ux, uy, uz, xi - jx, yi - jy, zi - jz);
       }
     }
-    const int H = lo, Tl = n - 1 - hi;
-    if (H > 0 && Tl > 0) {
-      // lane side = the one that wastes fewer lanes; r = x_L − x_B, so r' = r − D (L = head) or r + D (L = tail)
-      const long long costH = (long long)((H + 31) >> 5) * Tl;
-      const long long costT = (long long)((Tl + 31) >> 5) * H;
-      const bool lanes_are_heads = costH <= costT;
-      const double sgn = lanes_are_heads ? 1.0 : -1.0;
-      a += rect_sum<TEAM, UNROLL, CUT, true>(S, lanes_are_heads ? 0 : hi + 1, lanes_are_heads ? H : Tl,
-                                             lanes_are_heads ? hi + 1 : 0, lanes_are_heads ? Tl : H, sgn * Dx, sgn * Dy,
-                                             sgn * Dz, P.crad2);
-    }
+    if (!EFLY) __syncthreads();  // S.E visible (uniform: every thread of the CTA takes this branch)
+    if (rect) a += rect_sum<TEAM, UR, CUT, EFLY>(S, baseA, A, baseB, B, sgn * Dx, sgn * Dy, sgn * Dz, P.crad2);
     acc[R_PAIR] += a;
   }
   // ---- reduce ------------------------------------------------------------------------------------------

@@ -48,8 +48,24 @@ def main(argv=None) -> int:
         for (name, _), v in zip(axes, combo):
             extra += [f"--{name}", v]
         pargs_list.append(host.parse_args(common + extra))
+    # under torchrun: one rank per GPU, chains sharded by global chain id, one all_gather of the results (NCCL)
+    rank, world, torch_device = 0, int(os.environ.get("WORLD_SIZE", "1")), None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        a.device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(a.device)
+        torch_device = torch.device("cuda", a.device)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch_device)
+        rank = dist.get_rank()
     header, rows, texts = sweep.sweep_table(pargs_list, driver=a.driver, runs=a.runs, seed=a.seed, device=a.device,
-                                            kappaflag=a.kappaflag)
+                                            torch_device=torch_device, kappaflag=a.kappaflag)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
     aggregate.write_table(a.out, header, rows)
     if a.pooled_out:
         ct = pargs_list[0]["chain-type"]

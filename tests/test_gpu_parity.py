@@ -303,7 +303,7 @@ def test_sweep_is_independent_of_gpu_count(pm):
         for rank in range(world):
             for gids, lo, block in sweep.run_shard(cases, replicas, 2000, seed=99, rank=rank, world=world):
                 key = tuple(gids)
-                parts.setdefault(key, np.zeros((len(gids), 35)))[lo:lo + len(block)] = block
+                parts.setdefault(key, np.zeros((len(gids), sweep.NCOL)))[lo:lo + len(block)] = block
         many = sweep.assemble(total, [(np.array(k), v) for k, v in parts.items()])
         for key in ("avg", "acc_rate", "normalizer", "sums"):
             np.testing.assert_array_equal(many[key], one[key])
