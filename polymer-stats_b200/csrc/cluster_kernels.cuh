@@ -617,95 +617,136 @@ __global__ void __launch_bounds__(T) k_delta_segment_cta(const SegDeltaArgs a) {
 // ---------------------------------------------------------------------------------------------
 // One chain per lane: non-interacting and Ising energies (+ bending), O(|cluster|) per trial.
 // ---------------------------------------------------------------------------------------------
+// refl_n! / flip_n! of one monomer by symmetry, without transcendentals: refl_n! maps θ → π−θ, i.e.
+// n̂ → (n̂x, n̂y, −n̂z) with sinθ unchanged (eap_chain.jl:263-265); the planar flip_n! maps ϕ → ϕ+π, i.e. n̂ → −n̂
+// (2D/inc/eap_chain.jl:189-191).  Equal to the reference's recomputed cos/sin in real arithmetic.
+__device__ __forceinline__ void flip_dir(int planar, double nx, double ny, double nz, double& fx, double& fy,
+                                         double& fz) {
+  if (planar) { fx = -nx; fy = -ny; fz = -nz; }
+  else { fx = nx; fy = ny; fz = -nz; }
+}
+
 struct LaneSeg {
   double dOmega, du_self, dbend, dpsi, dcos2, dpair;  // dpair: 4π × Σ(new − old) of U_Ising terms
   double dpx, dpy, dpz, sx, sy, sz;                   // Δp, ΣΔn̂
 };
 
-// n̂', μ', sinθ' of segment monomer c (and its old record).
-struct LaneMono {
-  double nx, ny, nz, mx, my, mz;
-};
+// Contribution of one flipped cluster monomer (not idx) with current direction (nx,ny,nz) to the sums.
+__device__ __forceinline__ void lane_add_flipped(const ChainParams& P, double nx, double ny, double nz, LaneSeg& o) {
+  double fx, fy, fz;
+  flip_dir(P.planar, nx, ny, nz, fx, fy, fz);
+  double ux, uy, uz, vx, vy, vz;
+  mu_of(P, nx, ny, nz, ux, uy, uz);
+  mu_of(P, fx, fy, fz, vx, vy, vz);
+  o.du_self += -0.5 * P.E0 * vz - (-0.5 * P.E0 * uz);
+  o.dpx += vx - ux; o.dpy += vy - uy; o.dpz += vz - uz;
+  o.sx += fx - nx; o.sy += fy - ny; o.sz += fz - nz;
+}
 
-__device__ __forceinline__ void lane_new_mono(const ChainParams& P, const MonoRec* __restrict__ mono, const Proposal& q,
-                                              int c, bool reflect, MonoRec& nrec, double& dOmega) {
-  if (!reflect) {  // c == idx
+// ψ, bending and (Ising) pair-term change of ONE bond between monomers a and b (b = a+1).
+template <bool ISING>
+__device__ __forceinline__ void lane_bond_delta(const ChainParams& P, double aox, double aoy, double aoz, double anx,
+                                                double any_, double anz, double box, double boy, double boz,
+                                                double bnx, double bny, double bnz, LaneSeg& o) {
+  const double psi_old = psi_of(aox, aoy, aoz, box, boy, boz);
+  const double psi_new = psi_of(anx, any_, anz, bnx, bny, bnz);
+  o.dpsi += psi_new - psi_old;
+  o.dbend += ubend_of(P, psi_new) - ubend_of(P, psi_old);
+  if (ISING) {  // U_Ising (eap_chain.jl:215-228): separation x_a − x_b = −(b/2)(n̂_a + n̂_b)
+    const double hb = -0.5 * P.b;
+    double uox, uoy, uoz, unx, uny, unz, vox, voy, voz, vnx, vny, vnz;
+    mu_of(P, aox, aoy, aoz, uox, uoy, uoz);
+    mu_of(P, anx, any_, anz, unx, uny, unz);
+    mu_of(P, box, boy, boz, vox, voy, voz);
+    mu_of(P, bnx, bny, bnz, vnx, vny, vnz);
+    o.dpair += pair_g(unx, uny, unz, vnx, vny, vnz, hb * (anx + bnx), hb * (any_ + bny), hb * (anz + bnz)) -
+               pair_g(uox, uoy, uoz, vox, voy, voz, hb * (aox + box), hb * (aoy + boy), hb * (aoz + boz));
+  }
+}
+
+// Final record of the moved monomer idx: move! (the proposal), then refl_n!/flip_n! if its cluster is flipped.
+// This one is computed literally from the angles (a θ clamped to π reflects to θ = 0 ⇒ sinθ = 0 ⇒ rejection).
+__device__ __forceinline__ void lane_idx_record(const ChainParams& P, const Proposal& q, bool reflect, MonoRec& nrec,
+                                                double& dOmega) {
+  if (!reflect) {
     nrec.phi = q.phi; nrec.theta = q.theta; nrec.nx = q.nx; nrec.ny = q.ny; nrec.nz = q.nz; nrec.sth = q.sth;
     dOmega = q.dOmega;
     return;
   }
-  double phi, theta, sb;
-  segment_angles(mono, q, c, true, P.planar, phi, theta, sb);
+  double phi = q.phi, theta = q.theta;
+  if (P.planar) phi += kPi; else theta = reflect_theta(theta);
   nrec.phi = phi; nrec.theta = theta;
   direction_of(P.planar, phi, theta, nrec.nx, nrec.ny, nrec.nz, nrec.sth);
-  dOmega = P.planar ? 0.0 : (c == q.idx ? q.dOmega : 0.0) + log(nrec.sth / sb);
+  dOmega = P.planar ? 0.0 : q.dOmega + log(nrec.sth / q.sth);
 }
 
-// Changed-term sums of the composite trial on segment [lo,hi] for O(1)-per-bond energies: one sweep over
-// the bonds lo−1..hi, carrying the old and new state of the left monomer of the bond in registers.
+// Changed-term sums of the composite trial for O(1)-per-bond energies.  Reflecting a whole cluster is an
+// orthogonal map of every direction in it (and μ' = ±Rμ for both chain types), so bond angles and
+// nearest-neighbour pair terms INSIDE the cluster are unchanged; what changes is: the bonds next to the moved
+// monomer idx, the two bonds at the ends of the cluster, and the single-monomer sums (u, p, r) of the flipped
+// monomers — no transcendental per cluster monomer.  `o` enters holding the flipped-monomer sums (c ≠ idx).
 template <bool ISING>
-__device__ __forceinline__ void lane_segment_sums(const MonoRec* __restrict__ mono, int n, const ChainParams& P,
-                                                  const MonoRec& rec_idx, const Proposal& q, int lo, int hi,
-                                                  bool reflect, LaneSeg& o, double& nlo_x, double& nlo_y,
-                                                  double& nlo_z, double& nhi_x, double& nhi_y, double& nhi_z) {
-  o.dOmega = o.du_self = o.dbend = o.dpsi = o.dcos2 = o.dpair = 0.0;
-  o.dpx = o.dpy = o.dpz = o.sx = o.sy = o.sz = 0.0;
-  const double hb = -0.5 * P.b;
-  // left neighbour of the segment (unchanged)
-  bool have_left = lo > 0;
-  double lox = 0, loy = 0, loz = 0, lnx = 0, lny = 0, lnz = 0;  // old / new n̂ of the left monomer of the bond
-  if (have_left) {
-    const MonoRec l = mono[lo - 1];
-    lox = lnx = l.nx; loy = lny = l.ny; loz = lnz = l.nz;
+__device__ __forceinline__ void lane_segment_finish(const MonoRec* __restrict__ mono, int n, const ChainParams& P,
+                                                    const MonoRec& rec, const MonoRec& nrec, int idx, int lo, int hi,
+                                                    bool reflect, LaneSeg& o, double& la, double up, double lp) {
+  // the moved monomer
+  {
+    double ux, uy, uz, vx, vy, vz;
+    mu_of(P, rec.nx, rec.ny, rec.nz, ux, uy, uz);
+    mu_of(P, nrec.nx, nrec.ny, nrec.nz, vx, vy, vz);
+    o.du_self += -0.5 * P.E0 * vz - (-0.5 * P.E0 * uz);
+    o.dpx += vx - ux; o.dpy += vy - uy; o.dpz += vz - uz;
+    o.dcos2 += nrec.nz * nrec.nz - rec.nz * rec.nz;
+    o.sx += nrec.nx - rec.nx; o.sy += nrec.ny - rec.ny; o.sz += nrec.nz - rec.nz;
   }
-  for (int c = lo; c <= hi + 1; ++c) {
-    if (c >= n) break;
-    double cox, coy, coz, cnx, cny, cnz;  // old / new n̂ of monomer c
-    if (c <= hi) {
-      const MonoRec orec = (c == q.idx) ? rec_idx : mono[c];
-      MonoRec nrec;
-      double dOm;
-      lane_new_mono(P, mono, q, c, reflect, nrec, dOm);
-      cox = orec.nx; coy = orec.ny; coz = orec.nz;
-      cnx = nrec.nx; cny = nrec.ny; cnz = nrec.nz;
-      double ux, uy, uz, vx, vy, vz;
-      mu_of(P, cox, coy, coz, ux, uy, uz);
-      mu_of(P, cnx, cny, cnz, vx, vy, vz);
-      o.dOmega += dOm;
-      o.du_self += -0.5 * P.E0 * vz - (-0.5 * P.E0 * uz);
-      o.dpx += vx - ux; o.dpy += vy - uy; o.dpz += vz - uz;
-      o.dcos2 += cnz * cnz - coz * coz;
-      o.sx += cnx - cox; o.sy += cny - coy; o.sz += cnz - coz;
-      if (c == lo) { nlo_x = cnx; nlo_y = cny; nlo_z = cnz; }
-      if (c == hi) { nhi_x = cnx; nhi_y = cny; nhi_z = cnz; }
-    } else {  // right neighbour of the segment (unchanged)
-      const MonoRec r = mono[c];
-      cox = cnx = r.nx; coy = cny = r.ny; coz = cnz = r.nz;
-    }
-    if (have_left) {  // bond (c−1, c)
-      const double psi_old = psi_of(lox, loy, loz, cox, coy, coz);
-      const double psi_new = psi_of(lnx, lny, lnz, cnx, cny, cnz);
-      o.dpsi += psi_new - psi_old;
-      o.dbend += ubend_of(P, psi_new) - ubend_of(P, psi_old);
-      if (ISING) {  // separation x_i − x_{i+1} = −(b/2)(n̂_i + n̂_{i+1})
-        double aox, aoy, aoz, anx, any_, anz, box, boy, boz, bnx, bny, bnz;
-        mu_of(P, lox, loy, loz, aox, aoy, aoz);
-        mu_of(P, lnx, lny, lnz, anx, any_, anz);
-        mu_of(P, cox, coy, coz, box, boy, boz);
-        mu_of(P, cnx, cny, cnz, bnx, bny, bnz);
-        o.dpair += pair_g(anx, any_, anz, bnx, bny, bnz, hb * (lnx + cnx), hb * (lny + cny), hb * (lnz + cnz)) -
-                   pair_g(aox, aoy, aoz, box, boy, boz, hb * (lox + cox), hb * (loy + coy), hb * (loz + coz));
-      }
-    }
-    lox = cox; loy = coy; loz = coz; lnx = cnx; lny = cny; lnz = cnz;
-    have_left = true;
+  // bonds (idx−1,idx) and (idx,idx+1)
+  if (idx > 0) {
+    const MonoRec l = mono[idx - 1];
+    double fx = l.nx, fy = l.ny, fz = l.nz;
+    if (reflect && idx - 1 >= lo) flip_dir(P.planar, l.nx, l.ny, l.nz, fx, fy, fz);
+    lane_bond_delta<ISING>(P, l.nx, l.ny, l.nz, fx, fy, fz, rec.nx, rec.ny, rec.nz, nrec.nx, nrec.ny, nrec.nz, o);
   }
+  if (idx + 1 < n) {
+    const MonoRec r = mono[idx + 1];
+    double fx = r.nx, fy = r.ny, fz = r.nz;
+    if (reflect && idx + 1 <= hi) flip_dir(P.planar, r.nx, r.ny, r.nz, fx, fy, fz);
+    lane_bond_delta<ISING>(P, rec.nx, rec.ny, rec.nz, nrec.nx, nrec.ny, nrec.nz, r.nx, r.ny, r.nz, fx, fy, fz, o);
+  }
+  la = 0.0;
+  if (!reflect) return;
+  // the two ends of the cluster (when they are not the bonds of idx) and α (eap_chain.jl:317-330)
+  double nup = 0.0, nlp = 0.0;
+  if (hi < n - 1) {
+    const MonoRec b = mono[hi + 1];
+    double hx, hy, hz;  // new direction of monomer hi
+    if (hi == idx) { hx = nrec.nx; hy = nrec.ny; hz = nrec.nz; }
+    else {
+      const MonoRec t = mono[hi];
+      flip_dir(P.planar, t.nx, t.ny, t.nz, hx, hy, hz);
+      lane_bond_delta<ISING>(P, t.nx, t.ny, t.nz, hx, hy, hz, b.nx, b.ny, b.nz, b.nx, b.ny, b.nz, o);
+    }
+    nup = link_prob(hx, hy, hz, b.nx, b.ny, b.nz);
+  }
+  if (lo > 0) {
+    const MonoRec b = mono[lo - 1];
+    double hx, hy, hz;  // new direction of monomer lo
+    if (lo == idx) { hx = nrec.nx; hy = nrec.ny; hz = nrec.nz; }
+    else {
+      const MonoRec t = mono[lo];
+      flip_dir(P.planar, t.nx, t.ny, t.nz, hx, hy, hz);
+      lane_bond_delta<ISING>(P, b.nx, b.ny, b.nz, b.nx, b.ny, b.nz, t.nx, t.ny, t.nz, hx, hy, hz, o);
+    }
+    nlp = link_prob(hx, hy, hz, b.nx, b.ny, b.nz);
+  }
+  la = log(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
 }
 
-// Sequential cluster growth for one lane (eap_chain.jl:276-305).
-__device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mono, const Proposal& q, int n,
-                                                  uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
-                                                  int& lo, int& hi, double& up, double& lp) {
+// Sequential cluster growth for one lane (eap_chain.jl:276-305) on the chain carrying the move; every monomer
+// that joins the cluster adds its flipped-monomer sums on the way.
+__device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mono, const Proposal& q,
+                                                  const ChainParams& P, int n, uint64_t seed, uint32_t chain_id,
+                                                  uint32_t init, long long step, int& lo, int& hi, double& up,
+                                                  double& lp, LaneSeg& o) {
   const int idx = q.idx;
   hi = idx;
   double ax = q.nx, ay = q.ny, az = q.nz;
@@ -713,8 +754,10 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
     if (hi >= n - 1) { up = 0.0; break; }
     const MonoRec b = mono[hi + 1];
     up = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
-    if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_UP, k) <= up) { hi += 1; ax = b.nx; ay = b.ny; az = b.nz; }
-    else break;
+    if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_UP, k) <= up) {
+      hi += 1; ax = b.nx; ay = b.ny; az = b.nz;
+      lane_add_flipped(P, b.nx, b.ny, b.nz, o);
+    } else break;
   }
   lo = idx;
   ax = q.nx; ay = q.ny; az = q.nz;
@@ -722,9 +765,16 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
     if (lo <= 0) { lp = 0.0; break; }
     const MonoRec b = mono[lo - 1];
     lp = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
-    if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k) <= lp) { lo -= 1; ax = b.nx; ay = b.ny; az = b.nz; }
-    else break;
+    if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k) <= lp) {
+      lo -= 1; ax = b.nx; ay = b.ny; az = b.nz;
+      lane_add_flipped(P, b.nx, b.ny, b.nz, o);
+    } else break;
   }
+}
+
+__device__ __forceinline__ void lane_seg_zero(LaneSeg& o) {
+  o.dOmega = o.du_self = o.dbend = o.dpsi = o.dcos2 = o.dpair = 0.0;
+  o.dpx = o.dpy = o.dpz = o.sx = o.sy = o.sz = 0.0;
 }
 
 template <int T, int MINB, bool ISING, bool COMP>
@@ -755,17 +805,13 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
       const bool g = draw_cluster_gate(a.seed, chain_id, (uint32_t)D.init, step) <= P.cluster_prob;
       reflect = P.planar ? g : !g;  // the gate has opposite senses in the two trees (see warp_cluster_grow)
     }
-    if (reflect) lane_cluster_grow(mono, q, n, a.seed, chain_id, (uint32_t)D.init, step, lo, hi, up, lp);
     LaneSeg g;
-    double nlx = 0, nly = 0, nlz = 0, nhx = 0, nhy = 0, nhz = 0;
-    lane_segment_sums<ISING>(mono, n, P, rec, q, lo, hi, reflect, g, nlx, nly, nlz, nhx, nhy, nhz);
-    double la = 0.0;
-    if (reflect) {  // eap_chain.jl:317-330
-      double nup = 0.0, nlp = 0.0;
-      if (hi < n - 1) { const MonoRec b = mono[hi + 1]; nup = link_prob(nhx, nhy, nhz, b.nx, b.ny, b.nz); }
-      if (lo > 0) { const MonoRec b = mono[lo - 1]; nlp = link_prob(nlx, nly, nlz, b.nx, b.ny, b.nz); }
-      la = log(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
-    }
+    lane_seg_zero(g);
+    if (reflect) lane_cluster_grow(mono, q, P, n, a.seed, chain_id, (uint32_t)D.init, step, lo, hi, up, lp, g);
+    MonoRec nrec;
+    lane_idx_record(P, q, reflect, nrec, g.dOmega);
+    double la;
+    lane_segment_finish<ISING>(mono, n, P, rec, nrec, d.idx, lo, hi, reflect, g, la, up, lp);
     const double Dx = P.b * g.sx, Dy = P.b * g.sy, Dz = P.b * g.sz;
     const double dpairs = kInv4Pi * g.dpair;
     const double dsu = g.du_self + g.dbend;
@@ -774,12 +820,15 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
     const double dlogpi = -dU * P.inv_kT + g.dOmega + dw + la - DX.carry;
     const bool accept = metropolis(dlogpi, q.eps);
     if (accept) {
-      for (int k = lo; k <= hi; ++k) {
-        MonoRec nrec;
-        double dOm;
-        lane_new_mono(P, mono, q, k, reflect, nrec, dOm);
-        mono[k] = nrec;
-      }
+      if (reflect)
+        for (int k = lo; k <= hi; ++k) {
+          if (k == d.idx) continue;
+          MonoRec r = mono[k];  // refl_n! / flip_n! of the record
+          if (P.planar) { r.phi += kPi; r.nx = -r.nx; r.ny = -r.ny; r.nz = -r.nz; }
+          else { r.theta = reflect_theta(r.theta); r.nz = -r.nz; }
+          mono[k] = r;
+        }
+      mono[d.idx] = nrec;
       D.U += dU; D.Omega += g.dOmega; D.su += dsu;
       D.r[0] += Dx; D.r[1] += Dy; D.r[2] += Dz;
       D.p[0] += g.dpx; D.p[1] += g.dpy; D.p[2] += g.dpz;
@@ -829,27 +878,32 @@ __global__ void k_delta_segment_lane(const SegDeltaArgs a) {
   const bool reflect = a.reflect != 0;
   const int lo = reflect ? a.lo : a.idx, hi = reflect ? a.hi : a.idx;
   LaneSeg g;
-  double nlx = 0, nly = 0, nlz = 0, nhx = 0, nhy = 0, nhz = 0;
-  lane_segment_sums<ISING>(mono, n, P, rec, q, lo, hi, reflect, g, nlx, nly, nlz, nhx, nhy, nhz);
-  double la = 0.0;
+  lane_seg_zero(g);
+  double up = 0.0, lp = 0.0;
   if (reflect) {
-    double up = 0.0, lp = 0.0, nup = 0.0, nlp = 0.0;
+    for (int k = lo; k <= hi; ++k) {
+      if (k == a.idx) continue;
+      const MonoRec r = mono[k];
+      lane_add_flipped(P, r.nx, r.ny, r.nz, g);
+    }
+    // link probabilities before the flip, on the chain carrying the move
     if (hi < n - 1) {
       const MonoRec b = mono[hi + 1];
       const MonoRec t = mono[hi];
       const bool m = hi == a.idx;
       up = link_prob(m ? q.nx : t.nx, m ? q.ny : t.ny, m ? q.nz : t.nz, b.nx, b.ny, b.nz);
-      nup = link_prob(nhx, nhy, nhz, b.nx, b.ny, b.nz);
     }
     if (lo > 0) {
       const MonoRec b = mono[lo - 1];
       const MonoRec t = mono[lo];
       const bool m = lo == a.idx;
       lp = link_prob(m ? q.nx : t.nx, m ? q.ny : t.ny, m ? q.nz : t.nz, b.nx, b.ny, b.nz);
-      nlp = link_prob(nlx, nly, nlz, b.nx, b.ny, b.nz);
     }
-    la = log(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
   }
+  MonoRec nrec;
+  lane_idx_record(P, q, reflect, nrec, g.dOmega);
+  double la;
+  lane_segment_finish<ISING>(mono, n, P, rec, nrec, a.idx, lo, hi, reflect, g, la, up, lp);
   const double Dx = P.b * g.sx, Dz = P.b * g.sz;
   const double dpairs = kInv4Pi * g.dpair;
   a.out[0] = g.du_self + g.dbend - (Dx * P.Fx + Dz * P.Fz) + dpairs;
