@@ -116,13 +116,55 @@ struct ChainDynX {
 // ---------------------------------------------------------------------------------------------
 // 1/sqrt(x) to ≈1 ulp: MUFU.RSQ64H seed + one cubically convergent correction
 //   y ← y (1 + e/2 + 3e²/8), e = 1 - x y²   (seed error ≲2^-20 ⇒ result error ≲2^-60).
-__device__ __forceinline__ double rsqrt_fast(double x) {
+__device__ __forceinline__ double rsqrt_cubic(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double e = fma(-x, y * y, 1.0);
   const double t = fma(e, 0.375, 0.5);
   return fma(y * e, t, y);
 }
+
+#ifndef PMC_RSQRT_VARIANT
+#define PMC_RSQRT_VARIANT 0
+#endif
+#if PMC_RSQRT_VARIANT != 0
+// Measured negative result (tools/rect_bench.cu, profiles/r01f_rect_bench_rsqrt_variants.txt), not in the product
+// build: 3 instead of 5 FP64-pipe instructions per 1/sqrt by refining the seed on the FP32 pipe (MUFU.RSQ of the
+// rounded x + one FP32 Newton step, error ≲2^-23) and one quadratic FP64 step y ← y + (y/2)e (≲3e-14 relative).
+// The FP64 pipe takes an issue slot every other cycle and the rectangle loop already fills most of the others,
+// so the ≈16 extra FP32/integer/XU instructions per 1/sqrt cost more than the 2 DFMA they save.
+// Variant 1: F2F width conversions; 2: conversions on the integer pipe; 3: 2 without the range check.
+__device__ __forceinline__ double rsqrt_mixed(double x) {
+#if PMC_RSQRT_VARIANT == 1
+  const float xf = (float)x;
+#else
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+#if PMC_RSQRT_VARIANT == 2
+  if ((unsigned)(hi - 0x38100000) >= 0x0fe00000u) return rsqrt_cubic(x);  // outside the FP32 normal range
+#endif
+  const float xf = __int_as_float(__funnelshift_l(lo, hi - 0x38000000, 3));  // truncated, not rounded
+#endif
+  float yf;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(xf));
+  const float ef = fmaf(-(xf * yf), yf, 1.0f);
+  yf = fmaf(0.5f * yf, ef, yf);
+#if PMC_RSQRT_VARIANT == 1
+  if (!(fabsf(ef) <= 1e-3f)) return rsqrt_cubic(x);
+  const double y = (double)yf;
+  const int yhi = __double2hiint(y), ylo = __double2loint(y);
+#else
+  const int yb = __float_as_int(yf);
+  const int yhi = (yb >> 3) + 0x38000000, ylo = yb << 29;
+  const double y = __hiloint2double(yhi, ylo);
+#endif
+  const double h = __hiloint2double(yhi - 0x00100000, ylo);  // y/2
+  const double e = fma(-x, y * y, 1.0);
+  return fma(h, e, y);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) { return rsqrt_mixed(x); }
+#else
+__device__ __forceinline__ double rsqrt_fast(double x) { return rsqrt_cubic(x); }
+#endif
 
 // 4π × one dipole-dipole pair term (eap_chain.jl:200-207): μa·μb/r³ − 3(μa·r)(μb·r)/r⁵.
 __device__ __forceinline__ double pair_g(double ax, double ay, double az, double bx, double by, double bz,
@@ -293,23 +335,42 @@ __device__ __forceinline__ bool metropolis(double dlogpi, double eps) {
 }
 
 // Step-size adaptation, mcmc_eap_chain.jl:301-322 (counters reset only when a change fires).
-__device__ __forceinline__ void adapt_steps(const ChainParams& P, long long step, double& phi_step,
-                                            double& theta_step, long long& nacc, long long& natt) {
-  if (P.adj_scale != 1.0 && P.steps_per_adjust > 0 && step % P.steps_per_adjust == 0) {
-    const double ratio = (double)nacc / (double)natt;
-    if (ratio > P.adj_ub && phi_step != kPi && theta_step != kPi / 2) {
-      nacc = 0;
-      natt = 0;
-      phi_step = fmin(kPi, phi_step * P.adj_scale);
-      theta_step = fmin(kPi / 2, theta_step * P.adj_scale);
-    } else if (ratio < P.adj_lb) {
-      nacc = 0;
-      natt = 0;
-      phi_step /= P.adj_scale;
-      theta_step /= P.adj_scale;
-    }
+__device__ __forceinline__ void adapt_apply(const ChainParams& P, double& phi_step, double& theta_step,
+                                            long long& nacc, long long& natt) {
+  const double ratio = (double)nacc / (double)natt;
+  if (ratio > P.adj_ub && phi_step != kPi && theta_step != kPi / 2) {
+    nacc = 0;
+    natt = 0;
+    phi_step = fmin(kPi, phi_step * P.adj_scale);
+    theta_step = fmin(kPi / 2, theta_step * P.adj_scale);
+  } else if (ratio < P.adj_lb) {
+    nacc = 0;
+    natt = 0;
+    phi_step /= P.adj_scale;
+    theta_step /= P.adj_scale;
   }
 }
+
+__device__ __forceinline__ void adapt_steps(const ChainParams& P, long long step, double& phi_step,
+                                            double& theta_step, long long& nacc, long long& natt) {
+  if (P.adj_scale != 1.0 && P.steps_per_adjust > 0 && step % P.steps_per_adjust == 0)
+    adapt_apply(P, phi_step, theta_step, nacc, natt);
+}
+
+// `step % period == 0` for consecutive steps without the 64-bit division: trials left until the next multiple.
+struct Countdown {
+  long long left, period;
+  __device__ __forceinline__ void start(long long step0, long long per) {  // the first step seen is step0 + 1
+    period = per;
+    left = per > 0 ? per - (step0 % per) : -1;
+  }
+  __device__ __forceinline__ bool tick() {
+    if (period <= 0) return false;
+    if (--left != 0) return false;
+    left = period;
+    return true;
+  }
+};
 
 // record! of the 8 averagers (average.jl:40-48; umbrella :63-73) on the current state.
 template <bool COMP = true>

@@ -25,26 +25,40 @@ struct ClusterCtl {
   int idx, lo, hi, reflect;
   double up, lp;      // link probabilities at the two ends of the cluster before the flip (eap_chain.jl:276-305)
   double Dx, Dy, Dz;  // tail translation bΣΔn̂ of a segment built by warp 0
+  unsigned dirty;     // proposals of the current window invalidated by an accepted trial
+  unsigned pad;
 };
+
+// What the composite trial needs of the single-monomer move (a Proposal without the single-monomer energy terms,
+// which the segment sums recompute), plus the gate decision of cluster_flip!: one entry of the proposal window.
+struct ClProposal {
+  double nx, ny, nz, sth;  // n̂', sinθ'
+  double phi, theta;       // new angles
+  double dOmega, eps;
+  int idx, reflect;
+};
+
+constexpr int kClWin = 32;  // proposals built at once, one per lane of warp 0
 
 struct ClView {
   double *nhx, *nhy, *nhz;  // n̂_i of the current state (eap_chain.jl:27)
   double *nnx, *nny, *nnz;  // n̂'_i of the trial, valid on the segment
   double *xnx, *xny, *xnz;  // x'_i of the trial, valid on the segment
   double *psi, *psn;        // bond angles ψ_i of the current state (eap_chain.jl:29) and of the trial (bonds lo−1..hi)
-  double* red;              // [kNumRed][32] warp partials
+  double* red;              // [kNumRed][warps] warp partials
+  ClProposal* win;          // [kClWin]
   ClusterCtl* ctl;
   ChainDynX* dx;
 };
 
-__host__ __device__ inline size_t cluster_smem_bytes(int n) {
+__host__ __device__ inline size_t cluster_smem_bytes(int n, int threads) {
   size_t b = cta_smem_bytes(n);
-  b += (size_t)11 * n * sizeof(double) + (size_t)kNumRed * 32 * sizeof(double);
-  b += sizeof(ClusterCtl) + sizeof(ChainDynX);
+  b += (size_t)11 * n * sizeof(double) + (size_t)kNumRed * (threads / 32) * sizeof(double);
+  b += kClWin * sizeof(ClProposal) + sizeof(ClusterCtl) + sizeof(ChainDynX);
   return (b + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ ClView carve_cluster(unsigned char* base, int n) {
+__device__ __forceinline__ ClView carve_cluster(unsigned char* base, int n, int threads) {
   ClView X;
   double* d = reinterpret_cast<double*>(base + cta_smem_bytes(n));
   X.nhx = d; X.nhy = d + n; X.nhz = d + 2 * n;
@@ -52,7 +66,8 @@ __device__ __forceinline__ ClView carve_cluster(unsigned char* base, int n) {
   X.xnx = d + 6 * n; X.xny = d + 7 * n; X.xnz = d + 8 * n;
   X.psi = d + 9 * n; X.psn = d + 10 * n;
   X.red = d + 11 * n;
-  X.ctl = reinterpret_cast<ClusterCtl*>(X.red + kNumRed * 32);
+  X.win = reinterpret_cast<ClProposal*>(X.red + kNumRed * (threads / 32));
+  X.ctl = reinterpret_cast<ClusterCtl*>(X.win + kClWin);
   X.dx = reinterpret_cast<ChainDynX*>(X.ctl + 1);
   return X;
 }
@@ -60,20 +75,20 @@ __device__ __forceinline__ ClView carve_cluster(unsigned char* base, int n) {
 // n̂ and the bond angles ψ of the staged chain.  Ends with a barrier.
 template <int T>
 __device__ __forceinline__ void load_nhat(const MonoRec* __restrict__ mono, int n, const ClView& X) {
-  for (int i = threadIdx.x; i < n; i += T) {
+  for (int i = team_tid<T>(); i < n; i += T) {
     const MonoRec r = mono[i];
     X.nhx[i] = r.nx; X.nhy[i] = r.ny; X.nhz[i] = r.nz;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i + 1 < n; i += T)
+  team_sync<T>();
+  for (int i = team_tid<T>(); i + 1 < n; i += T)
     X.psi[i] = psi_of(X.nhx[i], X.nhy[i], X.nhz[i], X.nhx[i + 1], X.nhy[i + 1], X.nhz[i + 1]);
-  __syncthreads();
+  team_sync<T>();
 }
 
 // n̂ of monomer i on the chain that carries the single-monomer move (cluster_flip! runs on the trial
 // chain AFTER move!, mcmc_clustering_eap_chain.jl:272-273).
-__device__ __forceinline__ void nhat_trial(const ClView& X, const Proposal& q, int i, double& x, double& y,
-                                           double& z) {
+template <class PQ>
+__device__ __forceinline__ void nhat_trial(const ClView& X, const PQ& q, int i, double& x, double& y, double& z) {
   if (i == q.idx) { x = q.nx; y = q.ny; z = q.nz; }
   else { x = X.nhx[i]; y = X.nhy[i]; z = X.nhz[i]; }
 }
@@ -90,25 +105,41 @@ __device__ __forceinline__ void make_proposal_cl(const RunArgs& a, const ChainPa
   else build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
 }
 
+// The gate of cluster_flip!.  3-D: `if rand() <= ϵflip; return 1.0; end` BEFORE the growth (eap_chain.jl:273):
+// flips with 1 − ϵflip;  2-D: `if rand() <= ϵflip … flip` AFTER the growth (2D/inc/eap_chain.jl:233): flips with ϵflip.
+__device__ __forceinline__ int cluster_gate(const ChainParams& P, uint64_t seed, uint32_t chain_id, uint32_t init,
+                                            long long step) {
+  if (!P.clustering) return 0;
+  const double gate = draw_cluster_gate(seed, chain_id, init, step);
+  return P.planar ? (gate <= P.cluster_prob) : !(gate <= P.cluster_prob);
+}
+
+// One entry of the proposal window: everything of trial `step` that depends on the chain only through the record
+// of its own monomer.
+__device__ __forceinline__ void make_window_entry(const RunArgs& a, const ChainParams& P, const ChainDyn& D,
+                                                  const MonoRec* mono, uint32_t chain_id, long long step,
+                                                  ClProposal& w) {
+  Proposal q;
+  make_proposal_cl(a, P, D, mono, chain_id, step, q);
+  w.nx = q.nx; w.ny = q.ny; w.nz = q.nz; w.sth = q.sth;
+  w.phi = q.phi; w.theta = q.theta;
+  w.dOmega = q.dOmega; w.eps = q.eps;
+  w.idx = q.idx;
+  w.reflect = cluster_gate(P, a.seed, chain_id, (uint32_t)D.init, step);
+}
+
 // cluster_flip! up to the flips (eap_chain.jl:273-309), by one warp: the growth draws are counter-based,
 // so 32 bonds are tested per round and the first failing one ends the growth — same result as the
 // reference's sequential loop on the same uniforms.
-__device__ __forceinline__ void warp_cluster_grow(const ClView& X, const Proposal& q, const ChainParams& P, int n,
+template <class PQ>
+__device__ __forceinline__ void warp_cluster_grow(const ClView& X, const PQ& q, int reflect, const ChainParams& P, int n,
                                                   uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
                                                   ClusterCtl& out) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int idx = q.idx;
-  int lo = idx, hi = idx, reflect = 0;
+  int lo = idx, hi = idx;
   double up = 0.0, lp = 0.0;
-  if (P.clustering) {
-    double gate = 0.0;
-    if (lane == 0) gate = draw_cluster_gate(seed, chain_id, init, step);
-    gate = __shfl_sync(FULL, gate, 0);
-    // 3-D: `if rand() <= ϵflip; return 1.0; end` BEFORE the growth (eap_chain.jl:273): flips with 1 − ϵflip;
-    // 2-D: `if rand() <= ϵflip … flip` AFTER the growth (2D/inc/eap_chain.jl:233): flips with ϵflip
-    reflect = P.planar ? (gate <= P.cluster_prob) : !(gate <= P.cluster_prob);
-  }
   if (reflect) {
     // upward: bond (u,u+1), eap_chain.jl:276-289
     for (int k0 = 0;; k0 += 32) {
@@ -161,7 +192,8 @@ __device__ __forceinline__ void warp_cluster_grow(const ClView& X, const Proposa
 
 // New angles of segment monomer c: move! for idx (already in the proposal), then refl_n! if the cluster
 // is flipped.  Returns ϕ', θ'.
-__device__ __forceinline__ void segment_angles(const MonoRec* __restrict__ mono, const Proposal& q, int c,
+template <class PQ>
+__device__ __forceinline__ void segment_angles(const MonoRec* __restrict__ mono, const PQ& q, int c,
                                                bool reflect, int planar, double& phi, double& theta,
                                                double& sth_before) {
   if (c == q.idx) {
@@ -190,14 +222,34 @@ __device__ __forceinline__ void direction_of(int planar, double phi, double thet
   }
 }
 
+// refl_n! / flip_n! of one monomer by symmetry, without transcendentals: refl_n! maps θ → π−θ, i.e.
+// n̂ → (n̂x, n̂y, −n̂z) with sinθ unchanged (eap_chain.jl:263-265); the planar flip_n! maps ϕ → ϕ+π, i.e. n̂ → −n̂
+// (2D/inc/eap_chain.jl:189-191).  Equal to the reference's recomputed cos/sin in real arithmetic.
+__device__ __forceinline__ void flip_dir(int planar, double nx, double ny, double nz, double& fx, double& fy,
+                                         double& fz) {
+  if (planar) { fx = -nx; fy = -ny; fz = -nz; }
+  else { fx = nx; fy = ny; fz = -nz; }
+}
+
+// S.E[c] of a segment monomer whose record keeps its sinθ (flipped by symmetry).
+constexpr double kKeepSinTheta = -1.0;
+
 // New direction of segment monomer c: n̂', sinθ' and this monomer's share of the changed single-monomer sums.
+template <class PQ>
 __device__ __forceinline__ void segment_monomer(const CtaView& S, const ClView& X, const MonoRec* __restrict__ mono,
-                                                const ChainParams& P, const Proposal& q, int c, bool reflect,
+                                                const ChainParams& P, const PQ& q, int c, bool reflect,
                                                 double* acc, double& dnx, double& dny, double& dnz) {
   double nx, ny, nz, sth;
   if (!reflect) {  // the segment is idx alone
     nx = q.nx; ny = q.ny; nz = q.nz; sth = q.sth;
     acc[R_OMEGA] += q.dOmega;
+  } else if (c != q.idx && (P.planar || X.nhz[c] != -1.0)) {
+    // refl_n! / flip_n! of an unmoved monomer by symmetry, no transcendental: θ → π−θ is n̂ → (n̂x, n̂y, −n̂z)
+    // with sinθ and hence Ω unchanged (eap_chain.jl:263-265); the planar ϕ → ϕ+π is n̂ → −n̂.  A monomer
+    // sitting at θ = π (cosθ = −1) reflects to sinθ' = 0 exactly and goes the literal way below.
+    double ox = X.nhx[c], oy = X.nhy[c], oz = X.nhz[c];
+    flip_dir(P.planar, ox, oy, oz, nx, ny, nz);
+    sth = kKeepSinTheta;  // the record keeps its sinθ
   } else {
     double phi, theta, sb;
     segment_angles(mono, q, c, true, P.planar, phi, theta, sb);
@@ -219,8 +271,9 @@ __device__ __forceinline__ void segment_monomer(const CtaView& S, const ClView& 
 // Segments of at most 32 monomers (nearly all of them) are built by the warp that selected the cluster:
 // one monomer per lane, positions by a warp scan (update_xs! restricted to the segment, eap_chain.jl:49-51).
 // Leaves n̂', x' in X.nn / X.xn, sinθ' in S.E, D = bΣΔn̂ in ctl; the lanes keep their partial sums in acc.
+template <class PQ>
 __device__ __forceinline__ void warp_segment_build(const CtaView& S, const ClView& X, const MonoRec* __restrict__ mono,
-                                                   const ChainParams& P, const Proposal& q, int lo, int hi,
+                                                   const ChainParams& P, const PQ& q, int lo, int hi,
                                                    bool reflect, double* acc, ClusterCtl& ctl) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -245,12 +298,12 @@ __device__ __forceinline__ void warp_segment_build(const CtaView& S, const ClVie
 
 // The same for longer segments, by the whole CTA: contiguous chunks per thread and a block scan.
 // Contains two CTA barriers.
-template <int T>
+template <int T, class PQ>
 __device__ __forceinline__ void cta_segment_build(const CtaView& S, const ClView& X, const MonoRec* __restrict__ mono,
-                                                  const ChainParams& P, const Proposal& q, int lo, int hi,
+                                                  const ChainParams& P, const PQ& q, int lo, int hi,
                                                   bool reflect, double* acc, double& Dx, double& Dy, double& Dz) {
   constexpr int W = T / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = team_tid<T>(), lane = tid & 31, warp = tid >> 5;
   const int m = hi - lo + 1;
   const int C = (m + T - 1) / T;
   const int c0 = min(hi + 1, lo + tid * C), c1 = min(hi + 1, c0 + C);
@@ -269,7 +322,7 @@ __device__ __forceinline__ void cta_segment_build(const CtaView& S, const ClView
     if (lane >= o) { ix += tx; iy += ty; iz += tz; }
   }
   if (lane == 31) { S.part[warp] = ix; S.part[32 + warp] = iy; S.part[64 + warp] = iz; }
-  __syncthreads();
+  team_sync<T>();
   double ox = 0, oy = 0, oz = 0, tx = 0, ty = 0, tz = 0;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
@@ -286,7 +339,7 @@ __device__ __forceinline__ void cta_segment_build(const CtaView& S, const ClView
     sxx += dx; syy += dy; szz += dz;
   }
   Dx = P.b * tx; Dy = P.b * ty; Dz = P.b * tz;
-  __syncthreads();  // X.nn, X.xn, S.E visible
+  team_sync<T>();  // X.nn, X.xn, S.E visible
 }
 
 // The changed-term sums over bonds and pairs for a built segment, added to this thread's acc and reduced
@@ -296,8 +349,8 @@ __device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, 
                                              int energy_type, int lo, int hi, double Dx, double Dy, double Dz,
                                              double* acc, double* sums) {
   constexpr int W = T / 32;
-  using TEAM = Team<W, 0>;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  using TEAM = typename std::conditional<T == 32, WarpTeam, Team<W, 0>>::type;
+  const int tid = team_tid<T>(), lane = tid & 31, warp = tid >> 5;
   // ---- bonds lo−1..hi: ψ and bending energy (eap_chain.jl:45-47,54-58,246-251) ---------------------------
   {
     const int b0 = max(lo - 1, 0), b1 = min(hi, n - 2);
@@ -356,7 +409,7 @@ __device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, 
                pair_g(oxm, oym, ozm, ux, uy, uz, xi - jx, yi - jy, zi - jz);
       }
     }
-    if (!EFLY) __syncthreads();  // S.E visible (uniform: every thread of the CTA takes this branch)
+    if (!EFLY) team_sync<T>();  // S.E visible (uniform: every thread of the CTA takes this branch)
     if (rect) a += rect_sum<TEAM, UR, CUT, EFLY>(S, baseA, A, baseB, B, sgn * Dx, sgn * Dy, sgn * Dz, P.crad2);
     acc[R_PAIR] += a;
   }
@@ -364,14 +417,14 @@ __device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, 
 #pragma unroll
   for (int k = 0; k < kNumRed; ++k) {
     const double v = warp_sum(acc[k]);
-    if (lane == 0) X.red[k * 32 + warp] = v;
+    if (lane == 0) X.red[k * W + warp] = v;
   }
-  __syncthreads();
+  team_sync<T>();
 #pragma unroll
   for (int k = 0; k < kNumRed; ++k) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < W; ++w) s += X.red[k * 32 + w];
+    for (int w = 0; w < W; ++w) s += X.red[k * W + w];
     sums[k] = s;
   }
   sums[R_PAIR] *= kInv4Pi;
@@ -400,13 +453,14 @@ __device__ __forceinline__ void record_extras(const ChainParams& P, ChainDynX& D
 }
 
 // Step adaptation, the 8 + 2 averagers: everything after the decision (mcmc_clustering_eap_chain.jl:287-311).
-__device__ __forceinline__ void bookkeep_cluster(const ChainParams& P, ChainDyn& D, ChainDynX& DX, long long step, int n,
+__device__ __forceinline__ void bookkeep_cluster(const ChainParams& P, ChainDyn& D, ChainDynX& DX, bool adapt_now, int n,
                                                  bool compensated) {
+  if (adapt_now) adapt_apply(P, D.phi_step, D.theta_step, D.nacc, D.natt);
   if (compensated) {
-    bookkeep<true>(P, D, step);
+    record_averages<true>(P, D.acc, D.comp, D.r, D.p, D.U, D.su, D.log_gauge);
     record_extras<true>(P, DX, D.su, D.log_gauge, n);
   } else {
-    bookkeep<false>(P, D, step);
+    record_averages<false>(P, D.acc, D.comp, D.r, D.p, D.U, D.su, D.log_gauge);
     record_extras<false>(P, DX, D.su, D.log_gauge, n);
   }
 }
@@ -439,15 +493,23 @@ __device__ __forceinline__ void stage_row_cluster(const ChainDyn& D, const Chain
 
 constexpr int kRowDoublesCluster = 28;
 
-// The hot loop of mcmc_clustering_eap_chain.jl:267-336 for one chain per CTA.
+// The hot loop of mcmc_clustering_eap_chain.jl:267-336 for one chain per CTA (T = 32: a one-warp CTA, the team
+// barriers are __syncwarp).
+//
+// Proposal window, as in k_run_cta_win: the serial head of a trial (3 Philox blocks, 2 sincos, log, the record
+// read from HBM/L2) is taken off the per-trial critical path by building the single-monomer moves and the gate
+// decisions of the next kClWin trials at once, one trial per lane of warp 0.  A window entry depends on the
+// chain only through the record of its own monomer: an accepted trial marks the later entries whose monomer
+// lies in its segment [lo, hi] dirty and those are rebuilt when their turn comes.  Windows never cross a
+// step-size adaptation boundary.  The cluster growth reads the neighbours' current directions and stays per trial.
 template <int T, int MINB, bool CUT>
 __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const CtaView S = carve(smem_raw, a.n);
-  const ClView X = carve_cluster(smem_raw, a.n);
   __shared__ double rowbuf[kRowDoublesCluster];
+  const CtaView S = carve(smem_raw, a.n);
+  const ClView X = carve_cluster(smem_raw, a.n, T);
   const int c = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = team_tid<T>();
   const int n = a.n;
   MonoRec* mono = a.mono + (size_t)c * n;
   if (tid == 0) {
@@ -455,103 +517,133 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
     *S.dyn = a.dyn[c];
     *X.dx = a.dynx[c];
   }
-  __syncthreads();
+  team_sync<T>();
   const ChainParams& P = *S.par;
   load_chain<T>(mono, P, n, S);
   load_nhat<T>(mono, n, X);
   const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
   const long long step0 = S.dyn->step;
   const uint32_t init = (uint32_t)S.dyn->init;
+  const bool adapt_on = P.adj_scale != 1.0 && P.steps_per_adjust > 0;
   long long row = 0;
-  Proposal* q = &S.prop[0];
+  Countdown row_due;
+  row_due.start(step0, a.stepout);
 
-  for (long long s = 1; s <= a.nsteps; ++s) {
-    const long long step = step0 + s;
-    __syncthreads();  // state of the previous trial (records, n̂, x, μ) is visible
-    double acc[kNumRed];
-#pragma unroll
-    for (int k = 0; k < kNumRed; ++k) acc[k] = 0.0;
+  long long s = 1;
+  while (s <= a.nsteps) {
+    // ---- window [s, s+wlen) ------------------------------------------------------------------------------
+    long long wl = a.nsteps - s + 1;
+    if (wl > kClWin) wl = kClWin;
+    long long to_boundary = 0;  // trials until the adaptation rule runs (0: never)
+    if (adapt_on) {
+      to_boundary = P.steps_per_adjust - ((step0 + s - 1) % P.steps_per_adjust);  // ≥ 1
+      if (wl > to_boundary) wl = to_boundary;
+    }
+    const int wlen = (int)wl;
     if (tid < 32) {
-      if (tid == 0) make_proposal_cl(a, P, *S.dyn, mono, chain_id, step, *q);
-      __syncwarp();
-      warp_cluster_grow(X, *q, P, n, a.seed, chain_id, init, step, *X.ctl);
-      __syncwarp();
-      if (X.ctl->hi - X.ctl->lo < 32)
-        warp_segment_build(S, X, mono, P, *q, X.ctl->lo, X.ctl->hi, X.ctl->reflect != 0, acc, *X.ctl);
+      if (tid < wlen) make_window_entry(a, P, *S.dyn, mono, chain_id, step0 + s + tid, X.win[tid]);
+      if (tid == 0) X.ctl->dirty = 0u;
     }
-    __syncthreads();  // proposal, cluster and (short) segment are visible
-    const int idx = X.ctl->idx, lo = X.ctl->lo, hi = X.ctl->hi;
-    const bool reflect = X.ctl->reflect != 0;
-    const double carry = X.dx->carry;
-    double sums[kNumRed], Dx = X.ctl->Dx, Dy = X.ctl->Dy, Dz = X.ctl->Dz;
-    if (hi - lo >= 32) cta_segment_build<T>(S, X, mono, P, *q, lo, hi, reflect, acc, Dx, Dy, Dz);
-    segment_sums<T, CUT>(S, X, P, n, a.energy_type, lo, hi, Dx, Dy, Dz, acc, sums);
-    const double la = reflect ? cluster_log_alpha(X, n, lo, hi, X.ctl->up, X.ctl->lp) : 0.0;
-    const SegDecision dec = segment_decision(P, a.energy_type, sums, Dx, Dz, la, carry);
-    const bool accept = metropolis(dec.dlogpi, q->eps);
-    if (accept) {  // the trial chain becomes the chain (mcmc_clustering_eap_chain.jl:274-275)
-      for (int k = lo + tid; k <= hi; k += T) {
-        double phi, theta, sb;
-        segment_angles(mono, *q, k, reflect, P.planar, phi, theta, sb);
-        MonoRec rec;
-        rec.phi = phi; rec.theta = theta;
-        rec.nx = X.nnx[k]; rec.ny = X.nny[k]; rec.nz = X.nnz[k]; rec.sth = S.E[k];
-        mono[k] = rec;
-        X.nhx[k] = rec.nx; X.nhy[k] = rec.ny; X.nhz[k] = rec.nz;
-        S.sx[k] = X.xnx[k]; S.sy[k] = X.xny[k]; S.sz[k] = X.xnz[k];
-        double ux, uy, uz;
-        mu_of(P, rec.nx, rec.ny, rec.nz, ux, uy, uz);
-        S.mx[k] = ux; S.my[k] = uy; S.mz[k] = uz;
-      }
-      for (int j = hi + 1 + tid; j < n; j += T) {
-        S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
-      }
-      for (int i = max(lo - 1, 0) + tid; i <= min(hi, n - 2); i += T) X.psi[i] = X.psn[i];
-    }
-    if (tid == 0) {
-      ChainDyn& D = *S.dyn;
-      ChainDynX& DX = *X.dx;
-      if (accept) {
-        D.U += dec.dU;
-        D.Omega += sums[R_OMEGA];
-        D.su += dec.dsu;
-        D.r[0] += Dx; D.r[1] += Dy; D.r[2] += Dz;
-        D.p[0] += sums[R_PX]; D.p[1] += sums[R_PY]; D.p[2] += sums[R_PZ];
-        DX.spsi += sums[R_PSI];
-        DX.scos2 += sums[R_COS2];
-        DX.carry = P.alpha_carry ? dec.la : 0.0;  // logπ_prev = logπ + log α (acceptance.jl:32-33)
-        D.nacc += 1;
-        D.nacc_total += 1;
-      }
-      D.natt += 1;
-      D.steps_total += 1;
-      D.step = step;
-      if (reflect) {
-        const double sz = (double)(hi - lo + 1);
-        DX.ncluster += 1.0; DX.cluster_sum += sz; DX.cluster_max = fmax(DX.cluster_max, sz);
-      }
-      bookkeep_cluster(P, D, DX, step, n, a.compensated != 0);
-    }
-    const bool isrow = a.stepout > 0 && (step % a.stepout) == 0;
-    if (isrow) {
-      __syncthreads();  // records of this trial are visible
-      if (row < a.rows) {
-        if (tid == 0) stage_row_cluster(*S.dyn, *X.dx, step, rowbuf);
-        if (a.state) {
-          double* st = a.state + ((size_t)c * a.rows + row) * 2 * (size_t)n;
-          for (int k = tid; k < n; k += T) {
-            const MonoRec r = mono[k];
-            st[2 * k] = r.phi; st[2 * k + 1] = r.theta;
-          }
+    team_sync<T>();  // window visible
+    for (int k = 0; k < wlen; ++k) {
+      const long long step = step0 + s + k;
+      const ClProposal* q = &X.win[k];
+      double acc[kNumRed];
+#pragma unroll
+      for (int r = 0; r < kNumRed; ++r) acc[r] = 0.0;
+      if (tid < 32) {
+        if ((X.ctl->dirty >> k) & 1u) {  // an earlier trial of this window changed this monomer: rebuild
+          __syncwarp();
+          if (tid == 0) make_window_entry(a, P, *S.dyn, mono, chain_id, step, X.win[k]);
+          __syncwarp();
         }
-        __syncthreads();
-        if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = rowbuf[tid];
-        if (tid < a.roll_cols) a.roll[((size_t)c * a.rows + row) * a.roll_cols + tid] = rowbuf[8 + tid];
+        warp_cluster_grow(X, *q, q->reflect, P, n, a.seed, chain_id, init, step, *X.ctl);
+        __syncwarp();
+        if (X.ctl->hi - X.ctl->lo < 32)
+          warp_segment_build(S, X, mono, P, *q, X.ctl->lo, X.ctl->hi, X.ctl->reflect != 0, acc, *X.ctl);
       }
-      ++row;
+      team_sync<T>();  // proposal, cluster and (short) segment are visible
+      const int lo = X.ctl->lo, hi = X.ctl->hi;
+      const bool reflect = X.ctl->reflect != 0;
+      const double carry = X.dx->carry;
+      double sums[kNumRed], Dx = X.ctl->Dx, Dy = X.ctl->Dy, Dz = X.ctl->Dz;
+      if (hi - lo >= 32) cta_segment_build<T>(S, X, mono, P, *q, lo, hi, reflect, acc, Dx, Dy, Dz);
+      segment_sums<T, CUT>(S, X, P, n, a.energy_type, lo, hi, Dx, Dy, Dz, acc, sums);
+      const double la = reflect ? cluster_log_alpha(X, n, lo, hi, X.ctl->up, X.ctl->lp) : 0.0;
+      const SegDecision dec = segment_decision(P, a.energy_type, sums, Dx, Dz, la, carry);
+      const bool accept = metropolis(dec.dlogpi, q->eps);
+      if (accept) {  // the trial chain becomes the chain (mcmc_clustering_eap_chain.jl:274-275)
+        for (int m = lo + tid; m <= hi; m += T) {
+          double phi, theta, sb;
+          segment_angles(mono, *q, m, reflect, P.planar, phi, theta, sb);
+          MonoRec rec;
+          rec.phi = phi; rec.theta = theta;
+          rec.nx = X.nnx[m]; rec.ny = X.nny[m]; rec.nz = X.nnz[m];
+          rec.sth = (S.E[m] == kKeepSinTheta) ? sb : S.E[m];
+          mono[m] = rec;
+          X.nhx[m] = rec.nx; X.nhy[m] = rec.ny; X.nhz[m] = rec.nz;
+          S.sx[m] = X.xnx[m]; S.sy[m] = X.xny[m]; S.sz[m] = X.xnz[m];
+          double ux, uy, uz;
+          mu_of(P, rec.nx, rec.ny, rec.nz, ux, uy, uz);
+          S.mx[m] = ux; S.my[m] = uy; S.mz[m] = uz;
+        }
+        for (int j = hi + 1 + tid; j < n; j += T) {
+          S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
+        }
+        for (int i = max(lo - 1, 0) + tid; i <= min(hi, n - 2); i += T) X.psi[i] = X.psn[i];
+        if (tid < 32) {  // later entries of the window on a monomer of the segment are stale now
+          const int widx = X.win[tid].idx;
+          const bool stale = tid > k && tid < wlen && widx >= lo && widx <= hi;
+          const unsigned m = __ballot_sync(0xffffffffu, stale);
+          if (tid == 0 && m) X.ctl->dirty |= m;
+        }
+      }
+      if (tid == 0) {
+        ChainDyn& D = *S.dyn;
+        ChainDynX& DX = *X.dx;
+        if (accept) {
+          D.U += dec.dU;
+          D.Omega += sums[R_OMEGA];
+          D.su += dec.dsu;
+          D.r[0] += Dx; D.r[1] += Dy; D.r[2] += Dz;
+          D.p[0] += sums[R_PX]; D.p[1] += sums[R_PY]; D.p[2] += sums[R_PZ];
+          DX.spsi += sums[R_PSI];
+          DX.scos2 += sums[R_COS2];
+          DX.carry = P.alpha_carry ? dec.la : 0.0;  // logπ_prev = logπ + log α (acceptance.jl:32-33)
+          D.nacc += 1;
+          D.nacc_total += 1;
+        }
+        D.natt += 1;
+        D.steps_total += 1;
+        D.step = step;
+        if (reflect) {
+          const double sz = (double)(hi - lo + 1);
+          DX.ncluster += 1.0; DX.cluster_sum += sz; DX.cluster_max = fmax(DX.cluster_max, sz);
+        }
+        bookkeep_cluster(P, D, DX, /*adapt_now=*/k + 1 == to_boundary, n, a.compensated != 0);
+      }
+      const bool isrow = row_due.tick();
+      if (isrow) {
+        team_sync<T>();  // records of this trial are visible
+        if (row < a.rows) {
+          if (tid == 0) stage_row_cluster(*S.dyn, *X.dx, step, rowbuf);
+          if (a.state) {
+            double* st = a.state + ((size_t)c * a.rows + row) * 2 * (size_t)n;
+            for (int m = tid; m < n; m += T) {
+              const MonoRec r = mono[m];
+              st[2 * m] = r.phi; st[2 * m + 1] = r.theta;
+            }
+          }
+          team_sync<T>();
+          if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = rowbuf[tid];
+          if (tid < a.roll_cols) a.roll[((size_t)c * a.rows + row) * a.roll_cols + tid] = rowbuf[8 + tid];
+        }
+        ++row;
+      }
+      team_sync<T>();  // state, records and the dirty mask of this trial are visible
     }
+    s += wlen;
   }
-  __syncthreads();
   if (tid == 0) {
     a.dyn[c] = *S.dyn;
     a.dynx[c] = *X.dx;
@@ -571,7 +663,7 @@ template <int T, bool CUT>
 __global__ void __launch_bounds__(T) k_delta_segment_cta(const SegDeltaArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const CtaView S = carve(smem_raw, a.n);
-  const ClView X = carve_cluster(smem_raw, a.n);
+  const ClView X = carve_cluster(smem_raw, a.n, T);
   const int tid = threadIdx.x, n = a.n;
   const MonoRec* mono = a.mono + (size_t)a.chain * n;
   if (tid == 0) *S.par = a.par[a.chain];
@@ -617,24 +709,18 @@ __global__ void __launch_bounds__(T) k_delta_segment_cta(const SegDeltaArgs a) {
 // ---------------------------------------------------------------------------------------------
 // One chain per lane: non-interacting and Ising energies (+ bending), O(|cluster|) per trial.
 // ---------------------------------------------------------------------------------------------
-// refl_n! / flip_n! of one monomer by symmetry, without transcendentals: refl_n! maps θ → π−θ, i.e.
-// n̂ → (n̂x, n̂y, −n̂z) with sinθ unchanged (eap_chain.jl:263-265); the planar flip_n! maps ϕ → ϕ+π, i.e. n̂ → −n̂
-// (2D/inc/eap_chain.jl:189-191).  Equal to the reference's recomputed cos/sin in real arithmetic.
-__device__ __forceinline__ void flip_dir(int planar, double nx, double ny, double nz, double& fx, double& fy,
-                                         double& fz) {
-  if (planar) { fx = -nx; fy = -ny; fz = -nz; }
-  else { fx = nx; fy = ny; fz = -nz; }
-}
-
 struct LaneSeg {
   double dOmega, du_self, dbend, dpsi, dcos2, dpair;  // dpair: 4π × Σ(new − old) of U_Ising terms
   double dpx, dpy, dpz, sx, sy, sz;                   // Δp, ΣΔn̂
 };
 
 // Contribution of one flipped cluster monomer (not idx) with current direction (nx,ny,nz) to the sums.
-__device__ __forceinline__ void lane_add_flipped(const ChainParams& P, double nx, double ny, double nz, LaneSeg& o) {
+__device__ __forceinline__ void lane_add_flipped(const ChainParams& P, const MonoRec& r, LaneSeg& o) {
+  const double nx = r.nx, ny = r.ny, nz = r.nz;
   double fx, fy, fz;
   flip_dir(P.planar, nx, ny, nz, fx, fy, fz);
+  // a monomer sitting at θ = π reflects to θ' = 0: sinθ' = 0 ⇒ Ω' = −Inf ⇒ the trial is rejected (eap_chain.jl:236-238)
+  if (!P.planar && reflect_theta(r.theta) == 0.0) o.dOmega = -INFINITY;
   double ux, uy, uz, vx, vy, vz;
   mu_of(P, nx, ny, nz, ux, uy, uz);
   mu_of(P, fx, fy, fz, vx, vy, vz);
@@ -756,7 +842,7 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
     up = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
     if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_UP, k) <= up) {
       hi += 1; ax = b.nx; ay = b.ny; az = b.nz;
-      lane_add_flipped(P, b.nx, b.ny, b.nz, o);
+      lane_add_flipped(P, b, o);
     } else break;
   }
   lo = idx;
@@ -767,7 +853,7 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
     lp = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
     if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k) <= lp) {
       lo -= 1; ax = b.nx; ay = b.ny; az = b.nz;
-      lane_add_flipped(P, b.nx, b.ny, b.nz, o);
+      lane_add_flipped(P, b, o);
     } else break;
   }
 }
@@ -809,7 +895,9 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
     lane_seg_zero(g);
     if (reflect) lane_cluster_grow(mono, q, P, n, a.seed, chain_id, (uint32_t)D.init, step, lo, hi, up, lp, g);
     MonoRec nrec;
-    lane_idx_record(P, q, reflect, nrec, g.dOmega);
+    double dOm_idx;
+    lane_idx_record(P, q, reflect, nrec, dOm_idx);
+    g.dOmega += dOm_idx;
     double la;
     lane_segment_finish<ISING>(mono, n, P, rec, nrec, d.idx, lo, hi, reflect, g, la, up, lp);
     const double Dx = P.b * g.sx, Dy = P.b * g.sy, Dz = P.b * g.sz;
@@ -884,7 +972,7 @@ __global__ void k_delta_segment_lane(const SegDeltaArgs a) {
     for (int k = lo; k <= hi; ++k) {
       if (k == a.idx) continue;
       const MonoRec r = mono[k];
-      lane_add_flipped(P, r.nx, r.ny, r.nz, g);
+      lane_add_flipped(P, r, g);
     }
     // link probabilities before the flip, on the chain carrying the move
     if (hi < n - 1) {
@@ -901,7 +989,9 @@ __global__ void k_delta_segment_lane(const SegDeltaArgs a) {
     }
   }
   MonoRec nrec;
-  lane_idx_record(P, q, reflect, nrec, g.dOmega);
+  double dOm_idx;
+  lane_idx_record(P, q, reflect, nrec, dOm_idx);
+  g.dOmega += dOm_idx;
   double la;
   lane_segment_finish<ISING>(mono, n, P, rec, nrec, a.idx, lo, hi, reflect, g, la, up, lp);
   const double Dx = P.b * g.sx, Dz = P.b * g.sz;

@@ -9,6 +9,8 @@
 // warp-wide broadcasts, and the partial sums are reduced with warp shuffles.
 #pragma once
 
+#include <type_traits>
+
 #include "chain_math.cuh"
 
 namespace pmc {
@@ -54,6 +56,16 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// A team = the threads that share one chain.  T = 32: one warp (several chains may share a CTA, see
+// k_run_cta_cluster), team-local thread id = lane and the team barrier is __syncwarp; T > 32: the whole CTA.
+template <int T>
+__device__ __forceinline__ int team_tid() { return T == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+template <int T>
+__device__ __forceinline__ void team_sync() {
+  if (T == 32) __syncwarp();
+  else __syncthreads();
+}
+
 // Sum over the CTA, result in every thread.  `trailing_sync` protects `part` for immediate reuse.
 template <int T>
 __device__ __forceinline__ double block_sum(double v, double* part, bool trailing_sync = true) {
@@ -73,7 +85,7 @@ __device__ __forceinline__ double block_sum(double v, double* part, bool trailin
 template <int T>
 __device__ void load_chain(const MonoRec* __restrict__ mono, const ChainParams& P, int n, const CtaView& S) {
   constexpr int W = T / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = team_tid<T>(), lane = tid & 31, warp = tid >> 5;
   const int C = (n + T - 1) / T;
   const int i0 = min(n, tid * C), i1 = min(n, i0 + C);
   double lx = 0, ly = 0, lz = 0;
@@ -92,7 +104,7 @@ __device__ void load_chain(const MonoRec* __restrict__ mono, const ChainParams& 
     if (lane >= o) { ix += tx; iy += ty; iz += tz; }
   }
   if (lane == 31) { S.part[warp] = ix; S.part[32 + warp] = iy; S.part[64 + warp] = iz; }
-  __syncthreads();
+  team_sync<T>();
   double ox = 0, oy = 0, oz = 0;
   for (int w = 0; w < warp && w < W; ++w) { ox += S.part[w]; oy += S.part[32 + w]; oz += S.part[64 + w]; }
   double sxx = ox + (ix - lx), syy = oy + (iy - ly), szz = oz + (iz - lz);  // exclusive prefix
@@ -106,7 +118,7 @@ __device__ void load_chain(const MonoRec* __restrict__ mono, const ChainParams& 
     mu_of(P, r.nx, r.ny, r.nz, ux, uy, uz);
     S.mx[i] = ux; S.my[i] = uy; S.mz[i] = uz;
   }
-  __syncthreads();
+  team_sync<T>();
 }
 
 // 4π × dipole-dipole energy of the staged chain: U_interaction (eap_chain.jl:196-211) or
@@ -159,6 +171,16 @@ struct Team {
     if (FIRST_WARP == 0) __syncthreads();
     else asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
   }
+};
+
+// One warp as the team (chains of ≤ 160 monomers in the composite-trial kernel).
+struct WarpTeam {
+  static constexpr int kWarps = 1;
+  static constexpr int kThreads = 32;
+  __device__ __forceinline__ static int tid() { return (int)(threadIdx.x & 31); }
+  __device__ __forceinline__ static int warp() { return 0; }
+  __device__ __forceinline__ static int lane() { return (int)(threadIdx.x & 31); }
+  __device__ __forceinline__ static void sync() { __syncwarp(); }
 };
 
 struct LaneItem {

@@ -1,0 +1,40 @@
+"""Developer tuning sweep: one warp per chain, several chains per CTA (PMC_CLUSTER_CFG = 320000 + CPB*100 + MINB)
+against the one-CTA-per-chain shapes of k_run_cta_cluster; run on the GPU box."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+child = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%r, "polymer-stats_b200"))
+import polymc as pm
+n, R, steps, et = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+c = pm.make_case(n=n, E0=1.0, Fz=0.25, energy_type=et, kappa=0.5, clustering=True, adj_ub=0.4)
+ens = pm.Ensemble(c, replicas=R, seed=20260101)
+ens.begin_stage(1.0)
+ens.run_ex(max(10, steps // 5), 0, fetch_rows=False)
+best = 1e30
+for _ in range(3):
+    ens.run_ex(steps, steps, fetch_rows=False)
+    best = min(best, ens.last_run_ms())
+print("%%s n=%%d R=%%d: %%.3f ms  %%.3f M updates/s" %% (et, n, R, best, R*steps/best/1e3))
+''' % ROOT
+G = [320206, 320304, 320403, 320602, 320802, 321001, 321201]
+SETS = {"full": ((100, 4096, 500, "interacting", [0] + G),
+                 (100, 14208, 300, "interacting", [0, 320403, 320602, 321201]),
+                 (25, 16384, 1000, "interacting", [0, 320403, 320602, 321201]),
+                 (50, 8192, 800, "interacting", [0, 320403, 320602, 321201]),
+                 (160, 4096, 400, "interacting", [0, 320403, 320602]),
+                 (200, 4096, 300, "interacting", [0, 3212, 320403, 320602])),
+        "quick": ((100, 4096, 500, "interacting", [0, 321201]),
+                  (25, 16384, 1000, "interacting", [0, 321201]),
+                  (50, 8192, 800, "interacting", [0, 321201]),
+                  (160, 4096, 400, "interacting", [0]),
+                  (200, 4096, 300, "interacting", [0]),
+                  (400, 2368, 200, "cutoff", [0]))}
+for n, R, steps, et, cfgs in SETS[sys.argv[1] if len(sys.argv) > 1 else "full"]:
+    for cfg in cfgs:
+        env = dict(os.environ)
+        if cfg:
+            env["PMC_CLUSTER_CFG"] = str(cfg)
+        out = subprocess.run([sys.executable, "-c", child, str(n), str(R), str(steps), et], env=env,
+                             capture_output=True, text=True)
+        print("cfg", cfg, "->", out.stdout.strip() or out.stderr.strip()[-300:], flush=True)
