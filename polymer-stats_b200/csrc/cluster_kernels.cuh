@@ -51,16 +51,23 @@ struct ClView {
   ChainDynX* dx;
 };
 
-__host__ __device__ inline size_t cluster_smem_bytes(int n, int threads) {
-  size_t b = cta_smem_bytes(n);
-  b += (size_t)11 * n * sizeof(double) + (size_t)kNumRed * (threads / 32) * sizeof(double);
+// Bytes of the composite-trial arrays that follow the CtaView part.
+__host__ __device__ inline size_t cluster_extra_bytes(int n, int threads) {
+  size_t b = (size_t)11 * n * sizeof(double) + (size_t)kNumRed * (threads / 32) * sizeof(double);
   b += kClWin * sizeof(ClProposal) + sizeof(ClusterCtl) + sizeof(ChainDynX);
   return (b + 15) & ~(size_t)15;
+}
+// run kernel (compact CtaView) / parity-seam kernel (full CtaView with its Proposal slots)
+__host__ __device__ inline size_t cluster_smem_bytes(int n, int threads) {
+  return cta_smem_bytes_compact(n, threads) + cluster_extra_bytes(n, threads);
+}
+__host__ __device__ inline size_t cluster_delta_smem_bytes(int n, int threads) {
+  return cta_smem_bytes(n) + cluster_extra_bytes(n, threads);
 }
 
 __device__ __forceinline__ ClView carve_cluster(unsigned char* base, int n, int threads) {
   ClView X;
-  double* d = reinterpret_cast<double*>(base + cta_smem_bytes(n));
+  double* d = reinterpret_cast<double*>(base);
   X.nhx = d; X.nhy = d + n; X.nhz = d + 2 * n;
   X.nnx = d + 3 * n; X.nny = d + 4 * n; X.nnz = d + 5 * n;
   X.xnx = d + 6 * n; X.xny = d + 7 * n; X.xnz = d + 8 * n;
@@ -321,12 +328,12 @@ __device__ __forceinline__ void cta_segment_build(const CtaView& S, const ClView
     const double tz = __shfl_up_sync(0xffffffffu, iz, o);
     if (lane >= o) { ix += tx; iy += ty; iz += tz; }
   }
-  if (lane == 31) { S.part[warp] = ix; S.part[32 + warp] = iy; S.part[64 + warp] = iz; }
+  if (lane == 31) { S.part[warp] = ix; S.part[W + warp] = iy; S.part[2 * W + warp] = iz; }
   team_sync<T>();
   double ox = 0, oy = 0, oz = 0, tx = 0, ty = 0, tz = 0;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    const double px = S.part[w], py = S.part[32 + w], pz = S.part[64 + w];
+    const double px = S.part[w], py = S.part[W + w], pz = S.part[2 * W + w];
     if (w < warp) { ox += px; oy += py; oz += pz; }
     tx += px; ty += py; tz += pz;
   }
@@ -505,9 +512,10 @@ constexpr int kRowDoublesCluster = 28;
 template <int T, int MINB, bool CUT>
 __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double rowbuf[kRowDoublesCluster];
-  const CtaView S = carve(smem_raw, a.n);
-  const ClView X = carve_cluster(smem_raw, a.n, T);
+  static_assert(kRowDoublesCluster <= kRowDoublesCompact, "row buffer");
+  const CtaView S = carve_compact(smem_raw, a.n, T);
+  const ClView X = carve_cluster(smem_raw + cta_smem_bytes_compact(a.n, T), a.n, T);
+  double* rowbuf = S.rowbuf;
   const int c = blockIdx.x;
   const int tid = team_tid<T>();
   const int n = a.n;
@@ -663,7 +671,7 @@ template <int T, bool CUT>
 __global__ void __launch_bounds__(T) k_delta_segment_cta(const SegDeltaArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const CtaView S = carve(smem_raw, a.n);
-  const ClView X = carve_cluster(smem_raw, a.n, T);
+  const ClView X = carve_cluster(smem_raw + cta_smem_bytes(a.n), a.n, T);
   const int tid = threadIdx.x, n = a.n;
   const MonoRec* mono = a.mono + (size_t)a.chain * n;
   if (tid == 0) *S.par = a.par[a.chain];

@@ -50,6 +50,31 @@ __device__ __forceinline__ CtaView carve(unsigned char* base, int n) {
   return S;
 }
 
+// Compact layout for the composite-trial run kernel (cluster_kernels.cuh), where shared memory per chain sets
+// the number of resident chains: 3 partials per warp, a 28-double row buffer, no ping-pong proposals.
+constexpr int kRowDoublesCompact = 28;
+
+__host__ __device__ inline size_t cta_smem_bytes_compact(int n, int threads) {
+  size_t b = (size_t)7 * n * sizeof(double);
+  b += (size_t)(3 * (threads / 32) + kRowDoublesCompact) * sizeof(double);
+  b += sizeof(ChainDyn) + sizeof(ChainParams);
+  return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ CtaView carve_compact(unsigned char* base, int n, int threads) {
+  CtaView S;
+  double* d = reinterpret_cast<double*>(base);
+  S.sx = d; S.sy = d + n; S.sz = d + 2 * n;
+  S.mx = d + 3 * n; S.my = d + 4 * n; S.mz = d + 5 * n;
+  S.E = d + 6 * n;
+  S.part = d + 7 * n;
+  S.rowbuf = S.part + 3 * (threads / 32);
+  S.prop = nullptr;
+  S.dyn = reinterpret_cast<ChainDyn*>(S.rowbuf + kRowDoublesCompact);
+  S.par = reinterpret_cast<ChainParams*>(S.dyn + 1);
+  return S;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -103,10 +128,10 @@ __device__ void load_chain(const MonoRec* __restrict__ mono, const ChainParams& 
     const double tz = __shfl_up_sync(0xffffffffu, iz, o);
     if (lane >= o) { ix += tx; iy += ty; iz += tz; }
   }
-  if (lane == 31) { S.part[warp] = ix; S.part[32 + warp] = iy; S.part[64 + warp] = iz; }
+  if (lane == 31) { S.part[warp] = ix; S.part[W + warp] = iy; S.part[2 * W + warp] = iz; }
   team_sync<T>();
   double ox = 0, oy = 0, oz = 0;
-  for (int w = 0; w < warp && w < W; ++w) { ox += S.part[w]; oy += S.part[32 + w]; oz += S.part[64 + w]; }
+  for (int w = 0; w < warp && w < W; ++w) { ox += S.part[w]; oy += S.part[W + w]; oz += S.part[2 * W + w]; }
   double sxx = ox + (ix - lx), syy = oy + (iy - ly), szz = oz + (iz - lz);  // exclusive prefix
   for (int i = i0; i < i1; ++i) {
     const MonoRec r = mono[i];

@@ -427,7 +427,7 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
   if (h->cluster_mode && cta_pairs) {
     h->cta_threads = pick_cluster_threads(n);
-    if (cluster_smem_bytes(n, h->cta_threads) > (size_t)kSmemMax) {
+    if (cluster_delta_smem_bytes(n, h->cta_threads) > (size_t)kSmemMax) {
       delete h;
       return fail(PMC_ERR_UNSUPPORTED, "chain too long for the clustering / bending / cut-off kernels: 18 n doubles "
                                        "must fit one CTA's 227 KB shared memory (num-monomers <= ~1570)");
@@ -675,7 +675,7 @@ static int launch_delta_segment(pmc_handle* h, const SegDeltaArgs& a) {
   const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
   if (cta_pairs) {
     const int tt = pick_cluster_threads(h->n);
-    const size_t smem = cluster_smem_bytes(h->n, tt);
+    const size_t smem = cluster_delta_smem_bytes(h->n, tt);
     if (smem > (size_t)kSmemMax) return fail(PMC_ERR_UNSUPPORTED, "chain too long for the composite-trial kernel");
     const bool cut = h->energy_type == PMC_ENERGY_CUTOFF;
 #define PMC_DS(TT)                                                                        \
