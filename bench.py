@@ -39,7 +39,8 @@ WORKLOADS = {
     "C4": (dict(n=100, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.5, Fx=0.0, chain_type="dielectric",
                 energy_type="noninteracting"), 16384, 20000, 500),
     "C5": (dict(n=4096, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.5, Fx=0.0, chain_type="dielectric",
-                energy_type="interacting"), 148, 50, 50),
+                energy_type="interacting"), 148, 200, 200),  # ≥ 200 trials per chain (one wave of CTAs:
+    # the launch ends with its slowest chain, and the spread of Σ idx(n−1−idx) shrinks as 1/sqrt(trials))
     # the clustering driver (mcmc_clustering_eap_chain.jl), shapes of its launchers:
     # run/phases-kT-small-n_2023-09-09.jl (all-pairs, bending), run/Ising_2025-12-17.jl, run/phases-big_2023-05-18.jl
     "K1": (dict(n=100, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.25, Fx=0.0, chain_type="dielectric",

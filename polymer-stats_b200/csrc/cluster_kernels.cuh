@@ -727,8 +727,9 @@ __device__ __forceinline__ void lane_add_flipped(const ChainParams& P, const Mon
   const double nx = r.nx, ny = r.ny, nz = r.nz;
   double fx, fy, fz;
   flip_dir(P.planar, nx, ny, nz, fx, fy, fz);
-  // a monomer sitting at θ = π reflects to θ' = 0: sinθ' = 0 ⇒ Ω' = −Inf ⇒ the trial is rejected (eap_chain.jl:236-238)
-  if (!P.planar && reflect_theta(r.theta) == 0.0) o.dOmega = -INFINITY;
+  // a monomer sitting at θ = π (the only θ in [0, π] with reflect_theta(θ) == 0) reflects to sinθ' = 0 ⇒ Ω' = −Inf ⇒
+  // the trial is rejected (eap_chain.jl:236-238)
+  if (!P.planar && r.theta == kPi) o.dOmega = -INFINITY;
   double ux, uy, uz, vx, vy, vz;
   mu_of(P, nx, ny, nz, ux, uy, uz);
   mu_of(P, fx, fy, fz, vx, vy, vz);

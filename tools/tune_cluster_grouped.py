@@ -24,6 +24,10 @@ SETS = {"full": ((100, 4096, 500, "interacting", [0] + G),
                  (50, 8192, 800, "interacting", [0, 320403, 320602, 321201]),
                  (160, 4096, 400, "interacting", [0, 320403, 320602]),
                  (200, 4096, 300, "interacting", [0, 3212, 320403, 320602])),
+        "occ": ((25, 16384, 1000, "interacting", [0, 3216]),
+                (50, 8192, 800, "interacting", [0, 3216]),
+                (64, 8192, 600, "interacting", [0, 3216]),
+                (80, 8192, 500, "interacting", [0, 3216])),
         "quick": ((100, 4096, 500, "interacting", [0, 321201]),
                   (25, 16384, 1000, "interacting", [0, 321201]),
                   (50, 8192, 800, "interacting", [0, 321201]),
