@@ -102,6 +102,14 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
 void pmc_destroy(pmc_handle* h);
 int64_t pmc_num_chains(const pmc_handle* h);
 int64_t pmc_num_monomers(const pmc_handle* h);
+/* Launch shape.  The block size of the CTA-per-chain kernels is chosen from the chain length AND the ensemble
+ * size: a small ensemble leaves SMs idle, so each chain gets more warps (same Markov chain, same Philox stream;
+ * only the order of the pair-sum reduction changes, i.e. results agree to rounding).  A sharded sweep passes the
+ * UNSHARDED chain count of the ensemble here so that its results stay bit-identical however it is sharded
+ * (polymc.sweep does); 0 = this handle's own chain count (the default).  No counterpart in the reference (its
+ * launchers run one single-threaded process per case, run/K1_Fz_long.jl:45). */
+int32_t pmc_set_ensemble_hint(pmc_handle* h, int64_t ensemble_chains);
+int32_t pmc_block_threads(const pmc_handle* h);   /* the block size in use (diagnostics) */
 /* Work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
 int32_t pmc_set_stream(pmc_handle* h, void* cuda_stream);
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "cluster_kernels.cuh"
@@ -72,6 +73,8 @@ struct pmc_handle {
   float last_ms = 0.f;
   int64_t launches = 0;
   int cta_threads = 256;      // block size of the CTA-per-chain kernels
+  int sm_count = 148;
+  int64_t shape_chains = 0;   // ensemble size the launch shape is chosen for (0 = nchains), pmc_set_ensemble_hint
   int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
   long long warp_mode_below = 20000;
   int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
@@ -352,6 +355,41 @@ ChainParams params_of(const pmc_case& c0, double kT_scale = 1.0) {
 // chain and many chains per SM; measured crossovers in profiles/r01e_tune_cluster.txt.
 int pick_cluster_threads(int n) { return n <= 160 ? 32 : n <= 256 ? 64 : n <= 1024 ? 128 : 256; }
 
+// Block size for the ensemble at hand.  `base` is the shape that wins on a full machine (many chains per SM).
+// A small ensemble leaves SMs idle — 148 chains of n=100 are one warp per SM — so each chain gets 2× or 4× the
+// threads until the warps resident per SM reach what the base shape has when the machine is full
+// (profiles/r01f_tune_small_ensembles.txt: +50–80 % at one chain per SM, nothing lost on large ensembles).
+static int scaled_threads(int base, int minb, size_t smem, int tmax, int64_t chains, int sms) {
+  const int fit = (int)std::max<size_t>(1, (size_t)233472 / (smem + 1024));  // CTAs per SM that fit in shared memory
+  const int resident_max = std::min(minb, fit);
+  const double sat = (double)resident_max * (base / 32);                     // warps per SM, full machine
+  const double res = std::min((double)chains / sms, (double)resident_max) * (base / 32);
+  int scale = 1;
+  while (scale < 4 && base * scale * 2 <= tmax && res * scale * 2 <= sat) scale *= 2;
+  return base * scale;
+}
+
+// (Re)choose cta_threads from n and the ensemble size.  Experiments pin it with PMC_CTA_THREADS / PMC_RUN_CFG.
+static void choose_shape(pmc_handle* h) {
+  const int64_t chains = h->shape_chains > 0 ? h->shape_chains : h->nchains;
+  const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
+  if (h->cluster_mode && cta_pairs) {
+    const int base = pick_cluster_threads(h->n);
+    const int minb = base == 32 ? 12 : base == 64 ? 6 : base == 128 ? 4 : 1;
+    int t = scaled_threads(base, minb, cluster_smem_bytes(h->n, base), 256, chains, h->sm_count);
+    while (t > base && cluster_delta_smem_bytes(h->n, t) > (size_t)kSmemMax) t /= 2;
+    h->cta_threads = t;
+    return;
+  }
+  const int base = pick_cta_threads(h->n);
+  if (env_int("PMC_CTA_THREADS", 0) > 0 || env_int("PMC_RUN_CFG", 0) > 0) {
+    h->cta_threads = base;
+    return;
+  }
+  const int minb = base == 64 ? 8 : base == 128 ? 4 : base == 256 ? 2 : 1;
+  h->cta_threads = scaled_threads(base, minb, cta_smem_bytes_win(h->n), 512, chains, h->sm_count);
+}
+
 int fetch_dyn(pmc_handle* h) {
   h->host_dyn.resize((size_t)h->nchains);
   PMC_CU(cudaMemcpyAsync(h->host_dyn.data(), h->dyn, sizeof(ChainDyn) * (size_t)h->nchains, cudaMemcpyDeviceToHost,
@@ -415,7 +453,11 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   h->energy_type = cases[0].energy_type;
   h->seed = seed;
   h->chain_id_base = chain_id_base;
-  h->cta_threads = pick_cta_threads(n);
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
+      h->sm_count = prop.multiProcessorCount;
+  }
   h->compensated = 0;
   for (int64_t i = 0; i < ncases; ++i)
     if (cases[i].accum_mode || cases[i].umbrella) h->compensated = 1;  // umbrella weights span many decades
@@ -425,8 +467,8 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   for (int64_t i = 0; i < ncases; ++i)
     if (needs_cluster_path(cases[i])) h->cluster_mode = 1;
   const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
+  choose_shape(h);
   if (h->cluster_mode && cta_pairs) {
-    h->cta_threads = pick_cluster_threads(n);
     if (cluster_delta_smem_bytes(n, h->cta_threads) > (size_t)kSmemMax) {
       delete h;
       return fail(PMC_ERR_UNSUPPORTED, "chain too long for the clustering / bending / cut-off kernels: 18 n doubles "
@@ -506,6 +548,17 @@ void pmc_destroy(pmc_handle* h) {
 
 int64_t pmc_num_chains(const pmc_handle* h) { return h ? h->nchains : 0; }
 int64_t pmc_num_monomers(const pmc_handle* h) { return h ? h->n : 0; }
+
+int32_t pmc_set_ensemble_hint(pmc_handle* h, int64_t ensemble_chains) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (ensemble_chains < 0) return fail(PMC_ERR_INVALID, "ensemble_chains must be >= 0");
+  h->shape_chains = ensemble_chains;
+  choose_shape(h);
+  return PMC_OK;
+}
+
+int32_t pmc_block_threads(const pmc_handle* h) { return h ? h->cta_threads : 0; }
 
 int32_t pmc_set_stream(pmc_handle* h, void* cuda_stream) {
   int rc = check_handle(h);

@@ -25,7 +25,7 @@ AVG_NAMES = ["r1", "r2", "r3", "r1sq", "r2sq", "r3sq", "rsq",
 
 EXPORTS = [
     "pmc_abi_version", "pmc_last_error", "pmc_device_count", "pmc_create", "pmc_destroy",
-    "pmc_num_chains", "pmc_num_monomers", "pmc_set_stream", "pmc_set_state", "pmc_get_state",
+    "pmc_num_chains", "pmc_num_monomers", "pmc_set_stream", "pmc_set_ensemble_hint", "pmc_block_threads", "pmc_set_state", "pmc_get_state",
     "pmc_set_state_all", "pmc_get_state_all", "pmc_energy", "pmc_energy_all", "pmc_observables",
     "pmc_delta_u", "pmc_run", "pmc_rows_for", "pmc_last_run_ms", "pmc_reinit", "pmc_averages",
     "pmc_accumulators", "pmc_diagnostics", "pmc_fp64_peak_probe", "pmc_launch_count",
@@ -118,6 +118,9 @@ def load():
     L.pmc_num_monomers.argtypes = [hp]
     L.pmc_num_monomers.restype = C.c_int64
     L.pmc_set_stream.argtypes = [hp, C.c_void_p]
+    L.pmc_set_ensemble_hint.argtypes = [hp, C.c_int64]
+    L.pmc_block_threads.argtypes = [hp]
+    L.pmc_block_threads.restype = C.c_int32
     L.pmc_set_state.argtypes = [hp, C.c_int64, dp, dp]
     L.pmc_get_state.argtypes = [hp, C.c_int64, dp, dp]
     L.pmc_set_state_all.argtypes = [hp, dp, dp]
@@ -186,7 +189,7 @@ class Ensemble:
 
     The methods map 1:1 onto the C ABI; docstrings there cite the reference seams."""
 
-    def __init__(self, cases, replicas=1, seed=0, device=0, chain_id_base=0):
+    def __init__(self, cases, replicas=1, seed=0, device=0, chain_id_base=0, ensemble_chains=0):
         if isinstance(cases, PmcCase):
             cases = [cases]
         self.cases = list(cases)
@@ -197,6 +200,16 @@ class Ensemble:
         self._h = h
         self.nchains = int(load().pmc_num_chains(h))
         self.n = int(load().pmc_num_monomers(h))
+        if ensemble_chains:
+            self.set_ensemble_hint(ensemble_chains)
+
+    def set_ensemble_hint(self, ensemble_chains: int):
+        """Choose the launch shape for an ensemble of `ensemble_chains` chains (a shard passes the unsharded
+        count so that results do not depend on the sharding, bit for bit); 0 = this handle's own count."""
+        _check(load().pmc_set_ensemble_hint(self._h, int(ensemble_chains)))
+
+    def block_threads(self) -> int:
+        return int(load().pmc_block_threads(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -111,8 +111,9 @@ def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
         mine = gids[lo:hi]
         block = np.zeros((hi - lo, NCOL))
         for pos, end, case0, ncases, nrep in _segments(mine, replicas):
+            # launch shape from the UNSHARDED bucket size: results are bit-identical for any rank count
             with lib.Ensemble(cases[case0:case0 + ncases], replicas=nrep, seed=seed, device=device,
-                              chain_id_base=int(mine[pos])) as ens:
+                              chain_id_base=int(mine[pos]), ensemble_chains=len(gids)) as ens:
                 if protocol is None:
                     ens.run(nsteps, stepout, fetch_rows=False)
                 else:

@@ -287,6 +287,36 @@ def test_sharding_by_global_chain_id_is_invisible(pm):
         np.testing.assert_array_equal(whole.averages()[0], np.concatenate([lo.averages()[0], hi.averages()[0]]))
 
 
+def test_block_size_follows_ensemble_size_and_results_agree(pm):
+    """pmc_set_ensemble_hint: a small ensemble gets more warps per chain (SMs would idle otherwise); the Markov
+    chain and its Philox stream are the same, only the order of the pair-sum reduction changes."""
+    c = pm.make_case(n=96, E0=1.0, K1=1.0, K2=0.1, Fz=0.5, Fx=0.1, energy_type="interacting", steps_per_adjust=100)
+    with pm.Ensemble(c, replicas=6, seed=11) as small, \
+            pm.Ensemble(c, replicas=6, seed=11, ensemble_chains=10 ** 6) as full:
+        assert small.block_threads() == 4 * full.block_threads()
+        t1, r1 = small.run(800, 100)
+        t2, r2 = full.run(800, 100)
+        np.testing.assert_allclose(t1, t2, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(r1, r2, rtol=1e-9, atol=1e-9)
+        np.testing.assert_array_equal(small.averages()[1], full.averages()[1])  # same accept/reject decisions
+        np.testing.assert_allclose(small.get_state_all()[0], full.get_state_all()[0], rtol=0, atol=1e-12)
+    k = pm.make_case(n=64, E0=1.0, K1=1.0, K2=0.1, Fz=0.5, energy_type="interacting", kappa=0.5, clustering=True,
+                     adj_ub=0.4, steps_per_adjust=100)
+    with pm.Ensemble(k, replicas=5, seed=12) as small, \
+            pm.Ensemble(k, replicas=5, seed=12, ensemble_chains=10 ** 6) as full:
+        assert small.block_threads() == 4 * full.block_threads() == 128
+        for e in (small, full):
+            e.begin_stage(1.0)
+        t1, r1, s1 = small.run_ex(600, 100, want_state=True)
+        t2, r2, s2 = full.run_ex(600, 100, want_state=True)
+        np.testing.assert_allclose(s1, s2, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(t1, t2, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(r1, r2, rtol=1e-9, atol=1e-8)
+        np.testing.assert_array_equal(small.cluster_stats(), full.cluster_stats())
+        small.set_ensemble_hint(10 ** 6)
+        assert small.block_threads() == 32
+
+
 def test_sweep_is_independent_of_gpu_count(pm):
     """polymc.sweep: a mixed-n sweep sharded as 1, 2 or 3 ranks (run back to back here) gives
     bit-identical per-chain results — the property behind the ≥7.5× scaling claim (no collective)."""
