@@ -961,6 +961,253 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
   a.dynx[c] = DX;
 }
 
+// One chain per WARP for O(1)-per-bond energies: every lane takes one TRIAL of the same chain (32 composite trials
+// per window), as k_run_warp does for mcmc_eap_chain.jl.  The reference's studies are a few hundred chains (20 cases
+// × 25 runs, run/Ising_2025-12-17.jl); with one chain per lane they are a handful of warps in which every lane walks
+// its Markov chain alone at the latency of a dependent chain of record reads.
+//
+// A composite trial reads the records lo−1..hi+1 of its segment (the grown cluster and the two bonds that ended the
+// growth; lo = hi = idx without a cluster) and, if accepted, writes lo..hi.  Its draws are counter-based, so every
+// lane can evaluate its trial speculatively on the current chain: segment, changed-term sums, log α, and
+// base = logπ' − logπ without the carried log α of the acceptor (acceptance.jl:30-33), which depends on the LAST
+// ACCEPTED trial and is applied when the trial's turn comes.  The window is then resolved in order: the warp walks the
+// undecided trials; a trial whose speculation is still valid is decided (carry threaded through the walk); an
+// accepted trial invalidates every undecided trial whose read interval meets its write interval; the walk stops at
+// the first invalid trial, the accepted trials write their (disjoint) segments, the invalid ones are re-evaluated on
+// the new chain, and the walk resumes.  Every trial is decided on exactly the state the sequential loop would
+// show it: the chain performs the reference's Markov chain (trajectory parity with the oracle).  Running r, p, U, Σu,
+// Σψ, Σcos²θ after each trial — the averagers record every trial — are inclusive prefix sums of the accepted
+// increments; each lane keeps its own accumulators, combined at output rows and at the end.  Windows never cross an
+// adaptation boundary or an output row.
+// STAGE: the chain's records are staged in shared memory for the launch (48 n bytes per warp; chains of up to
+// kWarpClusterStageMax monomers) — the evaluations are dependent chains of record reads.
+constexpr int kWarpClusterStageMax = 1024;
+
+template <bool ISING, int MINB, bool COMP, bool STAGE>
+__global__ void __launch_bounds__(128, MINB) k_run_warp_cluster(const RunArgs a) {
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int c = (int)((blockIdx.x * 128u + threadIdx.x) >> 5);
+  if (c >= a.nchains) return;
+  const int n = a.n;
+  MonoRec* const gmono = a.mono + (size_t)c * n;
+  MonoRec* mono = gmono;
+  if (STAGE) {
+    mono = reinterpret_cast<MonoRec*>(smem_raw) + (size_t)(threadIdx.x >> 5) * n;
+    for (int k = lane; k < n; k += 32) mono[k] = gmono[k];
+    __syncwarp();
+  }
+  const ChainParams P = a.par[c];
+  ChainDyn D = a.dyn[c];      // uniform scalars (every lane holds a copy); accumulators: per lane
+  ChainDynX DX = a.dynx[c];
+  double acc[kNumAcc], comp[kNumAcc], xacc[2], xcomp[2];
+#pragma unroll
+  for (int k = 0; k < kNumAcc; ++k) {
+    acc[k] = lane == 0 ? D.acc[k] : 0.0;
+    comp[k] = lane == 0 ? D.comp[k] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    xacc[k] = lane == 0 ? DX.acc[k] : 0.0;
+    xcomp[k] = lane == 0 ? DX.comp[k] : 0.0;
+  }
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const uint32_t init = (uint32_t)D.init;
+  const long long step0 = D.step;
+  const bool adapt_on = P.adj_scale != 1.0 && P.steps_per_adjust > 0;
+  long long row = 0;
+  long long s = 1;
+  while (s <= a.nsteps) {
+    long long wl = a.nsteps - s + 1;
+    if (wl > a.window) wl = a.window;
+    if (adapt_on) {
+      const long long tb = P.steps_per_adjust - ((step0 + s - 1) % P.steps_per_adjust);
+      if (wl > tb) wl = tb;
+    }
+    if (a.stepout > 0) {
+      const long long tr = a.stepout - ((step0 + s - 1) % a.stepout);
+      if (wl > tr) wl = tr;
+    }
+    const int wlen = (int)wl;
+    const bool active = lane < wlen;
+    const long long step = step0 + s + lane;
+    Draws d;
+    d.idx = 0; d.flipbit = 0; d.u_phi = d.u_theta = d.eps = 0.0;
+    int reflect = 0;
+    if (active) {
+      d = draw_step(a.seed, chain_id, init, step, n);
+      reflect = cluster_gate(P, a.seed, chain_id, init, step);
+    }
+    // the speculative evaluation of this lane's trial
+    int lo = d.idx, hi = d.idx;
+    double base = 0.0, la = 0.0;
+    double dU = 0, dOm = 0, dsu = 0, Dx = 0, Dy = 0, Dz = 0, dpx = 0, dpy = 0, dpz = 0, dpsi = 0, dcos2 = 0;
+    MonoRec nrec;
+    nrec.phi = nrec.theta = nrec.nx = nrec.ny = nrec.nz = nrec.sth = 0.0;
+    bool pending = active, valid = false, accepted = false, written = false, acc0 = false;
+    double carry = DX.carry;
+    unsigned pmask;
+    while ((pmask = __ballot_sync(FULL, pending)) != 0u) {
+      if (pending && !valid) {
+        const MonoRec rec = mono[d.idx];
+        double dphi, dtheta;
+        increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
+        Proposal q;
+        if (P.planar) build_proposal_planar(P, rec, d.idx, dphi, d.eps, q);
+        else build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+        lo = hi = d.idx;
+        double up = 0.0, lp = 0.0;
+        LaneSeg g;
+        lane_seg_zero(g);
+        if (reflect) lane_cluster_grow(mono, q, P, n, a.seed, chain_id, init, step, lo, hi, up, lp, g);
+        double dOm_idx;
+        lane_idx_record(P, q, reflect != 0, nrec, dOm_idx);
+        g.dOmega += dOm_idx;
+        lane_segment_finish<ISING>(mono, n, P, rec, nrec, d.idx, lo, hi, reflect != 0, g, la, up, lp);
+        Dx = P.b * g.sx; Dy = P.b * g.sy; Dz = P.b * g.sz;
+        const double dpairs = kInv4Pi * g.dpair;
+        dsu = g.du_self + g.dbend;
+        dU = dsu - (Dx * P.Fx + Dz * P.Fz) + dpairs;
+        const double dw = P.umbrella ? dsu * P.inv_kT * P.cF : 0.0;
+        base = -dU * P.inv_kT + g.dOmega + dw + la;  // Δlogπ of the lane kernel before `- carry`
+        acc0 = metropolis(base, d.eps);              // the decision when nothing is carried (the usual case)
+        dOm = g.dOmega; dpx = g.dpx; dpy = g.dpy; dpz = g.dpz; dpsi = g.dpsi; dcos2 = g.dcos2;
+        valid = true;
+      }
+      // ---- walk the undecided trials in order ---------------------------------------------------------------
+      unsigned walk = pmask;
+      while (walk) {
+        const int j = __ffs(walk) - 1;
+        walk &= walk - 1;
+        const int fj = __shfl_sync(FULL, (int)valid | ((int)acc0 << 1), j);
+        if (!(fj & 1)) break;  // stale: re-evaluate after the writes of this pass
+        bool aj = (fj & 2) != 0;
+        if (carry != 0.0)  // uniform; x − 0 = x exactly, so the precomputed decision is the same one otherwise
+          aj = metropolis(__shfl_sync(FULL, base, j) - carry, __shfl_sync(FULL, d.eps, j));
+        if (lane == j) { accepted = aj; pending = false; }
+        if (aj) {
+          const double lj = __shfl_sync(FULL, la, j);
+          const int wlo = __shfl_sync(FULL, lo, j), whi = __shfl_sync(FULL, hi, j);
+          carry = P.alpha_carry ? lj : 0.0;  // logπ_prev = logπ + log α (acceptance.jl:32-33)
+          if (pending && lo - 1 <= whi && hi + 1 >= wlo) valid = false;
+        }
+      }
+      // ---- the trials accepted in this pass write their segments (pairwise disjoint) --------------------------
+      if (accepted && !written) {
+        if (reflect)
+          for (int k = lo; k <= hi; ++k) {
+            if (k == d.idx) continue;
+            MonoRec r = mono[k];  // refl_n! / flip_n! of the record
+            if (P.planar) { r.phi += kPi; r.nx = -r.nx; r.ny = -r.ny; r.nz = -r.nz; }
+            else { r.theta = reflect_theta(r.theta); r.nz = -r.nz; }
+            mono[k] = r;
+          }
+        mono[d.idx] = nrec;
+        written = true;
+      }
+      __syncwarp();  // record writes of this pass are visible to the re-evaluations
+    }
+    // ---- running state after each trial: inclusive prefix sums of the accepted increments ---------------------
+    if (!accepted) { dU = dOm = dsu = Dx = Dy = Dz = dpx = dpy = dpz = dpsi = dcos2 = 0.0; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t0 = __shfl_up_sync(FULL, Dx, o), t1 = __shfl_up_sync(FULL, Dy, o), t2 = __shfl_up_sync(FULL, Dz, o);
+      const double t3 = __shfl_up_sync(FULL, dpx, o), t4 = __shfl_up_sync(FULL, dpy, o), t5 = __shfl_up_sync(FULL, dpz, o);
+      const double t6 = __shfl_up_sync(FULL, dU, o), t7 = __shfl_up_sync(FULL, dsu, o), t8 = __shfl_up_sync(FULL, dOm, o);
+      const double t9 = __shfl_up_sync(FULL, dpsi, o), t10 = __shfl_up_sync(FULL, dcos2, o);
+      if (lane >= o) {
+        Dx += t0; Dy += t1; Dz += t2; dpx += t3; dpy += t4; dpz += t5; dU += t6; dsu += t7; dOm += t8;
+        dpsi += t9; dcos2 += t10;
+      }
+    }
+    if (active) {
+      const double r[3] = {D.r[0] + Dx, D.r[1] + Dy, D.r[2] + Dz};
+      const double p[3] = {D.p[0] + dpx, D.p[1] + dpy, D.p[2] + dpz};
+      const double su = D.su + dsu;
+      record_averages<COMP>(P, acc, comp, r, p, D.U + dU, su, D.log_gauge);
+      double wgt = 1.0;  // record_extras (mcmc_clustering_eap_chain.jl:243-244)
+      if (P.umbrella) wgt = 1.0 / exp(su * P.inv_kT * P.cF - D.log_gauge);
+      const double v0 = (DX.scos2 + dcos2) * wgt, v1 = (DX.spsi + dpsi) / (double)(n - 1) * wgt;
+      if (COMP) { comp_add(xacc[0], xcomp[0], v0); comp_add(xacc[1], xcomp[1], v1); }
+      else { xacc[0] += v0; xacc[1] += v1; }
+    }
+    const int last = wlen - 1;
+    D.r[0] += __shfl_sync(FULL, Dx, last); D.r[1] += __shfl_sync(FULL, Dy, last); D.r[2] += __shfl_sync(FULL, Dz, last);
+    D.p[0] += __shfl_sync(FULL, dpx, last); D.p[1] += __shfl_sync(FULL, dpy, last); D.p[2] += __shfl_sync(FULL, dpz, last);
+    D.U += __shfl_sync(FULL, dU, last);
+    D.su += __shfl_sync(FULL, dsu, last);
+    D.Omega += __shfl_sync(FULL, dOm, last);
+    DX.spsi += __shfl_sync(FULL, dpsi, last);
+    DX.scos2 += __shfl_sync(FULL, dcos2, last);
+    DX.carry = carry;
+    const int nacc_w = __popc(__ballot_sync(FULL, accepted));
+    D.nacc += nacc_w; D.nacc_total += nacc_w;
+    D.natt += wlen; D.steps_total += wlen;
+    {  // cluster statistics: trials with a flip, Σ sizes, largest (counted whether accepted or not)
+      const bool fl = active && reflect;
+      int sz = fl ? hi - lo + 1 : 0, mx = sz;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sz += __shfl_xor_sync(FULL, sz, o);
+        mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+      }
+      DX.ncluster += (double)__popc(__ballot_sync(FULL, fl));
+      DX.cluster_sum += (double)sz;
+      DX.cluster_max = fmax(DX.cluster_max, (double)mx);
+    }
+    const long long step_last = step0 + s + last;
+    D.step = step_last;
+    adapt_steps(P, step_last, D.phi_step, D.theta_step, D.nacc, D.natt);  // no-op unless a boundary
+    if (a.stepout > 0 && (step_last % a.stepout) == 0) {
+      double tot[kNumAcc], xt[2];
+#pragma unroll
+      for (int k = 0; k < kNumAcc; ++k) tot[k] = warp_sum(acc[k] + comp[k]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) xt[k] = warp_sum(xacc[k] + xcomp[k]);
+      if (row < a.rows) {
+        if (lane == 0) {
+          double* t = a.traj + ((size_t)c * a.rows + row) * 8;
+          double* rr = a.roll + ((size_t)c * a.rows + row) * a.roll_cols;
+          t[0] = (double)step_last;
+          t[1] = D.r[0]; t[2] = D.r[1]; t[3] = D.r[2];
+          t[4] = D.p[0]; t[5] = D.p[1]; t[6] = D.p[2];
+          t[7] = D.U;
+          rr[0] = (double)step_last;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) rr[1 + k] = tot[k] / tot[16];
+          if (a.roll_cols > 17) { rr[17] = xt[0] / tot[16]; rr[18] = xt[1] / tot[16]; }
+        }
+        if (a.state) {
+          double* st = a.state + ((size_t)c * a.rows + row) * 2 * (size_t)n;
+          for (int k = lane; k < n; k += 32) { st[2 * k] = mono[k].phi; st[2 * k + 1] = mono[k].theta; }
+        }
+      }
+      ++row;
+    }
+    s += wlen;
+  }
+  // combine the per-lane accumulators
+#pragma unroll
+  for (int k = 0; k < kNumAcc; ++k) {
+    D.acc[k] = warp_sum(acc[k] + comp[k]);
+    D.comp[k] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    DX.acc[k] = warp_sum(xacc[k] + xcomp[k]);
+    DX.comp[k] = 0.0;
+  }
+  if (lane == 0) {
+    a.dyn[c] = D;
+    a.dynx[c] = DX;
+  }
+  if (STAGE) {
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) gmono[k] = mono[k];
+  }
+}
+
 // Non-mutating sums of one scripted composite trial through the lane path's device code.
 template <bool ISING>
 __global__ void k_delta_segment_lane(const SegDeltaArgs a) {

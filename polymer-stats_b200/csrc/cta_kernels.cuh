@@ -403,6 +403,7 @@ struct RunArgs {
   double* state;   // [chains][rows][2n] (phi,theta interleaved) or null
   int roll_cols;   // 17, or 19 with the two extra averagers
   int compensated; // Neumaier-compensated accumulators (accum_mode 1 or umbrella weights), else plain sums
+  int window;      // k_run_warp_cluster: trials per window (≤ 32)
 };
 
 // Thread 0: draw and build the proposal of trial `step`.

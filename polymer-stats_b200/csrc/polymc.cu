@@ -77,6 +77,7 @@ struct pmc_handle {
   int64_t shape_chains = 0;   // ensemble size the launch shape is chosen for (0 = nchains), pmc_set_ensemble_hint
   int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
   long long warp_mode_below = 20000;
+  long long warp_cluster_below = 6000;  // composite trials: chain per warp below this many chains, else per lane
   int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
   int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;
@@ -698,7 +699,35 @@ static int launch_run_cluster(pmc_handle* h, const RunArgs& a) {
     constexpr int TB = 64;
     const unsigned nb = (unsigned)((h->nchains + TB - 1) / TB);
     const bool ising = h->energy_type == PMC_ENERGY_ISING;
-    if (h->compensated) {
+    // few chains: one chain per warp with 32-trial windows; many chains: one per lane
+    const int mode = env_int("PMC_LANE_CLUSTER_MODE", 0);  // 1 = lane, 2 = warp, 0 = by chain count
+    if (mode == 2 || (mode == 0 && h->nchains < h->warp_cluster_below)) {
+      const unsigned nbw = (unsigned)((h->nchains + 3) / 4);
+      const bool stage = h->n <= kWarpClusterStageMax;
+      // Trials per window: an accepted trial invalidates the later trials of the window that read its segment and
+      // every invalidation costs a serial re-evaluation pass, but the per-window work (draws, prefix sums,
+      // averagers) is amortised over the window: 32 wins from n = 25 to 400 (profiles/r01f_tune_warp_cluster.txt).
+      RunArgs aw = a;
+      aw.window = 32;
+      {
+        const int w = env_int("PMC_WARP_CLUSTER_WIN", 0);  // experiments only
+        if (w >= 1 && w <= 32) aw.window = w;
+      }
+      const size_t smem = stage ? (size_t)4 * h->n * sizeof(MonoRec) : 0;
+#define PMC_WC(IS, CP)                                                                         \
+  {                                                                                            \
+    if (stage) {                                                                               \
+      int rc = set_smem(k_run_warp_cluster<IS, 2, CP, true>, smem);                            \
+      if (rc) return rc;                                                                       \
+      k_run_warp_cluster<IS, 2, CP, true><<<nbw, 128, smem, h->stream>>>(aw);                  \
+    } else {                                                                                   \
+      k_run_warp_cluster<IS, 2, CP, false><<<nbw, 128, 0, h->stream>>>(aw);                   \
+    }                                                                                          \
+  }
+      if (h->compensated) { if (ising) PMC_WC(true, true) else PMC_WC(false, true) }
+      else { if (ising) PMC_WC(true, false) else PMC_WC(false, false) }
+#undef PMC_WC
+    } else if (h->compensated) {
       if (ising) k_run_lane_cluster<TB, 4, true, true><<<nb, TB, 0, h->stream>>>(a);
       else k_run_lane_cluster<TB, 4, false, true><<<nb, TB, 0, h->stream>>>(a);
     } else {

@@ -104,9 +104,16 @@ def test_segment_delta_vs_oracle(pm, O, et, ct, extra, n):
 @pytest.mark.parametrize("et,n,steps", [("noninteracting", 100, 6000), ("Ising", 100, 6000), ("interacting", 64, 2000),
                                         ("interacting", 200, 600), ("cutoff", 64, 2000)])
 @pytest.mark.parametrize("ct,umb,carry", [("dielectric", False, True), ("polar", True, False)])
-def test_clustering_trajectory_matches_oracle(pm, O, et, n, steps, ct, umb, carry):
+@pytest.mark.parametrize("packing", ["by chain count", "chain per lane"])
+def test_clustering_trajectory_matches_oracle(pm, O, et, n, steps, ct, umb, carry, packing, monkeypatch):
     """The hot loop of mcmc_clustering_eap_chain.jl:267-336 through a two-stage kT ladder: same clusters,
-    same decisions, same rows (8 + 19 + state) as the oracle on the shared Philox stream."""
+    same decisions, same rows (8 + 19 + state) as the oracle on the shared Philox stream.  Non-interacting and
+    Ising chains run one chain per WARP for ensembles this small (speculative trials resolved in order) and one
+    chain per lane for large ones; both packings are held to the same sequence."""
+    if packing == "chain per lane":
+        if et not in ("noninteracting", "Ising"):
+            pytest.skip("one packing for the CTA-per-chain energies")
+        monkeypatch.setenv("PMC_LANE_CLUSTER_MODE", "1")
     kw = dict(n=n, E0=1.0, K1=1.0, K2=0.2, mu=0.6, Fz=0.5, Fx=0.1, chain_type=ct, energy_type=et, kappa=0.5, psi0=0.2,
               cutoff_radius=3.0, clustering=True, alpha_carry=carry, umbrella=umb, adj_ub=0.4, steps_per_adjust=250)
     pc, oc = both_cases(pm, O, **kw)
