@@ -49,6 +49,12 @@ WORKLOADS = {
                 energy_type="Ising", kappa=0.5, clustering=True, adj_ub=0.40), 65536, 2000, 250),
     "K3": (dict(n=400, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.25, Fx=0.0, chain_type="dielectric",
                 energy_type="cutoff", cutoff_radius=7.5, kappa=0.5, clustering=True, adj_ub=0.40), 2368, 200, 100),
+    # the size of the reference's own studies: 20 cases × 25 runs (run/Ising_2025-12-17.jl) — one chain per warp /
+    # more warps per chain (DESIGN.md §3.1 "Small ensembles", §9)
+    "K4": (dict(n=100, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.25, Fx=0.0, chain_type="dielectric",
+                energy_type="Ising", kappa=0.5, clustering=True, adj_ub=0.40), 500, 20000, 2500),
+    "K5": (dict(n=100, E0=1.0, K1=1.0, K2=0.0, kT=1.0, b=1.0, Fz=0.25, Fx=0.0, chain_type="dielectric",
+                energy_type="interacting", kappa=0.5, clustering=True, adj_ub=0.40), 500, 2000, 250),
 }
 SEED = 20260101
 
