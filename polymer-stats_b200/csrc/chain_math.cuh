@@ -34,10 +34,35 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// Shared (not inlined) copies of the long library routines.  The chain-per-lane and chain-per-warp composite-trial
+// kernels are serial, latency-bound code whose top stall is instruction fetch (profiles/r01f_*): a trial calls
+// acos up to 8 times, sincos 4, log 3, Philox 5+, and one inlined copy per call site (≈100–200 SASS instructions
+// each) makes the loop body several times the 32 KB instruction cache.  With SH = true every call site jumps to
+// the same copy (K4 +31 %, K2 +11 % from acos alone).  The CTA kernels, where these calls are rare next to the
+// pair loops, keep the inlined versions (SH = false, the default everywhere).
+__device__ __noinline__ uint4 philox_shared(uint4 c, uint2 k) { return philox4x32_10(c, k); }
+__device__ __noinline__ void sincos_shared(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __noinline__ double log_shared(double x) { return log(x); }
+__device__ __noinline__ double exp_shared(double x) { return exp(x); }
+__device__ __noinline__ double acos_shared(double x) { return acos(x); }
+
+template <bool SH>
+struct Lib {
+  __device__ __forceinline__ static uint4 philox(uint4 c, uint2 k) { return SH ? philox_shared(c, k) : philox4x32_10(c, k); }
+  __device__ __forceinline__ static void sincos_(double x, double* s, double* c) {
+    if (SH) sincos_shared(x, s, c);
+    else sincos(x, s, c);
+  }
+  __device__ __forceinline__ static double log_(double x) { return SH ? log_shared(x) : log(x); }
+  __device__ __forceinline__ static double exp_(double x) { return SH ? exp_shared(x) : exp(x); }
+  __device__ __forceinline__ static double acos_(double x) { return SH ? acos_shared(x) : acos(x); }
+};
+
+template <bool SH = false>
 __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint32_t chain_id, uint32_t init, uint32_t sub,
                                            uint64_t pos) {
-  return philox4x32_10(make_uint4((uint32_t)pos, (uint32_t)(pos >> 32), chain_id, (init << 8) | sub),
-                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return Lib<SH>::philox(make_uint4((uint32_t)pos, (uint32_t)(pos >> 32), chain_id, (init << 8) | sub),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
 __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
@@ -48,15 +73,17 @@ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
 // cluster_flip! draws an unbounded number of uniforms per trial (eap_chain.jl:273,291,307): uniform #k
 // of the upward / downward growth is word pair (k&1) of the Philox block at position
 // step + ((k>>1) << 40) of stream SUB_CLUSTER_UP / _DOWN (steps stay below 2^40).
+template <bool SH = false>
 __device__ __forceinline__ double draw_cluster(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
                                                uint32_t sub, int k) {
-  const uint4 w = philox_at(seed, chain_id, init, sub, (uint64_t)step + (((uint64_t)k >> 1) << 40));
+  const uint4 w = philox_at<SH>(seed, chain_id, init, sub, (uint64_t)step + (((uint64_t)k >> 1) << 40));
   return (k & 1) ? u53(w.z, w.w) : u53(w.x, w.y);
 }
 
+template <bool SH = false>
 __device__ __forceinline__ double draw_cluster_gate(uint64_t seed, uint32_t chain_id, uint32_t init,
                                                     long long step) {
-  const uint4 w = philox_at(seed, chain_id, init, SUB_CLUSTER_GATE, (uint64_t)step);
+  const uint4 w = philox_at<SH>(seed, chain_id, init, SUB_CLUSTER_GATE, (uint64_t)step);
   return u53(w.x, w.y);
 }
 
@@ -188,9 +215,10 @@ __device__ __forceinline__ double pair_g_cut(double ax, double ay, double az, do
 }
 
 // ψ (eap_chain.jl:45-47): acos(min(1, max(-1, n̂_a·n̂_b)))
+template <bool SH = false>
 __device__ __forceinline__ double psi_of(double ax, double ay, double az, double bx, double by, double bz) {
   const double d = fma(az, bz, fma(ay, by, ax * bx));
-  return acos(fmin(1.0, fmax(-1.0, d)));
+  return Lib<SH>::acos_(fmin(1.0, fmax(-1.0, d)));
 }
 
 // ubend (eap_chain.jl:54-58)
@@ -248,10 +276,11 @@ struct Draws {
   int idx, flipbit;
 };
 
+template <bool SH = false>
 __device__ __forceinline__ Draws draw_step(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
                                            int n) {
-  const uint4 a = philox_at(seed, chain_id, init, SUB_STEP_A, (uint64_t)step);
-  const uint4 b = philox_at(seed, chain_id, init, SUB_STEP_B, (uint64_t)step);
+  const uint4 a = philox_at<SH>(seed, chain_id, init, SUB_STEP_A, (uint64_t)step);
+  const uint4 b = philox_at<SH>(seed, chain_id, init, SUB_STEP_B, (uint64_t)step);
   Draws d;
   const uint64_t v = ((uint64_t)a.y << 32) | a.x;
   d.idx = (int)__umul64hi(v, (uint64_t)n);
@@ -263,6 +292,7 @@ __device__ __forceinline__ Draws draw_step(uint64_t seed, uint32_t chain_id, uin
 }
 
 // move! up to the energy (eap_chain.jl:232-251) for given increments.
+template <bool SH = false>
 __device__ __forceinline__ void build_proposal(const ChainParams& P, const MonoRec& rec, int idx, double dphi,
                                                double dtheta, double eps, Proposal& q) {
   q.idx = idx;
@@ -272,8 +302,8 @@ __device__ __forceinline__ void build_proposal(const ChainParams& P, const MonoR
   q.theta = fmin(kPi, fmax(0.0, traw));  // clamped, not reflected (:236)
   q.clamped = (q.theta != traw);
   double sph, cph, sth, cth;
-  sincos(q.phi, &sph, &cph);
-  sincos(q.theta, &sth, &cth);
+  Lib<SH>::sincos_(q.phi, &sph, &cph);
+  Lib<SH>::sincos_(q.theta, &sth, &cth);
   q.sth = sth;
   q.nx = cph * sth;
   q.ny = sph * sth;
@@ -287,7 +317,7 @@ __device__ __forceinline__ void build_proposal(const ChainParams& P, const MonoR
   q.dmx = q.mx - omx;
   q.dmy = q.my - omy;
   q.dmz = q.mz - omz;
-  q.dOmega = log(sth / rec.sth);                       // :238
+  q.dOmega = Lib<SH>::log_(sth / rec.sth);             // :238
   q.du = -0.5 * P.E0 * q.mz - (-0.5 * P.E0 * omz);     // u = −½E0μz, :53
   q.drF = -P.b * (q.dnx * P.Fx + q.dnz * P.Fz);        // −Δr·F, energy.jl:8
   const double dw = P.umbrella ? q.du * P.inv_kT * P.cF : 0.0;  // average.jl:120-124
@@ -298,6 +328,7 @@ __device__ __forceinline__ void build_proposal(const ChainParams& P, const MonoR
 // move! of the planar chain (2D/inc/eap_chain.jl:171-187): ϕ += dϕ, n̂ = (cosϕ, sinϕ) in the x–z plane
 // (the field is along the second axis, 2D/inc/dipole_response.jl:7-10), no θ and no solid-angle term.
 // In the record: n̂y = 0, sinθ ≡ 1 (so every log(sinθ'/sinθ) is exactly 0), θ ≡ 0.
+template <bool SH = false>
 __device__ __forceinline__ void build_proposal_planar(const ChainParams& P, const MonoRec& rec, int idx, double dphi,
                                                       double eps, Proposal& q) {
   q.idx = idx;
@@ -306,7 +337,7 @@ __device__ __forceinline__ void build_proposal_planar(const ChainParams& P, cons
   q.theta = 0.0;
   q.clamped = 0;
   double sph, cph;
-  sincos(q.phi, &sph, &cph);
+  Lib<SH>::sincos_(q.phi, &sph, &cph);
   q.sth = 1.0;
   q.nx = cph; q.ny = 0.0; q.nz = sph;
   mu_of(P, q.nx, q.ny, q.nz, q.mx, q.my, q.mz);
@@ -330,8 +361,9 @@ __device__ __forceinline__ void increments(const ChainParams& P, const Draws& d,
 }
 
 // Metropolis on Δlogπ (acceptance.jl:32): NaN and −Inf both reject.
+template <bool SH = false>
 __device__ __forceinline__ bool metropolis(double dlogpi, double eps) {
-  return (dlogpi >= 0.0) || (eps < exp(dlogpi));
+  return (dlogpi >= 0.0) || (eps < Lib<SH>::exp_(dlogpi));
 }
 
 // Step-size adaptation, mcmc_eap_chain.jl:301-322 (counters reset only when a change fires).

@@ -114,10 +114,11 @@ __device__ __forceinline__ void make_proposal_cl(const RunArgs& a, const ChainPa
 
 // The gate of cluster_flip!.  3-D: `if rand() <= ϵflip; return 1.0; end` BEFORE the growth (eap_chain.jl:273):
 // flips with 1 − ϵflip;  2-D: `if rand() <= ϵflip … flip` AFTER the growth (2D/inc/eap_chain.jl:233): flips with ϵflip.
+template <bool SH = false>
 __device__ __forceinline__ int cluster_gate(const ChainParams& P, uint64_t seed, uint32_t chain_id, uint32_t init,
                                             long long step) {
   if (!P.clustering) return 0;
-  const double gate = draw_cluster_gate(seed, chain_id, init, step);
+  const double gate = draw_cluster_gate<SH>(seed, chain_id, init, step);
   return P.planar ? (gate <= P.cluster_prob) : !(gate <= P.cluster_prob);
 }
 
@@ -216,15 +217,16 @@ __device__ __forceinline__ void segment_angles(const MonoRec* __restrict__ mono,
 }
 
 // n̂ and sinθ from the angles: (cosϕ sinθ, sinϕ sinθ, cosθ) (eap_chain.jl:40) or the planar (cosϕ, 0, sinϕ).
+template <bool SH = false>
 __device__ __forceinline__ void direction_of(int planar, double phi, double theta, double& nx, double& ny, double& nz,
                                              double& sth) {
   double sph, cph;
-  sincos(phi, &sph, &cph);
+  Lib<SH>::sincos_(phi, &sph, &cph);
   if (planar) {
     nx = cph; ny = 0.0; nz = sph; sth = 1.0;
   } else {
     double cth;
-    sincos(theta, &sth, &cth);
+    Lib<SH>::sincos_(theta, &sth, &cth);
     nx = cph * sth; ny = sph * sth; nz = cth;
   }
 }
@@ -739,12 +741,12 @@ __device__ __forceinline__ void lane_add_flipped(const ChainParams& P, const Mon
 }
 
 // ψ, bending and (Ising) pair-term change of ONE bond between monomers a and b (b = a+1).
-template <bool ISING>
+template <bool ISING, bool SH = false>
 __device__ __forceinline__ void lane_bond_delta(const ChainParams& P, double aox, double aoy, double aoz, double anx,
                                                 double any_, double anz, double box, double boy, double boz,
                                                 double bnx, double bny, double bnz, LaneSeg& o) {
-  const double psi_old = psi_of(aox, aoy, aoz, box, boy, boz);
-  const double psi_new = psi_of(anx, any_, anz, bnx, bny, bnz);
+  const double psi_old = psi_of<SH>(aox, aoy, aoz, box, boy, boz);
+  const double psi_new = psi_of<SH>(anx, any_, anz, bnx, bny, bnz);
   o.dpsi += psi_new - psi_old;
   o.dbend += ubend_of(P, psi_new) - ubend_of(P, psi_old);
   if (ISING) {  // U_Ising (eap_chain.jl:215-228): separation x_a − x_b = −(b/2)(n̂_a + n̂_b)
@@ -761,6 +763,7 @@ __device__ __forceinline__ void lane_bond_delta(const ChainParams& P, double aox
 
 // Final record of the moved monomer idx: move! (the proposal), then refl_n!/flip_n! if its cluster is flipped.
 // This one is computed literally from the angles (a θ clamped to π reflects to θ = 0 ⇒ sinθ = 0 ⇒ rejection).
+template <bool SH = false>
 __device__ __forceinline__ void lane_idx_record(const ChainParams& P, const Proposal& q, bool reflect, MonoRec& nrec,
                                                 double& dOmega) {
   if (!reflect) {
@@ -771,8 +774,8 @@ __device__ __forceinline__ void lane_idx_record(const ChainParams& P, const Prop
   double phi = q.phi, theta = q.theta;
   if (P.planar) phi += kPi; else theta = reflect_theta(theta);
   nrec.phi = phi; nrec.theta = theta;
-  direction_of(P.planar, phi, theta, nrec.nx, nrec.ny, nrec.nz, nrec.sth);
-  dOmega = P.planar ? 0.0 : q.dOmega + log(nrec.sth / q.sth);
+  direction_of<SH>(P.planar, phi, theta, nrec.nx, nrec.ny, nrec.nz, nrec.sth);
+  dOmega = P.planar ? 0.0 : q.dOmega + Lib<SH>::log_(nrec.sth / q.sth);
 }
 
 // Changed-term sums of the composite trial for O(1)-per-bond energies.  Reflecting a whole cluster is an
@@ -780,7 +783,7 @@ __device__ __forceinline__ void lane_idx_record(const ChainParams& P, const Prop
 // nearest-neighbour pair terms INSIDE the cluster are unchanged; what changes is: the bonds next to the moved
 // monomer idx, the two bonds at the ends of the cluster, and the single-monomer sums (u, p, r) of the flipped
 // monomers — no transcendental per cluster monomer.  `o` enters holding the flipped-monomer sums (c ≠ idx).
-template <bool ISING>
+template <bool ISING, bool SH = false>
 __device__ __forceinline__ void lane_segment_finish(const MonoRec* __restrict__ mono, int n, const ChainParams& P,
                                                     const MonoRec& rec, const MonoRec& nrec, int idx, int lo, int hi,
                                                     bool reflect, LaneSeg& o, double& la, double up, double lp) {
@@ -799,13 +802,13 @@ __device__ __forceinline__ void lane_segment_finish(const MonoRec* __restrict__ 
     const MonoRec l = mono[idx - 1];
     double fx = l.nx, fy = l.ny, fz = l.nz;
     if (reflect && idx - 1 >= lo) flip_dir(P.planar, l.nx, l.ny, l.nz, fx, fy, fz);
-    lane_bond_delta<ISING>(P, l.nx, l.ny, l.nz, fx, fy, fz, rec.nx, rec.ny, rec.nz, nrec.nx, nrec.ny, nrec.nz, o);
+    lane_bond_delta<ISING, SH>(P, l.nx, l.ny, l.nz, fx, fy, fz, rec.nx, rec.ny, rec.nz, nrec.nx, nrec.ny, nrec.nz, o);
   }
   if (idx + 1 < n) {
     const MonoRec r = mono[idx + 1];
     double fx = r.nx, fy = r.ny, fz = r.nz;
     if (reflect && idx + 1 <= hi) flip_dir(P.planar, r.nx, r.ny, r.nz, fx, fy, fz);
-    lane_bond_delta<ISING>(P, rec.nx, rec.ny, rec.nz, nrec.nx, nrec.ny, nrec.nz, r.nx, r.ny, r.nz, fx, fy, fz, o);
+    lane_bond_delta<ISING, SH>(P, rec.nx, rec.ny, rec.nz, nrec.nx, nrec.ny, nrec.nz, r.nx, r.ny, r.nz, fx, fy, fz, o);
   }
   la = 0.0;
   if (!reflect) return;
@@ -818,7 +821,7 @@ __device__ __forceinline__ void lane_segment_finish(const MonoRec* __restrict__ 
     else {
       const MonoRec t = mono[hi];
       flip_dir(P.planar, t.nx, t.ny, t.nz, hx, hy, hz);
-      lane_bond_delta<ISING>(P, t.nx, t.ny, t.nz, hx, hy, hz, b.nx, b.ny, b.nz, b.nx, b.ny, b.nz, o);
+      lane_bond_delta<ISING, SH>(P, t.nx, t.ny, t.nz, hx, hy, hz, b.nx, b.ny, b.nz, b.nx, b.ny, b.nz, o);
     }
     nup = link_prob(hx, hy, hz, b.nx, b.ny, b.nz);
   }
@@ -829,15 +832,16 @@ __device__ __forceinline__ void lane_segment_finish(const MonoRec* __restrict__ 
     else {
       const MonoRec t = mono[lo];
       flip_dir(P.planar, t.nx, t.ny, t.nz, hx, hy, hz);
-      lane_bond_delta<ISING>(P, b.nx, b.ny, b.nz, b.nx, b.ny, b.nz, t.nx, t.ny, t.nz, hx, hy, hz, o);
+      lane_bond_delta<ISING, SH>(P, b.nx, b.ny, b.nz, b.nx, b.ny, b.nz, t.nx, t.ny, t.nz, hx, hy, hz, o);
     }
     nlp = link_prob(hx, hy, hz, b.nx, b.ny, b.nz);
   }
-  la = log(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
+  la = Lib<SH>::log_(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
 }
 
 // Sequential cluster growth for one lane (eap_chain.jl:276-305) on the chain carrying the move; every monomer
 // that joins the cluster adds its flipped-monomer sums on the way.
+template <bool SH = false>
 __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mono, const Proposal& q,
                                                   const ChainParams& P, int n, uint64_t seed, uint32_t chain_id,
                                                   uint32_t init, long long step, int& lo, int& hi, double& up,
@@ -849,7 +853,7 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
     if (hi >= n - 1) { up = 0.0; break; }
     const MonoRec b = mono[hi + 1];
     up = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
-    if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_UP, k) <= up) {
+    if (draw_cluster<SH>(seed, chain_id, init, step, SUB_CLUSTER_UP, k) <= up) {
       hi += 1; ax = b.nx; ay = b.ny; az = b.nz;
       lane_add_flipped(P, b, o);
     } else break;
@@ -860,7 +864,7 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
     if (lo <= 0) { lp = 0.0; break; }
     const MonoRec b = mono[lo - 1];
     lp = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
-    if (draw_cluster(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k) <= lp) {
+    if (draw_cluster<SH>(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k) <= lp) {
       lo -= 1; ax = b.nx; ay = b.ny; az = b.nz;
       lane_add_flipped(P, b, o);
     } else break;
@@ -886,36 +890,36 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane_cluster(const RunArgs a) {
   long long row = 0;
   for (long long s = 1; s <= a.nsteps; ++s) {
     const long long step = step0 + s;
-    const Draws d = draw_step(a.seed, chain_id, (uint32_t)D.init, step, n);
+    const Draws d = draw_step<true>(a.seed, chain_id, (uint32_t)D.init, step, n);
     const MonoRec rec = mono[d.idx];
     double dphi, dtheta;
     increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
     Proposal q;
-    if (P.planar) build_proposal_planar(P, rec, d.idx, dphi, d.eps, q);
-    else build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+    if (P.planar) build_proposal_planar<true>(P, rec, d.idx, dphi, d.eps, q);
+    else build_proposal<true>(P, rec, d.idx, dphi, dtheta, d.eps, q);
     int lo = d.idx, hi = d.idx;
     double up = 0.0, lp = 0.0;
     bool reflect = false;
     if (P.clustering) {
-      const bool g = draw_cluster_gate(a.seed, chain_id, (uint32_t)D.init, step) <= P.cluster_prob;
+      const bool g = draw_cluster_gate<true>(a.seed, chain_id, (uint32_t)D.init, step) <= P.cluster_prob;
       reflect = P.planar ? g : !g;  // the gate has opposite senses in the two trees (see warp_cluster_grow)
     }
     LaneSeg g;
     lane_seg_zero(g);
-    if (reflect) lane_cluster_grow(mono, q, P, n, a.seed, chain_id, (uint32_t)D.init, step, lo, hi, up, lp, g);
+    if (reflect) lane_cluster_grow<true>(mono, q, P, n, a.seed, chain_id, (uint32_t)D.init, step, lo, hi, up, lp, g);
     MonoRec nrec;
     double dOm_idx;
-    lane_idx_record(P, q, reflect, nrec, dOm_idx);
+    lane_idx_record<true>(P, q, reflect, nrec, dOm_idx);
     g.dOmega += dOm_idx;
     double la;
-    lane_segment_finish<ISING>(mono, n, P, rec, nrec, d.idx, lo, hi, reflect, g, la, up, lp);
+    lane_segment_finish<ISING, true>(mono, n, P, rec, nrec, d.idx, lo, hi, reflect, g, la, up, lp);
     const double Dx = P.b * g.sx, Dy = P.b * g.sy, Dz = P.b * g.sz;
     const double dpairs = kInv4Pi * g.dpair;
     const double dsu = g.du_self + g.dbend;
     const double dU = dsu - (Dx * P.Fx + Dz * P.Fz) + dpairs;
     const double dw = P.umbrella ? dsu * P.inv_kT * P.cF : 0.0;
     const double dlogpi = -dU * P.inv_kT + g.dOmega + dw + la - DX.carry;
-    const bool accept = metropolis(dlogpi, q.eps);
+    const bool accept = metropolis<true>(dlogpi, q.eps);
     if (accept) {
       if (reflect)
         for (int k = lo; k <= hi; ++k) {
@@ -1036,8 +1040,8 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp_cluster(const RunArgs a)
     d.idx = 0; d.flipbit = 0; d.u_phi = d.u_theta = d.eps = 0.0;
     int reflect = 0;
     if (active) {
-      d = draw_step(a.seed, chain_id, init, step, n);
-      reflect = cluster_gate(P, a.seed, chain_id, init, step);
+      d = draw_step<true>(a.seed, chain_id, init, step, n);
+      reflect = cluster_gate<true>(P, a.seed, chain_id, init, step);
     }
     // the speculative evaluation of this lane's trial
     int lo = d.idx, hi = d.idx;
@@ -1054,24 +1058,24 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp_cluster(const RunArgs a)
         double dphi, dtheta;
         increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
         Proposal q;
-        if (P.planar) build_proposal_planar(P, rec, d.idx, dphi, d.eps, q);
-        else build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+        if (P.planar) build_proposal_planar<true>(P, rec, d.idx, dphi, d.eps, q);
+        else build_proposal<true>(P, rec, d.idx, dphi, dtheta, d.eps, q);
         lo = hi = d.idx;
         double up = 0.0, lp = 0.0;
         LaneSeg g;
         lane_seg_zero(g);
-        if (reflect) lane_cluster_grow(mono, q, P, n, a.seed, chain_id, init, step, lo, hi, up, lp, g);
+        if (reflect) lane_cluster_grow<true>(mono, q, P, n, a.seed, chain_id, init, step, lo, hi, up, lp, g);
         double dOm_idx;
-        lane_idx_record(P, q, reflect != 0, nrec, dOm_idx);
+        lane_idx_record<true>(P, q, reflect != 0, nrec, dOm_idx);
         g.dOmega += dOm_idx;
-        lane_segment_finish<ISING>(mono, n, P, rec, nrec, d.idx, lo, hi, reflect != 0, g, la, up, lp);
+        lane_segment_finish<ISING, true>(mono, n, P, rec, nrec, d.idx, lo, hi, reflect != 0, g, la, up, lp);
         Dx = P.b * g.sx; Dy = P.b * g.sy; Dz = P.b * g.sz;
         const double dpairs = kInv4Pi * g.dpair;
         dsu = g.du_self + g.dbend;
         dU = dsu - (Dx * P.Fx + Dz * P.Fz) + dpairs;
         const double dw = P.umbrella ? dsu * P.inv_kT * P.cF : 0.0;
         base = -dU * P.inv_kT + g.dOmega + dw + la;  // Δlogπ of the lane kernel before `- carry`
-        acc0 = metropolis(base, d.eps);              // the decision when nothing is carried (the usual case)
+        acc0 = metropolis<true>(base, d.eps);              // the decision when nothing is carried (the usual case)
         dOm = g.dOmega; dpx = g.dpx; dpy = g.dpy; dpz = g.dpz; dpsi = g.dpsi; dcos2 = g.dcos2;
         valid = true;
       }
@@ -1084,7 +1088,7 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp_cluster(const RunArgs a)
         if (!(fj & 1)) break;  // stale: re-evaluate after the writes of this pass
         bool aj = (fj & 2) != 0;
         if (carry != 0.0)  // uniform; x − 0 = x exactly, so the precomputed decision is the same one otherwise
-          aj = metropolis(__shfl_sync(FULL, base, j) - carry, __shfl_sync(FULL, d.eps, j));
+          aj = metropolis<true>(__shfl_sync(FULL, base, j) - carry, __shfl_sync(FULL, d.eps, j));
         if (lane == j) { accepted = aj; pending = false; }
         if (aj) {
           const double lj = __shfl_sync(FULL, la, j);

@@ -77,7 +77,7 @@ struct pmc_handle {
   int64_t shape_chains = 0;   // ensemble size the launch shape is chosen for (0 = nchains), pmc_set_ensemble_hint
   int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
   long long warp_mode_below = 20000;
-  long long warp_cluster_below = 6000;  // composite trials: chain per warp below this many chains, else per lane
+  long long warp_cluster_below = 11000;  // composite trials: chain per warp below this many chains, else per lane
   int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
   int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;

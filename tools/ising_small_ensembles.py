@@ -4,7 +4,7 @@ import polymc as pm
 # PMC_LANE_CLUSTER_MODE=1 forces one chain per lane, 2 one chain per warp (default: by chain count)
 for et in ("Ising", "noninteracting"):
     for cl in (1, 0):
-        for R in (500, 2048, 8192):
+        for R in [int(x) for x in os.environ.get("PMC_PROBE_R", "500,2048,8192").split(",")]:
             kw = dict(n=100, E0=1.0, Fz=0.25, energy_type=et)
             if cl: kw.update(kappa=0.5, clustering=True, adj_ub=0.4)
             c = pm.make_case(**kw)
