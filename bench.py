@@ -363,9 +363,10 @@ def main():
     achieved_tf = per_gpu * S * F / (kavg_ms * 1e-3) / 1e12
     derived_tf = 148 * 64 * 2 * 1.965e9 / 1e12
     kernel = "k_run_cta_win" if kw["energy_type"] == "interacting" and n <= 3000 else (
-        "k_run_cta" if kw["energy_type"] == "interacting" else "k_run_lane")
-    if clustering:
-        kernel = "k_run_cta_cluster" if kw["energy_type"] in ("interacting", "cutoff") else "k_run_lane_cluster"
+        "k_run_cta" if kw["energy_type"] == "interacting" else ("k_run_warp" if per_gpu < 20000 else "k_run_lane"))
+    if clustering:  # the library picks the packing of the O(1)-energy kernels by chain count (polymc.cu)
+        kernel = "k_run_cta_cluster" if kw["energy_type"] in ("interacting", "cutoff") else (
+            "k_run_warp_cluster" if per_gpu < 11000 else "k_run_lane_cluster")
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the C2 launch, from
     # profiles/r01d_dram_traffic_k_run_cta_win_bench_launch.csv (ncu, same command): 105.3 MB read (the
     # chain records, once per launch) + 2.8-6.3 MB written.  Other workloads: not captured.
