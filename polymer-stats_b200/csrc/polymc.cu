@@ -171,6 +171,7 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
     PMC_CU(cudaGetLastError());                                             \
     return PMC_OK;                                                          \
   }
+#ifdef PMC_TUNING_VARIANTS  // measured negative result (profiles/r01c_tune_warp_specialised.txt): tuning builds only
   if (cfg == 0) {
     if (ws == 34) PMC_LAUNCH_WS(3, 4)
     if (ws == 43) PMC_LAUNCH_WS(4, 3)
@@ -181,6 +182,9 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
     if (ws == 14) PMC_LAUNCH_WS(1, 4)
     if (ws == 18) PMC_LAUNCH_WS(1, 8)
   }
+#else
+  (void)ws;
+#endif
 #undef PMC_LAUNCH_WS
   // windowed kernel (32 proposals built at once by warp 0): needs 6.7 KB more shared memory
   const int use_win = env_int("PMC_RUN_WIN", h->use_win);
@@ -195,12 +199,14 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
     return PMC_OK;                                                          \
   }
   if (cfg == 0 && use_win && smem_win <= (size_t)kSmemMax) {
+#ifdef PMC_TUNING_VARIANTS
     if (use_win == 648) PMC_LAUNCH_WIN(64, 8)
     if (use_win == 1286) PMC_LAUNCH_WIN(128, 6)
     if (use_win == 1285) PMC_LAUNCH_WIN(128, 5)
     if (use_win == 2562) PMC_LAUNCH_WIN(256, 2)
     if (use_win == 643) PMC_LAUNCH_WIN(64, 10)
     if (use_win == 2563) PMC_LAUNCH_WIN(256, 3)
+#endif
     switch (h->cta_threads) {
       case 64: PMC_LAUNCH_WIN(64, 8)
       case 128: PMC_LAUNCH_WIN(128, 4)
@@ -217,6 +223,7 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
     k_run_cta<TT, MB, UR><<<nblocks, TT, smem, h->stream>>>(a);             \
     ++h->launches;                                                          \
   }
+#ifdef PMC_TUNING_VARIANTS
   if (cfg == 12842) PMC_LAUNCH(128, 4, 2)
   else if (cfg == 12841) PMC_LAUNCH(128, 4, 1)
   else if (cfg == 25621) PMC_LAUNCH(256, 2, 1)
@@ -234,7 +241,9 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
   else if (cfg == 51222) PMC_LAUNCH(512, 2, 2)
   else if (cfg == 102412) PMC_LAUNCH(1024, 1, 2)
   else if (cfg == 102411) PMC_LAUNCH(1024, 1, 1)
-  else switch (h->cta_threads) {
+  else
+#endif
+  switch (h->cta_threads) {
     case 64: PMC_LAUNCH(64, 8, 2) break;
     case 128: PMC_LAUNCH(128, 4, 2) break;
     case 256: PMC_LAUNCH(256, 2, 2) break;
@@ -676,6 +685,7 @@ static int launch_run_cluster(pmc_handle* h, const RunArgs& a) {
   }
     // PMC_CLUSTER_CFG = threads*100 + minblocks selects a tuning variant (experiments only)
     const int ccfg = env_int("PMC_CLUSTER_CFG", 0);
+#ifdef PMC_TUNING_VARIANTS
     if (ccfg == 3216) PMC_CL(32, 16)
     else if (ccfg == 3212) PMC_CL(32, 12)
     else if (ccfg == 6408) PMC_CL(64, 8)
@@ -685,7 +695,11 @@ static int launch_run_cluster(pmc_handle* h, const RunArgs& a) {
     else if (ccfg == 12803) PMC_CL(128, 3)
     else if (ccfg == 12805) PMC_CL(128, 5)
     else if (ccfg == 25602) PMC_CL(256, 2)
-    else switch (h->cta_threads) {
+    else
+#else
+    (void)ccfg;
+#endif
+    switch (h->cta_threads) {
       case 32:  // very short chains fit 16 per SM in shared memory: worth the 128-register build (+9 % at n=25)
         if (h->n <= 40) PMC_CL(32, 16) else PMC_CL(32, 12)
         break;
@@ -739,13 +753,18 @@ static int launch_run_cluster(pmc_handle* h, const RunArgs& a) {
     if (ising) k_run_lane_cluster<TT, MB, true, false><<<nbb, TT, 0, h->stream>>>(a);                          \
     else k_run_lane_cluster<TT, MB, false, false><<<nbb, TT, 0, h->stream>>>(a);                               \
   }
+#ifdef PMC_TUNING_VARIANTS
       if (lcfg == 6403) PMC_LC(64, 3)
       else if (lcfg == 6404) PMC_LC(64, 4)
       else if (lcfg == 6408) PMC_LC(64, 8)
       else if (lcfg == 3208) PMC_LC(32, 8)
       else if (lcfg == 3212) PMC_LC(32, 12)
       else if (lcfg == 3216) PMC_LC(32, 16)
-      else if (h->nchains >= 32768) PMC_LC(64, 8)  // many chains: occupancy beats the spills of the 128-register build
+      else
+#else
+      (void)lcfg;
+#endif
+      if (h->nchains >= 32768) PMC_LC(64, 8)  // many chains: occupancy beats the spills of the 128-register build
       else PMC_LC(64, 4)
 #undef PMC_LC
     }
@@ -939,7 +958,10 @@ static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj
     if (ising) { if (comp) PMC_W(1, MB, true); else PMC_W(1, MB, false); }  \
     else { if (comp) PMC_W(0, MB, true); else PMC_W(0, MB, false); }        \
   }
-      if (mb == 3) PMC_WSEL(3) else if (mb == 2) PMC_WSEL(2) else PMC_WSEL(4)
+#ifdef PMC_TUNING_VARIANTS
+      if (mb == 3) PMC_WSEL(3) else if (mb == 2) PMC_WSEL(2) else
+#endif
+      PMC_WSEL(4)
 #undef PMC_WSEL
 #undef PMC_W
     } else {
@@ -947,7 +969,9 @@ static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj
       const unsigned nb = (unsigned)((h->nchains + TB - 1) / TB);
 #define PMC_L(MB, CP) k_run_lane<TB, MB, CP><<<nb, TB, 0, h->stream>>>(a)
       if (mb == 6 || (mb == 0 && !comp)) { if (comp) PMC_L(6, true); else PMC_L(6, false); }
+#ifdef PMC_TUNING_VARIANTS
       else if (mb == 8) { if (comp) PMC_L(8, true); else PMC_L(8, false); }
+#endif
       else { if (comp) PMC_L(4, true); else PMC_L(4, false); }
 #undef PMC_L
     }

@@ -1,4 +1,6 @@
 """Developer tuning sweep over k_run_cta_cluster variants (PMC_CLUSTER_CFG); run on the GPU box."""
+# NOTE: the PMC_*_CFG launch-shape variants exist only in tuning builds: `make -C polymer-stats_b200/csrc clean all TUNING=1`.
+
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 child = r'''

@@ -1,5 +1,7 @@
-"""Developer tuning sweep: one warp per chain, several chains per CTA (PMC_CLUSTER_CFG = 320000 + CPB*100 + MINB)
-against the one-CTA-per-chain shapes of k_run_cta_cluster; run on the GPU box."""
+"""Developer sweep of k_run_cta_cluster over chain lengths (and PMC_CLUSTER_CFG = threads*100 + minblocks shapes);
+run on the GPU box.  Used for profiles/r01f_tune_cluster_cta_window.txt."""
+# NOTE: the PMC_*_CFG launch-shape variants exist only in tuning builds: `make -C polymer-stats_b200/csrc clean all TUNING=1`.
+
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 child = r'''
@@ -17,24 +19,17 @@ for _ in range(3):
     best = min(best, ens.last_run_ms())
 print("%%s n=%%d R=%%d: %%.3f ms  %%.3f M updates/s" %% (et, n, R, best, R*steps/best/1e3))
 ''' % ROOT
-G = [320206, 320304, 320403, 320602, 320802, 321001, 321201]
-SETS = {"full": ((100, 4096, 500, "interacting", [0] + G),
-                 (100, 14208, 300, "interacting", [0, 320403, 320602, 321201]),
-                 (25, 16384, 1000, "interacting", [0, 320403, 320602, 321201]),
-                 (50, 8192, 800, "interacting", [0, 320403, 320602, 321201]),
-                 (160, 4096, 400, "interacting", [0, 320403, 320602]),
-                 (200, 4096, 300, "interacting", [0, 3212, 320403, 320602])),
-        "occ": ((25, 16384, 1000, "interacting", [0, 3216]),
+SETS = {"occ": ((25, 16384, 1000, "interacting", [0, 3216]),
                 (50, 8192, 800, "interacting", [0, 3216]),
                 (64, 8192, 600, "interacting", [0, 3216]),
                 (80, 8192, 500, "interacting", [0, 3216])),
-        "quick": ((100, 4096, 500, "interacting", [0, 321201]),
-                  (25, 16384, 1000, "interacting", [0, 321201]),
-                  (50, 8192, 800, "interacting", [0, 321201]),
+        "quick": ((100, 4096, 500, "interacting", [0]),
+                  (25, 16384, 1000, "interacting", [0]),
+                  (50, 8192, 800, "interacting", [0]),
                   (160, 4096, 400, "interacting", [0]),
                   (200, 4096, 300, "interacting", [0]),
                   (400, 2368, 200, "cutoff", [0]))}
-for n, R, steps, et, cfgs in SETS[sys.argv[1] if len(sys.argv) > 1 else "full"]:
+for n, R, steps, et, cfgs in SETS[sys.argv[1] if len(sys.argv) > 1 else "quick"]:
     for cfg in cfgs:
         env = dict(os.environ)
         if cfg:

@@ -1,4 +1,6 @@
 """Developer timing of the O(1)-ΔU kernels: chain-per-lane vs chain-per-warp (run on the GPU box)."""
+# NOTE: the PMC_*_CFG launch-shape variants exist only in tuning builds: `make -C polymer-stats_b200/csrc clean all TUNING=1`.
+
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 child = r'''

@@ -1,3 +1,4 @@
+# NOTE: the PMC_*_CFG launch-shape variants exist only in tuning builds: `make -C polymer-stats_b200/csrc clean all TUNING=1`.
 import os, subprocess, sys
 child = r'''
 import os, sys

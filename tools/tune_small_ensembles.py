@@ -1,5 +1,7 @@
 """Developer tuning sweep: block size against ensemble size (few chains leave SMs idle, so a chain wants more warps);
 PMC_CTA_THREADS for the single-monomer kernels, PMC_CLUSTER_CFG for the composite-trial kernel.  Run on the GPU box."""
+# NOTE: the PMC_*_CFG launch-shape variants exist only in tuning builds: `make -C polymer-stats_b200/csrc clean all TUNING=1`.
+
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 child = r'''
