@@ -74,9 +74,15 @@ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
 // of the upward / downward growth is word pair (k&1) of the Philox block at position
 // step + ((k>>1) << 40) of stream SUB_CLUSTER_UP / _DOWN (steps stay below 2^40).
 template <bool SH = false>
+__device__ __forceinline__ uint4 cluster_block(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
+                                               uint32_t sub, int k) {
+  return philox_at<SH>(seed, chain_id, init, sub, (uint64_t)step + (((uint64_t)k >> 1) << 40));
+}
+
+template <bool SH = false>
 __device__ __forceinline__ double draw_cluster(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
                                                uint32_t sub, int k) {
-  const uint4 w = philox_at<SH>(seed, chain_id, init, sub, (uint64_t)step + (((uint64_t)k >> 1) << 40));
+  const uint4 w = cluster_block<SH>(seed, chain_id, init, step, sub, k);
   return (k & 1) ? u53(w.z, w.w) : u53(w.x, w.y);
 }
 

@@ -849,11 +849,13 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
   const int idx = q.idx;
   hi = idx;
   double ax = q.nx, ay = q.ny, az = q.nz;
+  uint4 w = make_uint4(0u, 0u, 0u, 0u);  // uniforms #k and #k+1 (k even) share one Philox block (draw_cluster)
   for (int k = 0;; ++k) {
     if (hi >= n - 1) { up = 0.0; break; }
     const MonoRec b = mono[hi + 1];
     up = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
-    if (draw_cluster<SH>(seed, chain_id, init, step, SUB_CLUSTER_UP, k) <= up) {
+    if (!(k & 1)) w = cluster_block<SH>(seed, chain_id, init, step, SUB_CLUSTER_UP, k);
+    if (((k & 1) ? u53(w.z, w.w) : u53(w.x, w.y)) <= up) {
       hi += 1; ax = b.nx; ay = b.ny; az = b.nz;
       lane_add_flipped(P, b, o);
     } else break;
@@ -864,7 +866,8 @@ __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mo
     if (lo <= 0) { lp = 0.0; break; }
     const MonoRec b = mono[lo - 1];
     lp = link_prob(ax, ay, az, b.nx, b.ny, b.nz);
-    if (draw_cluster<SH>(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k) <= lp) {
+    if (!(k & 1)) w = cluster_block<SH>(seed, chain_id, init, step, SUB_CLUSTER_DOWN, k);
+    if (((k & 1) ? u53(w.z, w.w) : u53(w.x, w.y)) <= lp) {
       lo -= 1; ax = b.nx; ay = b.ny; az = b.nz;
       lane_add_flipped(P, b, o);
     } else break;
