@@ -139,6 +139,41 @@ def test_clustering_trajectory_matches_oracle(pm, O, et, n, steps, ct, umb, carr
         assert r17.shape == (3, 1, 17)
 
 
+@pytest.mark.parametrize("case_seed", range(24))
+def test_random_cases_match_oracle(pm, O, case_seed):
+    """Randomised cases of the composite trial (all energies, both chain types, bending, cluster_prob 0 … 0.9,
+    alpha_carry on/off, short adaptation periods so that proposal windows are cut often): the CUDA path takes the
+    oracle's decisions — same final state, cluster statistics and acceptance counts."""
+    rng = np.random.default_rng(1000 + case_seed)
+    et = ["noninteracting", "Ising", "interacting", "cutoff"][case_seed % 4]
+    sizes = [3, 9, 33, 64, 100, 170] if et in ("interacting", "cutoff") else [2, 5, 33, 64, 100, 257]
+    n = sizes[(case_seed // 4) % len(sizes)]
+    kw = dict(n=n, E0=float(rng.choice([0.0, 0.5, 2.0])), K1=1.0, K2=float(rng.choice([0.0, 0.3])), mu=0.5,
+              Fz=float(rng.choice([0.0, 0.7])), Fx=float(rng.choice([0.0, 0.2])), kT=float(rng.choice([0.5, 1.0])),
+              chain_type=str(rng.choice(["dielectric", "polar"])), energy_type=et,
+              kappa=float(rng.choice([0.0, 0.5, 3.0])), psi0=float(rng.choice([0.0, 0.3])), cutoff_radius=3.0,
+              clustering=True, cluster_prob=float(rng.choice([0.0, 0.3, 0.5, 0.9])),
+              alpha_carry=bool(rng.integers(0, 2)), adj_ub=0.4, steps_per_adjust=int(rng.choice([37, 100, 1000])))
+    steps = 1200 if et in ("interacting", "cutoff") else 4000
+    pc, oc = both_cases(pm, O, **kw)
+    seed = int(rng.integers(1, 10 ** 6))
+    with pm.Ensemble(pc, replicas=2, seed=seed, chain_id_base=5) as ens:
+        run = O.Run(oc, seed, 6, 1)
+        for mult in (5.0, 1.0):
+            ens.begin_stage(mult)            # the C ABI takes the kT multiplier of the ladder (:367-381) …
+            run.begin_stage(mult * kw["kT"])  # … the oracle the stage's temperature
+            traj, roll, state = ens.run_ex(steps, steps // 2, want_state=True)
+            ot, orl, ost = run.steps_ex(steps, steps // 2, True)
+            if not np.all(np.abs(ot[:, 7]) < 1e6):
+                pytest.skip("chain collapsed into a singular well (no excluded volume): resolution of U lost")
+            np.testing.assert_allclose(state[1], ost, rtol=0, atol=1e-11, err_msg=str(kw))
+            cs, ocs = ens.cluster_stats()[1], run.cluster_stats()
+            assert (cs[0], cs[1], cs[2]) == (ocs["ncluster"], ocs["cluster_sum"], ocs["cluster_max"]), kw
+            d, od = ens.diagnostics()[1], run.diag()
+            assert d[4] == od["nacc_total"] and d[5] == od["steps_total"], kw
+            np.testing.assert_allclose(traj[1], ot, rtol=1e-8, atol=1e-8, err_msg=str(kw))
+
+
 def test_matches_the_reference_sequence_of_full_recomputes(pm, O):
     """Against oracle algo 0 — deep copy, move!, refl_n! per cluster monomer with full recomputes,
     stateful acceptor with α (the reference's own sequence of operations)."""
