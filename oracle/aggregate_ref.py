@@ -1,4 +1,4 @@
-"""Restatement of scripts/aggregate_mcmc.jl and scripts/reduce_tabular_data.jl working on `.out` FILES, the
+"""Restatement of scripts/aggregate_mcmc.jl, scripts/aggregate_by.jl and scripts/reduce_tabular_data.jl working on `.out` FILES, the
 way the reference does (TEST INFRASTRUCTURE ONLY — the checker for polymc.aggregate, which builds the same
 tables in memory).  Each step cites the script line it follows."""
 from __future__ import annotations
@@ -58,3 +58,47 @@ def reduce_tabular_data(header, rows, chain_type: str, kappaflag=False):
         v, cnt = pooled[k]
         out.append(list(k) + [x / cnt for x in v])
     return header, out
+
+
+def aggregate_by(indir: str, param_arg: str, chain_type: str, kappaflag=False, runflag=False):
+    """aggregate_by.jl:11-60 → {basename of the CSV it would write: (header, rows)}; Julia's 1-based string
+    indices are kept literally (helper `J`) so that the slicing quirks carry over."""
+    fxfz = param_arg == "FxFz"                                                   # :14-18
+    param = "Fz" if fxfz else param_arg
+
+    def find(hay, needle, start1):   # findnext(needle, hay, start) → (first, last) 1-based, or None
+        k = hay.find(needle, start1 - 1)
+        return None if k < 0 else (k + 1, k + len(needle))
+
+    def J(text, a, b):               # text[a:b], 1-based inclusive
+        return text[a - 1:b] if b >= a else ""
+
+    out, params_ran = {}, []
+    datafiles = sorted(f for f in os.listdir(indir) if fnmatch.fnmatchcase(f, "*.out"))   # :24
+    for datafile in datafiles:
+        fileparams = "".join(datafile.split(".")[:-1]).split("_")                # :28
+        if runflag:
+            fileparams.pop()                                                    # :29
+        if fxfz:
+            filtered = [x for x in fileparams if not x.startswith("Fz") and not x.startswith("Fx")]   # :31
+        else:
+            filtered = [x for x in fileparams if not x.startswith(param)]       # :33
+        if filtered in params_ran:                                              # :35-39
+            continue
+        params_ran.append(filtered)
+        strspan = find(datafile, param + "-", 1)                                # :41
+        if strspan is None:
+            continue                                                            # :42
+        value_start = strspan[1] + 1                                            # :43
+        strspan2 = find(datafile, "_", value_start)                             # :44
+        value_end = strspan2[0] if strspan2 is not None else len(datafile) - 3   # :45
+        if fxfz:
+            start_index = find(datafile, "Fz-", 1)[0]                           # :49
+            end_index = find(datafile, "_", find(datafile, "Fx-", 1)[1])[1] - 1   # :50
+            pattern = J(datafile, 1, start_index - 1) + "Fz-*_Fx-*" + J(datafile, end_index + 1, len(datafile))   # :51
+        else:
+            pattern = J(datafile, 1, value_start - 1) + "*" + J(datafile, value_end, len(datafile))   # :53
+        if runflag:
+            pattern = J(pattern, 1, len(pattern) - 5) + "*" + J(pattern, len(pattern) - 3, len(pattern))   # :55
+        out["_".join(filtered) + ".csv"] = aggregate_mcmc(indir, pattern, chain_type, kappaflag, runflag)  # :57-59
+    return out

@@ -94,6 +94,60 @@ def aggregate_table(entries, chain_type: str, kappaflag: bool = False, runflag: 
     return header, rows
 
 
+def _by_pattern(name: str, param: str, runflag: bool):
+    """The glob pattern scripts/aggregate_by.jl builds from one file NAME (:40-57), or None when the name does not
+    carry `param` (:41-42).  param "FxFz" sweeps both force components (:14-18,48-51)."""
+    if param == "FxFz":
+        start = name.find("Fz-")                                                # :49
+        fx = name.find("Fx-")
+        if start < 0 or fx < 0:
+            return None
+        us = name.find("_", fx + 3)                                             # :50 (the "_" after the Fx value)
+        pattern = name[:start] + "Fz-*_Fx-*" + (name[us:] if us >= 0 else "")
+    else:
+        at = name.find(param + "-")                                             # :40
+        if at < 0:
+            return None
+        vstart = at + len(param) + 1                                            # :43
+        us = name.find("_", vstart)                                             # :44
+        vend = us if us >= 0 else len(name) - 4                                 # :45 (`length(datafile)-3`, 1-based)
+        pattern = name[:vstart] + "*" + name[vend:]                             # :52
+    if runflag:
+        pattern = pattern[:-5] + "*" + pattern[-4:]                             # :54 (see aggregate_by)
+    return pattern
+
+
+def aggregate_by(entries, param: str, chain_type: str, kappaflag: bool = False, runflag: bool = False):
+    """scripts/aggregate_by.jl:25-60 in memory: one table per combination of the parameters other than `param`
+    — the sweep over `param` at fixed everything else — as {"<other tokens joined by _>.csv": (header, rows)}.
+
+    Walks the file names in sorted order; the first name of each group defines a glob pattern with `param`'s
+    value (and, with runflag, the LAST DIGIT of the run number, :54) wildcarded, and every name matching it goes
+    through aggregate_mcmc.jl.  Upstream behaviour kept: with runflag the pattern is `…_run-00*.out`, so only
+    runs 000-009 of a group reach its table."""
+    import fnmatch
+    entries = sorted(entries, key=lambda e: os.path.basename(e[0]) + ".out")
+    names = [os.path.basename(e[0]) + ".out" for e in entries]
+    tables, seen = {}, []
+    for name in names:
+        fileparams = "".join(name.split(".")[:-1]).split("_")                   # :28
+        if runflag:
+            fileparams.pop()                                                    # :29
+        if param == "FxFz":
+            filtered = [t for t in fileparams if not t.startswith("Fz") and not t.startswith("Fx")]   # :31
+        else:
+            filtered = [t for t in fileparams if not t.startswith(param)]       # :33
+        if filtered in seen:                                                    # :35-37
+            continue
+        seen.append(filtered)
+        pattern = _by_pattern(name, param, runflag)
+        if pattern is None:
+            continue
+        chosen = [e for e, nm in zip(entries, names) if fnmatch.fnmatchcase(nm, pattern)]
+        tables["_".join(filtered) + ".csv"] = aggregate_table(chosen, chain_type, kappaflag, runflag)   # :56-58
+    return tables
+
+
 def reduce_table(header, rows, nparams: int):
     """reduce_tabular_data.jl:36-56: pool rows with identical parameter columns — plain mean over the runs of
     every output column — sorted by the parameter tuple."""

@@ -162,7 +162,7 @@ def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
 
 
 def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0, device: int = 0, torch_device=None,
-                kappaflag: bool = False, pooled: bool = False):
+                kappaflag: bool = False, pooled: bool = False, with_entries: bool = False):
     """A whole launcher + aggregate_mcmc.jl (+ reduce_tabular_data.jl) pipeline in one call (SURVEY §8f
     rank 3): every pargs dict of `pargs_list` is one case (one launcher command line), run `runs` times as
     independent replica chains (the launchers' `run-NNN` cases); the result is the aggregated table the
@@ -198,4 +198,6 @@ def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0,
     header, rows = agg.aggregate_table(entries, chain_type, kappaflag, runflag)
     if pooled:
         header, rows = agg.reduce_table(header, rows, len(agg.input_headers(chain_type, kappaflag)))
+    if with_entries:  # [(prefix, output values)]: the input of agg.aggregate_by (scripts/aggregate_by.jl)
+        return header, rows, texts, entries
     return header, rows, texts

@@ -33,6 +33,10 @@ def main(argv=None) -> int:
     ap.add_argument("--out", required=True, help="aggregated CSV (aggregate_mcmc.jl format)")
     ap.add_argument("--pooled-out", default=None, help="pooled CSV (reduce_tabular_data.jl format)")
     ap.add_argument("--outdir", default=None, help="also write the per-case <prefix>.out files here")
+    ap.add_argument("--by", default=None, metavar="PARAM",
+                    help="also write one CSV per combination of the OTHER parameters (the sweep over PARAM; FxFz for "
+                         "both force components), as scripts/aggregate_by.jl does, into --by-outdir")
+    ap.add_argument("--by-outdir", default=None)
     ap.add_argument("--kappaflag", action="store_true", help="file names / table carry the kappa column")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", type=int, default=0)
@@ -59,8 +63,11 @@ def main(argv=None) -> int:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch_device)
         rank = dist.get_rank()
-    header, rows, texts = sweep.sweep_table(pargs_list, driver=a.driver, runs=a.runs, seed=a.seed, device=a.device,
-                                            torch_device=torch_device, kappaflag=a.kappaflag)
+    if a.by and not a.by_outdir:
+        ap.error("--by needs --by-outdir")
+    header, rows, texts, entries = sweep.sweep_table(pargs_list, driver=a.driver, runs=a.runs, seed=a.seed,
+                                                     device=a.device, torch_device=torch_device,
+                                                     kappaflag=a.kappaflag, with_entries=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -73,6 +80,11 @@ def main(argv=None) -> int:
         aggregate.write_table(a.pooled_out, h2, r2)
     if a.outdir:
         aggregate.write_out_files(a.outdir, texts)
+    if a.by:
+        os.makedirs(a.by_outdir, exist_ok=True)
+        ct = pargs_list[0]["chain-type"]
+        for name, (h, r) in aggregate.aggregate_by(entries, a.by, ct, a.kappaflag, runflag=a.runs > 1).items():
+            aggregate.write_table(os.path.join(a.by_outdir, name), h, r)
     print(f"{len(pargs_list)} cases x {a.runs} runs -> {a.out}", file=sys.stderr)
     return 0
 

@@ -69,6 +69,43 @@ def test_in_memory_table_equals_the_file_pipeline(pm, tmp_path, chain_type, clus
     np.testing.assert_array_equal(back, rows[0])
 
 
+@pytest.mark.parametrize("param", ["Fz", "E0", "n", "FxFz"])
+@pytest.mark.parametrize("runs", [1, 12])
+def test_aggregate_by_equals_the_file_pipeline(pm, tmp_path, param, runs):
+    """scripts/aggregate_by.jl: one table per combination of the other parameters (the sweep over `param`), in
+    memory against the script's restatement on files — including its run-number wildcard, which keeps only runs
+    000-009 of a group."""
+    import aggregate_ref as REF
+    from polymc import aggregate as agg
+    from polymc import mcmc_clustering as host
+    rng = np.random.default_rng(11)
+    plist = [host.default_pargs(E0=e0, Fz=fz, Fx=fx, num_monomers=n, bend_mod=0.5)
+             for e0 in (0.1, 1.0) for fz in (0.0, 0.5, 2.0) for fx in (0.0, 0.25) for n in (100, 25)]
+    res = _fake_results(rng, len(plist), runs, True)
+    entries, texts = [], []
+    for i, p in enumerate(plist):
+        for r in range(runs):
+            avg, ar, ex = res[i * runs + r]
+            prefix = agg.prefix_of(p, "dielectric", True, run=(r + 1) if runs > 1 else None)
+            entries.append((prefix, agg.output_values(avg, ar, p["mlen"], p["num-monomers"], ex)))
+            texts.append((prefix, agg.out_text(avg, ar, p["mlen"], p["num-monomers"], ex)))
+    outdir = tmp_path / "outs"
+    agg.write_out_files(str(outdir), texts)
+    mine = agg.aggregate_by(entries, param, "dielectric", kappaflag=True, runflag=runs > 1)
+    ref = REF.aggregate_by(str(outdir), param, "dielectric", kappaflag=True, runflag=runs > 1)
+    assert sorted(mine) == sorted(ref) and len(mine) > 1
+    swept = {"Fz": 3, "E0": 2, "n": 2, "FxFz": 6}[param]
+    assert len(mine) == len(plist) // swept
+    for name in mine:
+        (h, rows), (rh, rrows) = mine[name], ref[name]
+        assert h == rh and len(rows) == len(rrows) == swept * min(runs, 9)   # runs 010.. are lost upstream
+        for a, b in zip(rows, rrows):
+            np.testing.assert_array_equal(np.array(a), np.array(b))
+        if param != "FxFz":   # every row of a table shares all parameters but the swept one
+            cols = [k for k, x in enumerate(h[:9]) if x != param]
+            assert all(all(r[k] == rows[0][k] for k in cols) for r in rows)
+
+
 def test_prefix_matches_the_launchers(pm):
     from polymc import aggregate as agg
     from polymc import mcmc_clustering as mc

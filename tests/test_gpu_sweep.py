@@ -58,6 +58,7 @@ def test_run_sweep_cli(pm, tmp_path):
     out, pooled, outdir = tmp_path / "study.csv", tmp_path / "pooled.csv", tmp_path / "outs"
     argv = [sys.executable, os.path.join(ROOT, "polymer-stats_b200", "run_sweep.py"), "--driver", "clustering",
             "--out", str(out), "--pooled-out", str(pooled), "--outdir", str(outdir), "--runs", "2", "--kappaflag",
+            "--by", "Fz", "--by-outdir", str(tmp_path / "by"),
             "--grid", "E0=0.5,1", "--grid", "Fz=0,0.25", "--seed", "11", "--",
             "--energy-type", "Ising", "--bend-mod", "0.5", "-n", "30", "--num-steps", "3000", "--burn-in", "300",
             "--burn-schedule", "[10; 1]", "-v", "0"]
@@ -71,3 +72,8 @@ def test_run_sweep_cli(pm, tmp_path):
     names = sorted(os.listdir(outdir))
     assert len(names) == 8 and names[0] == "E0-0000500_K1-0001000_K2-0000000_kT-0001000_Fz-0000000_Fx-0000000_n-0030000_b-0001000_kappa-0000500_run-001.out"
     assert len(open(outdir / names[0]).read().strip().split("\n")) == 12
+    # scripts/aggregate_by.jl: one table per E0 (the sweep over Fz), 2 Fz values x 2 runs each
+    by = sorted(os.listdir(tmp_path / "by"))
+    assert by == ["E0-0000500_K1-0001000_K2-0000000_kT-0001000_Fx-0000000_n-0030000_b-0001000_kappa-0000500.csv",
+                  "E0-0001000_K1-0001000_K2-0000000_kT-0001000_Fx-0000000_n-0030000_b-0001000_kappa-0000500.csv"]
+    assert len(open(tmp_path / "by" / by[0]).read().strip().split("\n")) == 1 + 4
