@@ -20,12 +20,16 @@ def _julia_eval(text: str):
     return list(v) if isinstance(v, (list, tuple)) else [v]
 
 
-def aggregate_mcmc(indir: str, pattern: str, chain_type: str, kappaflag=False, runflag=False):
+OUTPUT_HEADERS_2D = ["r1", "r2", "lambda1", "lambda2", "r1sq", "r2sq", "rsquared", "p1", "p2", "p1sq", "p2sq",
+                     "psquared", "U", "Usquared", "AR"]                                                           # :56-57
+
+
+def aggregate_mcmc(indir: str, pattern: str, chain_type: str, kappaflag=False, runflag=False, dims=3):
     """aggregate_mcmc.jl:36-77 → (header, rows)."""
     header = list(INPUT_HEADERS[chain_type])
     if kappaflag:
         header.append("kappa")                                                  # :50-52
-    header += OUTPUT_HEADERS_3D
+    header += OUTPUT_HEADERS_3D if dims == 3 else OUTPUT_HEADERS_2D             # :53-57
     rows = []
     for name in sorted(os.listdir(indir)):                                      # readdir(pattern, indir), :61
         if not fnmatch.fnmatchcase(name, pattern):
@@ -60,7 +64,7 @@ def reduce_tabular_data(header, rows, chain_type: str, kappaflag=False):
     return header, out
 
 
-def aggregate_by(indir: str, param_arg: str, chain_type: str, kappaflag=False, runflag=False):
+def aggregate_by(indir: str, param_arg: str, chain_type: str, kappaflag=False, runflag=False, dims=3):
     """aggregate_by.jl:11-60 → {basename of the CSV it would write: (header, rows)}; Julia's 1-based string
     indices are kept literally (helper `J`) so that the slicing quirks carry over."""
     fxfz = param_arg == "FxFz"                                                   # :14-18
@@ -100,5 +104,5 @@ def aggregate_by(indir: str, param_arg: str, chain_type: str, kappaflag=False, r
             pattern = J(datafile, 1, value_start - 1) + "*" + J(datafile, value_end, len(datafile))   # :53
         if runflag:
             pattern = J(pattern, 1, len(pattern) - 5) + "*" + J(pattern, len(pattern) - 3, len(pattern))   # :55
-        out["_".join(filtered) + ".csv"] = aggregate_mcmc(indir, pattern, chain_type, kappaflag, runflag)  # :57-59
+        out["_".join(filtered) + ".csv"] = aggregate_mcmc(indir, pattern, chain_type, kappaflag, runflag, dims)  # :57-59
     return out

@@ -17,7 +17,7 @@ import os
 
 import numpy as np
 
-from .output import julia_float, result_lines, result_lines_clustering
+from .output import julia_float, result_lines, result_lines_2d, result_lines_clustering
 
 # aggregate_mcmc.jl:40-47 (+ "kappa" :50-52)
 INPUT_HEADERS = {"dielectric": ["E0", "K1", "K2", "kT", "Fz", "Fx", "n", "b"],
@@ -25,6 +25,9 @@ INPUT_HEADERS = {"dielectric": ["E0", "K1", "K2", "kT", "Fz", "Fx", "n", "b"],
 # aggregate_mcmc.jl:54-58
 OUTPUT_HEADERS_3D = ["r1", "r2", "r3", "lambda1", "lambda2", "lambda3", "r1sq", "r2sq", "r3sq", "rsquared",
                      "p1", "p2", "p3", "p1sq", "p2sq", "p3sq", "psquared", "U", "Usquared", "Ealign", "psi", "AR"]
+# aggregate_mcmc.jl:56-57 (dims == 2): the 10 lines of the 2-D driver, vectors with two components
+OUTPUT_HEADERS_2D = ["r1", "r2", "lambda1", "lambda2", "r1sq", "r2sq", "rsquared", "p1", "p2", "p1sq", "p2sq",
+                     "psquared", "U", "Usquared", "AR"]
 # pargs key of each file-name token
 _PARG_OF = {"E0": "E0", "K1": "K1", "K2": "K2", "mu": "mu", "kT": "kT", "Fz": "Fz", "Fx": "Fx", "n": "num-monomers",
             "b": "mlen", "kappa": "bend-mod"}
@@ -76,6 +79,18 @@ def output_values(avg16, acc_rate, mlen, n, extras=None):
     return [float(x) for x in v] + [float(acc_rate)]
 
 
+def output_values_2d(avg16, acc_rate, mlen, n):
+    """The 15 output columns of one 2-D case in stdout line order (2D/mcmc_clustering_eap_chain.jl:338-347)."""
+    nb = mlen * n
+    r, rj2, p, pj2 = ([a[0], a[2]] for a in (avg16[0:3], avg16[3:6], avg16[7:10], avg16[10:13]))
+    v = r + [x / nb for x in r] + rj2 + [avg16[6]] + p + pj2 + [avg16[13], avg16[14], avg16[15]]
+    return [float(x) for x in v] + [float(acc_rate)]
+
+
+def out_text_2d(avg16, acc_rate, mlen, n) -> str:
+    return "\n".join(result_lines_2d(avg16, acc_rate, mlen, n)) + "\n"
+
+
 def out_text(avg16, acc_rate, mlen, n, extras=None) -> str:
     """Content of `<prefix>.out`: exactly the stdout of the driver."""
     lines = (result_lines(avg16, acc_rate, mlen, n) if extras is None
@@ -83,11 +98,12 @@ def out_text(avg16, acc_rate, mlen, n, extras=None) -> str:
     return "\n".join(lines) + "\n"
 
 
-def aggregate_table(entries, chain_type: str, kappaflag: bool = False, runflag: bool = False):
+def aggregate_table(entries, chain_type: str, kappaflag: bool = False, runflag: bool = False, dims: int = 3):
     """entries: iterable of (prefix, output value list).  Returns (header list, rows) exactly as
     aggregate_mcmc.jl writes them: one row per file in sorted file-name order, parameter columns parsed back
-    from the NAME (so they carry the launchers' 1e-3 rounding), then the output columns."""
-    header = input_headers(chain_type, kappaflag) + OUTPUT_HEADERS_3D
+    from the NAME (so they carry the launchers' 1e-3 rounding), then the output columns (dims = 2: the 2-D
+    tree's, aggregate_mcmc.jl:23-35,56-57)."""
+    header = input_headers(chain_type, kappaflag) + (OUTPUT_HEADERS_3D if dims == 3 else OUTPUT_HEADERS_2D)
     rows = []
     for prefix, values in sorted(entries, key=lambda e: os.path.basename(e[0]) + ".out"):
         rows.append(params_from_prefix(prefix, runflag) + list(values))
@@ -117,7 +133,8 @@ def _by_pattern(name: str, param: str, runflag: bool):
     return pattern
 
 
-def aggregate_by(entries, param: str, chain_type: str, kappaflag: bool = False, runflag: bool = False):
+def aggregate_by(entries, param: str, chain_type: str, kappaflag: bool = False, runflag: bool = False,
+                 dims: int = 3):
     """scripts/aggregate_by.jl:25-60 in memory: one table per combination of the parameters other than `param`
     — the sweep over `param` at fixed everything else — as {"<other tokens joined by _>.csv": (header, rows)}.
 
@@ -144,7 +161,7 @@ def aggregate_by(entries, param: str, chain_type: str, kappaflag: bool = False, 
         if pattern is None:
             continue
         chosen = [e for e, nm in zip(entries, names) if fnmatch.fnmatchcase(nm, pattern)]
-        tables["_".join(filtered) + ".csv"] = aggregate_table(chosen, chain_type, kappaflag, runflag)   # :56-58
+        tables["_".join(filtered) + ".csv"] = aggregate_table(chosen, chain_type, kappaflag, runflag, dims)   # :56-58
     return tables
 
 

@@ -63,6 +63,26 @@ def result_lines(avg16, acc_rate, mlen, n):
     ]
 
 
+def result_lines_2d(avg16, acc_rate, mlen, n):
+    """The 10 stdout lines of the 2-D driver, 2D/mcmc_clustering_eap_chain.jl:338-347: the same as result_lines
+    with 2-vectors — the planar chain lives in the x–z plane of the 3-D rows (columns "1" and "3")."""
+    xz = [0, 2]
+    pick = lambda v: [v[k] for k in xz]
+    nb = mlen * n
+    return [
+        f"<r>    =   {julia_vector(pick(avg16[0:3]))}",
+        f"<r/nb> =   {julia_vector([x / nb for x in pick(avg16[0:3])])}",
+        f"<rj2>  =   {julia_vector(pick(avg16[3:6]))}",
+        f"<r2>   =   {julia_float(avg16[6])}",
+        f"<p>    =   {julia_vector(pick(avg16[7:10]))}",
+        f"<pj2>  =   {julia_vector(pick(avg16[10:13]))}",
+        f"<p2>   =   {julia_float(avg16[13])}",
+        f"<U>    =   {julia_float(avg16[14])}",
+        f"<U2>   =   {julia_float(avg16[15])}",
+        f"AR     =   {julia_float(acc_rate)}",
+    ]
+
+
 def write_rows(fh, rows):
     """`writedlm(file, hcat(...), ',')` of Float64 rows (step is promoted to Float64, :331,:336)."""
     for row in rows:

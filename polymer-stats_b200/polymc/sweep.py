@@ -171,9 +171,13 @@ def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0,
     from . import aggregate as agg
     from . import mcmc as plain_host
     from . import mcmc_clustering as cl_host
+    from . import mcmc_clustering_2d as cl2d_host
     if not pargs_list:
         raise lib.PolymcError(-1, "empty sweep")
-    host = cl_host if driver == "clustering" else plain_host
+    if driver not in ("plain", "clustering", "clustering2d"):
+        raise lib.PolymcError(-1, "driver must be plain, clustering or clustering2d")
+    planar = driver == "clustering2d"   # the 2-D tree: 2D/mcmc_clustering_eap_chain.jl, aggregate_mcmc.jl … 2D
+    host = cl2d_host if planar else cl_host if driver == "clustering" else plain_host
     chain_type = pargs_list[0]["chain-type"]
     for p in pargs_list:
         host.validate({**p, "replicas": 1})
@@ -182,7 +186,7 @@ def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0,
     cases = [host.case_from_pargs(p) for p in pargs_list]
     p0 = pargs_list[0]
     protocol = None
-    if driver == "clustering":
+    if driver != "plain":
         protocol = dict(burn_in=p0["burn-in"], schedule=cl_host.parse_julia_vector(p0["burn-schedule"], "burn-schedule"))
     res = run_sweep(cases, runs, p0["num-steps"], 0, seed, device, torch_device, protocol)
     runflag = runs > 1
@@ -192,10 +196,14 @@ def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0,
             g = i * runs + r
             prefix = agg.prefix_of(p, chain_type, kappaflag, run=(r + 1) if runflag else None)
             avg = res["avg"][g]
+            if planar:
+                entries.append((prefix, agg.output_values_2d(avg, res["acc_rate"][g], p["mlen"], p["num-monomers"])))
+                texts.append((prefix, agg.out_text_2d(avg, res["acc_rate"][g], p["mlen"], p["num-monomers"])))
+                continue
             ex = (res["extra_sums"][g] / res["normalizer"][g]) if driver == "clustering" else None
             entries.append((prefix, agg.output_values(avg, res["acc_rate"][g], p["mlen"], p["num-monomers"], ex)))
             texts.append((prefix, agg.out_text(avg, res["acc_rate"][g], p["mlen"], p["num-monomers"], ex)))
-    header, rows = agg.aggregate_table(entries, chain_type, kappaflag, runflag)
+    header, rows = agg.aggregate_table(entries, chain_type, kappaflag, runflag, dims=2 if planar else 3)
     if pooled:
         header, rows = agg.reduce_table(header, rows, len(agg.input_headers(chain_type, kappaflag)))
     if with_entries:  # [(prefix, output values)]: the input of agg.aggregate_by (scripts/aggregate_by.jl)

@@ -17,7 +17,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from polymc import aggregate, mcmc, mcmc_clustering, sweep  # noqa: E402
+from polymc import aggregate, mcmc, mcmc_clustering, mcmc_clustering_2d, sweep  # noqa: E402
 
 
 def main(argv=None) -> int:
@@ -27,7 +27,8 @@ def main(argv=None) -> int:
         k = argv.index("--")
         argv, common = argv[:k], argv[k + 1:]
     ap = argparse.ArgumentParser(prog="run_sweep")
-    ap.add_argument("--driver", choices=["plain", "clustering"], default="plain")
+    ap.add_argument("--driver", choices=["plain", "clustering", "clustering2d"], default="plain",
+                    help="mcmc_eap_chain.jl, mcmc_clustering_eap_chain.jl or 2D/mcmc_clustering_eap_chain.jl")
     ap.add_argument("--grid", action="append", default=[], help="NAME=v1,v2,... (long option name of the driver)")
     ap.add_argument("--runs", type=int, default=1, help="independent runs per case (the launchers' run-NNN)")
     ap.add_argument("--out", required=True, help="aggregated CSV (aggregate_mcmc.jl format)")
@@ -41,7 +42,7 @@ def main(argv=None) -> int:
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
-    host = mcmc_clustering if a.driver == "clustering" else mcmc
+    host = {"plain": mcmc, "clustering": mcmc_clustering, "clustering2d": mcmc_clustering_2d}[a.driver]
     axes = []
     for g in a.grid:
         name, vals = g.split("=", 1)
@@ -83,7 +84,8 @@ def main(argv=None) -> int:
     if a.by:
         os.makedirs(a.by_outdir, exist_ok=True)
         ct = pargs_list[0]["chain-type"]
-        for name, (h, r) in aggregate.aggregate_by(entries, a.by, ct, a.kappaflag, runflag=a.runs > 1).items():
+        for name, (h, r) in aggregate.aggregate_by(entries, a.by, ct, a.kappaflag, runflag=a.runs > 1,
+                                                         dims=2 if a.driver == "clustering2d" else 3).items():
             aggregate.write_table(os.path.join(a.by_outdir, name), h, r)
     print(f"{len(pargs_list)} cases x {a.runs} runs -> {a.out}", file=sys.stderr)
     return 0

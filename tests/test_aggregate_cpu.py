@@ -69,6 +69,33 @@ def test_in_memory_table_equals_the_file_pipeline(pm, tmp_path, chain_type, clus
     np.testing.assert_array_equal(back, rows[0])
 
 
+def test_2d_table_equals_the_file_pipeline(pm, tmp_path):
+    """aggregate_mcmc.jl … 2D: 15 output columns from the 10 lines of the 2-D driver."""
+    import aggregate_ref as REF
+    from polymc import aggregate as agg
+    from polymc import mcmc_clustering_2d as host
+    rng = np.random.default_rng(3)
+    plist = [host.default_pargs(E0=e0, Fz=fz, num_monomers=50, energy_type="Ising") for e0 in (0.5, 2.0) for fz in (0.0, 1.0)]
+    entries, texts = [], []
+    for p in plist:
+        avg, ar = rng.normal(size=16) * 10.0 ** rng.integers(-3, 4, size=16), float(rng.uniform(0, 1))
+        prefix = agg.prefix_of(p, "dielectric")
+        entries.append((prefix, agg.output_values_2d(avg, ar, p["mlen"], p["num-monomers"])))
+        texts.append((prefix, agg.out_text_2d(avg, ar, p["mlen"], p["num-monomers"])))
+    outdir = tmp_path / "outs"
+    agg.write_out_files(str(outdir), texts)
+    header, rows = agg.aggregate_table(entries, "dielectric", dims=2)
+    rheader, rrows = REF.aggregate_mcmc(str(outdir), "*.out", "dielectric", dims=2)
+    assert header == rheader and len(header) == 8 + 15
+    np.testing.assert_array_equal(np.array(rows), np.array(rrows))
+    # the 2-D host prints the same lines from its averagers
+    from polymc.mcmc import Average
+    avg = np.arange(1.0, 17.0)
+    vas = [Average(avg[[0, 2]], 1.0), Average(avg[[3, 5]], 1.0), Average(avg[[7, 9]], 1.0), Average(avg[[10, 12]], 1.0)]
+    sas = [Average(avg[6], 1.0), Average(avg[13], 1.0), Average(avg[14], 1.0), Average(avg[15], 1.0)]
+    assert host.result_lines_2d(sas, vas, 0.25, 0.5, 50) == agg.out_text_2d(avg, 0.25, 0.5, 50).strip().split("\n")
+
+
 @pytest.mark.parametrize("param", ["Fz", "E0", "n", "FxFz"])
 @pytest.mark.parametrize("runs", [1, 12])
 def test_aggregate_by_equals_the_file_pipeline(pm, tmp_path, param, runs):

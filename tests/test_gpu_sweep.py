@@ -10,25 +10,28 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("driver", ["plain", "clustering"])
+@pytest.mark.parametrize("driver", ["plain", "clustering", "clustering2d"])
 def test_sweep_table_equals_file_pipeline_and_is_sharding_invariant(pm, tmp_path, driver):
     import aggregate_ref as REF
     from polymc import aggregate as agg
-    from polymc import mcmc, mcmc_clustering, sweep
-    host = mcmc_clustering if driver == "clustering" else mcmc
+    from polymc import mcmc, mcmc_clustering, mcmc_clustering_2d, sweep
+    host = {"plain": mcmc, "clustering": mcmc_clustering, "clustering2d": mcmc_clustering_2d}[driver]
     plist = []
     for e0 in (0.0, 1.0):
         for fz in (0.0, 0.5, 1.0):
             kw = dict(E0=e0, Fz=fz, num_monomers=20, energy_type="interacting", num_steps=1500)
             if driver == "clustering":
                 kw.update(bend_mod=0.5, burn_in=200, burn_schedule="[10; 1]")
+            if driver == "clustering2d":   # the 2-D launchers are Ising studies (2D/run/Ising_2024-11-06.jl)
+                kw.update(energy_type="Ising", burn_in=200, burn_schedule="[10; 1]")
             plist.append(host.default_pargs(**kw))
     kappa = driver == "clustering"
+    dims = 2 if driver == "clustering2d" else 3
     header, rows, texts = sweep.sweep_table(plist, driver=driver, runs=3, seed=5, kappaflag=kappa)
-    assert len(rows) == 18 and len(rows[0]) == (9 if kappa else 8) + (22 if kappa else 20)
+    assert len(rows) == 18 and len(rows[0]) == (9 if kappa else 8) + {"plain": 20, "clustering": 22, "clustering2d": 15}[driver]
     outdir = tmp_path / "outs"
     agg.write_out_files(str(outdir), texts)
-    rheader, rrows = REF.aggregate_mcmc(str(outdir), "*.out", "dielectric", kappaflag=kappa, runflag=True)
+    rheader, rrows = REF.aggregate_mcmc(str(outdir), "*.out", "dielectric", kappaflag=kappa, runflag=True, dims=dims)
     assert header == rheader
     np.testing.assert_array_equal(np.array(rows), np.array(rrows))
     ar = np.array(rows)[:, -1]
@@ -36,6 +39,10 @@ def test_sweep_table_equals_file_pipeline_and_is_sharding_invariant(pm, tmp_path
     # sharding by global chain id is invisible: 3 emulated ranks reproduce the single-rank result bit for bit
     cases = [host.case_from_pargs(p) for p in plist]
     proto = None if driver == "plain" else dict(burn_in=200, schedule=[10.0, 1.0])
+    if driver == "clustering2d":
+        assert header[-15:] == ["r1", "r2", "lambda1", "lambda2", "r1sq", "r2sq", "rsquared", "p1", "p2", "p1sq", "p2sq",
+                                "psquared", "U", "Usquared", "AR"]
+        assert len(open(outdir / sorted(os.listdir(outdir))[0]).read().strip().split("\n")) == 10
     one = sweep.run_shard(cases, 3, 1500, 0, 5, 0, 0, 1, proto)
     parts = []
     for gids, lo, block in one:
