@@ -3,7 +3,9 @@
  * of grasingerm/polymer-stats, i.e. everything inside `mcmc(nsteps, pargs)` of
  * mcmc_eap_chain.jl:171-376 for thousands of independent chains at once — and, since ABI version 2,
  * inside `mcmc(nsteps, pargs, chain)` of its clustering twin mcmc_clustering_eap_chain.jl:171-352
- * (cluster_flip!, bending energy, cut-off pair sum, burn-in stages).
+ * (cluster_flip!, bending energy, cut-off pair sum, burn-in stages).  ABI version 3
+ * adds the multi-GPU ensemble (pmc_multi_*: one host thread per device, one final NCCL all-gather — the
+ * fan-out of run/interacting_dielectric_study.jl:37-47), checkpoints and pmc_kernel_name.
  *
  * The reference has no FFI of its own (pure Julia).  The seams this ABI replaces are ordinary
  * Julia functions; each entry point below cites the one it stands in for.  A Julia host binds
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PMC_ABI_VERSION 2
+#define PMC_ABI_VERSION 3
 
 typedef enum pmc_status {
   PMC_OK = 0,
@@ -173,6 +175,10 @@ int32_t pmc_init_x0(pmc_handle* h, const double* x0, int64_t x0_len, const doubl
 int32_t pmc_last_run_ms(const pmc_handle* h, float* ms);
 /* Number of CUDA kernels this handle has launched so far (bench.py's `gpu_launches`). */
 int64_t pmc_launch_count(const pmc_handle* h);
+/* Name of the MCMC kernel pmc_run / pmc_run_ex launches for this handle as it is now (driver, energy type, chain
+ * length, ensemble size and hint select it), e.g. "k_run_cta_win<128,4,2>".  The library's own launch decision,
+ * taken without launching anything. */
+int32_t pmc_kernel_name(pmc_handle* h, char* buf, int32_t buflen);
 
 /* Re-initialisation between inits, mcmc_eap_chain.jl:352-361 (metropolis_acc, inc/acceptance.jl:1-3):
  * draws a fresh random chain per chain and swaps it in iff force_init or
@@ -197,6 +203,61 @@ int32_t pmc_cluster_stats(pmc_handle* h, double* out);
 /* diag [chains][8] = {phi_step, theta_step, nacc, natt, nacc_total, trials, U_running, max |U_running -
  * U_recomputed| seen at re-synchronisation}. */
 int32_t pmc_diagnostics(pmc_handle* h, double* diag);
+
+/* ---- checkpoint / resume ------------------------------------------------------------------ */
+/* Everything a later process needs to continue the run exactly where it stopped: the chain records (phi, theta
+ * and caches), the running scalars, step sizes, counters, the 17+2 accumulators (both parts of the compensated
+ * sums), the init / stage number and the stage temperature.  The reference has no checkpointing (a killed
+ * `julia mcmc_eap_chain.jl` starts over); its closest seam is --x0 (inc/eap_chain.jl:63-78), which restores
+ * angles only.  Load into a handle created with the same cases, replicas, seed and chain_id_base; continuing
+ * with pmc_run then gives bit-identical results to an uninterrupted run. */
+int64_t pmc_checkpoint_bytes(const pmc_handle* h);
+int32_t pmc_checkpoint_save(pmc_handle* h, void* buf, int64_t bytes);
+int32_t pmc_checkpoint_load(pmc_handle* h, const void* buf, int64_t bytes);
+
+/* Both parts of the error-free-transformation sums: value = hi + lo with |lo| <= ulp(hi), i.e. double-double
+ * accumulators — what `--numeric-type float128|dec128|big` asks of the averagers (mcmc_eap_chain.jl:186-197,
+ * inc/average.jl:8-48).  hi, lo: [chains][19] = the 16 sums, the normaliser, and the two extra sums of the
+ * clustering driver. */
+int32_t pmc_accumulators_dd(pmc_handle* h, double* hi, double* lo);
+
+/* ---- one ensemble over several GPUs of one box (ABI v3) ------------------------------------ */
+/* Replaces the fan-out of the reference's launchers — `julia -p N run/interacting_dielectric_study.jl workdir`,
+ * run/interacting_dielectric_study.jl:37-47 (pmap over cases, one single-threaded process per case).  The
+ * ncases*replicas_per_case chains are split into contiguous blocks of global chain ids, one per device (device g
+ * owns [g·R/G, (g+1)·R/G)); Philox streams are keyed by the global id, so results do not depend on the number of
+ * devices.  Every device is driven from its own internal host thread; there is no data-path collective.  The only
+ * exchange is pmc_multi_gather: the final per-chain result rows, one ncclAllGather over NVLink (libnccl.so.2 is
+ * opened with dlopen; without it the rows travel by device-to-device copies).
+ * devices = NULL: devices 0..ndevices-1; ndevices <= 0: every device of the box. */
+typedef struct pmc_multi pmc_multi;
+#define PMC_RESULT_COLS 24 /* one gathered row: 16 averages (rolling.csv order), acc_rate, normalizer, phi_step,
+                              theta_step, trials, U_running, <sum cos^2 theta>, <sum(psi)/(n-1)>               */
+int32_t pmc_multi_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_case, uint64_t seed,
+                         const int32_t* devices, int32_t ndevices, pmc_multi** out);
+void pmc_multi_destroy(pmc_multi* m);
+int32_t pmc_multi_num_devices(const pmc_multi* m);
+int64_t pmc_multi_num_chains(const pmc_multi* m);
+const char* pmc_multi_gather_backend(const pmc_multi* m);   /* "nccl", "peer" or "none" (one device) */
+/* The single-device handle behind slot `slot` (for the per-chain seams: pmc_set_state, pmc_energy, pmc_delta_u,
+ * pmc_reinit, pmc_checkpoint_*, ...), the device it lives on and its block of global chain ids. */
+pmc_handle* pmc_multi_shard(pmc_multi* m, int32_t slot, int32_t* device, int64_t* first_chain, int64_t* nchains);
+int32_t pmc_multi_set_ensemble_hint(pmc_multi* m, int64_t ensemble_chains);
+int32_t pmc_multi_begin_stage(pmc_multi* m, double kT_scale);
+int32_t pmc_multi_set_state_all(pmc_multi* m, const double* phi, const double* theta);   /* [chains][n] */
+int32_t pmc_multi_get_state_all(pmc_multi* m, double* phi, double* theta);
+int64_t pmc_multi_rows_for(const pmc_multi* m, int64_t nsteps, int64_t stepout);
+/* pmc_run / pmc_run_ex on every device at once; traj/roll/state are [chains][rows][...] over the WHOLE ensemble
+ * and every device fills its own slice.  _async returns at once (the host may format the previous interval's
+ * rows meanwhile); pmc_multi_wait joins and reports the first error. */
+int32_t pmc_multi_run(pmc_multi* m, int64_t nsteps, int64_t stepout, double* traj, double* roll);
+int32_t pmc_multi_run_ex(pmc_multi* m, int64_t nsteps, int64_t stepout, double* traj, double* roll19, double* state);
+int32_t pmc_multi_run_async(pmc_multi* m, int64_t nsteps, int64_t stepout, double* traj, double* roll);
+int32_t pmc_multi_wait(pmc_multi* m);
+/* table [chains][PMC_RESULT_COLS]: packed on each device, gathered device-to-device, read from the first device. */
+int32_t pmc_multi_gather(pmc_multi* m, double* table);
+int32_t pmc_multi_last_run_ms(const pmc_multi* m, float* ms_max);   /* slowest device's MCMC kernel time */
+int64_t pmc_multi_launch_count(const pmc_multi* m);
 
 /* ---- measurement helper ------------------------------------------------------------------ */
 /* Dependent-free DFMA loop on all SMs of `device`; returns achieved FP64 TFLOP/s (2 flop per DFMA)

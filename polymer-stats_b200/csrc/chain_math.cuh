@@ -40,11 +40,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // each) makes the loop body several times the 32 KB instruction cache.  With SH = true every call site jumps to
 // the same copy (K4 +31 %, K2 +11 % from acos alone).  The CTA kernels, where these calls are rare next to the
 // pair loops, keep the inlined versions (SH = false, the default everywhere).
-__device__ __noinline__ uint4 philox_shared(uint4 c, uint2 k) { return philox4x32_10(c, k); }
-__device__ __noinline__ void sincos_shared(double x, double* s, double* c) { sincos(x, s, c); }
-__device__ __noinline__ double log_shared(double x) { return log(x); }
-__device__ __noinline__ double exp_shared(double x) { return exp(x); }
-__device__ __noinline__ double acos_shared(double x) { return acos(x); }
+static __device__ __noinline__ uint4 philox_shared(uint4 c, uint2 k) { return philox4x32_10(c, k); }
+static __device__ __noinline__ void sincos_shared(double x, double* s, double* c) { sincos(x, s, c); }
+static __device__ __noinline__ double log_shared(double x) { return log(x); }
+static __device__ __noinline__ double exp_shared(double x) { return exp(x); }
+static __device__ __noinline__ double acos_shared(double x) { return acos(x); }
 
 template <bool SH>
 struct Lib {

@@ -1268,7 +1268,7 @@ __global__ void k_delta_segment_lane(const SegDeltaArgs a) {
 // A fresh `mcmc(nsteps, pargs, chain)` call on the current chains (mcmc_clustering_eap_chain.jl:171-265):
 // new averagers, counters, step sizes and acceptor; the RNG stream tag advances.  The running scalars and
 // the weight function are re-synchronised by k_energy_cta afterwards (rebind_gauge).
-__global__ void k_begin_stage(ChainDyn* dyn, ChainDynX* dynx, const ChainParams* par, int nchains, int new_init) {
+static __global__ void k_begin_stage(ChainDyn* dyn, ChainDynX* dynx, const ChainParams* par, int nchains, int new_init) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchains) return;
   ChainDyn& D = dyn[c];
@@ -1286,7 +1286,7 @@ __global__ void k_begin_stage(ChainDyn* dyn, ChainDynX* dynx, const ChainParams*
 
 // --x0/--dx0 initial chains (eap_chain.jl:63-78): ϕ = ϕ0 + U(0,dx0[1]), θ = θ0 + U(0,dx0[2]); the uniforms
 // are those of the random-init stream.
-__global__ void k_fill_x0(MonoRec* mono, long long total, int n, uint64_t seed, uint32_t chain_id_base,
+static __global__ void k_fill_x0(MonoRec* mono, long long total, int n, uint64_t seed, uint32_t chain_id_base,
                           uint32_t init, const double* x0, int x0_len, double dx0_phi, double dx0_theta) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;

@@ -1,0 +1,117 @@
+// handle.h — what the translation units of libpolymc_b200.so share: the handle behind the C ABI, error
+// plumbing, and the launch helpers each kernel family's TU exports (one TU per family so that `make -j`
+// compiles them in parallel).
+#pragma once
+
+#include "../../include/polymc.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <algorithm>
+#include <vector>
+
+#include "cluster_kernels.cuh"
+
+using namespace pmc;
+
+// sets the calling thread's pmc_last_error() text and returns `code`
+int pmc_fail(int code, const std::string& msg);
+
+#define PMC_CU(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      cudaGetLastError();                                                                         \
+      return pmc_fail((e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? PMC_ERR_NO_DEVICE \
+                      : (e__ == cudaErrorMemoryAllocation)                              ? PMC_ERR_NOMEM \
+                                                                                        : PMC_ERR_CUDA, \
+                      std::string(#expr) + ": " + cudaGetErrorString(e__));                       \
+    }                                                                                             \
+  } while (0)
+
+constexpr int kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// Every launch helper records the kernel it picks; with dry_run set it stops there (pmc_kernel_name).
+#define PMC_PICK(name_literal)        \
+  do {                                \
+    h->kernel_name = name_literal;    \
+    if (h->dry_run) return PMC_OK;    \
+  } while (0)
+
+struct pmc_handle {
+  int device = 0;
+  int64_t nchains = 0;
+  int n = 0;
+  int energy_type = 0;
+  uint64_t seed = 0;
+  uint32_t chain_id_base = 0;
+  int init = 0;
+  cudaStream_t stream = nullptr;
+  MonoRec* mono = nullptr;
+  MonoRec* cand = nullptr;
+  ChainParams* par = nullptr;
+  ChainDyn* dyn = nullptr;
+  double* traj = nullptr;
+  double* roll = nullptr;
+  size_t traj_cap = 0, roll_cap = 0;
+  double* scratch = nullptr;  // 2·nchains·n doubles (state staging) — also small outputs
+  size_t scratch_cap = 0;
+  int* flags = nullptr;       // nchains ints
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int64_t launches = 0;
+  int cta_threads = 256;      // block size of the CTA-per-chain kernels
+  int sm_count = 148;
+  int64_t shape_chains = 0;   // ensemble size the launch shape is chosen for (0 = nchains), pmc_set_ensemble_hint
+  int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
+  long long warp_mode_below = 20000;
+  long long warp_cluster_below = 11000;  // composite trials: chain per warp below this many chains, else per lane
+  int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
+  int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
+  std::vector<ChainDyn> host_dyn;
+  // clustering driver (mcmc_clustering_eap_chain.jl)
+  int cluster_mode = 0;       // 1: the composite-trial kernels of cluster_kernels.cuh run this handle
+  ChainDynX* dynx = nullptr;
+  double* state = nullptr;    // [chains][rows][2n] state rows of the last pmc_run_ex
+  size_t state_cap = 0;
+  double* x0buf = nullptr;
+  std::vector<pmc_case> cases;
+  int replicas = 1;
+  double kT_scale = 1.0;
+  std::vector<ChainDynX> host_dynx;
+  int planar = 0;             // 2-D tree
+  const char* kernel_name = "";  // the MCMC kernel the last (dry or real) launch decision picked, pmc_kernel_name
+  int dry_run = 0;               // launch helpers only record their decision
+};
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  PMC_CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return PMC_OK;
+}
+
+// Ensemble size the chain-per-lane / chain-per-warp packing is chosen for: like the block size it follows the
+// hint, so a shard of a sweep runs the kernel the whole ensemble would (the packings sum the per-trial averager
+// contributions in different orders; same kernel ⇒ results bit-identical however the sweep is sharded).
+inline int64_t packing_chains(const pmc_handle* h) { return h->shape_chains > 0 ? h->shape_chains : h->nchains; }
+
+// Block size of the composite-trial CTA kernels.
+// Short chains are latency bound (one serial proposal/cluster/decision chain per trial), so one warp per
+// chain and many chains per SM; measured crossovers in profiles/r01e_tune_cluster.txt.
+inline int pick_cluster_threads(int n) { return n <= 160 ? 32 : n <= 256 ? 64 : n <= 1024 ? 128 : 256; }
+
+// ---- launch helpers, one translation unit per kernel family -------------------------------------------------
+int launch_run_cta(pmc_handle* h, const pmc::RunArgs& a);                    // run_cta.cu
+int launch_run_lane(pmc_handle* h, const pmc::RunArgs& a);                   // run_lane.cu
+int launch_run_cluster_cta(pmc_handle* h, const pmc::RunArgs& a);            // run_cluster_cta.cu
+int launch_delta_segment_cta(pmc_handle* h, const pmc::SegDeltaArgs& a);     // run_cluster_cta.cu
+int launch_run_cluster_lane(pmc_handle* h, const pmc::RunArgs& a);           // run_cluster_lane.cu

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
 }
 
 // Non-mutating ΔU of one scripted move through the lane path's device code.
-__global__ void k_delta_lane(const DeltaArgs a) {
+static __global__ void k_delta_lane(const DeltaArgs a) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const MonoRec* mono = a.mono + (size_t)a.chain * a.n;
   const ChainParams P = a.par[a.chain];
@@ -262,7 +262,7 @@ __device__ __forceinline__ MonoRec make_record(double phi, double theta, int pla
 }
 
 // Random initial chains: ϕ~U(0,2π), θ~U(0,π) (eap_chain.jl:6-7,62).
-__global__ void k_fill_random(MonoRec* mono, long long total, int n, uint64_t seed, uint32_t chain_id_base,
+static __global__ void k_fill_random(MonoRec* mono, long long total, int n, uint64_t seed, uint32_t chain_id_base,
                               uint32_t init, int planar = 0) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
@@ -272,14 +272,14 @@ __global__ void k_fill_random(MonoRec* mono, long long total, int n, uint64_t se
   mono[g] = make_record(0.0 + (2.0 * kPi - 0.0) * u53(w.x, w.y), 0.0 + (kPi - 0.0) * u53(w.z, w.w), planar);
 }
 
-__global__ void k_build_records(MonoRec* mono, const double* phi, const double* theta, long long total,
+static __global__ void k_build_records(MonoRec* mono, const double* phi, const double* theta, long long total,
                                 int planar = 0) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
   mono[g] = make_record(phi[g], theta[g], planar);
 }
 
-__global__ void k_extract_state(const MonoRec* mono, double* phi, double* theta, long long total) {
+static __global__ void k_extract_state(const MonoRec* mono, double* phi, double* theta, long long total) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
   phi[g] = mono[g].phi;
@@ -287,7 +287,7 @@ __global__ void k_extract_state(const MonoRec* mono, double* phi, double* theta,
 }
 
 // FP64 roofline probe: 8 independent DFMA chains per thread, no memory traffic.
-__global__ void k_fp64_probe(double* sink, int iters, double a, double b) {
+static __global__ void k_fp64_probe(double* sink, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
          x7 = x0 + 7;
   for (int i = 0; i < iters; ++i) {

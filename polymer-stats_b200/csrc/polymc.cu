@@ -2,97 +2,23 @@
 //
 // No CPU fallback: every compute entry point needs a CUDA device and reports
 // PMC_ERR_NO_DEVICE / PMC_ERR_CUDA otherwise.
-#include "../../include/polymc.h"
-
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <new>
-#include <string>
-#include <algorithm>
-#include <vector>
-
-#include "cluster_kernels.cuh"
-
-using namespace pmc;
+#include "handle.h"
 
 namespace {
 
 thread_local std::string g_err;
 
-int fail(int code, const std::string& msg) {
-  g_err = msg;
-  return code;
-}
-
-#define PMC_CU(expr)                                                                              \
-  do {                                                                                            \
-    cudaError_t e__ = (expr);                                                                     \
-    if (e__ != cudaSuccess) {                                                                     \
-      cudaGetLastError();                                                                         \
-      return fail((e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? PMC_ERR_NO_DEVICE \
-                  : (e__ == cudaErrorMemoryAllocation)                              ? PMC_ERR_NOMEM \
-                                                                                    : PMC_ERR_CUDA, \
-                  std::string(#expr) + ": " + cudaGetErrorString(e__));                           \
-    }                                                                                             \
-  } while (0)
-
-constexpr int kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
-
 // the FFI mirrors of pmc_case (ctypes in polymc/lib.py, the Julia struct in julia/polymc_host.jl) rely on it
 static_assert(sizeof(pmc_case) == 13 * 8 + 2 * 8 + 6 * 4 + 4 * 8 + 4 * 4, "pmc_case layout changed: bump PMC_ABI_VERSION");
 
-int env_int(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return (v && *v) ? std::atoi(v) : dflt;
-}
+int fail(int code, const std::string& msg) { return pmc_fail(code, msg); }
 
 }  // namespace
 
-struct pmc_handle {
-  int device = 0;
-  int64_t nchains = 0;
-  int n = 0;
-  int energy_type = 0;
-  uint64_t seed = 0;
-  uint32_t chain_id_base = 0;
-  int init = 0;
-  cudaStream_t stream = nullptr;
-  MonoRec* mono = nullptr;
-  MonoRec* cand = nullptr;
-  ChainParams* par = nullptr;
-  ChainDyn* dyn = nullptr;
-  double* traj = nullptr;
-  double* roll = nullptr;
-  size_t traj_cap = 0, roll_cap = 0;
-  double* scratch = nullptr;  // 2·nchains·n doubles (state staging) — also small outputs
-  size_t scratch_cap = 0;
-  int* flags = nullptr;       // nchains ints
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  float last_ms = 0.f;
-  int64_t launches = 0;
-  int cta_threads = 256;      // block size of the CTA-per-chain kernels
-  int sm_count = 148;
-  int64_t shape_chains = 0;   // ensemble size the launch shape is chosen for (0 = nchains), pmc_set_ensemble_hint
-  int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
-  long long warp_mode_below = 20000;
-  long long warp_cluster_below = 11000;  // composite trials: chain per warp below this many chains, else per lane
-  int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
-  int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
-  std::vector<ChainDyn> host_dyn;
-  // clustering driver (mcmc_clustering_eap_chain.jl)
-  int cluster_mode = 0;       // 1: the composite-trial kernels of cluster_kernels.cuh run this handle
-  ChainDynX* dynx = nullptr;
-  double* state = nullptr;    // [chains][rows][2n] state rows of the last pmc_run_ex
-  size_t state_cap = 0;
-  double* x0buf = nullptr;
-  std::vector<pmc_case> cases;
-  int replicas = 1;
-  double kT_scale = 1.0;
-  std::vector<ChainDynX> host_dynx;
-  int planar = 0;             // 2-D tree
-};
+int pmc_fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
 
 namespace {
 
@@ -129,12 +55,6 @@ int pick_cta_threads(int n) {
   return t;
 }
 
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-  PMC_CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return PMC_OK;
-}
-
 // Launch helpers: dispatch on the block size chosen at create time.
 int launch_energy(pmc_handle* h, const EnergyArgs& a, int nblocks) {
   const size_t smem = cta_smem_bytes(h->n);
@@ -151,107 +71,6 @@ int launch_energy(pmc_handle* h, const EnergyArgs& a, int nblocks) {
     default: return fail(PMC_ERR_INVALID, "bad cta_threads");
   }
 #undef PMC_CASE
-  PMC_CU(cudaGetLastError());
-  return PMC_OK;
-}
-
-int launch_run_cta(pmc_handle* h, const RunArgs& a) {
-  const size_t smem = cta_smem_bytes(h->n);
-  const int nblocks = (int)h->nchains;
-  // PMC_RUN_CFG = threads*100 + minblocks*10 + unroll selects a tuning variant (experiments only)
-  const int cfg = env_int("PMC_RUN_CFG", 0);
-  // PMC_RUN_WS = workers*10 + minblocks selects the warp-specialised kernel (control warp + workers)
-  const int ws = env_int("PMC_RUN_WS", h->ws_cfg);
-#define PMC_LAUNCH_WS(WK, MB)                                               \
-  {                                                                         \
-    int rc = set_smem(k_run_cta_ws<WK, MB, 2>, smem);                       \
-    if (rc) return rc;                                                      \
-    k_run_cta_ws<WK, MB, 2><<<nblocks, (WK + 1) * 32, smem, h->stream>>>(a); \
-    ++h->launches;                                                          \
-    PMC_CU(cudaGetLastError());                                             \
-    return PMC_OK;                                                          \
-  }
-#ifdef PMC_TUNING_VARIANTS  // measured negative result (profiles/r01c_tune_warp_specialised.txt): tuning builds only
-  if (cfg == 0) {
-    if (ws == 34) PMC_LAUNCH_WS(3, 4)
-    if (ws == 43) PMC_LAUNCH_WS(4, 3)
-    if (ws == 72) PMC_LAUNCH_WS(7, 2)
-    if (ws == 52) PMC_LAUNCH_WS(5, 2)
-    if (ws == 71) PMC_LAUNCH_WS(7, 1)
-    if (ws == 151) PMC_LAUNCH_WS(15, 1)
-    if (ws == 14) PMC_LAUNCH_WS(1, 4)
-    if (ws == 18) PMC_LAUNCH_WS(1, 8)
-  }
-#else
-  (void)ws;
-#endif
-#undef PMC_LAUNCH_WS
-  // windowed kernel (32 proposals built at once by warp 0): needs 6.7 KB more shared memory
-  const int use_win = env_int("PMC_RUN_WIN", h->use_win);
-  const size_t smem_win = cta_smem_bytes_win(h->n);
-#define PMC_LAUNCH_WIN(TT, MB)                                              \
-  {                                                                         \
-    int rc = set_smem(k_run_cta_win<TT, MB, 2>, smem_win);                  \
-    if (rc) return rc;                                                      \
-    k_run_cta_win<TT, MB, 2><<<nblocks, TT, smem_win, h->stream>>>(a);      \
-    ++h->launches;                                                          \
-    PMC_CU(cudaGetLastError());                                             \
-    return PMC_OK;                                                          \
-  }
-  if (cfg == 0 && use_win && smem_win <= (size_t)kSmemMax) {
-#ifdef PMC_TUNING_VARIANTS
-    if (use_win == 648) PMC_LAUNCH_WIN(64, 8)
-    if (use_win == 1286) PMC_LAUNCH_WIN(128, 6)
-    if (use_win == 1285) PMC_LAUNCH_WIN(128, 5)
-    if (use_win == 2562) PMC_LAUNCH_WIN(256, 2)
-    if (use_win == 643) PMC_LAUNCH_WIN(64, 10)
-    if (use_win == 2563) PMC_LAUNCH_WIN(256, 3)
-#endif
-    switch (h->cta_threads) {
-      case 64: PMC_LAUNCH_WIN(64, 8)
-      case 128: PMC_LAUNCH_WIN(128, 4)
-      case 256: PMC_LAUNCH_WIN(256, 2)
-      case 512: PMC_LAUNCH_WIN(512, 1)
-      default: break;
-    }
-  }
-#undef PMC_LAUNCH_WIN
-#define PMC_LAUNCH(TT, MB, UR)                                              \
-  {                                                                         \
-    int rc = set_smem(k_run_cta<TT, MB, UR>, smem);                         \
-    if (rc) return rc;                                                      \
-    k_run_cta<TT, MB, UR><<<nblocks, TT, smem, h->stream>>>(a);             \
-    ++h->launches;                                                          \
-  }
-#ifdef PMC_TUNING_VARIANTS
-  if (cfg == 12842) PMC_LAUNCH(128, 4, 2)
-  else if (cfg == 12841) PMC_LAUNCH(128, 4, 1)
-  else if (cfg == 25621) PMC_LAUNCH(256, 2, 1)
-  else if (cfg == 51211) PMC_LAUNCH(512, 1, 1)
-  else if (cfg == 12862) PMC_LAUNCH(128, 6, 2)
-  else if (cfg == 12861) PMC_LAUNCH(128, 6, 1)
-  else if (cfg == 12882) PMC_LAUNCH(128, 8, 2)
-  else if (cfg == 12881) PMC_LAUNCH(128, 8, 1)
-  else if (cfg == 25632) PMC_LAUNCH(256, 3, 2)
-  else if (cfg == 25631) PMC_LAUNCH(256, 3, 1)
-  else if (cfg == 25642) PMC_LAUNCH(256, 4, 2)
-  else if (cfg == 25641) PMC_LAUNCH(256, 4, 1)
-  else if (cfg == 25622) PMC_LAUNCH(256, 2, 2)
-  else if (cfg == 51212) PMC_LAUNCH(512, 1, 2)
-  else if (cfg == 51222) PMC_LAUNCH(512, 2, 2)
-  else if (cfg == 102412) PMC_LAUNCH(1024, 1, 2)
-  else if (cfg == 102411) PMC_LAUNCH(1024, 1, 1)
-  else
-#endif
-  switch (h->cta_threads) {
-    case 64: PMC_LAUNCH(64, 8, 2) break;
-    case 128: PMC_LAUNCH(128, 4, 2) break;
-    case 256: PMC_LAUNCH(256, 2, 2) break;
-    case 512: PMC_LAUNCH(512, 1, 2) break;
-    case 1024: PMC_LAUNCH(1024, 1, 2) break;
-    default: return fail(PMC_ERR_INVALID, "bad cta_threads");
-  }
-#undef PMC_LAUNCH
   PMC_CU(cudaGetLastError());
   return PMC_OK;
 }
@@ -359,11 +178,6 @@ ChainParams params_of(const pmc_case& c0, double kT_scale = 1.0) {
   P.planar = c.planar;
   return P;
 }
-
-// Block size of the composite-trial CTA kernels.
-// Short chains are latency bound (one serial proposal/cluster/decision chain per trial), so one warp per
-// chain and many chains per SM; measured crossovers in profiles/r01e_tune_cluster.txt.
-int pick_cluster_threads(int n) { return n <= 160 ? 32 : n <= 256 ? 64 : n <= 1024 ? 128 : 256; }
 
 // Block size for the ensemble at hand.  `base` is the shape that wins on a full machine (many chains per SM).
 // A small ensemble leaves SMs idle — 148 chains of n=100 are one warp per SM — so each chain gets 2× or 4× the
@@ -663,142 +477,17 @@ static int energy_range(pmc_handle* h, int64_t first, int64_t count, double* out
   return PMC_OK;
 }
 
-// Launch helpers of the composite-trial kernels.
+// Composite-trial kernels: CTA per chain for the pair-sum energies, chain per lane / warp otherwise.
 static int launch_run_cluster(pmc_handle* h, const RunArgs& a) {
   const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
-  if (cta_pairs) {
-    const int nblocks = (int)h->nchains;
-    const bool cut = h->energy_type == PMC_ENERGY_CUTOFF;
-#define PMC_CL(TT, MB)                                                                    \
-  {                                                                                       \
-    const size_t smem = cluster_smem_bytes(h->n, TT);                                     \
-    if (smem > (size_t)kSmemMax) return fail(PMC_ERR_UNSUPPORTED, "chain too long for this block size"); \
-    if (cut) {                                                                            \
-      int rc = set_smem(k_run_cta_cluster<TT, MB, true>, smem);                           \
-      if (rc) return rc;                                                                  \
-      k_run_cta_cluster<TT, MB, true><<<nblocks, TT, smem, h->stream>>>(a);               \
-    } else {                                                                              \
-      int rc = set_smem(k_run_cta_cluster<TT, MB, false>, smem);                          \
-      if (rc) return rc;                                                                  \
-      k_run_cta_cluster<TT, MB, false><<<nblocks, TT, smem, h->stream>>>(a);              \
-    }                                                                                     \
-  }
-    // PMC_CLUSTER_CFG = threads*100 + minblocks selects a tuning variant (experiments only)
-    const int ccfg = env_int("PMC_CLUSTER_CFG", 0);
-#ifdef PMC_TUNING_VARIANTS
-    if (ccfg == 3216) PMC_CL(32, 16)
-    else if (ccfg == 3212) PMC_CL(32, 12)
-    else if (ccfg == 6408) PMC_CL(64, 8)
-    else if (ccfg == 6410) PMC_CL(64, 10)
-    else if (ccfg == 6406) PMC_CL(64, 6)
-    else if (ccfg == 12804) PMC_CL(128, 4)
-    else if (ccfg == 12803) PMC_CL(128, 3)
-    else if (ccfg == 12805) PMC_CL(128, 5)
-    else if (ccfg == 25602) PMC_CL(256, 2)
-    else
-#else
-    (void)ccfg;
-#endif
-    switch (h->cta_threads) {
-      case 32:  // very short chains fit 16 per SM in shared memory: worth the 128-register build (+9 % at n=25)
-        if (h->n <= 40) PMC_CL(32, 16) else PMC_CL(32, 12)
-        break;
-      case 64: PMC_CL(64, 6) break;
-      case 128: PMC_CL(128, 4) break;
-      case 256: PMC_CL(256, 1) break;
-      default: return fail(PMC_ERR_INVALID, "bad cta_threads");
-    }
-#undef PMC_CL
-  } else {
-    constexpr int TB = 64;
-    const unsigned nb = (unsigned)((h->nchains + TB - 1) / TB);
-    const bool ising = h->energy_type == PMC_ENERGY_ISING;
-    // few chains: one chain per warp with 32-trial windows; many chains: one per lane
-    const int mode = env_int("PMC_LANE_CLUSTER_MODE", 0);  // 1 = lane, 2 = warp, 0 = by chain count
-    if (mode == 2 || (mode == 0 && h->nchains < h->warp_cluster_below)) {
-      const unsigned nbw = (unsigned)((h->nchains + 3) / 4);
-      const bool stage = h->n <= kWarpClusterStageMax;
-      // Trials per window: an accepted trial invalidates the later trials of the window that read its segment and
-      // every invalidation costs a serial re-evaluation pass, but the per-window work (draws, prefix sums,
-      // averagers) is amortised over the window: 32 wins from n = 25 to 400 (profiles/r01f_tune_warp_cluster.txt).
-      RunArgs aw = a;
-      aw.window = 32;
-      {
-        const int w = env_int("PMC_WARP_CLUSTER_WIN", 0);  // experiments only
-        if (w >= 1 && w <= 32) aw.window = w;
-      }
-      const size_t smem = stage ? (size_t)4 * h->n * sizeof(MonoRec) : 0;
-#define PMC_WC(IS, CP)                                                                         \
-  {                                                                                            \
-    if (stage) {                                                                               \
-      int rc = set_smem(k_run_warp_cluster<IS, 2, CP, true>, smem);                            \
-      if (rc) return rc;                                                                       \
-      k_run_warp_cluster<IS, 2, CP, true><<<nbw, 128, smem, h->stream>>>(aw);                  \
-    } else {                                                                                   \
-      k_run_warp_cluster<IS, 2, CP, false><<<nbw, 128, 0, h->stream>>>(aw);                   \
-    }                                                                                          \
-  }
-      if (h->compensated) { if (ising) PMC_WC(true, true) else PMC_WC(false, true) }
-      else { if (ising) PMC_WC(true, false) else PMC_WC(false, false) }
-#undef PMC_WC
-    } else if (h->compensated) {
-      if (ising) k_run_lane_cluster<TB, 4, true, true><<<nb, TB, 0, h->stream>>>(a);
-      else k_run_lane_cluster<TB, 4, false, true><<<nb, TB, 0, h->stream>>>(a);
-    } else {
-      // PMC_LANE_CLUSTER_CFG = threads*100 + minblocks selects a tuning variant (experiments only)
-      const int lcfg = env_int("PMC_LANE_CLUSTER_CFG", 0);
-#define PMC_LC(TT, MB)                                                                                         \
-  {                                                                                                            \
-    const unsigned nbb = (unsigned)((h->nchains + TT - 1) / TT);                                               \
-    if (ising) k_run_lane_cluster<TT, MB, true, false><<<nbb, TT, 0, h->stream>>>(a);                          \
-    else k_run_lane_cluster<TT, MB, false, false><<<nbb, TT, 0, h->stream>>>(a);                               \
-  }
-#ifdef PMC_TUNING_VARIANTS
-      if (lcfg == 6403) PMC_LC(64, 3)
-      else if (lcfg == 6404) PMC_LC(64, 4)
-      else if (lcfg == 6408) PMC_LC(64, 8)
-      else if (lcfg == 3208) PMC_LC(32, 8)
-      else if (lcfg == 3212) PMC_LC(32, 12)
-      else if (lcfg == 3216) PMC_LC(32, 16)
-      else
-#else
-      (void)lcfg;
-#endif
-      if (h->nchains >= 32768) PMC_LC(64, 8)  // many chains: occupancy beats the spills of the 128-register build
-      else PMC_LC(64, 4)
-#undef PMC_LC
-    }
-  }
-  ++h->launches;
-  PMC_CU(cudaGetLastError());
-  return PMC_OK;
+  return cta_pairs ? launch_run_cluster_cta(h, a) : launch_run_cluster_lane(h, a);
 }
 
 static int launch_delta_segment(pmc_handle* h, const SegDeltaArgs& a) {
   const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
-  if (cta_pairs) {
-    const int tt = pick_cluster_threads(h->n);
-    const size_t smem = cluster_delta_smem_bytes(h->n, tt);
-    if (smem > (size_t)kSmemMax) return fail(PMC_ERR_UNSUPPORTED, "chain too long for the composite-trial kernel");
-    const bool cut = h->energy_type == PMC_ENERGY_CUTOFF;
-#define PMC_DS(TT)                                                                        \
-  {                                                                                       \
-    if (cut) {                                                                            \
-      int rc = set_smem(k_delta_segment_cta<TT, true>, smem);                             \
-      if (rc) return rc;                                                                  \
-      k_delta_segment_cta<TT, true><<<1, TT, smem, h->stream>>>(a);                       \
-    } else {                                                                              \
-      int rc = set_smem(k_delta_segment_cta<TT, false>, smem);                            \
-      if (rc) return rc;                                                                  \
-      k_delta_segment_cta<TT, false><<<1, TT, smem, h->stream>>>(a);                      \
-    }                                                                                     \
-  }
-    if (tt == 32) PMC_DS(32) else if (tt == 64) PMC_DS(64) else if (tt == 128) PMC_DS(128) else PMC_DS(256)
-#undef PMC_DS
-  } else {
-    if (h->energy_type == PMC_ENERGY_ISING) k_delta_segment_lane<true><<<1, 32, 0, h->stream>>>(a);
-    else k_delta_segment_lane<false><<<1, 32, 0, h->stream>>>(a);
-  }
+  if (cta_pairs) return launch_delta_segment_cta(h, a);
+  if (h->energy_type == PMC_ENERGY_ISING) k_delta_segment_lane<true><<<1, 32, 0, h->stream>>>(a);
+  else k_delta_segment_lane<false><<<1, 32, 0, h->stream>>>(a);
   ++h->launches;
   PMC_CU(cudaGetLastError());
   return PMC_OK;
@@ -877,6 +566,13 @@ int64_t pmc_rows_for(const pmc_handle* h, int64_t nsteps, int64_t stepout) {
   return (step0 + nsteps) / stepout - step0 / stepout;
 }
 
+// The MCMC kernel of this handle: driver (plain / clustering), energy type, n and ensemble size select it.
+static int dispatch_run(pmc_handle* h, const RunArgs& a) {
+  if (h->cluster_mode) return launch_run_cluster(h, a);
+  if (h->energy_type == PMC_ENERGY_INTERACTING) return launch_run_cta(h, a);
+  return launch_run_lane(h, a);
+}
+
 static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj, double* roll, int roll_cols,
                     double* state);
 
@@ -937,47 +633,7 @@ static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj
   a.dynx = h->dynx; a.state = nstate ? h->state : nullptr; a.roll_cols = roll_cols;
   a.compensated = h->compensated;
   PMC_CU(cudaEventRecord(h->ev0, h->stream));
-  if (h->cluster_mode) {
-    if ((rc = launch_run_cluster(h, a))) return rc;
-  } else if (h->energy_type == PMC_ENERGY_INTERACTING) {
-    if ((rc = launch_run_cta(h, a))) return rc;
-  } else {
-    // few chains: one chain per warp with 32-trial windows fills the machine; many chains: one per lane
-    const int mode = env_int("PMC_LANE_MODE", 0);  // 1 = lane, 2 = warp, 0 = by chain count
-    const bool use_warp = mode == 2 || (mode == 0 && h->nchains < h->warp_mode_below);
-    // PMC_LANE_CFG = minblocks*10 + compensated selects a tuning variant (experiments only)
-    const int lcfg = env_int("PMC_LANE_CFG", -1);
-    const bool comp = lcfg >= 0 ? (lcfg % 10) != 0 : h->compensated != 0;
-    const int mb = lcfg >= 0 ? lcfg / 10 : 0;
-    if (use_warp) {
-      const unsigned nb = (unsigned)((h->nchains + 3) / 4);
-      const bool ising = h->energy_type == PMC_ENERGY_ISING;
-#define PMC_W(IS, MB, CP) k_run_warp<IS, MB, CP><<<nb, 128, 0, h->stream>>>(a)
-#define PMC_WSEL(MB)                                                        \
-  {                                                                         \
-    if (ising) { if (comp) PMC_W(1, MB, true); else PMC_W(1, MB, false); }  \
-    else { if (comp) PMC_W(0, MB, true); else PMC_W(0, MB, false); }        \
-  }
-#ifdef PMC_TUNING_VARIANTS
-      if (mb == 3) PMC_WSEL(3) else if (mb == 2) PMC_WSEL(2) else
-#endif
-      PMC_WSEL(4)
-#undef PMC_WSEL
-#undef PMC_W
-    } else {
-      constexpr int TB = 64;
-      const unsigned nb = (unsigned)((h->nchains + TB - 1) / TB);
-#define PMC_L(MB, CP) k_run_lane<TB, MB, CP><<<nb, TB, 0, h->stream>>>(a)
-      if (mb == 6 || (mb == 0 && !comp)) { if (comp) PMC_L(6, true); else PMC_L(6, false); }
-#ifdef PMC_TUNING_VARIANTS
-      else if (mb == 8) { if (comp) PMC_L(8, true); else PMC_L(8, false); }
-#endif
-      else { if (comp) PMC_L(4, true); else PMC_L(4, false); }
-#undef PMC_L
-    }
-    ++h->launches;
-    PMC_CU(cudaGetLastError());
-  }
+  if ((rc = dispatch_run(h, a))) return rc;
   PMC_CU(cudaEventRecord(h->ev1, h->stream));
   if (traj && rows > 0)
     PMC_CU(cudaMemcpyAsync(traj, h->traj, ntraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -998,6 +654,20 @@ int32_t pmc_last_run_ms(const pmc_handle* h, float* ms) {
 }
 
 int64_t pmc_launch_count(const pmc_handle* h) { return h ? h->launches : 0; }
+
+int32_t pmc_kernel_name(pmc_handle* h, char* buf, int32_t buflen) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!buf || buflen < 1) return fail(PMC_ERR_INVALID, "null or empty name buffer");
+  RunArgs a{};
+  a.n = h->n; a.nchains = (int)h->nchains; a.energy_type = h->energy_type; a.compensated = h->compensated;
+  h->dry_run = 1;  // the launch helpers record their decision and stop
+  rc = dispatch_run(h, a);
+  h->dry_run = 0;
+  if (rc) return rc;
+  std::snprintf(buf, (size_t)buflen, "%s", h->kernel_name);
+  return PMC_OK;
+}
 
 int32_t pmc_reinit(pmc_handle* h, int32_t* replaced) {
   int rc = check_handle(h);
@@ -1181,6 +851,96 @@ int32_t pmc_cluster_stats(pmc_handle* h, double* out) {
   for (int64_t c = 0; c < h->nchains; ++c) {
     const ChainDynX& d = h->host_dynx[(size_t)c];
     out[c * 3 + 0] = d.ncluster; out[c * 3 + 1] = d.cluster_sum; out[c * 3 + 2] = d.cluster_max;
+  }
+  return PMC_OK;
+}
+
+// ---- checkpoint / resume ---------------------------------------------------------------------------------
+namespace {
+struct CkptHeader {
+  uint64_t magic;        // "PMCCKPT3"
+  int32_t abi, n, energy_type, cluster_mode, planar, init;
+  int64_t nchains;
+  uint64_t seed;
+  uint32_t chain_id_base, pad;
+  double kT_scale;
+  int64_t host_step;
+};
+constexpr uint64_t kCkptMagic = 0x3354504b43434d50ull;
+}  // namespace
+
+int64_t pmc_checkpoint_bytes(const pmc_handle* h) {
+  if (!h) return 0;
+  const size_t c = (size_t)h->nchains;
+  return (int64_t)(sizeof(CkptHeader) + c * (size_t)h->n * sizeof(MonoRec) + c * sizeof(ChainDyn) + c * sizeof(ChainDynX));
+}
+
+int32_t pmc_checkpoint_save(pmc_handle* h, void* buf, int64_t bytes) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!buf || bytes < pmc_checkpoint_bytes(h)) return fail(PMC_ERR_INVALID, "checkpoint buffer too small");
+  CkptHeader hd{};
+  hd.magic = kCkptMagic; hd.abi = PMC_ABI_VERSION; hd.n = h->n; hd.energy_type = h->energy_type;
+  hd.cluster_mode = h->cluster_mode; hd.planar = h->planar; hd.init = h->init; hd.nchains = h->nchains;
+  hd.seed = h->seed; hd.chain_id_base = h->chain_id_base; hd.kT_scale = h->kT_scale;
+  hd.host_step = h->host_dyn.empty() ? 0 : (int64_t)h->host_dyn[0].step;
+  unsigned char* p = static_cast<unsigned char*>(buf);
+  std::memcpy(p, &hd, sizeof(hd));
+  p += sizeof(hd);
+  const size_t c = (size_t)h->nchains, nm = c * (size_t)h->n * sizeof(MonoRec);
+  PMC_CU(cudaMemcpyAsync(p, h->mono, nm, cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaMemcpyAsync(p + nm, h->dyn, c * sizeof(ChainDyn), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaMemcpyAsync(p + nm + c * sizeof(ChainDyn), h->dynx, c * sizeof(ChainDynX), cudaMemcpyDeviceToHost, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  return PMC_OK;
+}
+
+int32_t pmc_checkpoint_load(pmc_handle* h, const void* buf, int64_t bytes) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!buf || bytes < (int64_t)sizeof(CkptHeader)) return fail(PMC_ERR_INVALID, "checkpoint buffer too small");
+  CkptHeader hd;
+  std::memcpy(&hd, buf, sizeof(hd));
+  if (hd.magic != kCkptMagic || hd.abi != PMC_ABI_VERSION) return fail(PMC_ERR_INVALID, "not a checkpoint of this ABI version");
+  if (hd.n != h->n || hd.nchains != h->nchains || hd.energy_type != h->energy_type || hd.cluster_mode != h->cluster_mode ||
+      hd.planar != h->planar || hd.seed != h->seed || hd.chain_id_base != h->chain_id_base)
+    return fail(PMC_ERR_INVALID, "checkpoint belongs to a different ensemble (n, chains, energy type, seed or chain ids differ)");
+  if (bytes < pmc_checkpoint_bytes(h)) return fail(PMC_ERR_INVALID, "truncated checkpoint");
+  const unsigned char* p = static_cast<const unsigned char*>(buf) + sizeof(hd);
+  const size_t c = (size_t)h->nchains, nm = c * (size_t)h->n * sizeof(MonoRec);
+  if (hd.kT_scale != h->kT_scale) {  // the stage temperature lives in the per-chain constants
+    std::vector<ChainParams> par(c);
+    for (size_t i = 0; i < c; ++i) par[i] = params_of(h->cases[i / (size_t)h->replicas], hd.kT_scale);
+    PMC_CU(cudaMemcpyAsync(h->par, par.data(), c * sizeof(ChainParams), cudaMemcpyHostToDevice, h->stream));
+    PMC_CU(cudaStreamSynchronize(h->stream));
+    h->kT_scale = hd.kT_scale;
+  }
+  PMC_CU(cudaMemcpyAsync(h->mono, p, nm, cudaMemcpyHostToDevice, h->stream));
+  PMC_CU(cudaMemcpyAsync(h->dyn, p + nm, c * sizeof(ChainDyn), cudaMemcpyHostToDevice, h->stream));
+  PMC_CU(cudaMemcpyAsync(h->dynx, p + nm + c * sizeof(ChainDyn), c * sizeof(ChainDynX), cudaMemcpyHostToDevice, h->stream));
+  PMC_CU(cudaStreamSynchronize(h->stream));
+  h->init = hd.init;
+  if (h->host_dyn.empty()) h->host_dyn.resize(c);
+  h->host_dyn[0].step = hd.host_step;
+  return PMC_OK;
+}
+
+int32_t pmc_accumulators_dd(pmc_handle* h, double* hi, double* lo) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!hi || !lo) return fail(PMC_ERR_INVALID, "null hi/lo");
+  if ((rc = fetch_dyn(h))) return rc;
+  if ((rc = fetch_dynx(h))) return rc;
+  auto two_sum = [](double a, double b, double& s, double& e) {  // renormalise: s + e = a + b exactly, |e| <= ulp(s)/2
+    s = a + b;
+    const double bb = s - a;
+    e = (a - (s - bb)) + (b - bb);
+  };
+  for (int64_t c = 0; c < h->nchains; ++c) {
+    const ChainDyn& d = h->host_dyn[(size_t)c];
+    const ChainDynX& x = h->host_dynx[(size_t)c];
+    for (int k = 0; k < kNumAcc; ++k) two_sum(d.acc[k], d.comp[k], hi[c * 19 + k], lo[c * 19 + k]);
+    for (int k = 0; k < 2; ++k) two_sum(x.acc[k], x.comp[k], hi[c * 19 + 17 + k], lo[c * 19 + 17 + k]);
   }
   return PMC_OK;
 }

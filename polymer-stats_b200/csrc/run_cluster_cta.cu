@@ -1,0 +1,84 @@
+// run_cluster_cta.cu — launches of the composite-trial CTA kernels (cluster_kernels.cuh): k_run_cta_cluster, k_delta_segment_cta.
+#include "handle.h"
+
+namespace {
+int fail(int code, const std::string& msg) { return pmc_fail(code, msg); }
+}  // namespace
+
+// Composite-trial kernels of the all-pairs and cut-off energies, one CTA (or warp) per chain.
+int launch_run_cluster_cta(pmc_handle* h, const RunArgs& a) {
+  {
+    const int nblocks = (int)h->nchains;
+    const bool cut = h->energy_type == PMC_ENERGY_CUTOFF;
+#define PMC_CL(TT, MB)                                                                    \
+  {                                                                                       \
+    const size_t smem = cluster_smem_bytes(h->n, TT);                                     \
+    if (smem > (size_t)kSmemMax) return fail(PMC_ERR_UNSUPPORTED, "chain too long for this block size"); \
+    PMC_PICK(cut ? "k_run_cta_cluster<" #TT "," #MB ",cut>" : "k_run_cta_cluster<" #TT "," #MB ">");  \
+    if (cut) {                                                                            \
+      int rc = set_smem(k_run_cta_cluster<TT, MB, true>, smem);                           \
+      if (rc) return rc;                                                                  \
+      k_run_cta_cluster<TT, MB, true><<<nblocks, TT, smem, h->stream>>>(a);               \
+    } else {                                                                              \
+      int rc = set_smem(k_run_cta_cluster<TT, MB, false>, smem);                          \
+      if (rc) return rc;                                                                  \
+      k_run_cta_cluster<TT, MB, false><<<nblocks, TT, smem, h->stream>>>(a);              \
+    }                                                                                     \
+  }
+    // PMC_CLUSTER_CFG = threads*100 + minblocks selects a tuning variant (experiments only)
+    const int ccfg = env_int("PMC_CLUSTER_CFG", 0);
+#ifdef PMC_TUNING_VARIANTS
+    if (ccfg == 3216) PMC_CL(32, 16)
+    else if (ccfg == 3212) PMC_CL(32, 12)
+    else if (ccfg == 6408) PMC_CL(64, 8)
+    else if (ccfg == 6410) PMC_CL(64, 10)
+    else if (ccfg == 6406) PMC_CL(64, 6)
+    else if (ccfg == 12804) PMC_CL(128, 4)
+    else if (ccfg == 12803) PMC_CL(128, 3)
+    else if (ccfg == 12805) PMC_CL(128, 5)
+    else if (ccfg == 25602) PMC_CL(256, 2)
+    else
+#else
+    (void)ccfg;
+#endif
+    switch (h->cta_threads) {
+      case 32:  // very short chains fit 16 per SM in shared memory: worth the 128-register build (+9 % at n=25)
+        if (h->n <= 40) PMC_CL(32, 16) else PMC_CL(32, 12)
+        break;
+      case 64: PMC_CL(64, 6) break;
+      case 128: PMC_CL(128, 4) break;
+      case 256: PMC_CL(256, 1) break;
+      default: return fail(PMC_ERR_INVALID, "bad cta_threads");
+    }
+#undef PMC_CL
+  }
+  ++h->launches;
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+
+int launch_delta_segment_cta(pmc_handle* h, const SegDeltaArgs& a) {
+  {
+    const int tt = pick_cluster_threads(h->n);
+    const size_t smem = cluster_delta_smem_bytes(h->n, tt);
+    if (smem > (size_t)kSmemMax) return fail(PMC_ERR_UNSUPPORTED, "chain too long for the composite-trial kernel");
+    const bool cut = h->energy_type == PMC_ENERGY_CUTOFF;
+#define PMC_DS(TT)                                                                        \
+  {                                                                                       \
+    if (cut) {                                                                            \
+      int rc = set_smem(k_delta_segment_cta<TT, true>, smem);                             \
+      if (rc) return rc;                                                                  \
+      k_delta_segment_cta<TT, true><<<1, TT, smem, h->stream>>>(a);                       \
+    } else {                                                                              \
+      int rc = set_smem(k_delta_segment_cta<TT, false>, smem);                            \
+      if (rc) return rc;                                                                  \
+      k_delta_segment_cta<TT, false><<<1, TT, smem, h->stream>>>(a);                      \
+    }                                                                                     \
+  }
+    if (tt == 32) PMC_DS(32) else if (tt == 64) PMC_DS(64) else if (tt == 128) PMC_DS(128) else PMC_DS(256)
+#undef PMC_DS
+  }
+  ++h->launches;
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}

@@ -1,0 +1,111 @@
+// run_cta.cu — launches of the single-monomer-trial CTA-per-chain run kernels (cta_kernels.cuh): k_run_cta_win, k_run_cta, k_run_cta_ws.
+#include "handle.h"
+
+namespace {
+int fail(int code, const std::string& msg) { return pmc_fail(code, msg); }
+}  // namespace
+
+int launch_run_cta(pmc_handle* h, const RunArgs& a) {
+  const size_t smem = cta_smem_bytes(h->n);
+  const int nblocks = (int)h->nchains;
+  // PMC_RUN_CFG = threads*100 + minblocks*10 + unroll selects a tuning variant (experiments only)
+  const int cfg = env_int("PMC_RUN_CFG", 0);
+  // PMC_RUN_WS = workers*10 + minblocks selects the warp-specialised kernel (control warp + workers)
+  const int ws = env_int("PMC_RUN_WS", h->ws_cfg);
+#define PMC_LAUNCH_WS(WK, MB)                                               \
+  {                                                                         \
+    PMC_PICK("k_run_cta_ws<" #WK "," #MB ",2>");                            \
+    int rc = set_smem(k_run_cta_ws<WK, MB, 2>, smem);                       \
+    if (rc) return rc;                                                      \
+    k_run_cta_ws<WK, MB, 2><<<nblocks, (WK + 1) * 32, smem, h->stream>>>(a); \
+    ++h->launches;                                                          \
+    PMC_CU(cudaGetLastError());                                             \
+    return PMC_OK;                                                          \
+  }
+#ifdef PMC_TUNING_VARIANTS  // measured negative result (profiles/r01c_tune_warp_specialised.txt): tuning builds only
+  if (cfg == 0) {
+    if (ws == 34) PMC_LAUNCH_WS(3, 4)
+    if (ws == 43) PMC_LAUNCH_WS(4, 3)
+    if (ws == 72) PMC_LAUNCH_WS(7, 2)
+    if (ws == 52) PMC_LAUNCH_WS(5, 2)
+    if (ws == 71) PMC_LAUNCH_WS(7, 1)
+    if (ws == 151) PMC_LAUNCH_WS(15, 1)
+    if (ws == 14) PMC_LAUNCH_WS(1, 4)
+    if (ws == 18) PMC_LAUNCH_WS(1, 8)
+  }
+#else
+  (void)ws;
+#endif
+#undef PMC_LAUNCH_WS
+  // windowed kernel (32 proposals built at once by warp 0): needs 6.7 KB more shared memory
+  const int use_win = env_int("PMC_RUN_WIN", h->use_win);
+  const size_t smem_win = cta_smem_bytes_win(h->n);
+#define PMC_LAUNCH_WIN(TT, MB)                                              \
+  {                                                                         \
+    PMC_PICK("k_run_cta_win<" #TT "," #MB ",2>");                           \
+    int rc = set_smem(k_run_cta_win<TT, MB, 2>, smem_win);                  \
+    if (rc) return rc;                                                      \
+    k_run_cta_win<TT, MB, 2><<<nblocks, TT, smem_win, h->stream>>>(a);      \
+    ++h->launches;                                                          \
+    PMC_CU(cudaGetLastError());                                             \
+    return PMC_OK;                                                          \
+  }
+  if (cfg == 0 && use_win && smem_win <= (size_t)kSmemMax) {
+#ifdef PMC_TUNING_VARIANTS
+    if (use_win == 648) PMC_LAUNCH_WIN(64, 8)
+    if (use_win == 1286) PMC_LAUNCH_WIN(128, 6)
+    if (use_win == 1285) PMC_LAUNCH_WIN(128, 5)
+    if (use_win == 2562) PMC_LAUNCH_WIN(256, 2)
+    if (use_win == 643) PMC_LAUNCH_WIN(64, 10)
+    if (use_win == 2563) PMC_LAUNCH_WIN(256, 3)
+#endif
+    switch (h->cta_threads) {
+      case 64: PMC_LAUNCH_WIN(64, 8)
+      case 128: PMC_LAUNCH_WIN(128, 4)
+      case 256: PMC_LAUNCH_WIN(256, 2)
+      case 512: PMC_LAUNCH_WIN(512, 1)
+      default: break;
+    }
+  }
+#undef PMC_LAUNCH_WIN
+#define PMC_LAUNCH(TT, MB, UR)                                              \
+  {                                                                         \
+    PMC_PICK("k_run_cta<" #TT "," #MB "," #UR ">");                         \
+    int rc = set_smem(k_run_cta<TT, MB, UR>, smem);                         \
+    if (rc) return rc;                                                      \
+    k_run_cta<TT, MB, UR><<<nblocks, TT, smem, h->stream>>>(a);             \
+    ++h->launches;                                                          \
+  }
+#ifdef PMC_TUNING_VARIANTS
+  if (cfg == 12842) PMC_LAUNCH(128, 4, 2)
+  else if (cfg == 12841) PMC_LAUNCH(128, 4, 1)
+  else if (cfg == 25621) PMC_LAUNCH(256, 2, 1)
+  else if (cfg == 51211) PMC_LAUNCH(512, 1, 1)
+  else if (cfg == 12862) PMC_LAUNCH(128, 6, 2)
+  else if (cfg == 12861) PMC_LAUNCH(128, 6, 1)
+  else if (cfg == 12882) PMC_LAUNCH(128, 8, 2)
+  else if (cfg == 12881) PMC_LAUNCH(128, 8, 1)
+  else if (cfg == 25632) PMC_LAUNCH(256, 3, 2)
+  else if (cfg == 25631) PMC_LAUNCH(256, 3, 1)
+  else if (cfg == 25642) PMC_LAUNCH(256, 4, 2)
+  else if (cfg == 25641) PMC_LAUNCH(256, 4, 1)
+  else if (cfg == 25622) PMC_LAUNCH(256, 2, 2)
+  else if (cfg == 51212) PMC_LAUNCH(512, 1, 2)
+  else if (cfg == 51222) PMC_LAUNCH(512, 2, 2)
+  else if (cfg == 102412) PMC_LAUNCH(1024, 1, 2)
+  else if (cfg == 102411) PMC_LAUNCH(1024, 1, 1)
+  else
+#endif
+  switch (h->cta_threads) {
+    case 64: PMC_LAUNCH(64, 8, 2) break;
+    case 128: PMC_LAUNCH(128, 4, 2) break;
+    case 256: PMC_LAUNCH(256, 2, 2) break;
+    case 512: PMC_LAUNCH(512, 1, 2) break;
+    case 1024: PMC_LAUNCH(1024, 1, 2) break;
+    default: return fail(PMC_ERR_INVALID, "bad cta_threads");
+  }
+#undef PMC_LAUNCH
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+

@@ -32,7 +32,15 @@ EXPORTS = [
     # ABI v2: the clustering driver (mcmc_clustering_eap_chain.jl)
     "pmc_energy_ex", "pmc_delta_segment", "pmc_run_ex", "pmc_begin_stage", "pmc_init_x0",
     "pmc_extra_averages", "pmc_extra_accumulators", "pmc_cluster_stats",
+    # ABI v3: kernel name, checkpoints, double-double accumulators, one ensemble over several GPUs
+    "pmc_kernel_name", "pmc_checkpoint_bytes", "pmc_checkpoint_save", "pmc_checkpoint_load", "pmc_accumulators_dd",
+    "pmc_multi_create", "pmc_multi_destroy", "pmc_multi_num_devices", "pmc_multi_num_chains",
+    "pmc_multi_gather_backend", "pmc_multi_shard", "pmc_multi_set_ensemble_hint", "pmc_multi_begin_stage",
+    "pmc_multi_set_state_all", "pmc_multi_get_state_all", "pmc_multi_rows_for", "pmc_multi_run", "pmc_multi_run_ex",
+    "pmc_multi_run_async", "pmc_multi_wait", "pmc_multi_gather", "pmc_multi_last_run_ms", "pmc_multi_launch_count",
 ]
+RESULT_COLS = 24
+RESULT_NAMES = AVG_NAMES + ["acc_rate", "normalizer", "phi_step", "theta_step", "trials", "U_running", "Ealign", "psi"]
 
 
 class PolymcError(RuntimeError):
@@ -149,11 +157,43 @@ def load():
     L.pmc_extra_averages.argtypes = [hp, dp]
     L.pmc_extra_accumulators.argtypes = [hp, dp]
     L.pmc_cluster_stats.argtypes = [hp, dp]
+    L.pmc_kernel_name.argtypes = [hp, C.c_char_p, C.c_int32]
+    L.pmc_checkpoint_bytes.argtypes = [hp]
+    L.pmc_checkpoint_bytes.restype = C.c_int64
+    L.pmc_checkpoint_save.argtypes = [hp, C.c_void_p, C.c_int64]
+    L.pmc_checkpoint_load.argtypes = [hp, C.c_void_p, C.c_int64]
+    L.pmc_accumulators_dd.argtypes = [hp, dp, dp]
+    L.pmc_multi_create.argtypes = [C.POINTER(PmcCase), C.c_int64, C.c_int32, C.c_uint64, C.POINTER(C.c_int32),
+                                   C.c_int32, C.POINTER(hp)]
+    L.pmc_multi_destroy.argtypes = [hp]
+    L.pmc_multi_destroy.restype = None
+    L.pmc_multi_num_devices.argtypes = [hp]
+    L.pmc_multi_num_devices.restype = C.c_int32
+    L.pmc_multi_num_chains.argtypes = [hp]
+    L.pmc_multi_num_chains.restype = C.c_int64
+    L.pmc_multi_gather_backend.argtypes = [hp]
+    L.pmc_multi_gather_backend.restype = C.c_char_p
+    L.pmc_multi_shard.argtypes = [hp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.pmc_multi_shard.restype = C.c_void_p
+    L.pmc_multi_set_ensemble_hint.argtypes = [hp, C.c_int64]
+    L.pmc_multi_begin_stage.argtypes = [hp, C.c_double]
+    L.pmc_multi_set_state_all.argtypes = [hp, dp, dp]
+    L.pmc_multi_get_state_all.argtypes = [hp, dp, dp]
+    L.pmc_multi_rows_for.argtypes = [hp, C.c_int64, C.c_int64]
+    L.pmc_multi_rows_for.restype = C.c_int64
+    L.pmc_multi_run.argtypes = [hp, C.c_int64, C.c_int64, dp, dp]
+    L.pmc_multi_run_ex.argtypes = [hp, C.c_int64, C.c_int64, dp, dp, dp]
+    L.pmc_multi_run_async.argtypes = [hp, C.c_int64, C.c_int64, dp, dp]
+    L.pmc_multi_wait.argtypes = [hp]
+    L.pmc_multi_gather.argtypes = [hp, dp]
+    L.pmc_multi_last_run_ms.argtypes = [hp, C.POINTER(C.c_float)]
+    L.pmc_multi_launch_count.argtypes = [hp]
+    L.pmc_multi_launch_count.restype = C.c_int64
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int:  # default restype: every status-returning entry point
             f.restype = C.c_int32
-    if L.pmc_abi_version() != 2:
+    if L.pmc_abi_version() != 3:
         raise PolymcError(-1, "ABI version mismatch")
     _lib = L
     return L
@@ -300,6 +340,29 @@ class Ensemble:
     def launch_count(self) -> int:
         return int(load().pmc_launch_count(self._h))
 
+    def kernel_name(self) -> str:
+        """The MCMC kernel `run` launches for this handle as it is now (the library's own decision)."""
+        buf = C.create_string_buffer(96)
+        _check(load().pmc_kernel_name(self._h, buf, len(buf)))
+        return buf.value.decode()
+
+    def checkpoint(self) -> bytes:
+        """Everything needed to continue this run in a later process (pmc_checkpoint_save)."""
+        nb = int(load().pmc_checkpoint_bytes(self._h))
+        buf = C.create_string_buffer(nb)
+        _check(load().pmc_checkpoint_save(self._h, buf, nb))
+        return buf.raw
+
+    def restore(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(load().pmc_checkpoint_load(self._h, buf, len(blob)))
+
+    def accumulators_dd(self):
+        """(hi, lo) [chains][19]: the double-double sums behind --numeric-type float128|dec128|big."""
+        hi, lo = np.empty((self.nchains, 19)), np.empty((self.nchains, 19))
+        _check(load().pmc_accumulators_dd(self._h, _dp(hi), _dp(lo)))
+        return hi, lo
+
     def reinit(self):
         flags = (C.c_int32 * self.nchains)()
         _check(load().pmc_reinit(self._h, flags))
@@ -371,3 +434,127 @@ class Ensemble:
         o = np.empty((self.nchains, 3))
         _check(load().pmc_cluster_stats(self._h, _dp(o)))
         return o
+
+
+class _Shard(Ensemble):
+    """The single-device handle behind one slot of a MultiEnsemble (owned by it: close() is a no-op)."""
+
+    def __init__(self, h, device, first, count, n):
+        self._h = h
+        self.device, self.first, self.nchains, self.n = device, first, count, n
+        self.cases, self.replicas = [], 1
+
+    def close(self):
+        self._h = None
+
+
+class MultiEnsemble:
+    """One ensemble over several GPUs of one box through pmc_multi_*: contiguous blocks of global chain ids, one
+    internal host thread per device, no data-path collective, one final NCCL all-gather of the result rows
+    (replaces `julia -p N run/interacting_dielectric_study.jl`, :37-47)."""
+
+    def __init__(self, cases, replicas=1, seed=0, devices=None, ndevices=0):
+        if isinstance(cases, PmcCase):
+            cases = [cases]
+        self.cases = list(cases)
+        self.replicas = int(replicas)
+        arr = (PmcCase * len(self.cases))(*self.cases)
+        dv = None
+        if devices is not None:
+            devices = list(devices)
+            dv = (C.c_int32 * len(devices))(*devices)
+            ndevices = len(devices)
+        h = C.c_void_p()
+        _check(load().pmc_multi_create(arr, len(self.cases), self.replicas, seed, dv, int(ndevices), C.byref(h)))
+        self._h = h
+        self.nchains = int(load().pmc_multi_num_chains(h))
+        self.ndevices = int(load().pmc_multi_num_devices(h))
+        self.n = int(self.cases[0].n)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().pmc_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = Ensemble.__del__
+    __enter__ = Ensemble.__enter__
+    __exit__ = Ensemble.__exit__
+
+    def gather_backend(self) -> str:
+        return load().pmc_multi_gather_backend(self._h).decode()
+
+    def shard(self, slot) -> _Shard:
+        dev, first, cnt = C.c_int32(), C.c_int64(), C.c_int64()
+        h = load().pmc_multi_shard(self._h, slot, C.byref(dev), C.byref(first), C.byref(cnt))
+        if not h:
+            _check(-1)
+        return _Shard(C.c_void_p(h), dev.value, first.value, cnt.value, self.n)
+
+    def set_ensemble_hint(self, chains):
+        _check(load().pmc_multi_set_ensemble_hint(self._h, int(chains)))
+
+    def begin_stage(self, kT_scale=1.0):
+        _check(load().pmc_multi_begin_stage(self._h, float(kT_scale)))
+
+    def set_state_all(self, phi, theta):
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if phi.shape != (self.nchains, self.n) or theta.shape != (self.nchains, self.n):
+            raise PolymcError(-1, "state arrays must be [chains][num-monomers]")
+        _check(load().pmc_multi_set_state_all(self._h, _dp(phi), _dp(theta)))
+
+    def get_state_all(self):
+        phi, theta = np.empty((self.nchains, self.n)), np.empty((self.nchains, self.n))
+        _check(load().pmc_multi_get_state_all(self._h, _dp(phi), _dp(theta)))
+        return phi, theta
+
+    def rows_for(self, nsteps, stepout):
+        return int(load().pmc_multi_rows_for(self._h, nsteps, stepout))
+
+    def _rows(self, nsteps, stepout, fetch_rows, traj, roll, cols):
+        rows = self.rows_for(nsteps, stepout)
+        if fetch_rows and rows > 0:
+            if traj is None:
+                traj = np.empty((self.nchains, rows, 8))
+            if roll is None:
+                roll = np.empty((self.nchains, rows, cols))
+            return rows, traj, roll
+        return rows, None, None
+
+    def run(self, nsteps, stepout=0, fetch_rows=True, traj=None, roll=None):
+        rows, traj, roll = self._rows(nsteps, stepout, fetch_rows, traj, roll, 17)
+        _check(load().pmc_multi_run(self._h, nsteps, stepout, _dp(traj), _dp(roll)))
+        return traj, roll
+
+    def run_async(self, nsteps, stepout=0, fetch_rows=True, traj=None, roll=None):
+        """Returns at once; the buffers are filled when wait() returns."""
+        rows, traj, roll = self._rows(nsteps, stepout, fetch_rows, traj, roll, 17)
+        _check(load().pmc_multi_run_async(self._h, nsteps, stepout, _dp(traj), _dp(roll)))
+        return traj, roll
+
+    def wait(self):
+        _check(load().pmc_multi_wait(self._h))
+
+    def run_ex(self, nsteps, stepout=0, fetch_rows=True, want_state=False):
+        rows, traj, roll = self._rows(nsteps, stepout, fetch_rows, None, None, 19)
+        state = np.empty((self.nchains, rows, 2 * self.n)) if (want_state and traj is not None) else None
+        _check(load().pmc_multi_run_ex(self._h, nsteps, stepout, _dp(traj), _dp(roll), _dp(state)))
+        return traj, roll, state
+
+    def gather(self):
+        """[chains][24] result rows (RESULT_NAMES), gathered device-to-device (NCCL) and read from the first device."""
+        t = np.empty((self.nchains, RESULT_COLS))
+        _check(load().pmc_multi_gather(self._h, _dp(t)))
+        return t
+
+    def averages(self):
+        t = self.gather()
+        return t[:, :16].copy(), t[:, 16].copy(), t[:, 17].copy()
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        _check(load().pmc_multi_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(load().pmc_multi_launch_count(self._h))

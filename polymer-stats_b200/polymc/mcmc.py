@@ -139,6 +139,27 @@ def get_avg(a: Average):
     return a.get_avg()
 
 
+def pool_replicas(sums: np.ndarray, umbrella: bool, extra: np.ndarray | None = None):
+    """Pool the accumulators of R replica chains of one case: (values [17 (+2)], normaliser).
+
+    Plain averagers (inc/average.jl:40-48): every replica has the same normaliser (its trial count), so
+    Σ values / Σ normalisers is the mean over all trials of all replicas.  Umbrella averagers (:63-97): replica r's
+    weights all carry the factor exp(log_gauge_r) with log_gauge_r = gauge0 + Ω0_r fixed at ITS initial chain
+    (average.jl:109-118); Ω0 = Σ log sinθ has a spread of ~9 at n=100, so pooled sums would be dominated by one
+    replica.  The gauge cancels inside each replica's own ratio value_r / normalizer_r (that ratio is the reference's
+    estimate for one run), so the replicas are pooled as the mean of their ratios — what reduce_tabular_data.jl:36-56
+    does with the `.out` files of repeated runs."""
+    sums = np.asarray(sums, dtype=np.float64)
+    if extra is not None:
+        sums = np.concatenate([sums, np.asarray(extra, dtype=np.float64)], axis=1)
+    if not umbrella:
+        pooled = sums.sum(axis=0)
+        return pooled, pooled[16]
+    ratios = sums / sums[:, 16:17]
+    pooled = ratios.mean(axis=0)          # pooled[16] == 1
+    return pooled, 1.0
+
+
 def mcmc(nsteps: int, pargs: dict):
     """`mcmc(nsteps, pargs)` of mcmc_eap_chain.jl:171-376.
 
@@ -182,8 +203,7 @@ def mcmc(nsteps: int, pargs: dict):
                     ens.reinit()  # mcmc_eap_chain.jl:352-361 (after the last init it has no observable effect)
         sums = ens.accumulators()          # [R][17]
         diag = ens.diagnostics()
-    pooled = sums.sum(axis=0)
-    norm = pooled[16]
+    pooled, norm = pool_replicas(sums, pargs["umbrella-sampling"])
     ar = float(diag[:, 4].sum() / (R * pargs["num-inits"] * pargs["num-steps"])) if pargs["num-steps"] else 0.0
     _log(pargs, "info", f"total time elapsed: {time.time() - start}")
     _log(pargs, "info", f"acceptance rate: {ar}")

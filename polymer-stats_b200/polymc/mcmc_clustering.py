@@ -18,7 +18,7 @@ import time
 import numpy as np
 
 from . import lib
-from .mcmc import Average, _log
+from .mcmc import Average, _log, pool_replicas
 from .output import (ROLL_HEADER_CLUSTERING, julia_float, julia_vector, result_lines_clustering,
                      traj_header_clustering, write_rows)
 
@@ -231,9 +231,8 @@ def mcmc_ladder(pargs: dict):
         sums = ens.accumulators()        # [R][17]
         xsums = ens.extra_accumulators()  # [R][2]
         diag = ens.diagnostics()
-    pooled = sums.sum(axis=0)
-    xpooled = xsums.sum(axis=0)
-    norm = pooled[16]
+    pooled, norm = pool_replicas(sums, pargs["umbrella-sampling"], extra=xsums)
+    xpooled = pooled[17:19]
     ar = float(diag[:, 4].sum() / (R * pargs["num-steps"])) if pargs["num-steps"] else 0.0  # :340
     _log(pargs, "info", f"total time elapsed: {time.time() - start}")
     _log(pargs, "info", f"acceptance rate: {ar}")

@@ -17,7 +17,7 @@ import time
 import numpy as np
 
 from . import lib
-from .mcmc import Average, _log
+from .mcmc import Average, _log, pool_replicas
 from .mcmc_clustering import parse_julia_vector
 from .output import julia_float, julia_vector, write_rows
 
@@ -162,8 +162,7 @@ def mcmc_ladder(pargs: dict):
         _stage(ens, pargs["num-steps"], pargs, 1.0, write_files=True, start=start)
         sums = ens.accumulators()
         diag = ens.diagnostics()
-    pooled = sums.sum(axis=0)
-    norm = pooled[16]
+    pooled, norm = pool_replicas(sums, pargs["umbrella-sampling"])
     ar = float(diag[:, 4].sum() / (R * pargs["num-steps"])) if pargs["num-steps"] else 0.0
     _log(pargs, "info", f"total time elapsed: {time.time() - start}")
     _log(pargs, "info", f"acceptance rate: {ar}")

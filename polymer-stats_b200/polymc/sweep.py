@@ -114,9 +114,16 @@ def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
             # launch shape from the UNSHARDED bucket size: results are bit-identical for any rank count
             with lib.Ensemble(cases[case0:case0 + ncases], replicas=nrep, seed=seed, device=device,
                               chain_id_base=int(mine[pos]), ensemble_chains=len(gids)) as ens:
-                if protocol is None:
-                    ens.run(nsteps, stepout, fetch_rows=False)
+                if protocol is None or protocol.get("plain"):
+                    # mcmc_eap_chain.jl:276-361: num-inits passes of nsteps trials with the re-initialisation rule between
+                    inits = int(protocol.get("num_inits", 1)) if protocol else 1
+                    for init in range(inits):
+                        ens.run(nsteps, stepout, fetch_rows=False)
+                        if init + 1 < inits:
+                            ens.reinit()
                 else:
+                    if protocol.get("x0") is not None:      # inc/eap_chain.jl:63-78
+                        ens.init_x0(protocol["x0"], protocol["dx0"])
                     for mult in protocol.get("schedule", []):
                         ens.begin_stage(float(mult))
                         ens.run_ex(int(protocol.get("burn_in", 0)), 0, fetch_rows=False)
@@ -185,9 +192,33 @@ def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0,
             raise lib.PolymcError(-1, "one aggregated table holds one chain type (aggregate_mcmc.jl:40-47)")
     cases = [host.case_from_pargs(p) for p in pargs_list]
     p0 = pargs_list[0]
-    protocol = None
-    if driver != "plain":
+    # Options that shape the PROTOCOL of a run (not the physics of a case) apply to the whole ensemble of one call:
+    # they must agree across the sweep, otherwise a row would claim a command line that was not run.
+    proto_keys = ["num-steps"] + (["num-inits", "force-init"] if driver == "plain" else ["burn-in", "burn-schedule"]) + \
+        ([] if driver != "clustering" else ["x0", "dx0"])
+    for p in pargs_list:
+        for k in proto_keys:
+            if p.get(k) != p0.get(k):
+                raise lib.PolymcError(-1, f"--{k} must be the same for every case of one sweep ({p.get(k)!r} vs "
+                                          f"{p0.get(k)!r}): run one sweep per value")
+    if driver == "plain":
+        protocol = dict(plain=True, num_inits=int(p0.get("num-inits", 1)))
+    else:
         protocol = dict(burn_in=p0["burn-in"], schedule=cl_host.parse_julia_vector(p0["burn-schedule"], "burn-schedule"))
+        if driver == "clustering" and p0.get("x0") is not None:
+            x0 = cl_host.parse_julia_vector(p0["x0"], "x0")
+            dx0 = cl_host.parse_julia_vector(p0["dx0"], "dx0")
+            if len(x0) != 2 or len(dx0) < 2:   # a per-monomer x0 belongs to one chain length, i.e. one case
+                raise lib.PolymcError(-1, f"a sweep takes --x0 as [phi, theta] (Invalid input for 'x0', {p0['x0']})")
+            protocol.update(x0=x0, dx0=dx0[:2])
+    # two cases with the same file-name prefix would overwrite each other's .out file and be indistinguishable rows
+    seen = {}
+    for i, p in enumerate(pargs_list):
+        pre = agg.prefix_of(p, chain_type, kappaflag, run=None)
+        if pre in seen:
+            raise lib.PolymcError(-1, f"cases {seen[pre]} and {i} share the output prefix '{pre}': the swept option is not "
+                                      "part of the file-name tokens (aggregate_mcmc.jl:40-57; use --kappaflag for bend-mod)")
+        seen[pre] = i
     res = run_sweep(cases, runs, p0["num-steps"], 0, seed, device, torch_device, protocol)
     runflag = runs > 1
     entries, texts = [], []

@@ -181,7 +181,7 @@ def test_abi_exports_every_declared_symbol(pm):
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(pm.lib.EXPORTS) == declared
-    assert pm.load().pmc_abi_version() == 2
+    assert pm.load().pmc_abi_version() == 3
     assert ctypes.sizeof(pm.PmcCase) == 13 * 8 + 2 * 8 + 6 * 4 + 4 * 8 + 4 * 4
 
 
@@ -257,3 +257,58 @@ def test_planar_cli_table_matches_reference(pm):
     assert c.planar == 1 and c.clustering == 1 and c.energy_type == 0 and c.theta_step == c.phi_step / 2
     lines = m2.result_lines_2d([m2.Average(1.0, 2.0)] * 4, [m2.Average(np.array([1.0, 3.0]), 2.0)] * 4, 0.25, 1.0, 10)
     assert lines[0] == "<r>    =   [0.5, 1.5]" and lines[-1] == "AR     =   0.25" and len(lines) == 10
+
+
+def test_sweep_refuses_mixed_protocols_and_colliding_prefixes(pm):
+    """protocol-level options apply to the whole ensemble of one sweep_table call and must agree across
+    its cases; two cases that differ only in an option outside the file-name tokens would overwrite each other."""
+    from polymc import mcmc, mcmc_clustering as mc, sweep
+    a = mcmc.default_pargs(E0=0.5, Fz=0.0, num_monomers=20, num_steps=1000)
+    with pytest.raises(pm.PolymcError, match="--num-steps must be the same"):
+        sweep.sweep_table([a, mcmc.default_pargs(E0=0.5, Fz=1.0, num_monomers=20, num_steps=2000)])
+    with pytest.raises(pm.PolymcError, match="--num-inits must be the same"):
+        sweep.sweep_table([a, mcmc.default_pargs(E0=0.5, Fz=1.0, num_monomers=20, num_steps=1000, num_inits=3)])
+    with pytest.raises(pm.PolymcError, match="share the output prefix"):
+        sweep.sweep_table([a, mcmc.default_pargs(E0=0.5, Fz=0.0, num_monomers=20, num_steps=1000, phi_step=0.1)])
+    k = mc.default_pargs(E0=0.5, Fz=0.25, num_monomers=20, bend_mod=0.5)
+    with pytest.raises(pm.PolymcError, match="share the output prefix"):   # bend-mod is a token only with --kappaflag
+        sweep.sweep_table([k, mc.default_pargs(E0=0.5, Fz=0.25, num_monomers=20, bend_mod=1.0)], driver="clustering")
+    with pytest.raises(pm.PolymcError, match="--burn-in must be the same"):
+        sweep.sweep_table([k, mc.default_pargs(E0=1.5, Fz=0.25, num_monomers=20, bend_mod=0.5, burn_in=7)],
+                          driver="clustering")
+    with pytest.raises(pm.PolymcError, match="--x0 must be the same"):
+        sweep.sweep_table([k, mc.default_pargs(E0=1.5, Fz=0.25, num_monomers=20, bend_mod=0.5, x0="[0.1, 0.2]")],
+                          driver="clustering")
+
+
+def test_umbrella_replicas_are_pooled_as_ratios():
+    """with --umbrella-sampling every replica's weights carry exp(Ω0_r) of ITS initial chain, so summed
+    accumulators are dominated by one replica; the pooled estimate is the mean of the per-replica ratios."""
+    from polymc.mcmc import pool_replicas
+    rng = np.random.default_rng(3)
+    R = 12
+    truth = rng.normal(size=16)
+    gauge = np.exp(rng.normal(0.0, 9.0, size=R))            # spread of exp(Ω0) at n ≈ 100
+    ratios = truth + 0.01 * rng.normal(size=(R, 16))
+    sums = np.concatenate([ratios * gauge[:, None], gauge[:, None]], axis=1) * 5000.0
+    pooled, norm = pool_replicas(sums, umbrella=True)
+    np.testing.assert_allclose(pooled[:16] / norm, ratios.mean(axis=0), rtol=1e-12)
+    assert np.abs(pooled[:16] / norm - truth).max() < 3 * 0.01 / np.sqrt(R) * 3     # every replica counts
+    naive = sums.sum(axis=0)
+    dominated = np.abs(naive[:16] / naive[16] - ratios[np.argmax(gauge)]).max()
+    assert dominated < 0.005                                                        # the old pooling: one replica
+    # plain averagers: unchanged, Σ values / Σ normalisers (with the extras of the clustering driver appended)
+    plain = np.concatenate([rng.normal(size=(R, 16)), np.full((R, 1), 5000.0)], axis=1)
+    extra = rng.normal(size=(R, 2))
+    pooled, norm = pool_replicas(plain, umbrella=False, extra=extra)
+    np.testing.assert_array_equal(pooled[:17], plain.sum(axis=0))
+    np.testing.assert_array_equal(pooled[17:], extra.sum(axis=0))
+    assert norm == 5000.0 * R
+
+
+def test_multi_device_entry_points_fail_loudly_without_a_device(pm):
+    if pm.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pm.PolymcError) as ei:
+        pm.MultiEnsemble(pm.make_case(n=10), replicas=4)
+    assert ei.value.code == -2
