@@ -335,6 +335,28 @@ class Run:
         return Chain(self.case, _ptr=lib().orc_run_chain(self._p))
 
 
-def bench(case: OrcCase, seed: int, algo: int, nchains: int, nsteps: int, nthreads: int) -> float:
+_native = None
+
+
+def native_lib():
+    """The `-O3 -march=native` build of the same source, compiled on THIS machine (timing only; bench.py).  Returns
+    (library, flags text); falls back to the portable build when the host has no compiler."""
+    global _native
+    if _native is not None:
+        return _native
+    path = os.path.join(_HERE, "_bench", "libpolymc_oracle_native.so")
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        L = C.CDLL(path)
+        L.orc_bench.argtypes = [C.POINTER(OrcCase), C.c_uint64, C.c_int32, C.c_int32, C.c_int64, C.c_int32]
+        L.orc_bench.restype = C.c_double
+        _native = (L, "gcc -O3 -march=native, built on the timed host")
+    except Exception:
+        _native = (lib(), "gcc -O3 -march=x86-64-v3 -ffp-contract=off (portable build; no compiler on the timed host)")
+    return _native
+
+
+def bench(case: OrcCase, seed: int, algo: int, nchains: int, nsteps: int, nthreads: int, native: bool = False) -> float:
     """Seconds to run nchains independent chains for nsteps trials each on nthreads pthreads."""
-    return lib().orc_bench(C.byref(case), seed, algo, nchains, nsteps, nthreads)
+    L = native_lib()[0] if native else lib()
+    return L.orc_bench(C.byref(case), seed, algo, nchains, nsteps, nthreads)
