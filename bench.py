@@ -72,9 +72,9 @@ WORKLOADS = {
     "C3": dict(cases=c3_grid(), replicas=64, S=500, stepout=500, scaling="weak", e2e="sweep",
                desc="C3: polar chains n=512 with dipole-dipole coupling, 4 mu x 4 E0 x 4 Fz sweep (64 points) x 64 replicas "
                     "per GPU"),
-    "C4": dict(cases=c4_grid(), replicas=1, S=20000, stepout=500, scaling="strong", e2e="sweep",
-               desc="C4: phase-diagram sweep, 32 Fz x 32 E0 x 16 kT = 16384 points x n=100 non-interacting chains, grid "
-                    "split over the GPUs"),
+    "C4": dict(cases=c4_grid(), replicas=1, S=100000, stepout=500, scaling="strong", e2e="sweep",
+               desc="C4: phase-diagram sweep, 32 Fz x 32 E0 x 16 kT = 16384 points x n=100 non-interacting chains, 1e5 "
+                    "trials per point (SURVEY 8d), grid split over the GPUs"),
     "C5": dict(cases=[C5_KW], replicas=148, S=200, stepout=200, scaling="weak", e2e="state",
                desc="C5: long interacting dielectric chains n=4096, 148 chains per GPU"),
     # the clustering driver (mcmc_clustering_eap_chain.jl), shapes of its launchers:
@@ -535,6 +535,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=cx.dev)
+        # a host-side barrier for the phase in which rank 0 alone drives every GPU: a rank parked in an NCCL barrier
+        # keeps a spinning kernel on its GPU, and two contexts on one GPU time-slice
+        cx.cpu_group = dist.new_group(backend="gloo")
     cx.stream = torch.cuda.current_stream(cx.dev)
     # L2 flush buffer (larger than the 126 MB L2), written between timed steps
     cx.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=cx.dev)
@@ -575,12 +578,13 @@ def main():
             strong[nm[:-1]] = r
         barrier()
         if world > 1:
+            torch.cuda.synchronize(cx.dev)
             if rank == 0:
                 try:
                     multi_abi = measure_multi_abi(cx, xs, 3)
                 except Exception as e:  # the multi-device ABI is reported, never fatal for the headline
                     multi_abi = {"error": str(e)}
-            barrier()
+            dist.barrier(group=cx.cpu_group)   # the other ranks wait on the host, their GPUs idle
     cx.sampler.stop()
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------

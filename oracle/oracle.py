@@ -120,6 +120,10 @@ def lib():
     L.orc_run_cluster_stats.argtypes = [vp, dp]
     L.orc_run_new.argtypes = [cp, C.c_uint64, C.c_uint32, C.c_int32]
     L.orc_run_new.restype = vp
+    L.orc_run_new_tape.argtypes = [cp, C.c_int32, dp, C.c_int64, C.c_int32]
+    L.orc_run_new_tape.restype = vp
+    L.orc_run_tape_pos.argtypes = [vp]
+    L.orc_run_tape_pos.restype = C.c_int64
     L.orc_run_set_state.argtypes = [vp, dp, dp]
     L.orc_run_steps.argtypes = [vp, C.c_int64, C.c_int64, dp, dp]
     L.orc_run_reinit.argtypes = [vp, C.c_int32]
@@ -266,9 +270,18 @@ class Run:
     """The mcmc() loop of mcmc_eap_chain.jl:171-376 for one chain.  algo 0 = the reference
     algorithm (deep copy + full recompute per trial), algo 1 = the changed-pair ΔU formulation."""
 
-    def __init__(self, case: OrcCase, seed: int, chain_id: int = 0, algo: int = 0):
+    def __init__(self, case: OrcCase, seed: int, chain_id: int = 0, algo: int = 0, tape=None, reinit_stale=False):
+        """tape: an array of uniforms consumed in the reference's rand() call order instead of the Philox stream
+        (polymc_oracle.h `orc_run_new_tape`); reinit_stale: the reference's literal stale acceptor after a re-init."""
         self.case = case
-        self._p = lib().orc_run_new(C.byref(case), seed, chain_id, algo)
+        if tape is None:
+            self._p = lib().orc_run_new(C.byref(case), seed, chain_id, algo)
+        else:
+            self._tape = np.ascontiguousarray(tape, dtype=np.float64)   # must outlive the run
+            self._p = lib().orc_run_new_tape(C.byref(case), algo, _dp(self._tape), self._tape.size, int(reinit_stale))
+
+    def tape_pos(self) -> int:
+        return int(lib().orc_run_tape_pos(self._p))
 
     def __del__(self):
         if getattr(self, "_p", None):

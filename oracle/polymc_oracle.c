@@ -728,7 +728,52 @@ struct orc_run {
   double acc_x[2];       /* Σ of the two extra averagers (mcmc_clustering_eap_chain.jl:243-244) */
   double spsi, scos2;    /* algo 1: running Σψ and Σcos²θ */
   double ncluster, cluster_sum, cluster_max;
+  /* tape mode (see orc_run_new_tape) */
+  const double* tape;
+  int64_t tape_len, tape_pos;
+  int32_t tape_underrun;
+  int32_t reinit_stale;   /* 1 = the reference's literal behaviour: logπ_prev is NOT refreshed after a re-init swap */
 };
+
+/* Tape mode (tests only).  The reference draws from Julia's global RNG; to compare the oracle with the reference's
+ * own code run on a scripted `rand` (tests/golden/ref_driver_*.jl), every random draw pops the next value of a
+ * caller-supplied array of uniforms, in the ORDER the reference calls rand():
+ *   EAPChain(pargs): n values for ϕ (ϕ = 2π·u), then n for θ (θ = π·u)                      eap_chain.jl:62
+ *   trial: idx = ⌊u·n⌋, dϕ = −s + 2s·u, [--do-flips: Bool = u < ½], dθ                      mcmc_eap_chain.jl:277-280
+ *          [cluster_flip!: 3-D gate, up-growth…, down-growth… / 2-D growth… then gate]      eap_chain.jl:269-333
+ *          ϵ                                                                                mcmc_eap_chain.jl:287
+ *   re-init: 2n values for the new chain, then ϵ unless --force-init                        mcmc_eap_chain.jl:352-357
+ * The Markov chain logic is the SAME code as in Philox mode; only the source of the uniforms differs. */
+static double tape_pop(orc_run* r) {
+  if (r->tape_pos >= r->tape_len) {
+    r->tape_underrun = 1;
+    return 0.5;
+  }
+  return r->tape[r->tape_pos++];
+}
+
+typedef struct {
+  int64_t idx;
+  double uphi, uth, eps;
+  int32_t flipbit;
+} step_draws;
+
+/* idx, dϕ, [Bool], dθ of trial `step` (mcmc_eap_chain.jl:277-280). */
+static void draw_head(orc_run* r, int64_t step, step_draws* d) {
+  const orc_case* c = &r->c;
+  if (!r->tape) {
+    orc_draw_step(r->seed, r->chain_id, r->init, step, c->n, &d->idx, &d->uphi, &d->flipbit, &d->uth, &d->eps);
+    return;
+  }
+  d->idx = (int64_t)floor(tape_pop(r) * (double)c->n);
+  d->uphi = tape_pop(r);
+  d->flipbit = c->do_flips ? (tape_pop(r) < 0.5) : 0;   /* `pargs["do-flips"] && rand(Bool)` short-circuits */
+  d->uth = c->planar ? 0.0 : tape_pop(r);               /* the 2-D driver draws no dθ */
+  d->eps = 0.0;
+}
+
+/* ϵ of the acceptor call (mcmc_eap_chain.jl:287): drawn after everything else of the trial. */
+static double draw_eps(orc_run* r, const step_draws* d) { return r->tape ? tape_pop(r) : d->eps; }
 
 static void orc_run_steps_impl(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, double* roll, int roll_cols,
                                double* state);
@@ -758,6 +803,20 @@ static void run_bind_gauge(orc_run* r) {
     r->log_gauge = -c->mu * c->E0 * (double)c->n / (3 * c->kT) + r->chain->Omega;
 }
 
+/* EAPChain(pargs) on a tape: `rand(ϕ_dist, n), rand(θ_dist, n)` (eap_chain.jl:62) — all ϕ first, then all θ.  The
+ * planar chain (2D/inc/eap_chain.jl:66) draws ϕ only. */
+static orc_chain* chain_from_tape(orc_run* r) {
+  const orc_case* c = &r->c;
+  double* phi = (double*)malloc(sizeof(double) * (size_t)c->n);
+  double* theta = (double*)malloc(sizeof(double) * (size_t)c->n);
+  for (int64_t k = 0; k < c->n; ++k) phi[k] = 0.0 + (2.0 * M_PI - 0.0) * tape_pop(r);
+  for (int64_t k = 0; k < c->n; ++k) theta[k] = c->planar ? 0.0 : 0.0 + (M_PI - 0.0) * tape_pop(r);
+  orc_chain* ch = orc_chain_new(c, phi, theta);
+  free(phi);
+  free(theta);
+  return ch;
+}
+
 orc_run* orc_run_new(const orc_case* c, uint64_t seed, uint32_t chain_id, int32_t algo) {
   orc_run* r = (orc_run*)calloc(1, sizeof(orc_run));
   r->c = *c;
@@ -785,7 +844,7 @@ void orc_run_begin_stage(orc_run* r, double kT) {
   r->chain->U = U_total(r->chain);
   r->init += 1; /* fresh random numbers for the new stage */
   if (r->c.planar) { /* 2D/mcmc_clustering_eap_chain.jl:151 `chain = EAPChain(pargs)`: every stage builds a NEW chain */
-    orc_chain* nc = orc_chain_new_random(&r->c, r->seed, r->chain_id, r->init);
+    orc_chain* nc = r->tape ? chain_from_tape(r) : orc_chain_new_random(&r->c, r->seed, r->chain_id, r->init);
     chain_assign(r->chain, nc);
     orc_chain_free(nc);
   }
@@ -801,7 +860,23 @@ void orc_run_begin_stage(orc_run* r, double kT) {
 }
 
 void orc_run_init_x0(orc_run* r, const double* x0, int64_t x0_len, const double dx0[2]) {
-  orc_chain* ch = orc_chain_new_x0(&r->c, r->seed, r->chain_id, 0, x0, x0_len, dx0);
+  orc_chain* ch;
+  if (r->tape) {
+    /* EAPChain(pargs) with --x0 draws only the perturbations: rand(Uniform(0, dx0[1]), n), then rand(Uniform(0, dx0[2]), n)
+     * (eap_chain.jl:70-75) — the tape restarts, the random chain of the constructor was never drawn by the reference */
+    if (x0_len != 2 && x0_len != 2 * r->c.n) return;
+    r->tape_pos = 0;
+    const int64_t n = r->c.n;
+    double* phi = (double*)malloc(sizeof(double) * (size_t)n);
+    double* theta = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int64_t k = 0; k < n; ++k) phi[k] = (x0_len == 2 ? x0[0] : x0[2 * k]) + (0.0 + (dx0[0] - 0.0) * tape_pop(r));
+    for (int64_t k = 0; k < n; ++k) theta[k] = (x0_len == 2 ? x0[1] : x0[2 * k + 1]) + (0.0 + (dx0[1] - 0.0) * tape_pop(r));
+    ch = orc_chain_new(&r->c, phi, theta);
+    free(phi);
+    free(theta);
+  } else {
+    ch = orc_chain_new_x0(&r->c, r->seed, r->chain_id, 0, x0, x0_len, dx0);
+  }
   if (!ch) return;
   chain_assign(r->chain, ch);
   orc_chain_free(ch);
@@ -876,23 +951,26 @@ static void emit_rows(const orc_run* r, int64_t step, double* traj_row, double* 
 /* cluster_flip! (eap_chain.jl:269-333) on the chain `t` that already carries the single-monomer move:
  * decides the cluster [lo,hi] and the link probabilities at its ends.  Returns 0 if the gate draw says
  * "no cluster" (rand() <= ϵflip → α = 1, :273). */
-static int cluster_grow(const orc_run* r, const orc_chain* t, int64_t step, int64_t idx, int64_t* lo, int64_t* hi,
+static int cluster_grow(orc_run* r, const orc_chain* t, int64_t step, int64_t idx, int64_t* lo, int64_t* hi,
                         double* upper_p, double* lower_p) {
   const orc_case* c = &r->c;
   if (!c->clustering) return 0; /* mcmc_eap_chain.jl has no cluster_flip! */
   /* 3-D: the gate comes first and a hit means "no cluster" (eap_chain.jl:273).  2-D: the cluster is grown
-   * first and a hit means "flip it" (2D/inc/eap_chain.jl:233).  The growth uniforms are counter-based, so
-   * growing after the gate changes nothing. */
-  {
-    const int hit = orc_draw_cluster_gate(r->seed, r->chain_id, r->init, step) <= c->cluster_prob;
-    if (c->planar ? !hit : hit) return 0;
+   * first and a hit means "flip it" (2D/inc/eap_chain.jl:233).  The Philox growth uniforms are counter-based, so
+   * growing after the gate changes nothing there; on a tape the calls happen in the reference's order. */
+  if (!c->planar) {
+    const double g = r->tape ? tape_pop(r) : orc_draw_cluster_gate(r->seed, r->chain_id, r->init, step);
+    if (g <= c->cluster_prob) return 0;
+  } else if (!r->tape) {
+    if (!(orc_draw_cluster_gate(r->seed, r->chain_id, r->init, step) <= c->cluster_prob)) return 0;
   }
   int64_t u = idx, k = 0;
   double up;
   for (;;) { /* :276-289 */
     if (u >= t->n - 1) { up = 0.0; break; }
     up = orc_chain_link_prob(t, u);
-    if (orc_draw_cluster(r->seed, r->chain_id, r->init, step, 0, k++) <= up) u += 1; else break;
+    const double x = r->tape ? tape_pop(r) : orc_draw_cluster(r->seed, r->chain_id, r->init, step, 0, k++);
+    if (x <= up) u += 1; else break;
   }
   int64_t l = idx;
   double lp;
@@ -900,8 +978,10 @@ static int cluster_grow(const orc_run* r, const orc_chain* t, int64_t step, int6
   for (;;) { /* :292-305 */
     if (l <= 0) { lp = 0.0; break; }
     lp = orc_chain_link_prob(t, l - 1);
-    if (orc_draw_cluster(r->seed, r->chain_id, r->init, step, 1, k++) <= lp) l -= 1; else break;
+    const double x = r->tape ? tape_pop(r) : orc_draw_cluster(r->seed, r->chain_id, r->init, step, 1, k++);
+    if (x <= lp) l -= 1; else break;
   }
+  if (c->planar && r->tape && !(tape_pop(r) <= c->cluster_prob)) return 0;  /* 2D/inc/eap_chain.jl:233 */
   *lo = l; *hi = u; *upper_p = up; *lower_p = lp;
   return 1;
 }
@@ -917,10 +997,11 @@ void orc_run_steps_ex(orc_run* r, int64_t nsteps, int64_t stepout, double* traj,
 /* One trial of mcmc_clustering_eap_chain.jl:267-279: move!, cluster_flip!, acceptor with α. */
 static int cluster_trial(orc_run* r, int64_t step) {
   const orc_case* c = &r->c;
-  int64_t idx;
-  double uphi, uth, eps;
-  int32_t flipbit;
-  orc_draw_step(r->seed, r->chain_id, r->init, step, c->n, &idx, &uphi, &flipbit, &uth, &eps);
+  step_draws sd;
+  draw_head(r, step, &sd);
+  const int64_t idx = sd.idx;
+  const double uphi = sd.uphi, uth = sd.uth;
+  const int32_t flipbit = sd.flipbit;
   const double dphi = -r->phi_step + (2 * r->phi_step) * uphi;   /* :268-270 */
   /* (--do-flips exists only in mcmc_eap_chain.jl:279, which reaches this path when it carries bending energy) */
   const double dth = c->planar ? 0.0 /* no dθ draw in 2D/mcmc_clustering_eap_chain.jl:238-241 */
@@ -933,6 +1014,7 @@ static int cluster_trial(orc_run* r, int64_t step) {
     chain_assign(r->trial, r->chain);                 /* :271 */
     orc_chain_move(r->trial, idx, dphi, dth);         /* :272 */
     reflect = cluster_grow(r, r->trial, step, idx, &lo, &hi, &up, &lp);
+    const double eps = draw_eps(r, &sd);              /* :274 `acceptor(trial_chain, rand(); α = α)` */
     if (reflect) {
       for (int64_t i = lo; i <= hi; ++i) {            /* eap_chain.jl:311-315 */
         chain_refl_caches(r->trial, i);
@@ -961,6 +1043,7 @@ static int cluster_trial(orc_run* r, int64_t step) {
       else nhat_of(cos(phi1), sin(phi1), cos(th1), sin(th1), &t->nhat[3 * idx]);
     }
     reflect = cluster_grow(r, t, step, idx, &lo, &hi, &up, &lp);
+    const double eps = draw_eps(r, &sd);
     double d[12];
     orc_chain_delta_segment(r->chain, idx, dphi, dth, reflect, lo, hi, d);
     if (reflect) {
@@ -1019,10 +1102,11 @@ static void orc_run_steps_impl(orc_run* r, int64_t nsteps, int64_t stepout, doub
       goto counted;
     }
     {
-    int64_t idx;
-    double uphi, uth, eps;
-    int32_t flipbit;
-    orc_draw_step(r->seed, r->chain_id, r->init, step, c->n, &idx, &uphi, &flipbit, &uth, &eps);
+    step_draws sd;
+    draw_head(r, step, &sd);
+    const int64_t idx = sd.idx;
+    const double uphi = sd.uphi, uth = sd.uth, eps = draw_eps(r, &sd);
+    const int32_t flipbit = sd.flipbit;
     /* rand(Uniform(-s, s)) = -s + 2s*u  (mcmc_eap_chain.jl:278-280) */
     double dphi = -r->phi_step + (2 * r->phi_step) * uphi;
     double dth = ((c->do_flips && flipbit) ? M_PI - 2 * r->chain->theta[idx] : 0.0) +
@@ -1087,16 +1171,44 @@ static void orc_run_steps_impl(orc_run* r, int64_t nsteps, int64_t stepout, doub
  * acceptor's logπ_prev stale after the swap (Appendix B); fixed here by rebinding. */
 int32_t orc_run_reinit(orc_run* r, int32_t force_init) {
   r->init += 1;
-  orc_chain* nc = orc_chain_new_random(&r->c, r->seed, r->chain_id, r->init);
-  double eps = orc_draw_reinit_eps(r->seed, r->chain_id, r->init);
+  orc_chain* nc;
+  double eps = 0.0;
+  if (r->tape) {
+    nc = chain_from_tape(r);
+    if (!force_init) eps = tape_pop(r);   /* `pargs["force-init"] || metropolis_acc(..., rand())` short-circuits */
+  } else {
+    nc = orc_chain_new_random(&r->c, r->seed, r->chain_id, r->init);
+    eps = orc_draw_reinit_eps(r->seed, r->chain_id, r->init);
+  }
   int32_t take = force_init || (eps <= exp(-(nc->U - r->chain->U) / r->c.kT + (nc->Omega - r->chain->Omega)));
   if (take) {
+    const double stale = r->logpi_prev;
     chain_assign(r->chain, nc);
     run_bind_chain(r);
+    if (r->reinit_stale) r->logpi_prev = stale;   /* mcmc_eap_chain.jl:360: `chain = new_chain`, acceptor untouched */
   }
   orc_chain_free(nc);
   return take;
 }
+
+/* Tape mode constructor: the initial chain comes from the tape too. */
+orc_run* orc_run_new_tape(const orc_case* c, int32_t algo, const double* tape, int64_t tape_len, int32_t reinit_stale) {
+  orc_run* r = (orc_run*)calloc(1, sizeof(orc_run));
+  r->c = *c;
+  r->algo = algo;
+  r->phi_step = c->phi_step;
+  r->theta_step = c->theta_step;
+  r->tape = tape;
+  r->tape_len = tape_len;
+  r->reinit_stale = reinit_stale;
+  r->chain = chain_from_tape(r);
+  r->trial = orc_chain_copy(r->chain);
+  run_bind_gauge(r);
+  run_bind_chain(r);
+  return r;
+}
+
+int64_t orc_run_tape_pos(const orc_run* r) { return r->tape_underrun ? -1 : r->tape_pos; }
 
 void orc_run_extra_averages(const orc_run* r, double ex[2]) {
   for (int k = 0; k < 2; ++k) ex[k] = r->acc_x[k] / r->normalizer;

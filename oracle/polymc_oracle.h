@@ -121,6 +121,14 @@ void orc_run_set_state(orc_run* r, const double* phi, const double* theta);
 void orc_run_steps(orc_run* r, int64_t nsteps, int64_t stepout, double* traj, double* roll);
 /* Re-initialisation between inits (mcmc_eap_chain.jl:352-361); returns 1 if the new chain replaced the old. */
 int32_t orc_run_reinit(orc_run* r, int32_t force_init);
+/* Tape mode (tests only): the same Markov chain code fed from a caller-owned array of uniforms in the order the
+ * reference's code calls rand() — initial chain, then per trial idx, dϕ, [Bool], dθ, [cluster_flip! draws], ϵ, and the
+ * re-init draws — so that the oracle can be compared with the reference's own scripts run on a scripted `rand`
+ * (tests/golden/ref_driver_*.jl).  reinit_stale = 1 keeps the acceptor's logπ_prev after a re-init swap, as the
+ * reference does (mcmc_eap_chain.jl:360 vs inc/acceptance.jl:33); algo 0 only.  The tape must outlive the run.
+ * orc_run_tape_pos: uniforms consumed so far, or -1 if the tape ran out. */
+orc_run* orc_run_new_tape(const orc_case* c, int32_t algo, const double* tape, int64_t tape_len, int32_t reinit_stale);
+int64_t orc_run_tape_pos(const orc_run* r);
 /* avg[16] in rolling.csv column order (r1..r3, r1sq..r3sq, rsq, p1..p3, p1sq..p3sq, psq, U, Usq). */
 void orc_run_averages(const orc_run* r, double avg[16], double* acc_rate, double* normalizer);
 void orc_run_diag(const orc_run* r, double out[8]); /* phi_step, theta_step, nacc, natt, nacc_total, steps_total, U, Omega */
