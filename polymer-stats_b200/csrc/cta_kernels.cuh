@@ -189,7 +189,9 @@ template <int NW, int FIRST_WARP>
 struct Team {
   static constexpr int kWarps = NW;
   static constexpr int kThreads = NW * 32;
+  static constexpr int kLocalThreads = NW * 32;   // threads that share ONE copy of the staged chain (see PairTeam)
   __device__ __forceinline__ static int tid() { return (int)threadIdx.x - FIRST_WARP * 32; }
+  __device__ __forceinline__ static int ltid() { return tid(); }
   __device__ __forceinline__ static int warp() { return (int)(threadIdx.x >> 5) - FIRST_WARP; }
   __device__ __forceinline__ static int lane() { return (int)(threadIdx.x & 31); }
   __device__ __forceinline__ static void sync() {
@@ -202,7 +204,9 @@ struct Team {
 struct WarpTeam {
   static constexpr int kWarps = 1;
   static constexpr int kThreads = 32;
+  static constexpr int kLocalThreads = 32;
   __device__ __forceinline__ static int tid() { return (int)(threadIdx.x & 31); }
+  __device__ __forceinline__ static int ltid() { return tid(); }
   __device__ __forceinline__ static int warp() { return 0; }
   __device__ __forceinline__ static int lane() { return (int)(threadIdx.x & 31); }
   __device__ __forceinline__ static void sync() { __syncwarp(); }
@@ -349,8 +353,8 @@ __device__ __forceinline__ double delta_pairs_partial(const CtaView& S, int n, i
   const double ex = sgn * Dx, ey = sgn * Dy, ez = sgn * Dz;
   const int baseA = lanes_are_heads ? 0 : idx + 1, A = lanes_are_heads ? H : Tl;
   const int baseB = lanes_are_heads ? idx + 1 : 0, B = lanes_are_heads ? Tl : H;
-  if (rect)
-    for (int k = tid; k < B; k += T)
+  if (rect)  // every copy of the staged chain needs its own E
+    for (int k = TEAM::ltid(); k < B; k += TEAM::kLocalThreads)
       S.E[baseB + k] = fma(S.mz[baseB + k], ez, fma(S.my[baseB + k], ey, S.mx[baseB + k] * ex));
   // row {idx}×rest: both μ_idx and the separation change.
   double acc = 0.0;

@@ -89,6 +89,10 @@ struct pmc_handle {
   double kT_scale = 1.0;
   std::vector<ChainDynX> host_dynx;
   int planar = 0;             // 2-D tree
+  // two SMs per chain (pair_kernels.cuh): predicted work, work-ordered queue
+  unsigned long long* pair_work = nullptr;
+  int* pair_order = nullptr;
+  int* pair_next = nullptr;
   const char* kernel_name = "";  // the MCMC kernel the last (dry or real) launch decision picked, pmc_kernel_name
   int dry_run = 0;               // launch helpers only record their decision
 };
@@ -111,6 +115,8 @@ inline int pick_cluster_threads(int n) { return n <= 160 ? 32 : n <= 256 ? 64 : 
 
 // ---- launch helpers, one translation unit per kernel family -------------------------------------------------
 int launch_run_cta(pmc_handle* h, const pmc::RunArgs& a);                    // run_cta.cu
+int launch_run_pair(pmc_handle* h, const pmc::RunArgs& a);                   // run_pair.cu
+bool use_pair_kernel(const pmc_handle* h);                                   // run_pair.cu
 int launch_run_lane(pmc_handle* h, const pmc::RunArgs& a);                   // run_lane.cu
 int launch_run_cluster_cta(pmc_handle* h, const pmc::RunArgs& a);            // run_cluster_cta.cu
 int launch_delta_segment_cta(pmc_handle* h, const pmc::SegDeltaArgs& a);     // run_cluster_cta.cu

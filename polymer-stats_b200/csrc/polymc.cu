@@ -365,6 +365,9 @@ void pmc_destroy(pmc_handle* h) {
   if (h->roll) cudaFree(h->roll);
   if (h->scratch) cudaFree(h->scratch);
   if (h->flags) cudaFree(h->flags);
+  if (h->pair_work) cudaFree(h->pair_work);
+  if (h->pair_order) cudaFree(h->pair_order);
+  if (h->pair_next) cudaFree(h->pair_next);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;

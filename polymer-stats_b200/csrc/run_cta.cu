@@ -6,6 +6,7 @@ int fail(int code, const std::string& msg) { return pmc_fail(code, msg); }
 }  // namespace
 
 int launch_run_cta(pmc_handle* h, const RunArgs& a) {
+  if (use_pair_kernel(h)) return launch_run_pair(h, a);
   const size_t smem = cta_smem_bytes(h->n);
   const int nblocks = (int)h->nchains;
   // PMC_RUN_CFG = threads*100 + minblocks*10 + unroll selects a tuning variant (experiments only)

@@ -1,0 +1,81 @@
+// run_pair.cu — launch of k_run_cta_pair (pair_kernels.cuh): long interacting chains, two SMs per chain.
+#include "handle.h"
+#include "pair_kernels.cuh"
+
+namespace {
+int fail(int code, const std::string& msg) { return pmc_fail(code, msg); }
+}  // namespace
+
+// Long chains whose staged copy leaves room for only one CTA per SM run on CTA pairs (PMC_RUN_PAIR=0 switches it off,
+// PMC_RUN_PAIR=2 forces it for any chain length — tests and experiments).
+bool use_pair_kernel(const pmc_handle* h) {
+  const int mode = env_int("PMC_RUN_PAIR", 1);
+  if (mode == 0 || h->energy_type != PMC_ENERGY_INTERACTING || h->cluster_mode) return false;
+  if (h->cta_threads != 128 && h->cta_threads != 256 && h->cta_threads != 512) return false;
+  if (mode == 2) return true;
+  return cta_smem_bytes(h->n) > (size_t)kSmemMax / 2;
+}
+
+template <int T>
+static int launch_pair_t(pmc_handle* h, const RunArgs& a, const PairQueue& q) {
+  const size_t smem = cta_smem_bytes(h->n);
+  int rc = set_smem(k_run_cta_pair<T, 2>, smem);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(T, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent: as many clusters as the device keeps resident (≤ one per chain); each runs chain after chain
+  cfg.gridDim = dim3(2, 1, 1);
+  int resident = 0;
+  PMC_CU(cudaOccupancyMaxActiveClusters(&resident, k_run_cta_pair<T, 2>, &cfg));
+  if (resident < 1) return fail(PMC_ERR_UNSUPPORTED, "no CTA pair fits on this device");
+  const int clusters = (int)std::min<int64_t>(h->nchains, resident);
+  cfg.gridDim = dim3(2 * clusters, 1, 1);
+  PMC_CU(cudaLaunchKernelEx(&cfg, k_run_cta_pair<T, 2>, a, q));
+  ++h->launches;
+  return PMC_OK;
+}
+
+int launch_run_pair(pmc_handle* h, const RunArgs& a) {
+  switch (h->cta_threads) {
+    case 128: PMC_PICK("k_run_cta_pair<128,2>"); break;
+    case 256: PMC_PICK("k_run_cta_pair<256,2>"); break;
+    default: PMC_PICK("k_run_cta_pair<512,2>"); break;
+  }
+  const int nch = (int)h->nchains;
+  if (!h->pair_work) {
+    PMC_CU(cudaMalloc(&h->pair_work, (size_t)nch * sizeof(unsigned long long)));
+    PMC_CU(cudaMalloc(&h->pair_order, (size_t)nch * sizeof(int)));
+    PMC_CU(cudaMalloc(&h->pair_next, sizeof(int)));
+  }
+  PairQueue q{};
+  q.next = h->pair_next;
+  if (nch <= 16384 && env_int("PMC_PAIR_ORDER", 1)) {   // heaviest predicted work first; beyond that the queue alone balances
+    const int tb = 128, nb = (nch + tb - 1) / tb;
+    k_predict_work<<<nb, tb, 0, h->stream>>>(h->dyn, nch, h->n, a.nsteps, h->seed, h->chain_id_base, h->pair_work);
+    k_order_by_work<<<nb, tb, 0, h->stream>>>(h->pair_work, nch, h->pair_order, h->pair_next);
+    h->launches += 2;
+    PMC_CU(cudaGetLastError());
+    q.order = h->pair_order;
+  } else {
+    PMC_CU(cudaMemsetAsync(h->pair_next, 0, sizeof(int), h->stream));
+    q.order = nullptr;
+  }
+  int rc;
+  switch (h->cta_threads) {
+    case 128: rc = launch_pair_t<128>(h, a, q); break;
+    case 256: rc = launch_pair_t<256>(h, a, q); break;
+    default: rc = launch_pair_t<512>(h, a, q); break;
+  }
+  if (rc) return rc;
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}

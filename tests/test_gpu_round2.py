@@ -54,7 +54,7 @@ def test_c5_run_kernel_trajectory_n4096(pm, O):
     pc, oc = both_cases(pm, O, n=n, E0=1.0, K1=1.0, K2=0.0, Fz=0.5, energy_type="interacting", steps_per_adjust=40)
     with pm.Ensemble(pc, replicas=2, seed=20260101, ensemble_chains=148) as ens:
         name = ens.kernel_name()
-        assert name.startswith(("k_run_cta<512,1", "k_run_cta_pair<")), name
+        assert name.startswith("k_run_cta_pair<512"), name
         traj, roll = ens.run(steps, 30)
         for c in (0, 1):
             _compare_run(ens, O.Run(oc, 20260101, c, 1), c, traj, roll, steps, 30, scale_pairs=True)
@@ -275,3 +275,30 @@ def test_umbrella_replicas_pooled_as_ratios_match_closed_form(pm):
         assert abs(pooled[k] / norm - cf[k]) <= 3.0 * sem[k] + 1e-9 * max(1.0, abs(cf[k])), (pm.AVG_NAMES[k], pooled[k], cf[k])
     w = sums[:, 16] / sums[:, 16].sum()
     assert w.max() > 2.0 / R              # the raw normalisers ARE unequal (why the sums are not pooled)
+
+
+@pytest.mark.parametrize("n,R,steps", [(96, 3, 2000), (512, 5, 600), (700, 150, 300)])
+def test_pair_kernel_trajectory(pm, O, monkeypatch, n, R, steps):
+    """k_run_cta_pair (two SMs per chain: a 2-CTA cluster splits the changed-pair set, partial sums exchanged through
+    distributed shared memory, chains taken from a work-ordered queue), forced for short chains with PMC_RUN_PAIR=2:
+    same decisions, rows, step sizes and final state as the oracle; launches chunk like the one-CTA kernels; more chains
+    than resident clusters (150 > 74) exercise the queue."""
+    monkeypatch.setenv("PMC_RUN_PAIR", "2")
+    pc, oc = both_cases(pm, O, n=n, E0=1.0, K2=0.1, Fz=0.5, Fx=0.2, energy_type="interacting", steps_per_adjust=100)
+    with pm.Ensemble(pc, replicas=R, seed=23, chain_id_base=7) as ens, pm.Ensemble(pc, replicas=R, seed=23, chain_id_base=7) as two:
+        assert ens.kernel_name().startswith("k_run_cta_pair<")
+        traj, roll = ens.run(steps, steps // 4)
+        for c in sorted({0, R // 2, R - 1}):
+            _compare_run(ens, O.Run(oc, 23, 7 + c, 1), c, traj, roll, steps, steps // 4, scale_pairs=True)
+        t1, _ = two.run(steps // 2, steps // 4)
+        t2, _ = two.run(steps // 2, steps // 4)
+        np.testing.assert_array_equal(np.concatenate([t1, t2], axis=1)[:, :, 0], traj[:, :, 0])
+        np.testing.assert_array_equal(two.diagnostics()[:, 4:6], ens.diagnostics()[:, 4:6])
+        np.testing.assert_allclose(np.concatenate([t1, t2], axis=1), traj, rtol=0, atol=1e-9 * max(1.0, np.abs(traj).max()))
+        counts = ens.diagnostics()[:, 4:6]
+    monkeypatch.setenv("PMC_RUN_PAIR", "0")
+    with pm.Ensemble(pc, replicas=R, seed=23, chain_id_base=7) as one:
+        assert not one.kernel_name().startswith("k_run_cta_pair<")
+        t0, _ = one.run(steps, steps // 4)
+        np.testing.assert_allclose(t0, traj, rtol=0, atol=1e-9 * max(1.0, np.abs(traj).max()))
+        np.testing.assert_array_equal(one.diagnostics()[:, 4:6], counts)
