@@ -259,6 +259,10 @@ int32_t pmc_multi_gather(pmc_multi* m, double* table);
 int32_t pmc_multi_last_run_ms(const pmc_multi* m, float* ms_max);   /* slowest device's MCMC kernel time */
 int64_t pmc_multi_launch_count(const pmc_multi* m);
 
+/* Device memory of destroyed handles is kept in a per-process cache and reused by the next pmc_create (a study
+ * creates one handle per bucket per call); this returns the cached blocks to the driver.  No reference counterpart. */
+int32_t pmc_release_cached_memory(void);
+
 /* ---- measurement helper ------------------------------------------------------------------ */
 /* Dependent-free DFMA loop on all SMs of `device`; returns achieved FP64 TFLOP/s (2 flop per DFMA)
  * and the device time in ms.  Used by bench.py as the measured FP64 roofline denominator. */

@@ -410,8 +410,9 @@ struct Countdown {
   }
 };
 
-// record! of the 8 averagers (average.jl:40-48; umbrella :63-73) on the current state.
-template <bool COMP = true>
+// record! of the 8 averagers (average.jl:40-48; umbrella :63-73) on the current state.  STRIDE: distance between
+// consecutive accumulators (1: a thread's own array; 32: one lane's column of a [17][32] shared-memory tile).
+template <bool COMP = true, int STRIDE = 1>
 __device__ __forceinline__ void record_averages(const ChainParams& P, double* acc, double* comp,
                                                 const double* r, const double* p, double U, double su,
                                                 double log_gauge) {
@@ -424,8 +425,8 @@ __device__ __forceinline__ void record_averages(const ChainParams& P, double* ac
                              U, U * U, 1.0};
 #pragma unroll
   for (int k = 0; k < kNumAcc; ++k) {
-    if (COMP) comp_add(acc[k], comp[k], v[k] * wgt);
-    else acc[k] += v[k] * wgt;  // plain Float64 sums, as the reference's default --numeric-type (average.jl:40-48)
+    if (COMP) comp_add(acc[k * STRIDE], comp[k * STRIDE], v[k] * wgt);
+    else acc[k * STRIDE] += v[k] * wgt;  // plain Float64 sums, as the reference's default --numeric-type (average.jl:40-48)
   }
 }
 

@@ -12,6 +12,9 @@
 #include <new>
 #include <string>
 #include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "cluster_kernels.cuh"
@@ -96,6 +99,14 @@ struct pmc_handle {
   const char* kernel_name = "";  // the MCMC kernel the last (dry or real) launch decision picked, pmc_kernel_name
   int dry_run = 0;               // launch helpers only record their decision
 };
+
+// Device memory of the handles comes from a per-device cache of freed blocks: a study creates and destroys one handle
+// per bucket per call (polymc.sweep), and cudaMalloc / cudaFree (which synchronises the device) dominated such calls.
+// pmc_release_cached_memory() returns everything to the driver.
+cudaError_t pmc_pool_alloc(void** ptr, size_t bytes);   // on the current device
+void pmc_pool_free(void* ptr);                          // back to the cache of the device it came from
+template <typename P>
+cudaError_t pool_alloc(P** ptr, size_t bytes) { return pmc_pool_alloc(reinterpret_cast<void**>(ptr), bytes); }
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {

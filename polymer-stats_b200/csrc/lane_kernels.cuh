@@ -36,8 +36,10 @@ __device__ __forceinline__ double lane_delta_pairs(const MonoRec* __restrict__ m
 // The hot loop (mcmc_eap_chain.jl:276-350), one chain per thread.
 template <int T, int MINB, bool COMP>
 __global__ void __launch_bounds__(T, MINB) k_run_lane(const RunArgs a) {
-  const int c = blockIdx.x * T + threadIdx.x;
-  if (c >= a.nchains) return;
+  __shared__ double rows_sm[T * kRowDoubles];
+  const int c0 = blockIdx.x * T + threadIdx.x;
+  const bool live = c0 < a.nchains;           // lanes past the last chain only help with the row stores of their warp
+  const int c = live ? c0 : a.nchains - 1;
   const int n = a.n;
   MonoRec* mono = a.mono + (size_t)c * n;
   const ChainParams P = a.par[c];
@@ -47,40 +49,49 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane(const RunArgs a) {
   long long row = 0;
   for (long long s = 1; s <= a.nsteps; ++s) {
     const long long step = step0 + s;
-    const Draws d = draw_step(a.seed, chain_id, (uint32_t)D.init, step, n);
-    const MonoRec rec = mono[d.idx];
-    double dphi, dtheta;
-    increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
-    Proposal q;
-    build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
-    double dsum = 0.0;
-    bool accept = false;
-    if (!q.skip) {
-      dsum = kInv4Pi * lane_delta_pairs(mono, n, a.energy_type, P, rec, q);
-      accept = metropolis(q.single - dsum * P.inv_kT, q.eps);
+    if (live) {
+      const Draws d = draw_step(a.seed, chain_id, (uint32_t)D.init, step, n);
+      const MonoRec rec = mono[d.idx];
+      double dphi, dtheta;
+      increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
+      Proposal q;
+      build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
+      double dsum = 0.0;
+      bool accept = false;
+      if (!q.skip) {
+        dsum = kInv4Pi * lane_delta_pairs(mono, n, a.energy_type, P, rec, q);
+        accept = metropolis(q.single - dsum * P.inv_kT, q.eps);
+      }
+      if (accept) {
+        MonoRec nr;
+        nr.phi = q.phi; nr.theta = q.theta;
+        nr.nx = q.nx; nr.ny = q.ny; nr.nz = q.nz; nr.sth = q.sth;
+        mono[d.idx] = nr;
+      }
+      after_decision<COMP>(P, D, q, accept, dsum, step);
     }
-    if (accept) {
-      MonoRec nr;
-      nr.phi = q.phi; nr.theta = q.theta;
-      nr.nx = q.nx; nr.ny = q.ny; nr.nz = q.nz; nr.sth = q.sth;
-      mono[d.idx] = nr;
-    }
-    after_decision<COMP>(P, D, q, accept, dsum, step);
-    if (a.stepout > 0 && (step % a.stepout) == 0) {
+    if (a.stepout > 0 && (step % a.stepout) == 0) {  // uniform over the block: all chains share the step counter
       if (row < a.rows) {
-        double rb[kRowDoubles];
-        stage_row(D, step, rb);
-        double* t = a.traj + ((size_t)c * a.rows + row) * 8;
-        double* r = a.roll + ((size_t)c * a.rows + row) * 17;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t[k] = rb[k];
-#pragma unroll
-        for (int k = 0; k < 17; ++k) r[k] = rb[8 + k];
+        // Output rows: every thread stages its 8 + 17 doubles in shared memory, then each warp writes the rows of its
+        // 32 chains one after the other with consecutive lanes on consecutive doubles (coalesced 64 B / 136 B stores
+        // instead of 25 scalar stores per thread scattered over 32 rows).
+        double* rb = rows_sm + (size_t)threadIdx.x * kRowDoubles;
+        if (live) stage_row(D, step, rb);
+        __syncwarp();
+        const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+        for (int k = 0; k < 32; ++k) {
+          const int ck = blockIdx.x * T + w0 + k;
+          if (ck >= a.nchains) break;
+          const double* src = rows_sm + (size_t)(w0 + k) * kRowDoubles;
+          if (lane < 8) a.traj[((size_t)ck * a.rows + row) * 8 + lane] = src[lane];
+          if (lane < 17) a.roll[((size_t)ck * a.rows + row) * 17 + lane] = src[8 + lane];
+        }
+        __syncwarp();
       }
       ++row;
     }
   }
-  a.dyn[c] = D;
+  if (live) a.dyn[c] = D;
 }
 
 // One chain per WARP, 32 trials per window: for few chains (a sweep of 16k points is only 512 warps
@@ -95,30 +106,50 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane(const RunArgs a) {
 // rows and at the end.  Windows never cross an adaptation boundary or an output row.
 template <int ISING, int MINB, bool COMP>
 __global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
-  const int lane = threadIdx.x & 31;
+  // The per-chain constants and running scalars are warp-uniform: they live in shared memory (one slot per warp),
+  // not in every lane's registers — with them in registers the kernel spilled 0.5–0.9 KB per thread at the 128
+  // registers that four CTAs per SM allow.  Lane 0 owns the writes; __syncwarp() publishes them.
+  __shared__ ChainParams sP[4];
+  __shared__ ChainDyn sD[4];
+  // per-lane partial accumulators, [accumulator][lane] (conflict-free): another 34–68 registers otherwise
+  __shared__ double sAcc[4][kNumAcc][32];
+  __shared__ double sComp[COMP ? 4 : 1][COMP ? kNumAcc : 1][32];
+  const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
   const int c = (int)((blockIdx.x * 128u + threadIdx.x) >> 5);
   if (c >= a.nchains) return;
   constexpr unsigned FULL = 0xffffffffu;
   const int n = a.n;
   MonoRec* mono = a.mono + (size_t)c * n;
-  const ChainParams P = a.par[c];
-  ChainDyn D = a.dyn[c];  // uniform scalars (every lane holds a copy); accumulators: lane 0 only
-  double acc[kNumAcc], comp[kNumAcc];
+  if (lane == 0) {
+    sP[wslot] = a.par[c];
+    sD[wslot] = a.dyn[c];
+  }
+  __syncwarp();
+  const ChainParams& P = sP[wslot];
+  ChainDyn& D = sD[wslot];
+  double* acc = &sAcc[wslot][0][lane];                      // this lane's column; lane 0 starts from the chain's sums
+  double* comp = &sComp[COMP ? wslot : 0][0][lane];
 #pragma unroll
   for (int k = 0; k < kNumAcc; ++k) {
-    acc[k] = lane == 0 ? D.acc[k] : 0.0;
-    comp[k] = lane == 0 ? D.comp[k] : 0.0;
+    if (COMP) {
+      acc[k * 32] = lane == 0 ? D.acc[k] : 0.0;
+      comp[k * 32] = lane == 0 ? D.comp[k] : 0.0;
+    } else {
+      acc[k * 32] = lane == 0 ? D.acc[k] + D.comp[k] : 0.0;
+    }
   }
   const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const uint32_t init = (uint32_t)D.init;
   const long long step0 = D.step;
-  const bool adapt_on = P.adj_scale != 1.0 && P.steps_per_adjust > 0;
+  const long long spa = P.steps_per_adjust;
+  const bool adapt_on = P.adj_scale != 1.0 && spa > 0;
   long long row = 0;
   long long s = 1;
   while (s <= a.nsteps) {
     long long wl = a.nsteps - s + 1;
     if (wl > 32) wl = 32;
     if (adapt_on) {
-      const long long tb = P.steps_per_adjust - ((step0 + s - 1) % P.steps_per_adjust);
+      const long long tb = spa - ((step0 + s - 1) % spa);
       if (wl > tb) wl = tb;
     }
     if (a.stepout > 0) {
@@ -130,7 +161,7 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
     const long long step = step0 + s + lane;
     Draws d;
     d.idx = 0; d.flipbit = 0; d.u_phi = d.u_theta = d.eps = 0.0;
-    if (active) d = draw_step(a.seed, chain_id, (uint32_t)D.init, step, n);
+    if (active) d = draw_step(a.seed, chain_id, init, step, n);
     // earlier trials of the window that conflict with this one
     unsigned cmask = 0;
     for (int j = 0; j < wlen; ++j) {
@@ -141,13 +172,14 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
     bool pending = active;
     bool accept = false;
     double drx = 0, dry = 0, drz = 0, dpx = 0, dpy = 0, dpz = 0, dU = 0, dsu = 0, dOm = 0;
+    const double phi_step = D.phi_step, theta_step = D.theta_step;  // fixed within a window
     unsigned pmask;
     while ((pmask = __ballot_sync(FULL, pending)) != 0u) {
       const bool ready = pending && (cmask & pmask) == 0u;
       if (ready) {
         const MonoRec rec = mono[d.idx];
         double dphi, dtheta;
-        increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);
+        increments(P, d, rec.theta, phi_step, theta_step, dphi, dtheta);
         Proposal q;
         build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
         if (!q.skip) {
@@ -180,39 +212,45 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
     if (active) {
       const double r[3] = {D.r[0] + drx, D.r[1] + dry, D.r[2] + drz};
       const double p[3] = {D.p[0] + dpx, D.p[1] + dpy, D.p[2] + dpz};
-      record_averages<COMP>(P, acc, comp, r, p, D.U + dU, D.su + dsu, D.log_gauge);
+      record_averages<COMP, 32>(P, acc, comp, r, p, D.U + dU, D.su + dsu, D.log_gauge);
     }
     const int last = wlen - 1;
-    D.r[0] += __shfl_sync(FULL, drx, last); D.r[1] += __shfl_sync(FULL, dry, last); D.r[2] += __shfl_sync(FULL, drz, last);
-    D.p[0] += __shfl_sync(FULL, dpx, last); D.p[1] += __shfl_sync(FULL, dpy, last); D.p[2] += __shfl_sync(FULL, dpz, last);
-    D.U += __shfl_sync(FULL, dU, last);
-    D.su += __shfl_sync(FULL, dsu, last);
-    D.Omega += __shfl_sync(FULL, dOm, last);
     const int nacc_w = __popc(__ballot_sync(FULL, accept));
-    D.nacc += nacc_w; D.nacc_total += nacc_w;
-    D.natt += wlen; D.steps_total += wlen;
     const long long step_last = step0 + s + last;
-    D.step = step_last;
-    adapt_steps(P, step_last, D.phi_step, D.theta_step, D.nacc, D.natt);  // no-op unless a boundary
+    __syncwarp();  // every lane has read the running scalars of this window
+    if (lane == last) {  // the last trial's prefix sums are the window's totals
+      D.r[0] += drx; D.r[1] += dry; D.r[2] += drz;
+      D.p[0] += dpx; D.p[1] += dpy; D.p[2] += dpz;
+      D.U += dU;
+      D.su += dsu;
+      D.Omega += dOm;
+      D.nacc += nacc_w; D.nacc_total += nacc_w;
+      D.natt += wlen; D.steps_total += wlen;
+      D.step = step_last;
+      adapt_steps(P, step_last, D.phi_step, D.theta_step, D.nacc, D.natt);  // no-op unless a boundary
+    }
+    __syncwarp();
     if (a.stepout > 0 && (step_last % a.stepout) == 0) {
       double tot[kNumAcc];
 #pragma unroll
       for (int k = 0; k < kNumAcc; ++k) {
-        double v = acc[k] + comp[k];
+        double v = COMP ? acc[k * 32] + comp[k * 32] : acc[k * 32];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         tot[k] = v;
       }
-      if (lane == 0 && row < a.rows) {
+      if (row < a.rows) {  // one 8-double and one 17-double row, written by consecutive lanes
         double* t = a.traj + ((size_t)c * a.rows + row) * 8;
         double* rr = a.roll + ((size_t)c * a.rows + row) * 17;
-        t[0] = (double)step_last;
-        t[1] = D.r[0]; t[2] = D.r[1]; t[3] = D.r[2];
-        t[4] = D.p[0]; t[5] = D.p[1]; t[6] = D.p[2];
-        t[7] = D.U;
-        rr[0] = (double)step_last;
+        if (lane == 0) t[0] = (double)step_last;
+        else if (lane < 4) t[lane] = D.r[lane - 1];
+        else if (lane < 7) t[lane] = D.p[lane - 4];
+        else if (lane == 7) t[7] = D.U;
+        double mine = (double)step_last;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) rr[1 + k] = tot[k] / tot[16];
+        for (int k = 0; k < 16; ++k)
+          if (lane == k + 1) mine = tot[k] / tot[16];
+        if (lane < 17) rr[lane] = mine;
       }
       ++row;
     }
@@ -221,12 +259,15 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
   // combine the per-lane accumulators
 #pragma unroll
   for (int k = 0; k < kNumAcc; ++k) {
-    double v = acc[k] + comp[k];
+    double v = COMP ? acc[k * 32] + comp[k * 32] : acc[k * 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    D.acc[k] = v;
-    D.comp[k] = 0.0;
+    if (lane == 0) {
+      D.acc[k] = v;
+      D.comp[k] = 0.0;
+    }
   }
+  __syncwarp();
   if (lane == 0) a.dyn[c] = D;
 }
 

@@ -20,14 +20,100 @@ int pmc_fail(int code, const std::string& msg) {
   return code;
 }
 
+// ---- cache of device blocks ------------------------------------------------------------------------------------
+namespace {
+struct PoolBlock {
+  void* ptr;
+  size_t bytes;
+  int device;
+};
+constexpr size_t kPoolCapBytes = (size_t)24 << 30;   // of the 180 GB per GPU
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool_free;                  // blocks waiting for reuse
+std::unordered_map<void*, PoolBlock> g_pool_live;    // blocks handed out
+}  // namespace
+
+cudaError_t pmc_pool_alloc(void** ptr, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (bytes == 0) bytes = 1;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t best = g_pool_free.size();
+    for (size_t k = 0; k < g_pool_free.size(); ++k) {   // best fit within 2× (a sweep asks for the same sizes again)
+      const PoolBlock& b = g_pool_free[k];
+      if (b.device == dev && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 &&
+          (best == g_pool_free.size() || b.bytes < g_pool_free[best].bytes))
+        best = k;
+    }
+    if (best != g_pool_free.size()) {
+      const PoolBlock b = g_pool_free[best];
+      g_pool_free.erase(g_pool_free.begin() + (long)best);
+      g_pool_live[b.ptr] = b;
+      *ptr = b.ptr;
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(ptr, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the cache back and try once more
+    cudaGetLastError();
+    pmc_release_cached_memory();
+    e = cudaMalloc(ptr, bytes);
+  }
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool_live[*ptr] = PoolBlock{*ptr, bytes, dev};
+  return cudaSuccess;
+}
+
+void pmc_pool_free(void* ptr) {
+  if (!ptr) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_pool_live.find(ptr);
+  if (it == g_pool_live.end()) {  // not ours
+    cudaFree(ptr);
+    return;
+  }
+  const PoolBlock b = it->second;
+  g_pool_live.erase(it);
+  size_t held = 0;
+  for (const PoolBlock& f : g_pool_free) held += f.bytes;
+  if (held + b.bytes > kPoolCapBytes) {  // the cache is bounded: beyond the cap a block goes straight back to the driver
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(b.device);
+    cudaFree(b.ptr);
+    cudaSetDevice(cur);
+    return;
+  }
+  g_pool_free.push_back(b);
+}
+
+extern "C" int32_t pmc_release_cached_memory(void) {
+  std::vector<PoolBlock> blocks;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    blocks.swap(g_pool_free);
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (const PoolBlock& b : blocks) {
+    cudaSetDevice(b.device);
+    cudaFree(b.ptr);
+  }
+  cudaSetDevice(cur);
+  return PMC_OK;
+}
+
 namespace {
 
 int ensure_scratch(pmc_handle* h, size_t doubles) {
   if (h->scratch_cap >= doubles) return PMC_OK;
-  if (h->scratch) cudaFree(h->scratch);
+  if (h->scratch) pmc_pool_free(h->scratch);
   h->scratch = nullptr;
   h->scratch_cap = 0;
-  PMC_CU(cudaMalloc(&h->scratch, doubles * sizeof(double)));
+  PMC_CU(pool_alloc(&h->scratch, doubles * sizeof(double)));
   h->scratch_cap = doubles;
   return PMC_OK;
 }
@@ -254,6 +340,14 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   }
   const int64_t nchains = ncases * (int64_t)replicas_per_case;
   if (nchains > (int64_t)0x7fffffff) return fail(PMC_ERR_INVALID, "too many chains for one handle");
+  const bool trace = env_int("PMC_TRACE_CREATE", 0) != 0;   // developer timing of the set-up phases, to stderr
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[pmc_create] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
   int ndev = 0;
   {
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -278,9 +372,8 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
   h->seed = seed;
   h->chain_id_base = chain_id_base;
   {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
-      h->sm_count = prop.multiProcessorCount;
+    int sms = 0;  // (cudaGetDeviceProperties costs tens of milliseconds; one attribute is all that is needed)
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
   }
   h->compensated = 0;
   for (int64_t i = 0; i < ncases; ++i)
@@ -300,6 +393,7 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
     }
   }
 
+  lap("validate + handle");
   std::vector<ChainParams> par((size_t)nchains);
   std::vector<ChainDyn> dyn((size_t)nchains);
   for (int64_t c = 0; c < nchains; ++c) {
@@ -322,17 +416,20 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
     }();                                 \
     if (rc__) return cleanup(rc__);      \
   } while (0)
+  lap("host tables");
   const size_t total = (size_t)nchains * (size_t)n;
-  PMC_TRY(PMC_CU(cudaMalloc(&h->mono, total * sizeof(MonoRec))));
-  PMC_TRY(PMC_CU(cudaMalloc(&h->par, (size_t)nchains * sizeof(ChainParams))));
-  PMC_TRY(PMC_CU(cudaMalloc(&h->dyn, (size_t)nchains * sizeof(ChainDyn))));
-  PMC_TRY(PMC_CU(cudaMalloc(&h->dynx, (size_t)nchains * sizeof(ChainDynX))));
+  PMC_TRY(PMC_CU(pool_alloc(&h->mono, total * sizeof(MonoRec))));
+  PMC_TRY(PMC_CU(pool_alloc(&h->par, (size_t)nchains * sizeof(ChainParams))));
+  PMC_TRY(PMC_CU(pool_alloc(&h->dyn, (size_t)nchains * sizeof(ChainDyn))));
+  PMC_TRY(PMC_CU(pool_alloc(&h->dynx, (size_t)nchains * sizeof(ChainDynX))));
   PMC_TRY(PMC_CU(cudaMemset(h->dynx, 0, (size_t)nchains * sizeof(ChainDynX))));
-  PMC_TRY(PMC_CU(cudaMalloc(&h->flags, (size_t)nchains * sizeof(int))));
+  PMC_TRY(PMC_CU(pool_alloc(&h->flags, (size_t)nchains * sizeof(int))));
   PMC_TRY(PMC_CU(cudaEventCreate(&h->ev0)));
   PMC_TRY(PMC_CU(cudaEventCreate(&h->ev1)));
+  lap("cudaMalloc + events");
   PMC_TRY(PMC_CU(cudaMemcpy(h->par, par.data(), (size_t)nchains * sizeof(ChainParams), cudaMemcpyHostToDevice)));
   PMC_TRY(PMC_CU(cudaMemcpy(h->dyn, dyn.data(), (size_t)nchains * sizeof(ChainDyn), cudaMemcpyHostToDevice)));
+  lap("H2D par + dyn");
   {
     const int tb = 256;
     const long long blocks = ((long long)total + tb - 1) / tb;
@@ -346,6 +443,7 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
     if (rc) return cleanup(rc);
   }
   PMC_TRY(PMC_CU(cudaStreamSynchronize(h->stream)));
+  lap("fill + energies");
 #undef PMC_TRY
   *out = h;
   return PMC_OK;
@@ -354,20 +452,21 @@ int32_t pmc_create(const pmc_case* cases, int64_t ncases, int32_t replicas_per_c
 void pmc_destroy(pmc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->mono) cudaFree(h->mono);
-  if (h->cand) cudaFree(h->cand);
-  if (h->par) cudaFree(h->par);
-  if (h->dyn) cudaFree(h->dyn);
-  if (h->dynx) cudaFree(h->dynx);
-  if (h->state) cudaFree(h->state);
-  if (h->x0buf) cudaFree(h->x0buf);
-  if (h->traj) cudaFree(h->traj);
-  if (h->roll) cudaFree(h->roll);
-  if (h->scratch) cudaFree(h->scratch);
-  if (h->flags) cudaFree(h->flags);
-  if (h->pair_work) cudaFree(h->pair_work);
-  if (h->pair_order) cudaFree(h->pair_order);
-  if (h->pair_next) cudaFree(h->pair_next);
+  cudaStreamSynchronize(h->stream);  // nothing in flight may still use blocks that return to the cache
+  if (h->mono) pmc_pool_free(h->mono);
+  if (h->cand) pmc_pool_free(h->cand);
+  if (h->par) pmc_pool_free(h->par);
+  if (h->dyn) pmc_pool_free(h->dyn);
+  if (h->dynx) pmc_pool_free(h->dynx);
+  if (h->state) pmc_pool_free(h->state);
+  if (h->x0buf) pmc_pool_free(h->x0buf);
+  if (h->traj) pmc_pool_free(h->traj);
+  if (h->roll) pmc_pool_free(h->roll);
+  if (h->scratch) pmc_pool_free(h->scratch);
+  if (h->flags) pmc_pool_free(h->flags);
+  if (h->pair_work) pmc_pool_free(h->pair_work);
+  if (h->pair_order) pmc_pool_free(h->pair_order);
+  if (h->pair_next) pmc_pool_free(h->pair_next);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -610,21 +709,21 @@ static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj
   const size_t ntraj = (size_t)h->nchains * (size_t)rows * 8, nroll = (size_t)h->nchains * (size_t)rows * roll_cols;
   const size_t nstate = state ? (size_t)h->nchains * (size_t)rows * 2 * (size_t)h->n : 0;
   if (nstate > h->state_cap) {
-    if (h->state) cudaFree(h->state);
+    if (h->state) pmc_pool_free(h->state);
     h->state = nullptr; h->state_cap = 0;
-    PMC_CU(cudaMalloc(&h->state, nstate * sizeof(double)));
+    PMC_CU(pool_alloc(&h->state, nstate * sizeof(double)));
     h->state_cap = nstate;
   }
   if (ntraj > h->traj_cap) {
-    if (h->traj) cudaFree(h->traj);
+    if (h->traj) pmc_pool_free(h->traj);
     h->traj = nullptr; h->traj_cap = 0;
-    PMC_CU(cudaMalloc(&h->traj, ntraj * sizeof(double)));
+    PMC_CU(pool_alloc(&h->traj, ntraj * sizeof(double)));
     h->traj_cap = ntraj;
   }
   if (nroll > h->roll_cap) {
-    if (h->roll) cudaFree(h->roll);
+    if (h->roll) pmc_pool_free(h->roll);
     h->roll = nullptr; h->roll_cap = 0;
-    PMC_CU(cudaMalloc(&h->roll, nroll * sizeof(double)));
+    PMC_CU(pool_alloc(&h->roll, nroll * sizeof(double)));
     h->roll_cap = nroll;
   }
   RunArgs a{};
@@ -676,7 +775,7 @@ int32_t pmc_reinit(pmc_handle* h, int32_t* replaced) {
   int rc = check_handle(h);
   if (rc) return rc;
   const size_t total = (size_t)h->nchains * (size_t)h->n;
-  if (!h->cand) PMC_CU(cudaMalloc(&h->cand, total * sizeof(MonoRec)));
+  if (!h->cand) PMC_CU(pool_alloc(&h->cand, total * sizeof(MonoRec)));
   h->init += 1;
   const int tb = 256;
   k_fill_random<<<(unsigned)((total + tb - 1) / tb), tb, 0, h->stream>>>(h->cand, (long long)total, h->n, h->seed,
@@ -803,7 +902,7 @@ int32_t pmc_init_x0(pmc_handle* h, const double* x0, int64_t x0_len, const doubl
   if (!x0 || !dx0) return fail(PMC_ERR_INVALID, "null x0/dx0");
   if (h->planar) return fail(PMC_ERR_UNSUPPORTED, "the 2-D tree has no --x0 (2D/inc/eap_chain.jl:66-67)");
   if (x0_len != 2 && x0_len != 2 * (int64_t)h->n) return fail(PMC_ERR_INVALID, "Invalid input for 'x0'");  // eap_chain.jl:76
-  if (!h->x0buf) PMC_CU(cudaMalloc(&h->x0buf, 2 * (size_t)h->n * sizeof(double)));
+  if (!h->x0buf) PMC_CU(pool_alloc(&h->x0buf, 2 * (size_t)h->n * sizeof(double)));
   PMC_CU(cudaMemcpyAsync(h->x0buf, x0, (size_t)x0_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   const size_t total = (size_t)h->nchains * (size_t)h->n;
   const int tb = 256;

@@ -52,9 +52,9 @@ int launch_run_pair(pmc_handle* h, const RunArgs& a) {
   }
   const int nch = (int)h->nchains;
   if (!h->pair_work) {
-    PMC_CU(cudaMalloc(&h->pair_work, (size_t)nch * sizeof(unsigned long long)));
-    PMC_CU(cudaMalloc(&h->pair_order, (size_t)nch * sizeof(int)));
-    PMC_CU(cudaMalloc(&h->pair_next, sizeof(int)));
+    PMC_CU(pool_alloc(&h->pair_work, (size_t)nch * sizeof(unsigned long long)));
+    PMC_CU(pool_alloc(&h->pair_order, (size_t)nch * sizeof(int)));
+    PMC_CU(pool_alloc(&h->pair_next, sizeof(int)));
   }
   PairQueue q{};
   q.next = h->pair_next;

@@ -38,6 +38,7 @@ EXPORTS = [
     "pmc_multi_gather_backend", "pmc_multi_shard", "pmc_multi_set_ensemble_hint", "pmc_multi_begin_stage",
     "pmc_multi_set_state_all", "pmc_multi_get_state_all", "pmc_multi_rows_for", "pmc_multi_run", "pmc_multi_run_ex",
     "pmc_multi_run_async", "pmc_multi_wait", "pmc_multi_gather", "pmc_multi_last_run_ms", "pmc_multi_launch_count",
+    "pmc_release_cached_memory",
 ]
 RESULT_COLS = 24
 RESULT_NAMES = AVG_NAMES + ["acc_rate", "normalizer", "phi_step", "theta_step", "trials", "U_running", "Ealign", "psi"]
@@ -215,6 +216,11 @@ def device_count() -> int:
     n = C.c_int32(0)
     rc = load().pmc_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def release_cached_memory():
+    """Return the library's cache of device blocks (kept across handles) to the driver."""
+    _check(load().pmc_release_cached_memory())
 
 
 def fp64_peak_probe(device=0, iters=1 << 17):

@@ -76,22 +76,27 @@ def _segments(mine: np.ndarray, replicas: int):
     """Split a rank's sorted global chain ids into runs that one handle can serve: a handle holds
     `ncases` consecutive cases × `replicas` chains with ids chain_id_base + local index
     (include/polymc.h), or a part of a single case.  Yields (pos, end, first_case, ncases, nrep)."""
-    pos, m = 0, len(mine)
-    while pos < m:
-        g0 = int(mine[pos])
-        case0, off = divmod(g0, replicas)
-        end = pos
-        while end < m and mine[end] == g0 + (end - pos):
-            end += 1
-        run = end - pos
-        if off != 0 or run < replicas:          # a partial case at a shard boundary
-            take = min(run, replicas - off)
-            yield pos, pos + take, case0, 1, take
-            pos += take
-        else:                                   # whole consecutive cases in one handle
-            ncases = run // replicas
-            yield pos, pos + ncases * replicas, case0, ncases, replicas
-            pos += ncases * replicas
+    m = len(mine)
+    if m == 0:
+        return
+    mine = np.asarray(mine, dtype=np.int64)
+    # maximal runs of consecutive ids (vectorised: a phase-diagram sweep has tens of thousands of chains)
+    breaks = np.flatnonzero(np.diff(mine) != 1) + 1
+    starts = np.concatenate([[0], breaks])
+    ends = np.concatenate([breaks, [m]])
+    for pos, run_end in zip(starts.tolist(), ends.tolist()):
+        while pos < run_end:
+            g0 = int(mine[pos])
+            case0, off = divmod(g0, replicas)
+            run = run_end - pos
+            if off != 0 or run < replicas:          # a partial case at a shard boundary
+                take = min(run, replicas - off)
+                yield pos, pos + take, case0, 1, take
+                pos += take
+            else:                                   # whole consecutive cases in one handle
+                ncases = run // replicas
+                yield pos, pos + ncases * replicas, case0, ncases, replicas
+                pos += ncases * replicas
 
 
 def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
@@ -106,7 +111,7 @@ def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
     out = []
     for (_, _), idxs in bucket_cases(cases).items():
         # global chain ids of this bucket, case-major
-        gids = np.concatenate([np.arange(i * replicas, (i + 1) * replicas) for i in idxs])
+        gids = (np.asarray(idxs, dtype=np.int64)[:, None] * replicas + np.arange(replicas, dtype=np.int64)).ravel()
         lo, hi = shard_range(len(gids), rank, world)
         mine = gids[lo:hi]
         block = np.zeros((hi - lo, NCOL))

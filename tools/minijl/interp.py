@@ -1173,6 +1173,26 @@ class Interp:
             return None
         return f
 
+    def c_try(self, node):
+        body = self.comp(node[1])
+        cvar = node[2]
+        cbody = self.comp(node[3]) if node[3] is not None else None
+        fin = self.comp(node[4]) if node[4] is not None else None
+
+        def f(env):
+            try:
+                return body(env)
+            except JlError as e:
+                if cbody is None:
+                    raise
+                if cvar:
+                    env.assign(cvar, str(e))
+                return cbody(env)
+            finally:
+                if fin is not None:
+                    fin(env)
+        return f
+
     def c_return(self, node):
         x = self.comp(node[1]) if node[1] is not None else None
 
@@ -1280,6 +1300,8 @@ class Interp:
         name, args = node[1], node[2]
         if name == "__DIR__":
             return lambda env: os.path.dirname(self.cur_file[-1])
+        if name == "__FILE__":
+            return lambda env: self.cur_file[-1]
         if name == "assert":
             cond = self.comp(args[0])
             msg = self.comp(args[1]) if len(args) > 1 else None
@@ -1627,7 +1649,13 @@ def _in(a, b):
     return False
 
 
-CMPOPS = {"==": jl_eq, "!=": lambda a, b: not jl_eq(a, b), "≠": lambda a, b: not jl_eq(a, b),
+def jl_egal(a, b):
+    if isinstance(a, (int, float, str, bool)) or a is None or isinstance(b, (int, float, str, bool)) or b is None:
+        return type(a) is type(b) and a == b
+    return a is b or (isinstance(a, Sym) and a == b)
+
+
+CMPOPS = {"===": jl_egal, "!==": lambda a, b: not jl_egal(a, b), "==": jl_eq, "!=": lambda a, b: not jl_eq(a, b), "≠": lambda a, b: not jl_eq(a, b),
           "<": lambda a, b: a < b, "<=": lambda a, b: a <= b, "≤": lambda a, b: a <= b,
           ">": lambda a, b: a > b, ">=": lambda a, b: a >= b, "≥": lambda a, b: a >= b,
           "in": _in, "isa": None, "<:": None, ">:": None}

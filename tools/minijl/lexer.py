@@ -15,7 +15,7 @@ KEYWORDS = {"function", "end", "if", "elseif", "else", "for", "while", "begin", 
             "isa"}
 
 # longest first
-OPERATORS = ["...", "&&", "||", "==", "!=", "<=", ">=", "->", "::", "<:", ">:", "+=", "-=", "*=", "/=", "^=", "%=",
+OPERATORS = ["...", "===", "!==", "&&", "||", "==", "!=", "<=", ">=", "->", "::", "<:", ">:", "+=", "-=", "*=", "/=", "^=", "%=",
              ".+", ".-", ".*", "./", ".^", ".=", "=>", "|>", "<<", ">>", "÷=",
              "+", "-", "*", "/", "^", "%", "<", ">", "=", "!", "?", ":", ",", ";", "(", ")", "[", "]", "{", "}", ".",
              "&", "|", "\\", "÷", "'", "$", "≤", "≥", "≠"]

@@ -25,7 +25,7 @@ BINARY_PREC = {
     "<<": 13, ">>": 13,
     "^": 15, ".^": 15,
 }
-COMPARISONS = {"==", "!=", "<", "<=", ">", ">=", "<:", ">:", "in", "isa", "≤", "≥", "≠"}
+COMPARISONS = {"==", "!=", "<", "<=", ">", ">=", "<:", ">:", "in", "isa", "≤", "≥", "≠", "===", "!=="}
 CMP_PREC = 7
 ASSIGN_OPS = {"=", "+=", "-=", "*=", "/=", "^=", "%=", ".=", "÷="}
 BLOCK_END = {"end", "else", "elseif", "catch", "finally"}
@@ -208,6 +208,9 @@ class Parser:
     def parse_expr(self, min_prec=0):
         """min_prec 0: assignment allowed; 1: no assignment (call arguments handle `k=v` themselves)."""
         left = self.parse_ternary()
+        while self.is_op("=>"):          # a => b  (a Pair)
+            self.next()
+            left = ("call", ("name", "Pair"), [left, self.parse_ternary()], [])
         if min_prec == 0:
             t = self.peek()
             if t.kind == "op" and t.val in ASSIGN_OPS and not self._array_space_break(t):
@@ -442,6 +445,17 @@ class Parser:
             if t.val == "(" and not t.sp_before:
                 args, kwargs = self.parse_call_args()
                 e = ("call", e, args, kwargs)
+                nt = self.toks[self.pos]
+                if nt.kind == "kw" and nt.val == "do":     # f(args) do x ... end  ≡  f(x -> ..., args)
+                    self.pos += 1
+                    params = []
+                    while self.toks[self.pos].kind not in ("nl",) and not (self.toks[self.pos].kind == "op" and self.toks[self.pos].val == ";"):
+                        params.append(self.to_param(self.parse_binary(CMP_PREC + 1)))
+                        if self.toks[self.pos].kind == "op" and self.toks[self.pos].val == ",":
+                            self.pos += 1
+                    body = self.parse_block()
+                    self.expect_kw("end")
+                    e = ("call", e[1], [("lambda", params, body)] + args, kwargs)
             elif t.val == "[" and not t.sp_before:
                 self.next()
                 idxs = self.parse_index_list()
@@ -611,6 +625,10 @@ class Parser:
         t = self.next()
         k = t.kind
         if k == "num":
+            nt = self.toks[self.pos]
+            if nt.kind == "id" and not nt.sp_before:      # numeric-literal coefficient: 3π = 3*π, binds tighter than * /
+                self.pos += 1
+                return ("binop", "*", ("num", t.val), ("name", nt.val))
             return ("num", t.val)
         if k == "str":
             parts = []
@@ -659,6 +677,30 @@ class Parser:
                 body = self.parse_block()
                 self.expect_kw("end")
                 return body
+            if v == "return":
+                nt = self.toks[self.pos]
+                if nt.kind in ("nl", "eof") or (nt.kind == "op" and nt.val in (";", ")", ",")) or (nt.kind == "kw" and nt.val in BLOCK_END):
+                    return ("return", None)
+                return ("return", self.parse_expr(1))
+            if v == "break":
+                return ("break",)
+            if v == "continue":
+                return ("continue",)
+            if v == "try":
+                body = self.parse_block()
+                catch_var, catch_body, fin = None, None, None
+                if self.is_kw("catch"):
+                    self.next()
+                    nt = self.toks[self.pos]
+                    if nt.kind == "id":
+                        self.pos += 1
+                        catch_var = nt.val
+                    catch_body = self.parse_block()
+                if self.is_kw("finally"):
+                    self.next()
+                    fin = self.parse_block()
+                self.expect_kw("end")
+                return ("try", body, catch_var, catch_body, fin)
             self.err(f"unexpected keyword {v!r}", t)
         if k == "op":
             v = t.val
@@ -770,7 +812,7 @@ class Parser:
         name = t.val
         if name in ("inline", "inbounds", "simd", "fastmath", "views", "noinline", "propagate_inbounds", "eval"):
             return self.parse_statement() if not self.nl_skip[-1] else self.parse_expr(0)
-        if name == "__DIR__":
+        if name in ("__DIR__", "__FILE__"):
             return ("macrocall", name, [])
         nt = self.toks[self.pos]
         if nt.kind == "op" and nt.val == "(" and not nt.sp_before:
