@@ -66,8 +66,11 @@ function stage2d!(h, nsteps, p, kT_scale, write_files)
   check(ccall((:pmc_begin_stage, LIBPOLYMC), Int32, (Ptr{Cvoid}, Cdouble), h, kT_scale))   # a fresh mcmc(...) call, :143-151
   rows = ccall((:pmc_rows_for, LIBPOLYMC), Int64, (Ptr{Cvoid}, Int64, Int64), h, nsteps, stepout)
   traj = Array{Float64}(undef, 8, rows, R); roll = Array{Float64}(undef, 17, rows, R)
+  t0 = time()
   check(ccall((:pmc_run, LIBPOLYMC), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
               h, nsteps, stepout, rows > 0 ? traj : C_NULL, rows > 0 ? roll : C_NULL))     # loop :236-300
+  @info "step:    $nsteps / $nsteps"                                                        # :254-258
+  @info "total time elapsed: $(time() - t0)"                                               # :302-303
   write_files || return
   open("$(p["prefix"])_trajectory.csv", "w") do io
     writedlm(io, ["step" "r1" "r3" "p1" "p3" "U"], ',')                                    # :228
@@ -81,6 +84,7 @@ end
 
 function cl2d_main()
   p = cl2d_cli()
+  setup_logging(p)                                                        # ConsoleLogger by --verbose
   p["profile"] && error("Not currently implemented...")
   p["numeric-type"] in ("float64", "float128", "dec128", "big") || error("numeric-type '$(p["numeric-type"])' not understood")
   R = p["replicas"]
@@ -96,8 +100,13 @@ function cl2d_main()
     sums = Array{Float64}(undef, 17, R); diag = Array{Float64}(undef, 8, R)
     check(ccall((:pmc_accumulators, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], sums))
     check(ccall((:pmc_diagnostics, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], diag))
-    pooled = vec(sum(sums, dims=2)); avg = pooled[1:16] ./ pooled[17]
+    if p["umbrella-sampling"]     # replicas carry different gauges: pool their ratios (polymc/mcmc.py pool_replicas)
+      avg = vec(sum(sums[1:16, :] ./ sums[17:17, :], dims=2)) ./ R
+    else
+      pooled = vec(sum(sums, dims=2)); avg = pooled[1:16] ./ pooled[17]
+    end
     ar = sum(diag[5, :]) / (R * p["num-steps"])
+    @info "acceptance rate: $ar"
     nb = p["mlen"] * p["num-monomers"]
     xz(v) = [v[1], v[3]]                                                   # the plane of the chain
     println("<r>    =   $(xz(avg[1:3]))");   println("<r/nb> =   $(xz(avg[1:3]) / nb)")

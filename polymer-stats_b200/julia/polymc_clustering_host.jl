@@ -62,31 +62,54 @@ function dipoles(p, ϕ, θ)
   p["chain-type"] == "dielectric" ? (p["K1"]-p["K2"])*p["E0"]*cos(θ)*n̂ + [0.0, 0.0, p["K2"]*p["E0"]] : p["mu"]*n̂
 end
 
+const T_START = Ref(time())
+const T_LAST = Ref(time())
+
+# One `mcmc(nsteps, pargs, chain)` call of the reference (:171-352) = pmc_begin_stage + the loop.  The loop runs in
+# chunks of whole --stepout intervals so that the progress log of :289-293 stays alive on long stages.
 function stage!(h, nsteps, p, kT_scale, write_files)
   R = p["replicas"]; n = p["num-monomers"]; stepout = write_files ? p["stepout"] : 0
   check(ccall((:pmc_begin_stage, LIBPOLYMC), Int32, (Ptr{Cvoid}, Cdouble), h, kT_scale))   # mcmc(nsteps, pargs, chain) :171-265
-  rows = ccall((:pmc_rows_for, LIBPOLYMC), Int64, (Ptr{Cvoid}, Int64, Int64), h, nsteps, stepout)
-  traj = Array{Float64}(undef, 8, rows, R); roll = Array{Float64}(undef, 19, rows, R); state = Array{Float64}(undef, 2n, rows, R)
-  check(ccall((:pmc_run_ex, LIBPOLYMC), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-              h, nsteps, stepout, rows > 0 ? traj : C_NULL, rows > 0 ? roll : C_NULL, rows > 0 ? state : C_NULL))  # loop :267-336
-  write_files || return
-  open("$(p["prefix"])_trajectory.csv", "w") do io
-    writedlm(io, hcat(["step" "r1" "r2" "r3" "p1" "p2" "p3" "U"],
-                      reshape(vcat(reshape(["phi$i" for i=1:n], 1, :), reshape(["theta$i" for i=1:n], 1, :)), 1, :),
-                      reshape(vcat(reshape(["mux$i" for i=1:n], 1, :), reshape(["muy$i" for i=1:n], 1, :), reshape(["muz$i" for i=1:n], 1, :)), 1, :)), ',')
-    for r in 1:rows
-      μs = hcat([dipoles(p, state[2i-1, r, 1], state[2i, r, 1]) for i in 1:n]...)
-      writedlm(io, hcat(transpose(traj[:, r, 1]), transpose(state[:, r, 1]), reshape(μs, 1, :)), ',')
+  traj_io = write_files ? open("$(p["prefix"])_trajectory.csv", "w") : nothing
+  roll_io = write_files ? open("$(p["prefix"])_rolling.csv", "w") : nothing
+  if write_files
+    writedlm(traj_io, hcat(["step" "r1" "r2" "r3" "p1" "p2" "p3" "U"],
+                           reshape(vcat(reshape(["phi$i" for i=1:n], 1, :), reshape(["theta$i" for i=1:n], 1, :)), 1, :),
+                           reshape(vcat(reshape(["mux$i" for i=1:n], 1, :), reshape(["muy$i" for i=1:n], 1, :), reshape(["muz$i" for i=1:n], 1, :)), 1, :)), ',')
+    writedlm(roll_io, ["step" "r1" "r2" "r3" "r1sq" "r2sq" "r3sq" "rsq" "p1" "p2" "p3" "p1sq" "p2sq" "p3sq" "psq" "U" "Usq" "Ealign" "psi"], ',')
+  end
+  chunk = nsteps <= 200000 ? nsteps : (stepout <= 0 ? 200000 : max(stepout, div(200000, stepout) * stepout))
+  done = 0
+  try
+    while done < nsteps
+      todo = min(chunk, nsteps - done)
+      rows = ccall((:pmc_rows_for, LIBPOLYMC), Int64, (Ptr{Cvoid}, Int64, Int64), h, todo, stepout)
+      traj = Array{Float64}(undef, 8, rows, R); roll = Array{Float64}(undef, 19, rows, R); state = Array{Float64}(undef, 2n, rows, R)
+      check(ccall((:pmc_run_ex, LIBPOLYMC), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                  h, todo, stepout, rows > 0 ? traj : C_NULL, rows > 0 ? roll : C_NULL, rows > 0 ? state : C_NULL))  # loop :267-336
+      if write_files
+        for r in 1:rows
+          μs = hcat([dipoles(p, state[2i-1, r, 1], state[2i, r, 1]) for i in 1:n]...)
+          writedlm(traj_io, hcat(transpose(traj[:, r, 1]), transpose(state[:, r, 1]), reshape(μs, 1, :)), ',')
+        end
+        rows > 0 && writedlm(roll_io, permutedims(roll[:, :, 1]), ',')
+      end
+      done += todo
+      if time() - T_LAST[] > p["update-freq"]                                                # :289-293
+        @info "elapsed: $(time() - T_START[])"
+        @info "step:    $done / $nsteps"
+        T_LAST[] = time()
+      end
     end
+  finally
+    write_files && (close(traj_io); close(roll_io))
   end
-  open("$(p["prefix"])_rolling.csv", "w") do io
-    writedlm(io, ["step" "r1" "r2" "r3" "r1sq" "r2sq" "r3sq" "rsq" "p1" "p2" "p3" "p1sq" "p2sq" "p3sq" "psq" "U" "Usq" "Ealign" "psi"], ',')
-    rows > 0 && writedlm(io, permutedims(roll[:, :, 1]), ',')
-  end
+  @info "total time elapsed: $(time() - T_START[])"                                          # :334-335
 end
 
 function cl_main()
   p = cl_cli()
+  setup_logging(p)                                                       # ConsoleLogger by --verbose, :157-165
   p["profile"] && error("Not currently implemented...")
   p["numeric-type"] in ("float64", "float128", "dec128", "big") || error("numeric-type '$(p["numeric-type"])' not understood")
   R = p["replicas"]
@@ -107,8 +130,13 @@ function cl_main()
     check(ccall((:pmc_accumulators, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], sums))
     check(ccall((:pmc_extra_accumulators, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], xs))
     check(ccall((:pmc_diagnostics, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], diag))
-    pooled = vec(sum(sums, dims=2)); avg = pooled[1:16] ./ pooled[17]; ex = vec(sum(xs, dims=2)) ./ pooled[17]
+    if p["umbrella-sampling"]     # replicas carry different gauges exp(Ω0): pool their ratios (polymc/mcmc.py pool_replicas)
+      avg = vec(sum(sums[1:16, :] ./ sums[17:17, :], dims=2)) ./ R; ex = vec(sum(xs ./ sums[17:17, :], dims=2)) ./ R
+    else
+      pooled = vec(sum(sums, dims=2)); avg = pooled[1:16] ./ pooled[17]; ex = vec(sum(xs, dims=2)) ./ pooled[17]
+    end
     ar = sum(diag[5, :]) / (R * p["num-steps"])
+    @info "acceptance rate: $ar"
     nb = p["mlen"] * p["num-monomers"]
     println("<r>    =   $(avg[1:3])");   println("<r/nb> =   $(avg[1:3] / nb)")
     println("<rj2>  =   $(avg[4:6])");   println("<r2>   =   $(avg[7])")

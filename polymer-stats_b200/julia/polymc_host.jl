@@ -5,9 +5,11 @@
 # body of `mcmc(nsteps, pargs)` (:171-376) is a handful of `ccall`s into the CUDA library.
 #
 # NOTE: Julia is not installed in the image this repository is built and tested in, so this file
-# has not been executed there; the Python twin (../polymc/mcmc.py) exercises the identical C ABI
-# call sequence under test.  See INTEGRATION.md.
-using ArgParse, Printf, DelimitedFiles
+# has not been executed by a Julia runtime there.  What IS checked (tests/test_host_cpu.py): it parses (tools/minijl,
+# the Julia-subset parser that also runs the reference sources for the fixtures), every `ccall` names an entry point
+# of include/polymc.h with the right number and kinds of arguments, and `PmcCase` mirrors `pmc_case` field by field.
+# The Python twin (../polymc/mcmc.py) exercises the identical C ABI call sequence under test.  See INTEGRATION.md.
+using ArgParse, Printf, DelimitedFiles, Logging
 
 const LIBPOLYMC = get(ENV, "POLYMC_LIB", joinpath(@__DIR__, "..", "libpolymc_b200.so"))
 
@@ -42,6 +44,8 @@ const OPTIONS = [
   ("--prefix", "-P", String, "eap-mcmc"), ("--postfix", "-Q", String, ""), ("--stepout", "-s", Int, 500),
   ("--numeric-type", nothing, String, "float64"),
   ("--replicas", nothing, Int, 1), ("--seed", nothing, Int, -1), ("--device", nothing, Int, 0),
+  # [B200 path] number of GPUs of this box the replicas are spread over (pmc_multi_*, ABI v3); 0 = all of them
+  ("--devices", nothing, Int, 1),
 ]
 const FLAGS = [("--force-init", "-I"), ("--do-flips", nothing), ("--umbrella-sampling", "-B"), ("--profile", "-Z")]
 
@@ -69,42 +73,118 @@ function case_of(p)
           0.0, 0.0, 7.5, 0.5, 0, 1, 0, 0)
 end
 
+# ConsoleLogger by --verbose, as mcmc_eap_chain.jl:157-165
+function setup_logging(p)
+  if p["verbose"] == 3
+    global_logger(ConsoleLogger(stderr, Logging.Info))
+  elseif p["verbose"] == 2
+    global_logger(ConsoleLogger(stderr, Logging.Warn))
+  elseif p["verbose"] == 1
+    global_logger(ConsoleLogger(stderr, Logging.Error))
+  else
+    global_logger(Logging.NullLogger())
+  end
+end
+
+# The hot loop in chunks, so that the progress log of mcmc_eap_chain.jl:294-299 stays alive on long runs: `run!` runs
+# `todo` trials and returns the rows of chain 1 (8 × rows, 17 × rows) or nothing.
+function run_init!(run!, p, nsteps, init, start, last_update, traj_io, rolling_io)
+  stepout = p["stepout"]
+  chunk = nsteps
+  if nsteps > 200000
+    chunk = stepout <= 0 ? 200000 : max(stepout, div(200000, stepout) * stepout)
+  end
+  done = 0
+  while done < nsteps
+    todo = min(chunk, nsteps - done)
+    rows = run!(todo)
+    if rows !== nothing
+      writedlm(traj_io, permutedims(rows[1]), ',')
+      writedlm(rolling_io, permutedims(rows[2]), ',')
+    end
+    done += todo
+    if time() - last_update[] > p["update-freq"]
+      @info "elapsed: $(time() - start)"
+      @info "init:    $init / $(p["num-inits"])"
+      @info "step:    $done / $nsteps"
+      last_update[] = time()
+    end
+  end
+end
+
 function mcmc(nsteps::Int, p)
   p["acc"] == "metropolis" || error("'$(p["acc"])' acceptance criteria has not yet been implemented.")
   p["numeric-type"] in ("float64", "float128", "dec128", "big") || error("numeric-type '$(p["numeric-type"])' not understood")
   p["ensemble-type"] == "force" || error("ensemble-type '$(p["ensemble-type"])' is not supported by the B200 path (fixed-force only)")
   R = p["replicas"]; n = p["num-monomers"]; stepout = p["stepout"]
   seed = p["seed"] < 0 ? UInt64(time_ns()) & 0xffffffffffff : UInt64(p["seed"])
-  h = Ref{Ptr{Cvoid}}(C_NULL)
   cases = [case_of(p)]
-  check(ccall((:pmc_create, LIBPOLYMC), Int32, (Ptr{PmcCase}, Int64, Int32, UInt64, Int32, UInt32, Ptr{Ptr{Cvoid}}),
-              cases, 1, R, seed, p["device"], 0, h))
+  multi = p["devices"] != 1
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  if multi   # the R replicas over the GPUs of this box: one host thread per device inside the library (ABI v3)
+    p["num-inits"] == 1 || error("--num-inits > 1 is per device handle: use --devices 1")
+    check(ccall((:pmc_multi_create, LIBPOLYMC), Int32,
+                (Ptr{PmcCase}, Int64, Int32, UInt64, Ptr{Int32}, Int32, Ptr{Ptr{Cvoid}}),
+                cases, 1, R, seed, C_NULL, p["devices"], h))
+  else
+    check(ccall((:pmc_create, LIBPOLYMC), Int32, (Ptr{PmcCase}, Int64, Int32, UInt64, Int32, UInt32, Ptr{Ptr{Cvoid}}),
+                cases, 1, R, seed, p["device"], 0, h))
+  end
   traj_io = open("$(p["prefix"])_trajectory.csv", "w"); rolling_io = open("$(p["prefix"])_rolling.csv", "w")
   writedlm(traj_io, ["step" "r1" "r2" "r3" "p1" "p2" "p3" "U"], ',')
   writedlm(rolling_io, permutedims(vcat(["step"], ["r1","r2","r3","r1sq","r2sq","r3sq","rsq","p1","p2","p3","p1sq","p2sq","p3sq","psq","U","Usq"])), ',')
+  start = time(); last_update = Ref(start)
   try
-    for init in 1:p["num-inits"]
-      rows = ccall((:pmc_rows_for, LIBPOLYMC), Int64, (Ptr{Cvoid}, Int64, Int64), h[], nsteps, stepout)
+    function run!(todo)
+      rows = multi ? ccall((:pmc_multi_rows_for, LIBPOLYMC), Int64, (Ptr{Cvoid}, Int64, Int64), h[], todo, stepout) :
+                     ccall((:pmc_rows_for, LIBPOLYMC), Int64, (Ptr{Cvoid}, Int64, Int64), h[], todo, stepout)
       traj = Array{Float64}(undef, 8, rows, R); roll = Array{Float64}(undef, 17, rows, R)   # C order [chain][row][k]
-      check(ccall((:pmc_run, LIBPOLYMC), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
-                  h[], nsteps, stepout, traj, roll))
-      rows > 0 && (writedlm(traj_io, permutedims(traj[:, :, 1]), ','); writedlm(rolling_io, permutedims(roll[:, :, 1]), ','))
+      if multi
+        check(ccall((:pmc_multi_run, LIBPOLYMC), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+                    h[], todo, stepout, traj, roll))
+      else
+        check(ccall((:pmc_run, LIBPOLYMC), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+                    h[], todo, stepout, traj, roll))
+      end
+      return rows > 0 ? (traj[:, :, 1], roll[:, :, 1]) : nothing
+    end
+    for init in 1:p["num-inits"]
+      run_init!(run!, p, nsteps, init, start, last_update, traj_io, rolling_io)
       init < p["num-inits"] && check(ccall((:pmc_reinit, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Int32}), h[], C_NULL))
     end
-    sums = Array{Float64}(undef, 17, R); diag = Array{Float64}(undef, 8, R)
-    check(ccall((:pmc_accumulators, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], sums))
-    check(ccall((:pmc_diagnostics, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], diag))
-    pooled = vec(sum(sums, dims=2)); avg = pooled[1:16] ./ pooled[17]
-    ar = sum(diag[5, :]) / (R * p["num-inits"] * p["num-steps"])
+    if multi    # one ncclAllGather of the [R][24] result rows inside the library
+      table = Array{Float64}(undef, 24, R)
+      check(ccall((:pmc_multi_gather, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], table))
+      nrm = table[18, :]
+      avg = [sum(table[k, :] .* nrm) for k in 1:16] ./ sum(nrm)      # pooled Σ values / Σ normalisers
+      ar = sum(table[17, :] .* table[21, :]) / (R * p["num-steps"])
+    else
+      sums = Array{Float64}(undef, 17, R); diag = Array{Float64}(undef, 8, R)
+      check(ccall((:pmc_accumulators, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], sums))
+      check(ccall((:pmc_diagnostics, LIBPOLYMC), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], diag))
+      if p["umbrella-sampling"]   # replicas carry different gauges exp(Ω0): pool their ratios (see polymc/mcmc.py)
+        avg = vec(sum(sums[1:16, :] ./ sums[17:17, :], dims=2)) ./ R
+      else
+        pooled = vec(sum(sums, dims=2)); avg = pooled[1:16] ./ pooled[17]
+      end
+      ar = sum(diag[5, :]) / (R * p["num-inits"] * p["num-steps"])
+    end
+    @info "total time elapsed: $(time() - start)"
+    @info "acceptance rate: $ar"
     return avg, ar
   finally
     close(traj_io); close(rolling_io)
-    ccall((:pmc_destroy, LIBPOLYMC), Cvoid, (Ptr{Cvoid},), h[])
+    if multi
+      ccall((:pmc_multi_destroy, LIBPOLYMC), Cvoid, (Ptr{Cvoid},), h[])
+    else
+      ccall((:pmc_destroy, LIBPOLYMC), Cvoid, (Ptr{Cvoid},), h[])
+    end
   end
 end
 
 function main()
   p = cli()
+  setup_logging(p)
   p["profile"] && error("not implemented for the HPC env")
   avg, ar = mcmc(p["num-steps"], p)
   nb = p["mlen"] * p["num-monomers"]

@@ -256,12 +256,19 @@ class Parser:
             return (p[0], p[1], None, True)
         self.err(f"unsupported parameter form {a[0]}")
 
+    def skip_nl(self):
+        """An operator at the end of a line continues the expression on the next line."""
+        while self.toks[self.pos].kind == "nl":
+            self.pos += 1
+
     def parse_ternary(self):
         cond = self.parse_arrow()
         if self.is_op("?") and not self._array_space_break(self.peek()):
             self.next()
+            self.skip_nl()
             a = self.parse_ternary_branch()
             self.expect_op(":")
+            self.skip_nl()
             b = self.parse_ternary_branch()
             return ("ternary", cond, a, b)
         return cond
@@ -336,6 +343,7 @@ class Parser:
                 if prec < min_prec:
                     break
                 self.next()
+                self.skip_nl()
                 right = self.parse_binary(prec + 1)
                 left = ("and" if op == "&&" else "or", left, right)
                 continue
@@ -358,6 +366,7 @@ class Parser:
             if prec is None or prec < min_prec:
                 break
             self.next()
+            self.skip_nl()
             if op in ("^", ".^"):
                 right = self.parse_unary_pow()
             else:
