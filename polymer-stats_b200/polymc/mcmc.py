@@ -41,7 +41,8 @@ def build_parser() -> argparse.ArgumentParser:
     a("--mlen", "-b", type=float, default=1.0, help="monomer length")
     a("--num-monomers", "-n", type=int, default=100, help="number of monomers")
     a("--num-steps", "-N", type=int, default=100000, help="number of steps")
-    a("--num-inits", "-M", type=int, default=1, help="number of random initializations")
+    a("--num-inits", "-M", type=int, default=1, help="number of random initializations (B200 path: the acceptor is re-bound to the new chain after a "
+                                                          "re-initialisation; the reference leaves it stale, mcmc_eap_chain.jl:360 — see DESIGN.md §5)")
     a("--force-init", "-I", action="store_true", help="force (no acceptance test) every initialization")
     a("--phi-step", "-p", type=float, default=3 * math.pi / 8, help="maximum phi step length")
     a("--do-flips", action="store_true", help="trial moves with flipping monomers")
@@ -203,6 +204,17 @@ def mcmc(nsteps: int, pargs: dict):
                     ens.reinit()  # mcmc_eap_chain.jl:352-361 (after the last init it has no observable effect)
         sums = ens.accumulators()          # [R][17]
         diag = ens.diagnostics()
+        if pargs.get("numeric-type", "float64") != "float64":
+            # float128 | dec128 | big (:186-197): the device sums are double-double (value = hi + lo exactly); pool them
+            # in exact rational arithmetic and keep the quotients for the printer
+            from fractions import Fraction
+            hi, lo = ens.accumulators_dd()
+            per = [[Fraction(float(hi[r, k])) + Fraction(float(lo[r, k])) for k in range(17)] for r in range(R)]
+            if pargs["umbrella-sampling"]:
+                pargs["_extended"] = [sum(per[r][k] / per[r][16] for r in range(R)) / R for k in range(16)]
+            else:
+                tot = [sum(per[r][k] for r in range(R)) for k in range(17)]
+                pargs["_extended"] = [tot[k] / tot[16] for k in range(16)]
     pooled, norm = pool_replicas(sums, pargs["umbrella-sampling"])
     ar = float(diag[:, 4].sum() / (R * pargs["num-inits"] * pargs["num-steps"])) if pargs["num-steps"] else 0.0
     _log(pargs, "info", f"total time elapsed: {time.time() - start}")
@@ -224,6 +236,11 @@ def main(argv=None) -> int:
     avg16 = np.concatenate([vas[0].get_avg(), vas[1].get_avg(), [sas[0].get_avg()],
                             vas[2].get_avg(), vas[3].get_avg(), [sas[1].get_avg()],
                             [sas[2].get_avg(), sas[3].get_avg()]])
-    for line in result_lines(avg16, ar, pargs["mlen"], pargs["num-monomers"]):
+    if "_extended" in pargs:
+        from .output import result_lines_extended
+        lines = result_lines_extended(pargs["_extended"], ar, pargs["mlen"], pargs["num-monomers"], pargs["numeric-type"])
+    else:
+        lines = result_lines(avg16, ar, pargs["mlen"], pargs["num-monomers"])
+    for line in lines:
         print(line)
     return 0

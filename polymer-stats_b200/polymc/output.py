@@ -38,6 +38,51 @@ def julia_float(x: float) -> str:
     return f"{s}{mant}e{pt - 1}"
 
 
+EXT_DIGITS = {"float128": 36, "dec128": 34, "big": 77}   # significant digits of Quadmath / DecFP / BigFloat(256) text
+
+
+def extended_text(x, numeric_type: str) -> str:
+    """A `fractions.Fraction` (the exact quotient of double-double sums) as Float128 / Dec128 / BigFloat would print
+    it: `d.ddd…e±XX` with the type's number of significant digits (mcmc_eap_chain.jl:186-197 selects the type)."""
+    from decimal import Decimal, localcontext
+    digits = EXT_DIGITS[numeric_type]
+    with localcontext() as ctx:
+        ctx.prec = digits + 10
+        d = Decimal(x.numerator) / Decimal(x.denominator)
+        if d == 0:
+            return "0.0"
+        ctx.prec = digits
+        d = +d
+    sign, dg, exp = d.as_tuple()
+    dg = "".join(map(str, dg))
+    e10 = exp + len(dg) - 1
+    mant = dg[0] + "." + (dg[1:].rstrip("0") if numeric_type == "big" else dg[1:].ljust(digits - 1, "0")) 
+    if mant.endswith("."):
+        mant += "0"
+    return f"{'-' if sign else ''}{mant}e{'+' if e10 >= 0 else '-'}{abs(e10):02d}"
+
+
+def result_lines_extended(fr16, acc_rate, mlen, n, numeric_type):
+    """The 10 stdout lines with --numeric-type float128|dec128|big: the averages are exact quotients of the device's
+    double-double sums (pmc_accumulators_dd), printed with the digits of the chosen type."""
+    from fractions import Fraction
+    t = lambda x: extended_text(x, numeric_type)
+    vec = lambda v: "[" + ", ".join(t(x) for x in v) + "]"
+    nb = Fraction(mlen) * n
+    return [
+        f"<r>    =   {vec(fr16[0:3])}",
+        f"<r/nb> =   {vec([x / nb for x in fr16[0:3]])}",
+        f"<rj2>  =   {vec(fr16[3:6])}",
+        f"<r2>   =   {t(fr16[6])}",
+        f"<p>    =   {vec(fr16[7:10])}",
+        f"<pj2>  =   {vec(fr16[10:13])}",
+        f"<p2>   =   {t(fr16[13])}",
+        f"<U>    =   {t(fr16[14])}",
+        f"<U2>   =   {t(fr16[15])}",
+        f"AR     =   {julia_float(acc_rate)}",
+    ]
+
+
 def julia_vector(v) -> str:
     """Julia `show(::Vector{Float64})`: `[a, b, c]`."""
     return "[" + ", ".join(julia_float(x) for x in v) + "]"

@@ -302,3 +302,28 @@ def test_pair_kernel_trajectory(pm, O, monkeypatch, n, R, steps):
         t0, _ = one.run(steps, steps // 4)
         np.testing.assert_allclose(t0, traj, rtol=0, atol=1e-9 * max(1.0, np.abs(traj).max()))
         np.testing.assert_array_equal(one.diagnostics()[:, 4:6], counts)
+
+
+def test_cli_numeric_type_float128_prints_double_double_averages(pm, tmp_path):
+    """--numeric-type float128: the device sums are double-double (pmc_accumulators_dd) and the CLI twin prints their
+    exact quotients with 36 significant digits; to double precision they equal the float64 run (same seed)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for nt in ("float64", "float128"):
+        argv = [sys.executable, os.path.join(root, "polymer-stats_b200", "mcmc_eap_chain.py"), "--energy-type", "Ising",
+                "--E0", "1.0", "--Fz", "0.5", "-n", "30", "--num-steps", "20000", "--stepout", "5000", "-v", "0",
+                "--prefix", str(tmp_path / nt), "--seed", "11", "--replicas", "3", "--numeric-type", nt]
+        p = subprocess.run(argv, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr
+        outs[nt] = p.stdout.strip().split("\n")
+    assert len(outs["float128"]) == 10
+    for a, b in zip(outs["float64"], outs["float128"]):
+        ka, va = a.split("=", 1)
+        kb, vb = b.split("=", 1)
+        assert ka == kb
+        xa = [float(x) for x in va.strip().strip("[]").split(",")]
+        xb = [float(x) for x in vb.strip().strip("[]").split(",")]
+        np.testing.assert_allclose(xa, xb, rtol=1e-13, atol=1e-13)
+    assert len(outs["float128"][3].split("=")[1].strip()) >= 40          # 36 significant digits + exponent

@@ -409,3 +409,21 @@ def test_julia_hosts_parse_and_bind_the_declared_abi():
     assert nstruct >= 1
     assert {"pmc_create", "pmc_run", "pmc_run_ex", "pmc_begin_stage", "pmc_multi_create", "pmc_multi_run",
             "pmc_multi_gather", "pmc_destroy", "pmc_multi_destroy"} <= seen
+
+
+def test_extended_precision_text():
+    """--numeric-type float128|dec128|big (mcmc_eap_chain.jl:186-197): exact quotients printed with the type's digits."""
+    from fractions import Fraction
+    from polymc.output import extended_text, result_lines_extended
+    assert extended_text(Fraction(1, 3), "float128") == "3." + "3" * 35 + "e-01"
+    assert extended_text(Fraction(-12345, 7), "dec128") == "-1.763571428571428571428571428571429e+03"
+    assert extended_text(Fraction(1, 8), "big") == "1.25e-01"
+    assert extended_text(Fraction(0), "big") == "0.0"
+    hi, lo = 0.1, 1e-18                       # a double-double: more than a double can hold
+    x = Fraction(hi) + Fraction(lo)
+    assert float(extended_text(x, "float128")) == 0.1
+    assert extended_text(x, "float128") != extended_text(Fraction(hi), "float128")
+    lines = result_lines_extended([Fraction(k + 1, 7) for k in range(16)], 0.25, 1.5, 10, "dec128")
+    assert len(lines) == 10 and lines[0].startswith("<r>    =   [1.428571428571428571428571428571429e-01, ")
+    assert lines[1].startswith("<r/nb> =   [9.523809523809523809523809523809524e-03")
+    assert lines[9] == "AR     =   0.25"
