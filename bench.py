@@ -99,8 +99,7 @@ WORKLOADS = {
 # ncu `--set full` capture of the headline launch (dram__bytes_read.sum + dram__bytes_write.sum per launch), from the
 # profile named here; other workloads: null unless listed
 TRAFFIC = {"C2": (1.136e8, "profiles/r02a_ncu_full_k_run_cta_win_C2.txt: 104.9 MB read (the chain records, once per launch) + 8.7 MB written"),
-           "C5": (2.93e7, "profiles/r02a_ncu_full_k_run_cta_pair_C5.txt (50 trials per launch)"),
-           "C4": (2.59e8, "profiles/r02a_ncu_full_k_run_warp_C4.txt (20 000 trials per launch, 40 rows per chain)")}
+           "C5": (2.93e7, "profiles/r02a_ncu_full_k_run_cta_pair_C5.txt (captured at 50 trials per launch; the records are read once per launch whatever its length)")}
 
 
 def flops_per_update(n: int, energy_type: str) -> float:
