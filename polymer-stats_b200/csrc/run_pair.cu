@@ -6,14 +6,29 @@ namespace {
 int fail(int code, const std::string& msg) { return pmc_fail(code, msg); }
 }  // namespace
 
-// Long chains whose staged copy leaves room for only one CTA per SM run on CTA pairs (PMC_RUN_PAIR=0 switches it off,
-// PMC_RUN_PAIR=2 forces it for any chain length — tests and experiments).
+// When do two SMs per chain pay?  (profiles/r02b_tune_pair_small.txt, one B200)
+//   * the staged copy leaves room for only one CTA per SM (n ≳ 2000): always — a launch of ≤ 148 chains is one wave and ends
+//     with its slowest chain; pairs + the work-ordered queue take C5 from 0.62 to 0.71 of the DFMA peak at 50 trials;
+//   * n > 768: at every ensemble size (n = 1024: 0.70–0.72 against 0.55–0.70), most for few chains;
+//   * 384 < n ≤ 768: only when the chains fill between 0.55 and 0.9 of the resident CTA slots, where whole chains per SM
+//     quantise badly (512 chains of n = 512 on 592 slots: 68 SMs carry four chains, 80 carry three: +15 % with pairs);
+//     elsewhere the windowed one-CTA kernel is ahead (its proposals are off the critical path);
+//   * shorter chains: never (the cluster barrier per trial is no longer small against the trial).
+// The ensemble size is the hint's (pmc_set_ensemble_hint), so a shard decides like the whole sweep.
+// PMC_RUN_PAIR=0 switches pairs off, PMC_RUN_PAIR=2 forces them for any chain length (tests and experiments).
 bool use_pair_kernel(const pmc_handle* h) {
   const int mode = env_int("PMC_RUN_PAIR", 1);
   if (mode == 0 || h->energy_type != PMC_ENERGY_INTERACTING || h->cluster_mode) return false;
   if (h->cta_threads != 128 && h->cta_threads != 256 && h->cta_threads != 512) return false;
   if (mode == 2) return true;
-  return cta_smem_bytes(h->n) > (size_t)kSmemMax / 2;
+  if (cta_smem_bytes(h->n) > (size_t)kSmemMax / 2) return true;
+  if (h->n > 768) return true;
+  if (h->n > 384) {
+    const int per_sm = h->cta_threads == 128 ? 4 : h->cta_threads == 256 ? 2 : 1;
+    const double fill = (double)packing_chains(h) / ((double)h->sm_count * per_sm);
+    return fill >= 0.55 && fill < 0.9;
+  }
+  return false;
 }
 
 template <int T>
