@@ -100,7 +100,7 @@ def _segments(mine: np.ndarray, replicas: int):
 
 
 def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
-              rank: int = 0, world: int = 1, protocol=None):
+              rank: int = 0, world: int = 1, protocol=None, bit_identical: bool = False):
     """Run this rank's contiguous block of every (n, energy) bucket.  Returns a list of
     (global chain ids of the bucket, lo, block [hi-lo][NCOL]).  No communication.
 
@@ -116,9 +116,13 @@ def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
         mine = gids[lo:hi]
         block = np.zeros((hi - lo, NCOL))
         for pos, end, case0, ncases, nrep in _segments(mine, replicas):
-            # launch shape from the UNSHARDED bucket size: results are bit-identical for any rank count
+            # The Markov chains (Philox streams keyed by global chain id) never depend on the sharding.  The launch shape —
+            # block size, packing, one or two SMs per chain — is chosen for THIS shard's size (fastest: a 512-chain
+            # share of a 4096-chain sweep runs 15 % faster in its own shape, profiles/r02b_tune_pair_small.txt), which
+            # changes the order of some floating-point sums; bit_identical=True chooses it from the UNSHARDED bucket
+            # size instead, and the results are then the same bit for bit for any rank count.
             with lib.Ensemble(cases[case0:case0 + ncases], replicas=nrep, seed=seed, device=device,
-                              chain_id_base=int(mine[pos]), ensemble_chains=len(gids)) as ens:
+                              chain_id_base=int(mine[pos]), ensemble_chains=len(gids) if bit_identical else 0) as ens:
                 if protocol is None or protocol.get("plain"):
                     # mcmc_eap_chain.jl:276-361: num-inits passes of nsteps trials with the re-initialisation rule between
                     inits = int(protocol.get("num_inits", 1)) if protocol else 1
@@ -159,7 +163,7 @@ def assemble(total: int, parts):
 
 
 def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
-              torch_device=None, protocol=None):
+              torch_device=None, protocol=None, bit_identical: bool = False):
     """Run every (case, replica) chain of a sweep for nsteps trials, sharded over the ranks of the
     current torch.distributed group (or a single process), then gather the final per-chain results on
     every rank.  Chain order = case-major: avg [ncases*replicas][16], acc_rate, normalizer, sums [..][17]."""
@@ -168,13 +172,13 @@ def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
     world = dist.get_world_size() if dist else 1
     cases = list(cases)
     parts = []
-    for gids, lo, block in run_shard(cases, replicas, nsteps, stepout, seed, device, rank, world, protocol):
+    for gids, lo, block in run_shard(cases, replicas, nsteps, stepout, seed, device, rank, world, protocol, bit_identical):
         parts.append((gids, gather_rows(block, len(gids), lo, device=torch_device)))
     return assemble(len(cases) * replicas, parts)
 
 
 def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0, device: int = 0, torch_device=None,
-                kappaflag: bool = False, pooled: bool = False, with_entries: bool = False):
+                kappaflag: bool = False, pooled: bool = False, with_entries: bool = False, bit_identical: bool = False):
     """A whole launcher + aggregate_mcmc.jl (+ reduce_tabular_data.jl) pipeline in one call (SURVEY §8f
     rank 3): every pargs dict of `pargs_list` is one case (one launcher command line), run `runs` times as
     independent replica chains (the launchers' `run-NNN` cases); the result is the aggregated table the
@@ -224,7 +228,7 @@ def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0,
             raise lib.PolymcError(-1, f"cases {seen[pre]} and {i} share the output prefix '{pre}': the swept option is not "
                                       "part of the file-name tokens (aggregate_mcmc.jl:40-57; use --kappaflag for bend-mod)")
         seen[pre] = i
-    res = run_sweep(cases, runs, p0["num-steps"], 0, seed, device, torch_device, protocol)
+    res = run_sweep(cases, runs, p0["num-steps"], 0, seed, device, torch_device, protocol, bit_identical)
     runflag = runs > 1
     entries, texts = [], []
     for i, p in enumerate(pargs_list):

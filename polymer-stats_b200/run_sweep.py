@@ -40,6 +40,9 @@ def main(argv=None) -> int:
     ap.add_argument("--by-outdir", default=None)
     ap.add_argument("--kappaflag", action="store_true", help="file names / table carry the kappa column")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--bit-identical", action="store_true",
+                    help="choose the launch shapes from the whole study instead of this rank's share: results are then the same "
+                         "bit for bit for any number of GPUs (a share runs up to ~15 %% slower than in its own shape)")
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
     host = {"plain": mcmc, "clustering": mcmc_clustering, "clustering2d": mcmc_clustering_2d}[a.driver]
@@ -68,7 +71,7 @@ def main(argv=None) -> int:
         ap.error("--by needs --by-outdir")
     header, rows, texts, entries = sweep.sweep_table(pargs_list, driver=a.driver, runs=a.runs, seed=a.seed,
                                                      device=a.device, torch_device=torch_device,
-                                                     kappaflag=a.kappaflag, with_entries=True)
+                                                     kappaflag=a.kappaflag, with_entries=True, bit_identical=a.bit_identical)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

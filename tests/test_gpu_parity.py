@@ -326,12 +326,12 @@ def test_sweep_is_independent_of_gpu_count(pm):
              pm.make_case(n=40, E0=2.0, Fz=0.0, kT=0.7, energy_type="interacting"),
              pm.make_case(n=100, E0=0.0, Fz=2.0)]
     replicas, total = 5, 20
-    one = sweep.run_sweep(cases, replicas, 2000, seed=99)
+    one = sweep.run_sweep(cases, replicas, 2000, seed=99, bit_identical=True)
     assert np.all(np.isfinite(one["avg"])) and np.all(one["normalizer"] == 2000)
     for world in (2, 3):
         parts = {}
         for rank in range(world):
-            for gids, lo, block in sweep.run_shard(cases, replicas, 2000, seed=99, rank=rank, world=world):
+            for gids, lo, block in sweep.run_shard(cases, replicas, 2000, seed=99, rank=rank, world=world, bit_identical=True):
                 key = tuple(gids)
                 parts.setdefault(key, np.zeros((len(gids), sweep.NCOL)))[lo:lo + len(block)] = block
         many = sweep.assemble(total, [(np.array(k), v) for k, v in parts.items()])

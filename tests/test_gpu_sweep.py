@@ -43,14 +43,14 @@ def test_sweep_table_equals_file_pipeline_and_is_sharding_invariant(pm, tmp_path
         assert header[-15:] == ["r1", "r2", "lambda1", "lambda2", "r1sq", "r2sq", "rsquared", "p1", "p2", "p1sq", "p2sq",
                                 "psquared", "U", "Usquared", "AR"]
         assert len(open(outdir / sorted(os.listdir(outdir))[0]).read().strip().split("\n")) == 10
-    one = sweep.run_shard(cases, 3, 1500, 0, 5, 0, 0, 1, proto)
+    one = sweep.run_shard(cases, 3, 1500, 0, 5, 0, 0, 1, proto, bit_identical=True)
     parts = []
     for gids, lo, block in one:
         parts.append((gids, block))
     ref = sweep.assemble(18, parts)
     blocks = {}
     for rank in range(3):
-        for gids, lo, block in sweep.run_shard(cases, 3, 1500, 0, 5, 0, rank, 3, proto):
+        for gids, lo, block in sweep.run_shard(cases, 3, 1500, 0, 5, 0, rank, 3, proto, bit_identical=True):
             blocks.setdefault(tuple(gids), []).append((lo, block))
     parts3 = []
     for gids, lst in blocks.items():
