@@ -159,19 +159,46 @@ def test_random_cases_match_oracle(pm, O, case_seed):
     seed = int(rng.integers(1, 10 ** 6))
     with pm.Ensemble(pc, replicas=2, seed=seed, chain_id_base=5) as ens:
         run = O.Run(oc, seed, 6, 1)
+        collapsed = False
         for mult in (5.0, 1.0):
             ens.begin_stage(mult)            # the C ABI takes the kT multiplier of the ladder (:367-381) …
             run.begin_stage(mult * kw["kT"])  # … the oracle the stage's temperature
             traj, roll, state = ens.run_ex(steps, steps // 2, want_state=True)
             ot, orl, ost = run.steps_ex(steps, steps // 2, True)
-            if not np.all(np.abs(ot[:, 7]) < 1e6):
-                pytest.skip("chain collapsed into a singular well (no excluded volume): resolution of U lost")
+            ok_rows = np.abs(ot[:, 7]) < 1e6
+            if not np.all(ok_rows):
+                # a singular well (no excluded volume): |U| ≳ 1e6, the acceptance test of ANY implementation has lost its
+                # resolution — trajectories may part from the first such row on; the rows before it must still agree
+                collapsed = True
+                good = int(np.argmin(ok_rows))
+                np.testing.assert_allclose(state[1][:good], ost[:good], rtol=0, atol=1e-11, err_msg=str(kw))
+                np.testing.assert_allclose(traj[1][:good], ot[:good], rtol=1e-8, atol=1e-8, err_msg=str(kw))
+                break
             np.testing.assert_allclose(state[1], ost, rtol=0, atol=1e-11, err_msg=str(kw))
             cs, ocs = ens.cluster_stats()[1], run.cluster_stats()
             assert (cs[0], cs[1], cs[2]) == (ocs["ncluster"], ocs["cluster_sum"], ocs["cluster_max"]), kw
             d, od = ens.diagnostics()[1], run.diag()
             assert d[4] == od["nacc_total"] and d[5] == od["steps_total"], kw
             np.testing.assert_allclose(traj[1], ot, rtol=1e-8, atol=1e-8, err_msg=str(kw))
+        if collapsed:
+            # Where cancellation is worst the trajectory test ends, and the changed-term sums take over: on the collapsed
+            # state itself (the oracle's), composite trials agree to 1e-12 of the sum of the magnitudes of their terms.
+            phi, th = run.chain().state()
+            ens.set_state(1, phi, th)
+            och = O.Chain(oc, phi, th)
+            for _ in range(12):
+                idx = int(rng.integers(0, n))
+                lo, hi = max(0, idx - int(rng.integers(0, 4))), min(n - 1, idx + int(rng.integers(0, 4)))
+                reflect = bool(rng.integers(0, 2))
+                if not reflect:
+                    lo = hi = idx
+                dphi, dth = float(rng.uniform(-1, 1)), float(rng.uniform(-0.5, 0.5))
+                dg = ens.delta_segment(1, idx, dphi, dth, reflect, lo, hi)
+                do = och.delta_segment(idx, dphi, dth, int(reflect), lo, hi)
+                scale = max(1.0, do["abs_sum"])
+                assert abs(dg["dU"] - do["dU"]) <= 1e-12 * scale, (kw, idx, lo, hi, dg["dU"], do["dU"], scale)
+                if math.isfinite(do["dOmega"]):
+                    assert dg["dOmega"] == pytest.approx(do["dOmega"], rel=1e-10, abs=1e-11)
 
 
 def test_matches_the_reference_sequence_of_full_recomputes(pm, O):
