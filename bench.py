@@ -571,11 +571,17 @@ def main():
         xs = max(2, min(args.steps, 3))
         for nm in ("C3", "C4", "C5", "K1"):
             workloads[nm] = measure(cx, nm, xs, 3, want_e2e=not args.no_e2e)
+        workloads["C4"]["limiter"] = ("device-timed: latency / transcendental bound (2 Philox, 2 sincos, log, exp per trial); e2e through "
+                                      "run_sweep: a fixed ~8-25 ms per call of handle set-up, result fetch and gather next to a kernel that "
+                                      "shrinks with the GPU count (21 ms per call at 8 GPUs)")
+        workloads["K1"]["limiter"] = ("one warp per chain, 12 chains per SM: instruction mix (0.24 FP64 of 0.53 instructions issued per cycle "
+                                      "per scheduler) and dependent-issue latency, DESIGN.md section 8")
         for nm in ("C2s", "C5s"):
             r = measure(cx, nm, xs, 3, want_e2e=not args.no_e2e)
-            r["limiter"] = ("one chain per SM and one wave of CTAs per launch at 148 chains per GPU: the launch ends with "
-                            "its slowest chain" if nm == "C5s" else
-                            "512 chains per GPU at 8 GPUs leave SMs short of warps: the library raises the threads per chain")
+            r["limiter"] = ("148 chains per GPU at 8 GPUs are one wave: two SMs per chain and the work-ordered queue keep the FP64 "
+                            "pipe busy for 0.97 of what 1184 chains on one GPU reach" if nm == "C5s" else
+                            "512 chains per GPU at 8 GPUs quantise badly over 592 CTA slots (80 SMs carry three chains, 68 four): the "
+                            "library switches to two SMs per chain for such fills")
             strong[nm[:-1]] = r
         barrier()
         if world > 1:

@@ -130,6 +130,12 @@ class JRange:
         """0-based Python slice for integer ranges."""
         return slice(self.start - 1, self.stop, self.step) if self.step > 0 else None
 
+    def __eq__(self, o):
+        return isinstance(o, JRange) and (len(self) == len(o)) and (len(self) == 0 or (self.start == o.start and self.step == o.step))
+
+    def __hash__(self):
+        return hash((self.start, self.step, len(self)))
+
     def __repr__(self):
         return f"{self.start}:{self.stop}" if self.step == 1 else f"{self.start}:{self.step}:{self.stop}"
 

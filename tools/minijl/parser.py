@@ -723,18 +723,23 @@ class Parser:
                         self.next()
                         return ("tuple", [])
                     first = self.parse_expr(0)
-                    if self.is_op(",") or self.is_op(";"):
+                    if self.is_op(";"):            # (a; b; c): a block whose value is its last expression
                         items = [first]
-                        named = False
-                        while self.is_op(",") or self.is_op(";"):
-                            if self.next().val == ";":
-                                named = True
+                        while self.is_op(";"):
+                            self.next()
                             if self.is_op(")"):
                                 break
                             items.append(self.parse_expr(0))
                         self.expect_op(")")
-                        if named and len(items) == 1:
-                            return ("paren", items[0])
+                        return ("paren", ("block", items)) if len(items) > 1 else ("paren", items[0])
+                    if self.is_op(","):
+                        items = [first]
+                        while self.is_op(","):
+                            self.next()
+                            if self.is_op(")"):
+                                break
+                            items.append(self.parse_expr(0))
+                        self.expect_op(")")
                         return ("tuple", items)
                     self.expect_op(")")
                     return ("paren", first)
