@@ -16,6 +16,10 @@
 
 #include "lane_kernels.cuh"
 
+#ifndef PMC_UR_SHORT
+#define PMC_UR_SHORT 1   // rectangle unroll of the one- and two-warp teams (experiments: -DPMC_UR_SHORT=2)
+#endif
+
 namespace pmc {
 
 // Sums reduced over the CTA for one composite trial.
@@ -382,7 +386,7 @@ __device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, 
     // short chains (≤ 2 warps): eB = μ_B·D on the fly — a barrier costs more than 3 DFMA per broadcast item;
     // longer chains: the pre-pass into S.E and its barrier are amortised, and the rectangle loop is unrolled
     constexpr bool EFLY = (T <= 64);
-    constexpr int UR = (T <= 64) ? 1 : 2;
+    constexpr int UR = (T <= 64) ? PMC_UR_SHORT : 2;
     const bool rect = H > 0 && Tl > 0;
     // lane side = the one that wastes fewer lanes; r = x_L − x_B, so r' = r − D (L = head) or r + D (L = tail)
     const long long costH = (long long)((H + 31) >> 5) * Tl;

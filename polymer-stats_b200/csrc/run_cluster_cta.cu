@@ -29,6 +29,7 @@ int launch_run_cluster_cta(pmc_handle* h, const RunArgs& a) {
     const int ccfg = env_int("PMC_CLUSTER_CFG", 0);
 #ifdef PMC_TUNING_VARIANTS
     if (ccfg == 3216) PMC_CL(32, 16)
+    else if (ccfg == 3214) PMC_CL(32, 14)
     else if (ccfg == 3212) PMC_CL(32, 12)
     else if (ccfg == 6408) PMC_CL(64, 8)
     else if (ccfg == 6410) PMC_CL(64, 10)
@@ -43,7 +44,9 @@ int launch_run_cluster_cta(pmc_handle* h, const RunArgs& a) {
 #endif
     switch (h->cta_threads) {
       case 32:  // very short chains fit 16 per SM in shared memory: worth the 128-register build (+9 % at n=25)
-        if (h->n <= 40) PMC_CL(32, 16) else PMC_CL(32, 12)
+        // registers beat occupancy for the one-warp teams (profiles/r02b_tune_k1.txt): 10 chains per SM at 204 registers are
+        // +6 % over 12 at 170 for n = 64 … 100, 8 per SM +11 % at n = 150; only very short chains gain from 16 per SM
+        if (h->n <= 40) PMC_CL(32, 16) else if (h->n <= 110) PMC_CL(32, 10) else PMC_CL(32, 8)
         break;
       case 64: PMC_CL(64, 6) break;
       case 128: PMC_CL(128, 4) break;

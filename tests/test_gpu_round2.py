@@ -151,7 +151,7 @@ def test_kernel_name_is_the_librarys_own_decision(pm):
         assert ens.kernel_name() == "k_run_cta_win<128,4,2>"
     k1 = pm.make_case(n=100, E0=1.0, Fz=0.25, energy_type="interacting", kappa=0.5, clustering=True)
     with pm.Ensemble(k1, replicas=8, seed=1, ensemble_chains=4096) as ens:
-        assert ens.kernel_name().startswith("k_run_cta_cluster<32,12")
+        assert ens.kernel_name().startswith("k_run_cta_cluster<32,10")
     c4 = pm.make_case(n=100, E0=1.0, Fz=0.5)
     with pm.Ensemble(c4, replicas=64, seed=1) as ens:
         assert ens.kernel_name().startswith("k_run_warp<0,")

@@ -1,0 +1,25 @@
+"""K1 launch-bound sweep (tuning build: make -C polymer-stats_b200/csrc clean all TUNING=1)."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+child = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%r, "polymer-stats_b200"))
+import polymc as pm
+n, R, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+c = pm.make_case(n=n, E0=1.0, Fz=0.25, energy_type="interacting", kappa=0.5, clustering=True, adj_ub=0.4)
+ens = pm.Ensemble(c, replicas=R, seed=20260101)
+ens.begin_stage(1.0)
+ens.run_ex(100, 0, fetch_rows=False)
+best = 1e30
+for _ in range(3):
+    ens.run_ex(steps, steps, fetch_rows=False)
+    best = min(best, ens.last_run_ms())
+print("n=%%d R=%%d %%s: %%.3f ms  %%.3f M updates/s" %% (n, R, ens.kernel_name(), best, R*steps/best/1e3))
+''' % ROOT
+for n, R, steps in ((100, 4096, 500), (100, 14208, 300), (64, 8192, 500), (150, 4096, 300)):
+    for cfg in (0, 3208, 3210, 3212, 3214, 3216):
+        env = dict(os.environ)
+        if cfg:
+            env["PMC_CLUSTER_CFG"] = str(cfg)
+        out = subprocess.run([sys.executable, "-c", child, str(n), str(R), str(steps)], env=env, capture_output=True, text=True)
+        print("cfg", cfg, "->", out.stdout.strip() or out.stderr.strip()[-300:], flush=True)
