@@ -121,8 +121,21 @@ inline int64_t packing_chains(const pmc_handle* h) { return h->shape_chains > 0 
 
 // Block size of the composite-trial CTA kernels.
 // Short chains are latency bound (one serial proposal/cluster/decision chain per trial), so one warp per
-// chain and many chains per SM; measured crossovers in profiles/r01e_tune_cluster.txt.
-inline int pick_cluster_threads(int n) { return n <= 160 ? 32 : n <= 256 ? 64 : n <= 1024 ? 128 : 256; }
+// chain and many chains per SM; measured crossovers in profiles/r01e_tune_cluster.txt.  Chains whose shared-memory
+// footprint (18 n doubles) leaves room for a single CTA per SM get 256 threads instead of 128: at n = 800 … 1000 one
+// 128-thread CTA per SM is four warps on the whole SM (+74 % with 256 threads, profiles/r02b_tune_k35.txt).
+inline int pick_cluster_threads(int n) {
+  if (n <= 160) return 32;
+  if (n <= 256) return 64;
+  return 2 * (pmc::cluster_smem_bytes(n, 128) + 1024) > (size_t)kSmemMax ? 256 : 128;
+}
+// CTAs of the 128-thread composite-trial kernel that fit one SM's shared memory (2 … 4): the launch bound follows it,
+// because a bound the shared memory cannot honour only takes registers away (n = 400: 3 per SM at 168 registers are
+// +8 % over a bound of 4 at 128; n = 640: 2 per SM +20 %).
+inline int cluster_fit128(int n) {
+  const int fit = (int)((size_t)kSmemMax / (pmc::cluster_smem_bytes(n, 128) + 1024));
+  return fit >= 4 ? 4 : fit >= 3 ? 3 : 2;
+}
 
 // ---- launch helpers, one translation unit per kernel family -------------------------------------------------
 int launch_run_cta(pmc_handle* h, const pmc::RunArgs& a);                    // run_cta.cu

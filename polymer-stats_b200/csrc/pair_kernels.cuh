@@ -78,8 +78,8 @@ __global__ void k_order_by_work(const unsigned long long* __restrict__ work, int
 }
 
 // The hot loop of mcmc_eap_chain.jl:276-350 for interacting chains, one chain per CTA PAIR.
-template <int T, int UNROLL = 2>
-__global__ void __launch_bounds__(T, 1) k_run_cta_pair(const RunArgs a, const PairQueue q) {
+template <int T, int MINB, int UNROLL = 2>
+__global__ void __launch_bounds__(T, MINB) k_run_cta_pair(const RunArgs a, const PairQueue q) {
   using TEAM = PairTeam<T / 32>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();

@@ -285,7 +285,7 @@ static void choose_shape(pmc_handle* h) {
   const bool cta_pairs = h->energy_type == PMC_ENERGY_INTERACTING || h->energy_type == PMC_ENERGY_CUTOFF;
   if (h->cluster_mode && cta_pairs) {
     const int base = pick_cluster_threads(h->n);
-    const int minb = base == 32 ? (h->n <= 40 ? 16 : h->n <= 110 ? 10 : 8) : base == 64 ? 6 : base == 128 ? 4 : 1;
+    const int minb = base == 32 ? (h->n <= 40 ? 16 : h->n <= 110 ? 10 : 8) : base == 64 ? 5 : base == 128 ? cluster_fit128(h->n) : 1;
     int t = scaled_threads(base, minb, cluster_smem_bytes(h->n, base), 256, chains, h->sm_count);
     while (t > base && cluster_delta_smem_bytes(h->n, t) > (size_t)kSmemMax) t /= 2;
     h->cta_threads = t;

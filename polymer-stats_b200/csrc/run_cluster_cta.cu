@@ -34,8 +34,8 @@ int launch_run_cluster_cta(pmc_handle* h, const RunArgs& a) {
     else if (ccfg == 6408) PMC_CL(64, 8)
     else if (ccfg == 6410) PMC_CL(64, 10)
     else if (ccfg == 6406) PMC_CL(64, 6)
+    else if (ccfg == 6404) PMC_CL(64, 4)
     else if (ccfg == 12804) PMC_CL(128, 4)
-    else if (ccfg == 12803) PMC_CL(128, 3)
     else if (ccfg == 12805) PMC_CL(128, 5)
     else if (ccfg == 25602) PMC_CL(256, 2)
     else
@@ -48,8 +48,12 @@ int launch_run_cluster_cta(pmc_handle* h, const RunArgs& a) {
         // +6 % over 12 at 170 for n = 64 … 100, 8 per SM +11 % at n = 150; only very short chains gain from 16 per SM
         if (h->n <= 40) PMC_CL(32, 16) else if (h->n <= 110) PMC_CL(32, 10) else PMC_CL(32, 8)
         break;
-      case 64: PMC_CL(64, 6) break;
-      case 128: PMC_CL(128, 4) break;
+      case 64: PMC_CL(64, 5) break;
+      case 128: {
+        const int fit = cluster_fit128(h->n);
+        if (fit >= 4) PMC_CL(128, 4) else if (fit == 3) PMC_CL(128, 3) else PMC_CL(128, 2)
+        break;
+      }
       case 256: PMC_CL(256, 1) break;
       default: return fail(PMC_ERR_INVALID, "bad cta_threads");
     }

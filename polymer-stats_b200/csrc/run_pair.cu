@@ -31,10 +31,10 @@ bool use_pair_kernel(const pmc_handle* h) {
   return false;
 }
 
-template <int T>
+template <int T, int MINB>
 static int launch_pair_t(pmc_handle* h, const RunArgs& a, const PairQueue& q) {
   const size_t smem = cta_smem_bytes(h->n);
-  int rc = set_smem(k_run_cta_pair<T, 2>, smem);
+  int rc = set_smem(k_run_cta_pair<T, MINB, 2>, smem);
   if (rc) return rc;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
@@ -50,20 +50,36 @@ static int launch_pair_t(pmc_handle* h, const RunArgs& a, const PairQueue& q) {
   // persistent: as many clusters as the device keeps resident (≤ one per chain); each runs chain after chain
   cfg.gridDim = dim3(2, 1, 1);
   int resident = 0;
-  PMC_CU(cudaOccupancyMaxActiveClusters(&resident, k_run_cta_pair<T, 2>, &cfg));
+  PMC_CU(cudaOccupancyMaxActiveClusters(&resident, k_run_cta_pair<T, MINB, 2>, &cfg));
   if (resident < 1) return fail(PMC_ERR_UNSUPPORTED, "no CTA pair fits on this device");
   const int clusters = (int)std::min<int64_t>(h->nchains, resident);
   cfg.gridDim = dim3(2 * clusters, 1, 1);
-  PMC_CU(cudaLaunchKernelEx(&cfg, k_run_cta_pair<T, 2>, a, q));
+  PMC_CU(cudaLaunchKernelEx(&cfg, k_run_cta_pair<T, MINB, 2>, a, q));
   ++h->launches;
   return PMC_OK;
 }
 
+// Resident CTAs per SM the launch bound asks for: what the shared memory admits (a bound it cannot honour only takes
+// registers away), at most 4 × 128, 2 × 256 or 1 × 512 threads.  PMC_PAIR_MINB overrides (experiments).
+static int pair_minb(const pmc_handle* h) {
+  const int fit = (int)((size_t)kSmemMax / (cta_smem_bytes(h->n) + 1024));
+  const int cap = h->cta_threads == 128 ? 4 : h->cta_threads == 256 ? 2 : 1;
+  int mb = std::max(1, std::min(fit, cap));
+  const int o = env_int("PMC_PAIR_MINB", 0);
+  if (o >= 1 && o <= cap) mb = o;
+  return mb;
+}
+
 int launch_run_pair(pmc_handle* h, const RunArgs& a) {
-  switch (h->cta_threads) {
-    case 128: PMC_PICK("k_run_cta_pair<128,2>"); break;
-    case 256: PMC_PICK("k_run_cta_pair<256,2>"); break;
-    default: PMC_PICK("k_run_cta_pair<512,2>"); break;
+  const int mb = pair_minb(h);
+  switch (h->cta_threads * 10 + mb) {
+    case 1284: PMC_PICK("k_run_cta_pair<128,4,2>"); break;
+    case 1283: PMC_PICK("k_run_cta_pair<128,3,2>"); break;
+    case 1282: PMC_PICK("k_run_cta_pair<128,2,2>"); break;
+    case 1281: PMC_PICK("k_run_cta_pair<128,1,2>"); break;
+    case 2562: PMC_PICK("k_run_cta_pair<256,2,2>"); break;
+    case 2561: PMC_PICK("k_run_cta_pair<256,1,2>"); break;
+    default: PMC_PICK("k_run_cta_pair<512,1,2>"); break;
   }
   const int nch = (int)h->nchains;
   if (!h->pair_work) {
@@ -85,10 +101,14 @@ int launch_run_pair(pmc_handle* h, const RunArgs& a) {
     q.order = nullptr;
   }
   int rc;
-  switch (h->cta_threads) {
-    case 128: rc = launch_pair_t<128>(h, a, q); break;
-    case 256: rc = launch_pair_t<256>(h, a, q); break;
-    default: rc = launch_pair_t<512>(h, a, q); break;
+  switch (h->cta_threads * 10 + mb) {
+    case 1284: rc = launch_pair_t<128, 4>(h, a, q); break;
+    case 1283: rc = launch_pair_t<128, 3>(h, a, q); break;
+    case 1282: rc = launch_pair_t<128, 2>(h, a, q); break;
+    case 1281: rc = launch_pair_t<128, 1>(h, a, q); break;
+    case 2562: rc = launch_pair_t<256, 2>(h, a, q); break;
+    case 2561: rc = launch_pair_t<256, 1>(h, a, q); break;
+    default: rc = launch_pair_t<512, 1>(h, a, q); break;
   }
   if (rc) return rc;
   PMC_CU(cudaGetLastError());
