@@ -55,6 +55,8 @@ int launch_run_cta(pmc_handle* h, const RunArgs& a) {
 #ifdef PMC_TUNING_VARIANTS
     if (use_win == 648) PMC_LAUNCH_WIN(64, 8)
     if (use_win == 1286) PMC_LAUNCH_WIN(128, 6)
+    if (use_win == 1283) PMC_LAUNCH_WIN(128, 3)
+    if (use_win == 1282) PMC_LAUNCH_WIN(128, 2)
     if (use_win == 1285) PMC_LAUNCH_WIN(128, 5)
     if (use_win == 2562) PMC_LAUNCH_WIN(256, 2)
     if (use_win == 643) PMC_LAUNCH_WIN(64, 10)
