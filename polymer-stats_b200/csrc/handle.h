@@ -81,6 +81,7 @@ struct pmc_handle {
   int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
   int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;
+  bool dyn_fresh = false, dynx_fresh = false;   // the host copies equal the device's (no launch since they were fetched)
   // clustering driver (mcmc_clustering_eap_chain.jl)
   int cluster_mode = 0;       // 1: the composite-trial kernels of cluster_kernels.cuh run this handle
   ChainDynX* dynx = nullptr;

@@ -202,6 +202,7 @@ int launch_reinit(pmc_handle* h, const ReinitArgs& a) {
 
 // Recompute the running scalars of every chain from its records (re-synchronisation).
 int refresh(pmc_handle* h, bool rebind_gauge, int first = 0, int count = -1) {
+  h->dyn_fresh = h->dynx_fresh = false;
   EnergyArgs a{};
   a.mono = h->mono; a.par = h->par; a.dyn = h->dyn;
   a.out4 = nullptr; a.obs6 = nullptr;
@@ -301,10 +302,12 @@ static void choose_shape(pmc_handle* h) {
 }
 
 int fetch_dyn(pmc_handle* h) {
+  if (h->dyn_fresh && h->host_dyn.size() == (size_t)h->nchains) return PMC_OK;  // averages + accumulators + diagnostics: one copy
   h->host_dyn.resize((size_t)h->nchains);
   PMC_CU(cudaMemcpyAsync(h->host_dyn.data(), h->dyn, sizeof(ChainDyn) * (size_t)h->nchains, cudaMemcpyDeviceToHost,
                          h->stream));
   PMC_CU(cudaStreamSynchronize(h->stream));
+  h->dyn_fresh = true;
   return PMC_OK;
 }
 
@@ -596,10 +599,12 @@ static int launch_delta_segment(pmc_handle* h, const SegDeltaArgs& a) {
 }
 
 static int fetch_dynx(pmc_handle* h) {
+  if (h->dynx_fresh && h->host_dynx.size() == (size_t)h->nchains) return PMC_OK;
   h->host_dynx.resize((size_t)h->nchains);
   PMC_CU(cudaMemcpyAsync(h->host_dynx.data(), h->dynx, sizeof(ChainDynX) * (size_t)h->nchains, cudaMemcpyDeviceToHost,
                          h->stream));
   PMC_CU(cudaStreamSynchronize(h->stream));
+  h->dynx_fresh = true;
   return PMC_OK;
 }
 
@@ -1022,6 +1027,7 @@ int32_t pmc_checkpoint_load(pmc_handle* h, const void* buf, int64_t bytes) {
   PMC_CU(cudaMemcpyAsync(h->dynx, p + nm + c * sizeof(ChainDyn), c * sizeof(ChainDynX), cudaMemcpyHostToDevice, h->stream));
   PMC_CU(cudaStreamSynchronize(h->stream));
   h->init = hd.init;
+  h->dyn_fresh = h->dynx_fresh = false;
   if (h->host_dyn.empty()) h->host_dyn.resize(c);
   h->host_dyn[0].step = hd.host_step;
   return PMC_OK;

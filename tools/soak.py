@@ -13,6 +13,8 @@ CASES = [
     ("clustering cut-off n=400", dict(n=400, E0=1.0, Fz=0.25, energy_type="cutoff", cutoff_radius=7.5, kappa=0.5, clustering=True, adj_ub=0.4), 592, 20000, True),
     ("clustering Ising n=100 (warp)", dict(n=100, E0=1.0, Fz=0.25, energy_type="Ising", kappa=0.5, clustering=True, adj_ub=0.4), 500, 2000000, True),
     ("clustering Ising n=100 (lane)", dict(n=100, E0=1.0, Fz=0.25, energy_type="Ising", kappa=0.5, clustering=True, adj_ub=0.4), 32768, 100000, True),
+    ("plain interacting n=1024 (two SMs per chain)", dict(n=1024, E0=1.0, Fz=0.5, energy_type="interacting"), 592, 6000, False),
+    ("plain interacting n=4096 (two SMs per chain, C5 shape)", dict(n=4096, E0=1.0, Fz=0.5, energy_type="interacting"), 148, 600, False),
     ("planar Ising n=100 (warp)", dict(n=100, E0=0.3, Fz=0.25, energy_type="Ising", clustering=True, planar=True, adj_ub=0.4), 500, 300000, True),
 ]
 bad = 0
@@ -34,4 +36,26 @@ for name, kw, R, steps, cl in CASES:
                                       d[:, 7].max(), (d[:, 7] / scale).max()), flush=True)
     bad += not ok
     ens.close()
+
+# Cross-kernel decision equality over long runs (compute-sanitizer is closed on this pool: a race in a barrier protocol
+# would show up as a different accept/reject sequence): the same ensemble through the windowed one-CTA kernel, the classic
+# one-CTA kernel and the CTA-pair kernel (cluster barrier + distributed shared memory) must count the same acceptances per
+# chain — the reduction orders differ, so only a decision within rounding of its threshold could legitimately differ.
+import os
+for n, R, steps in ((512, 444, 20000), (1024, 300, 6000), (200, 1000, 40000)):
+    counts = {}
+    for tag, env in (("windowed", dict(PMC_RUN_PAIR="0", PMC_RUN_WIN="1")), ("classic", dict(PMC_RUN_PAIR="0", PMC_RUN_WIN="0")),
+                     ("pair", dict(PMC_RUN_PAIR="2", PMC_RUN_WIN="1"))):
+        os.environ.update(env)
+        with pm.Ensemble(pm.make_case(n=n, E0=1.0, Fz=0.5, energy_type="interacting"), replicas=R, seed=4242) as ens:
+            name = ens.kernel_name()
+            t0 = time.time()
+            ens.run(steps, 0, fetch_rows=False)
+            counts[tag] = (ens.diagnostics()[:, 4].copy(), name, time.time() - t0)
+    same = all(np.array_equal(counts["windowed"][0], counts[k][0]) for k in ("classic", "pair"))
+    diff = max(int((counts["windowed"][0] != counts[k][0]).sum()) for k in ("classic", "pair"))
+    print("decision equality n=%d, %d chains x %d trials: %s (%s %.1f s, %s %.1f s, %s %.1f s); chains with a different acceptance "
+          "count: %d" % (n, R, steps, "ok " if same else "DIFF", counts["windowed"][1], counts["windowed"][2], counts["classic"][1],
+                         counts["classic"][2], counts["pair"][1], counts["pair"][2], diff), flush=True)
+    bad += not same
 sys.exit(1 if bad else 0)
