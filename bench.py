@@ -421,7 +421,7 @@ def measure(cx: Ctx, name: str, steps: int, warmup: int, want_e2e=True, chains_o
         # the call a study makes: polymc.sweep.run_sweep — case table in (H2D of the per-chain constants, chains drawn
         # on the device), S trials, per-chain averages + raw sums out (D2H), gathered over the ranks (NCCL all_gather)
         from polymc import sweep
-        all_cases = [pm.make_case(**kw) for kw in W["cases"]]
+        all_cases = pm.CaseTable([pm.make_case(**kw) for kw in W["cases"]])   # the host-resident case table
         reps = rep * cx.world if W["scaling"] == "weak" else rep
 
         def sweep_step():

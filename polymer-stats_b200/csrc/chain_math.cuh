@@ -46,6 +46,12 @@ static __device__ __noinline__ double log_shared(double x) { return log(x); }
 static __device__ __noinline__ double exp_shared(double x) { return exp(x); }
 static __device__ __noinline__ double acos_shared(double x) { return acos(x); }
 
+// Default of a translation unit: -DPMC_SH_DEFAULT=true makes every call site without an explicit choice use the shared copies.
+#ifndef PMC_SH_DEFAULT
+#define PMC_SH_DEFAULT false
+#endif
+constexpr bool kSharedLib = PMC_SH_DEFAULT;
+
 template <bool SH>
 struct Lib {
   __device__ __forceinline__ static uint4 philox(uint4 c, uint2 k) { return SH ? philox_shared(c, k) : philox4x32_10(c, k); }
@@ -58,7 +64,7 @@ struct Lib {
   __device__ __forceinline__ static double acos_(double x) { return SH ? acos_shared(x) : acos(x); }
 };
 
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ uint4 philox_at(uint64_t seed, uint32_t chain_id, uint32_t init, uint32_t sub,
                                            uint64_t pos) {
   return Lib<SH>::philox(make_uint4((uint32_t)pos, (uint32_t)(pos >> 32), chain_id, (init << 8) | sub),
@@ -73,20 +79,20 @@ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
 // cluster_flip! draws an unbounded number of uniforms per trial (eap_chain.jl:273,291,307): uniform #k
 // of the upward / downward growth is word pair (k&1) of the Philox block at position
 // step + ((k>>1) << 40) of stream SUB_CLUSTER_UP / _DOWN (steps stay below 2^40).
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ uint4 cluster_block(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
                                                uint32_t sub, int k) {
   return philox_at<SH>(seed, chain_id, init, sub, (uint64_t)step + (((uint64_t)k >> 1) << 40));
 }
 
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ double draw_cluster(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
                                                uint32_t sub, int k) {
   const uint4 w = cluster_block<SH>(seed, chain_id, init, step, sub, k);
   return (k & 1) ? u53(w.z, w.w) : u53(w.x, w.y);
 }
 
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ double draw_cluster_gate(uint64_t seed, uint32_t chain_id, uint32_t init,
                                                     long long step) {
   const uint4 w = philox_at<SH>(seed, chain_id, init, SUB_CLUSTER_GATE, (uint64_t)step);
@@ -221,7 +227,7 @@ __device__ __forceinline__ double pair_g_cut(double ax, double ay, double az, do
 }
 
 // ψ (eap_chain.jl:45-47): acos(min(1, max(-1, n̂_a·n̂_b)))
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ double psi_of(double ax, double ay, double az, double bx, double by, double bz) {
   const double d = fma(az, bz, fma(ay, by, ax * bx));
   return Lib<SH>::acos_(fmin(1.0, fmax(-1.0, d)));
@@ -282,7 +288,7 @@ struct Draws {
   int idx, flipbit;
 };
 
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ Draws draw_step(uint64_t seed, uint32_t chain_id, uint32_t init, long long step,
                                            int n) {
   const uint4 a = philox_at<SH>(seed, chain_id, init, SUB_STEP_A, (uint64_t)step);
@@ -298,7 +304,7 @@ __device__ __forceinline__ Draws draw_step(uint64_t seed, uint32_t chain_id, uin
 }
 
 // move! up to the energy (eap_chain.jl:232-251) for given increments.
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ void build_proposal(const ChainParams& P, const MonoRec& rec, int idx, double dphi,
                                                double dtheta, double eps, Proposal& q) {
   q.idx = idx;
@@ -334,7 +340,7 @@ __device__ __forceinline__ void build_proposal(const ChainParams& P, const MonoR
 // move! of the planar chain (2D/inc/eap_chain.jl:171-187): ϕ += dϕ, n̂ = (cosϕ, sinϕ) in the x–z plane
 // (the field is along the second axis, 2D/inc/dipole_response.jl:7-10), no θ and no solid-angle term.
 // In the record: n̂y = 0, sinθ ≡ 1 (so every log(sinθ'/sinθ) is exactly 0), θ ≡ 0.
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ void build_proposal_planar(const ChainParams& P, const MonoRec& rec, int idx, double dphi,
                                                       double eps, Proposal& q) {
   q.idx = idx;
@@ -367,7 +373,7 @@ __device__ __forceinline__ void increments(const ChainParams& P, const Draws& d,
 }
 
 // Metropolis on Δlogπ (acceptance.jl:32): NaN and −Inf both reject.
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ bool metropolis(double dlogpi, double eps) {
   return (dlogpi >= 0.0) || (eps < Lib<SH>::exp_(dlogpi));
 }
@@ -417,7 +423,7 @@ __device__ __forceinline__ void record_averages(const ChainParams& P, double* ac
                                                 const double* r, const double* p, double U, double su,
                                                 double log_gauge) {
   double wgt = 1.0;
-  if (P.umbrella) wgt = 1.0 / exp(su * P.inv_kT * P.cF - log_gauge);
+  if (P.umbrella) wgt = 1.0 / Lib<kSharedLib>::exp_(su * P.inv_kT * P.cF - log_gauge);
   const double v[kNumAcc] = {r[0], r[1], r[2], r[0] * r[0], r[1] * r[1], r[2] * r[2],
                              r[0] * r[0] + r[1] * r[1] + r[2] * r[2],
                              p[0], p[1], p[2], p[0] * p[0], p[1] * p[1], p[2] * p[2],

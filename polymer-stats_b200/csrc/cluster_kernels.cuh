@@ -118,7 +118,7 @@ __device__ __forceinline__ void make_proposal_cl(const RunArgs& a, const ChainPa
 
 // The gate of cluster_flip!.  3-D: `if rand() <= ϵflip; return 1.0; end` BEFORE the growth (eap_chain.jl:273):
 // flips with 1 − ϵflip;  2-D: `if rand() <= ϵflip … flip` AFTER the growth (2D/inc/eap_chain.jl:233): flips with ϵflip.
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ int cluster_gate(const ChainParams& P, uint64_t seed, uint32_t chain_id, uint32_t init,
                                             long long step) {
   if (!P.clustering) return 0;
@@ -221,7 +221,7 @@ __device__ __forceinline__ void segment_angles(const MonoRec* __restrict__ mono,
 }
 
 // n̂ and sinθ from the angles: (cosϕ sinθ, sinϕ sinθ, cosθ) (eap_chain.jl:40) or the planar (cosϕ, 0, sinϕ).
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ void direction_of(int planar, double phi, double theta, double& nx, double& ny, double& nz,
                                              double& sth) {
   double sph, cph;
@@ -267,7 +267,7 @@ __device__ __forceinline__ void segment_monomer(const CtaView& S, const ClView& 
     double phi, theta, sb;
     segment_angles(mono, q, c, true, P.planar, phi, theta, sb);
     direction_of(P.planar, phi, theta, nx, ny, nz, sth);
-    if (!P.planar) acc[R_OMEGA] += (c == q.idx ? q.dOmega : 0.0) + log(sth / sb);  // Ω += log(sθ'/sθ), eap_chain.jl:238
+    if (!P.planar) acc[R_OMEGA] += (c == q.idx ? q.dOmega : 0.0) + Lib<kSharedLib>::log_(sth / sb);  // Ω += log(sθ'/sθ), eap_chain.jl:238
   }
   X.nnx[c] = nx; X.nny[c] = ny; X.nnz[c] = nz;
   S.E[c] = sth;
@@ -447,7 +447,7 @@ __device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, 
 __device__ __forceinline__ double cluster_log_alpha(const ClView& X, int n, int lo, int hi, double up, double lp) {
   const double nup = (hi < n - 1) ? link_prob(X.nnx[hi], X.nny[hi], X.nnz[hi], X.nhx[hi + 1], X.nhy[hi + 1], X.nhz[hi + 1]) : 0.0;
   const double nlp = (lo > 0) ? link_prob(X.nnx[lo], X.nny[lo], X.nnz[lo], X.nhx[lo - 1], X.nhy[lo - 1], X.nhz[lo - 1]) : 0.0;
-  return log(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
+  return Lib<kSharedLib>::log_(((1.0 - nup) * (1.0 - nlp)) / ((1.0 - up) * (1.0 - lp)));
 }
 
 // record! of the two extra averagers (mcmc_clustering_eap_chain.jl:243-244), same weight as the others.
@@ -455,7 +455,7 @@ template <bool COMP>
 __device__ __forceinline__ void record_extras(const ChainParams& P, ChainDynX& DX, double su, double log_gauge,
                                               int n) {
   double wgt = 1.0;
-  if (P.umbrella) wgt = 1.0 / exp(su * P.inv_kT * P.cF - log_gauge);
+  if (P.umbrella) wgt = 1.0 / Lib<kSharedLib>::exp_(su * P.inv_kT * P.cF - log_gauge);
   if (COMP) {
     comp_add(DX.acc[0], DX.comp[0], DX.scos2 * wgt);
     comp_add(DX.acc[1], DX.comp[1], DX.spsi / (double)(n - 1) * wgt);
@@ -745,7 +745,7 @@ __device__ __forceinline__ void lane_add_flipped(const ChainParams& P, const Mon
 }
 
 // ψ, bending and (Ising) pair-term change of ONE bond between monomers a and b (b = a+1).
-template <bool ISING, bool SH = false>
+template <bool ISING, bool SH = kSharedLib>
 __device__ __forceinline__ void lane_bond_delta(const ChainParams& P, double aox, double aoy, double aoz, double anx,
                                                 double any_, double anz, double box, double boy, double boz,
                                                 double bnx, double bny, double bnz, LaneSeg& o) {
@@ -767,7 +767,7 @@ __device__ __forceinline__ void lane_bond_delta(const ChainParams& P, double aox
 
 // Final record of the moved monomer idx: move! (the proposal), then refl_n!/flip_n! if its cluster is flipped.
 // This one is computed literally from the angles (a θ clamped to π reflects to θ = 0 ⇒ sinθ = 0 ⇒ rejection).
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ void lane_idx_record(const ChainParams& P, const Proposal& q, bool reflect, MonoRec& nrec,
                                                 double& dOmega) {
   if (!reflect) {
@@ -787,7 +787,7 @@ __device__ __forceinline__ void lane_idx_record(const ChainParams& P, const Prop
 // nearest-neighbour pair terms INSIDE the cluster are unchanged; what changes is: the bonds next to the moved
 // monomer idx, the two bonds at the ends of the cluster, and the single-monomer sums (u, p, r) of the flipped
 // monomers — no transcendental per cluster monomer.  `o` enters holding the flipped-monomer sums (c ≠ idx).
-template <bool ISING, bool SH = false>
+template <bool ISING, bool SH = kSharedLib>
 __device__ __forceinline__ void lane_segment_finish(const MonoRec* __restrict__ mono, int n, const ChainParams& P,
                                                     const MonoRec& rec, const MonoRec& nrec, int idx, int lo, int hi,
                                                     bool reflect, LaneSeg& o, double& la, double up, double lp) {
@@ -845,7 +845,7 @@ __device__ __forceinline__ void lane_segment_finish(const MonoRec* __restrict__ 
 
 // Sequential cluster growth for one lane (eap_chain.jl:276-305) on the chain carrying the move; every monomer
 // that joins the cluster adds its flipped-monomer sums on the way.
-template <bool SH = false>
+template <bool SH = kSharedLib>
 __device__ __forceinline__ void lane_cluster_grow(const MonoRec* __restrict__ mono, const Proposal& q,
                                                   const ChainParams& P, int n, uint64_t seed, uint32_t chain_id,
                                                   uint32_t init, long long step, int& lo, int& hi, double& up,

@@ -145,60 +145,82 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
   const bool adapt_on = P.adj_scale != 1.0 && spa > 0;
   long long row = 0;
   long long s = 1;
+  // trials left until the next adaptation boundary / output row (one 64-bit division each per launch, not per window)
+  long long to_adapt = adapt_on ? spa - (step0 % spa) : 0;
+  long long to_row = a.stepout > 0 ? a.stepout - (step0 % a.stepout) : 0;
   while (s <= a.nsteps) {
     long long wl = a.nsteps - s + 1;
     if (wl > 32) wl = 32;
-    if (adapt_on) {
-      const long long tb = spa - ((step0 + s - 1) % spa);
-      if (wl > tb) wl = tb;
-    }
-    if (a.stepout > 0) {
-      const long long tr = a.stepout - ((step0 + s - 1) % a.stepout);
-      if (wl > tr) wl = tr;
-    }
+    if (adapt_on && wl > to_adapt) wl = to_adapt;
+    if (a.stepout > 0 && wl > to_row) wl = to_row;
     const int wlen = (int)wl;
     const bool active = lane < wlen;
     const long long step = step0 + s + lane;
     Draws d;
     d.idx = 0; d.flipbit = 0; d.u_phi = d.u_theta = d.eps = 0.0;
     if (active) d = draw_step(a.seed, chain_id, init, step, n);
-    // earlier trials of the window that conflict with this one
+    // earlier trials of the window that conflict with this one (same monomer; Ising: or a neighbour)
     unsigned cmask = 0;
-    for (int j = 0; j < wlen; ++j) {
-      const int ij = __shfl_sync(FULL, d.idx, j);
-      const int dist = ij > d.idx ? ij - d.idx : d.idx - ij;
-      if (j < lane && dist <= ISING) cmask |= 1u << j;
+    if (ISING == 0) {
+      cmask = __match_any_sync(FULL, d.idx) & ((1u << lane) - 1u);
+    } else {
+      for (int j = 0; j < wlen; ++j) {
+        const int ij = __shfl_sync(FULL, d.idx, j);
+        const int dist = ij > d.idx ? ij - d.idx : d.idx - ij;
+        if (j < lane && dist <= ISING) cmask |= 1u << j;
+      }
     }
     bool pending = active;
     bool accept = false;
     double drx = 0, dry = 0, drz = 0, dpx = 0, dpy = 0, dpz = 0, dU = 0, dsu = 0, dOm = 0;
-    const double phi_step = D.phi_step, theta_step = D.theta_step;  // fixed within a window
     unsigned pmask;
+    // Rounds.  EVERY undecided trial is evaluated against the current records — a trial behind an undecided conflicting
+    // one speculates that it will be rejected (acceptance rates are below one half).  A trial's outcome is final when all
+    // its earlier conflicting trials are final rejections: then the records it read are the ones the sequential chain
+    // would have shown it.  The others go to the next round.  Reads of a round precede its record writes.
     while ((pmask = __ballot_sync(FULL, pending)) != 0u) {
-      const bool ready = pending && (cmask & pmask) == 0u;
-      if (ready) {
+      bool acc_spec = false;
+      MonoRec nr;
+      if (pending) {
         const MonoRec rec = mono[d.idx];
         double dphi, dtheta;
-        increments(P, d, rec.theta, phi_step, theta_step, dphi, dtheta);
+        increments(P, d, rec.theta, D.phi_step, D.theta_step, dphi, dtheta);  // step sizes are fixed within a window
         Proposal q;
         build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, q);
         if (!q.skip) {
           const double dsum = kInv4Pi * lane_delta_pairs(mono, n, ISING ? 2 : 0, P, rec, q);
-          accept = metropolis(q.single - dsum * P.inv_kT, q.eps);
-          if (accept) {
-            MonoRec nr;
-            nr.phi = q.phi; nr.theta = q.theta;
-            nr.nx = q.nx; nr.ny = q.ny; nr.nz = q.nz; nr.sth = q.sth;
-            mono[d.idx] = nr;
-            drx = P.b * q.dnx; dry = P.b * q.dny; drz = P.b * q.dnz;
-            dpx = q.dmx; dpy = q.dmy; dpz = q.dmz;
-            dU = q.du + q.drF + dsum;
-            dsu = q.du;
-            dOm = q.dOmega;
-          }
+          acc_spec = metropolis(q.single - dsum * P.inv_kT, q.eps);
+          // what an accepted trial changes (kept only if the outcome is final)
+          nr.phi = q.phi; nr.theta = q.theta;
+          nr.nx = q.nx; nr.ny = q.ny; nr.nz = q.nz; nr.sth = q.sth;
+          drx = P.b * q.dnx; dry = P.b * q.dny; drz = P.b * q.dnz;
+          dpx = q.dmx; dpy = q.dmy; dpz = q.dmz;
+          dU = q.du + q.drF + dsum;
+          dsu = q.du;
+          dOm = q.dOmega;
         }
+      }
+      const unsigned need = cmask & pmask;  // earlier conflicting trials undecided at the start of this round
+      // "bad" trials: speculatively accepted, or behind a bad conflicting one; final = undecided and not behind a bad one
+      unsigned bad = __ballot_sync(FULL, acc_spec);
+      if (ISING != 0) {
+        // neighbour conflicts are not transitive: iterate to the fixed point (conflicts point to earlier lanes only).
+        // Equal-idx conflicts (ISING == 0) are classes: one pass is exact — by induction every undecided member before
+        // the first accepted one read the right record and is a final rejection.
+        for (;;) {
+          const unsigned nb = bad | __ballot_sync(FULL, pending && (need & bad) != 0u);
+          if (nb == bad) break;
+          bad = nb;
+        }
+      }
+      const bool fin = pending && (need & bad) == 0u;
+      __syncwarp();  // every record read of this round is done
+      if (fin) {
+        accept = acc_spec;
+        if (accept) mono[d.idx] = nr;
         pending = false;
       }
+      if (pending || !accept) { drx = dry = drz = dpx = dpy = dpz = dU = dsu = dOm = 0.0; }
       __syncwarp();  // record writes of this round are visible to the next
     }
     // running state after each trial of the window: inclusive prefix sums of the increments
@@ -227,10 +249,13 @@ __global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
       D.nacc += nacc_w; D.nacc_total += nacc_w;
       D.natt += wlen; D.steps_total += wlen;
       D.step = step_last;
-      adapt_steps(P, step_last, D.phi_step, D.theta_step, D.nacc, D.natt);  // no-op unless a boundary
+      if (adapt_on && to_adapt == wlen) adapt_apply(P, D.phi_step, D.theta_step, D.nacc, D.natt);  // step_last is a boundary
     }
     __syncwarp();
-    if (a.stepout > 0 && (step_last % a.stepout) == 0) {
+    if (adapt_on && (to_adapt -= wlen) == 0) to_adapt = spa;
+    bool isrow = false;
+    if (a.stepout > 0 && (to_row -= wlen) == 0) { to_row = a.stepout; isrow = true; }
+    if (isrow) {
       double tot[kNumAcc];
 #pragma unroll
       for (int k = 0; k < kNumAcc; ++k) {

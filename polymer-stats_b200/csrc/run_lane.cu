@@ -28,7 +28,7 @@ int launch_run_lane(pmc_handle* h, const RunArgs& a) {
     else { if (comp) PMC_W(0, MB, true) else PMC_W(0, MB, false) }        \
   }
 #ifdef PMC_TUNING_VARIANTS
-      if (mb == 3) PMC_WSEL(3) else if (mb == 2) PMC_WSEL(2) else
+      if (mb == 3) PMC_WSEL(3) else if (mb == 2) PMC_WSEL(2) else if (mb == 5) PMC_WSEL(5) else if (mb == 6) PMC_WSEL(6) else
 #endif
       PMC_WSEL(4)
 #undef PMC_WSEL

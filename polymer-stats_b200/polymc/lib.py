@@ -14,7 +14,8 @@ import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG_DIR)                      # polymer-stats_b200/
-LIB_PATH = os.path.join(_ROOT, "libpolymc_b200.so")
+# PMC_LIB_PATH: an experiment build of the same library (tools/tune_*.py A/B runs); never a different implementation
+LIB_PATH = os.environ.get("PMC_LIB_PATH") or os.path.join(_ROOT, "libpolymc_b200.so")
 CSRC_DIR = os.path.join(_ROOT, "csrc")
 
 CHAIN_TYPES = {"dielectric": 0, "polar": 1}
@@ -88,6 +89,41 @@ def make_case(n=100, E0=0.0, K1=1.0, K2=0.0, mu=1e-2, kT=1.0, Fz=0.0, Fx=0.0, b=
                    int(do_flips), int(umbrella), int(force_init), int(accum_mode),
                    kappa, psi0, cutoff_radius, cluster_prob, int(clustering), int(alpha_carry), int(cutoff_full),
                    int(planar))
+
+
+class CaseTable:
+    """A contiguous array of `pmc_case` records — the form `pmc_create` takes, so handles are created from slices of it
+    without copying, and the (n, energy_type) bucketing of a large sweep is vectorised.  Behaves like a read-only
+    sequence of PmcCase; built once from a list (a phase-diagram grid has tens of thousands of cases)."""
+
+    def __init__(self, cases=None, _rec=None):
+        if _rec is not None:
+            self.rec = _rec
+        elif isinstance(cases, CaseTable):
+            self.rec = cases.rec
+        else:
+            cases = [cases] if isinstance(cases, PmcCase) else list(cases)
+            arr = (PmcCase * len(cases))(*cases)
+            self.rec = np.frombuffer(arr, dtype=np.dtype(PmcCase)).copy() if cases else np.zeros(0, np.dtype(PmcCase))
+
+    def __len__(self):
+        return int(self.rec.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return CaseTable(_rec=self.rec[i])
+        return PmcCase.from_buffer_copy(self.rec[i].tobytes())
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def column(self, name):
+        return self.rec[name]
+
+    def pointer(self):
+        rec = self.rec if self.rec.flags["C_CONTIGUOUS"] else np.ascontiguousarray(self.rec)
+        self._keep = rec
+        return C.cast(rec.ctypes.data, C.POINTER(PmcCase))
 
 
 def build(force: bool = False) -> str:
@@ -238,9 +274,9 @@ class Ensemble:
     def __init__(self, cases, replicas=1, seed=0, device=0, chain_id_base=0, ensemble_chains=0):
         if isinstance(cases, PmcCase):
             cases = [cases]
-        self.cases = list(cases)
+        self.cases = cases if isinstance(cases, CaseTable) else list(cases)
         self.replicas = int(replicas)
-        arr = (PmcCase * len(self.cases))(*self.cases)
+        arr = self.cases.pointer() if isinstance(cases, CaseTable) else (PmcCase * len(self.cases))(*self.cases)
         h = C.c_void_p()
         _check(load().pmc_create(arr, len(self.cases), self.replicas, seed, device, chain_id_base, C.byref(h)))
         self._h = h

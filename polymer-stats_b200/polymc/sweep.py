@@ -28,6 +28,13 @@ def shard_range(total: int, rank: int, world: int):
 def bucket_cases(cases):
     """Group case indices by (n, energy_type): one handle/kernel per bucket (include/polymc.h)."""
     buckets = OrderedDict()
+    if isinstance(cases, lib.CaseTable):   # vectorised: a phase-diagram grid has tens of thousands of cases
+        ns, es = cases.column("n"), cases.column("energy_type")
+        key = ns.astype(np.int64) * 8 + es.astype(np.int64)
+        uniq, first = np.unique(key, return_index=True)
+        for k in uniq[np.argsort(first)].tolist():   # buckets in order of first appearance, like the loop below
+            buckets[(int(k // 8), int(k % 8))] = np.flatnonzero(key == k)
+        return buckets
     for i, c in enumerate(cases):
         buckets.setdefault((int(c.n), int(c.energy_type)), []).append(i)
     return buckets
@@ -60,12 +67,16 @@ def gather_rows(local: np.ndarray, total_rows: int, lo: int, device=None) -> np.
     t = torch.from_numpy(pad)
     if device is not None:
         t = t.to(device)
-    outs = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(outs, t)
+    out = torch.empty((world * maxrows, k), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)        # one collective (concatenated form: NCCL and gloo), one copy back
+    out = out.cpu().numpy()
+    if total_rows == world * maxrows:          # equal shards: the gathered buffer is the result
+        return out
+    out = out.reshape(world, maxrows, k)
     full = np.empty((total_rows, k))
     for r in range(world):
         a, b = shard_range(total_rows, r, world)
-        full[a:b] = outs[r].cpu().numpy()[: b - a]
+        full[a:b] = out[r, : b - a]
     return full
 
 
@@ -107,7 +118,8 @@ def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
     protocol None: `nsteps` trials of mcmc_eap_chain.jl's loop.  protocol = dict(burn_in=…, schedule=[…]):
     the clustering driver's ladder (mcmc_clustering_eap_chain.jl:365-386) — a burn-in stage per kT
     multiplier, then `nsteps` production trials at kT."""
-    cases = list(cases)
+    if not isinstance(cases, lib.CaseTable):
+        cases = list(cases)
     out = []
     for (_, _), idxs in bucket_cases(cases).items():
         # global chain ids of this bucket, case-major
@@ -150,6 +162,12 @@ def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
 
 def assemble(total: int, parts):
     """dict of result arrays from [(gids, full [len(gids)][NCOL]), ...]."""
+    if len(parts) == 1 and len(parts[0][0]) == total:
+        gids, full = parts[0]
+        if total == 0 or (gids[0] == 0 and gids[-1] == total - 1 and np.all(np.diff(gids) == 1)):
+            # one bucket holding every chain in order (the usual sweep): columns of the gathered block, no scatter
+            return {"avg": full[:, :16], "acc_rate": full[:, 16], "normalizer": full[:, 17], "sums": full[:, 18:35],
+                    "extra_sums": full[:, 35:37]}
     res = {"avg": np.full((total, 16), np.nan), "acc_rate": np.full(total, np.nan),
            "normalizer": np.full(total, np.nan), "sums": np.full((total, 17), np.nan),
            "extra_sums": np.full((total, 2), np.nan)}
@@ -170,7 +188,8 @@ def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
     dist = _dist()
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
-    cases = list(cases)
+    if not isinstance(cases, lib.CaseTable):
+        cases = list(cases)
     parts = []
     for gids, lo, block in run_shard(cases, replicas, nsteps, stepout, seed, device, rank, world, protocol, bit_identical):
         parts.append((gids, gather_rows(block, len(gids), lo, device=torch_device)))

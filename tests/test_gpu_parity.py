@@ -337,6 +337,10 @@ def test_sweep_is_independent_of_gpu_count(pm):
         many = sweep.assemble(total, [(np.array(k), v) for k, v in parts.items()])
         for key in ("avg", "acc_rate", "normalizer", "sums"):
             np.testing.assert_array_equal(many[key], one[key])
+    # the same sweep from a contiguous case table (handles created from slices of it, vectorised bucketing)
+    tab = sweep.run_sweep(pm.CaseTable(cases), replicas, 2000, seed=99, bit_identical=True)
+    for key in ("avg", "acc_rate", "normalizer", "sums"):
+        np.testing.assert_array_equal(tab[key], one[key])
 
 
 def test_mixed_cases_in_one_handle(pm, O):

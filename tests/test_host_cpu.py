@@ -234,6 +234,32 @@ def test_bucket_and_shard(pm):
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_case_table_is_a_contiguous_list_of_cases(pm):
+    """CaseTable: same buckets and items as the list it was built from; slices are views (no copy at pmc_create)."""
+    import numpy as np
+    from polymc import sweep
+    cases = [pm.make_case(n=100, Fz=0.1 * i, energy_type=("noninteracting", "Ising")[i % 2]) for i in range(9)]
+    cases.insert(4, pm.make_case(n=64, energy_type="interacting"))
+    tab = pm.CaseTable(cases)
+    assert len(tab) == 10 and tab[3].Fz == cases[3].Fz and tab[4].n == 64 and tab[-1].energy_type == cases[-1].energy_type
+    assert [c.Fz for c in tab] == [c.Fz for c in cases]
+    bl, bt = sweep.bucket_cases(cases), sweep.bucket_cases(tab)
+    assert list(bl.keys()) == list(bt.keys())
+    for k in bl:
+        assert list(bl[k]) == bt[k].tolist()
+    sl = tab[2:6]
+    assert len(sl) == 4 and sl[2].n == 64 and np.shares_memory(sl.rec, tab.rec)
+    assert ctypes.addressof(sl.pointer().contents) == tab.rec[2:].ctypes.data
+    assert len(pm.CaseTable([])) == 0 and len(pm.CaseTable(cases[0])) == 1
+    # assemble: the single in-order bucket is returned as columns of the gathered block
+    full = np.arange(10 * sweep.NCOL, dtype=float).reshape(10, sweep.NCOL)
+    res = sweep.assemble(10, [(np.arange(10), full)])
+    assert np.shares_memory(res["avg"], full) and res["sums"].shape == (10, 17) and res["acc_rate"][3] == full[3, 16]
+    perm = np.arange(10)[::-1].copy()
+    res2 = sweep.assemble(10, [(perm, full)])
+    assert np.array_equal(res2["avg"][perm], full[:, :16])
+
+
 def test_planar_cli_table_matches_reference(pm):
     """Every option of 2D/mcmc_clustering_eap_chain.jl:19-133: same long/short names, types and defaults."""
     import json

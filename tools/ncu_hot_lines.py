@@ -14,8 +14,13 @@ ci = {h: i for i, h in enumerate(hdr)}
 inst = [r for r in rows[2:] if len(r) == len(hdr)]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
+dis = []   # one cubin per translation unit: take the one that holds the kernel
+for f in sorted(os.listdir(tmp)):
+    if f.endswith(".cubin"):
+        d = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if kern in d:
+            dis = d.split("\n")
+            break
 lines, cur, inside = [], ("?", 0), False
 for ln in dis:
     if ln.startswith("//---------------------"):
