@@ -31,6 +31,8 @@ int launch_run_cluster_cta(pmc_handle* h, const RunArgs& a) {
     if (ccfg == 3216) PMC_CL(32, 16)
     else if (ccfg == 3214) PMC_CL(32, 14)
     else if (ccfg == 3212) PMC_CL(32, 12)
+    else if (ccfg == 3210) PMC_CL(32, 10)
+    else if (ccfg == 3208) PMC_CL(32, 8)
     else if (ccfg == 6408) PMC_CL(64, 8)
     else if (ccfg == 6410) PMC_CL(64, 10)
     else if (ccfg == 6406) PMC_CL(64, 6)

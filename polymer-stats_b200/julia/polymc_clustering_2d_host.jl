@@ -11,9 +11,8 @@
 # host keeps the x ("1") and z ("3") columns.  As upstream, every `mcmc()` call starts from a NEW random chain
 # (`chain = EAPChain(pargs)`, :151): `pmc_begin_stage` on a planar handle redraws the chain.
 #
-# NOTE: Julia is not installed in the image this repository is built and tested in, so this file has not
-# been executed there; the Python twin (../polymc/mcmc_clustering_2d.py) runs the identical call sequence
-# under test.  See INTEGRATION.md §4.
+# NOTE: no Julia runtime in the build image; tools/minijl executes this file against the real library (ccall through
+# ctypes) and tests/test_gpu_julia_hosts.py compares stdout and both CSV files with the Python twin byte for byte.
 using ArgParse, Printf, DelimitedFiles
 include(joinpath(@__DIR__, "polymc_host.jl"))   # PmcCase, check, LIBPOLYMC
 

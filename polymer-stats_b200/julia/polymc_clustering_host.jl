@@ -6,9 +6,8 @@
 #   pmc_create [+ pmc_init_x0]  →  for each kT multiplier: pmc_begin_stage, pmc_run_ex  →  pmc_begin_stage(1),
 #   pmc_run_ex with rows  →  pmc_accumulators, pmc_extra_accumulators, pmc_diagnostics.
 #
-# NOTE: Julia is not installed in the image this repository is built and tested in, so this file has not
-# been executed there; the Python twin (../polymc/mcmc_clustering.py) runs the identical call sequence
-# under test.  See INTEGRATION.md.
+# NOTE: no Julia runtime in the build image; tools/minijl executes this file against the real library (ccall through
+# ctypes) and tests/test_gpu_julia_hosts.py compares stdout and both CSV files with the Python twin byte for byte.
 using ArgParse, Printf, DelimitedFiles
 include(joinpath(@__DIR__, "polymc_host.jl"))   # PmcCase, check, LIBPOLYMC
 

@@ -4,11 +4,12 @@
 # mcmc_eap_chain.jl:19-153), same 10 stdout lines (:386-395), same two CSV files (:256-259), but the
 # body of `mcmc(nsteps, pargs)` (:171-376) is a handful of `ccall`s into the CUDA library.
 #
-# NOTE: Julia is not installed in the image this repository is built and tested in, so this file
-# has not been executed by a Julia runtime there.  What IS checked (tests/test_host_cpu.py): it parses (tools/minijl,
-# the Julia-subset parser that also runs the reference sources for the fixtures), every `ccall` names an entry point
-# of include/polymc.h with the right number and kinds of arguments, and `PmcCase` mirrors `pmc_case` field by field.
-# The Python twin (../polymc/mcmc.py) exercises the identical C ABI call sequence under test.  See INTEGRATION.md.
+# NOTE: Julia is not installed in the image this repository is built and tested in.  This file IS executed there all the
+# same: tools/minijl (the Julia-subset interpreter that also runs the unmodified reference sources for the fixtures) runs it
+# with `ccall` marshalled through ctypes into the real libpolymc_b200.so — `python -m minijl polymc_host.jl <options>` with
+# tools/ on PYTHONPATH.  tests/test_gpu_julia_hosts.py: stdout and both CSV files equal the Python twin's
+# (../polymc/mcmc.py) byte for byte on the GPU; tests/test_julia_hosts_cpu.py: against a stand-in library without a GPU
+# (case struct field by field, call sequence, pooling, formatting).  See INTEGRATION.md.
 using ArgParse, Printf, DelimitedFiles, Logging
 
 const LIBPOLYMC = get(ENV, "POLYMC_LIB", joinpath(@__DIR__, "..", "libpolymc_b200.so"))

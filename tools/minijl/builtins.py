@@ -293,6 +293,18 @@ def transpose(x):
     return x.T.copy()
 
 
+def permutedims(x, perm=None):
+    """permutedims(v) of a vector is the 1×n row matrix; of a matrix, its (non-recursive) transpose."""
+    if isinstance(x, (JList, list)):
+        x = np.array(list(x), dtype=object if any(isinstance(e, str) for e in x) else None)
+    x = _arr(x)
+    if perm is not None:
+        return np.asfortranarray(np.transpose(x, [int(p) - 1 for p in iterate(perm)]))
+    if x.ndim == 1:
+        return x.reshape(1, -1)
+    return np.asfortranarray(x.T)
+
+
 def jl_copy(x):
     if isinstance(x, np.ndarray):
         return x.copy()
@@ -450,8 +462,16 @@ def split(s, sep=None):
     return JList(parts)
 
 
-def jl_open(path, mode="r"):
-    return open(path, mode, encoding="utf-8")
+def jl_open(*a):
+    """open(path[, mode]) or the do-block form open(f, path[, mode]): f(io), then close — also when f throws."""
+    if a and not isinstance(a[0], str):
+        f, rest = a[0], a[1:]
+        io = open(rest[0], rest[1] if len(rest) > 1 else "r", encoding="utf-8")
+        try:
+            return _interp.call(f, [io])
+        finally:
+            io.close()
+    return open(a[0], a[1] if len(a) > 1 else "r", encoding="utf-8")
 
 
 def jl_close(io):
@@ -594,6 +614,21 @@ def add_arg_table(settings: ArgSettings, entries, env):
         settings.entries.append((names, props))
 
 
+def add_arg_table_fn(settings: ArgSettings, *rest):
+    """The function form: add_arg_table!(s, "--opt" | ["--opt", "-o"], Dict(:arg_type => T, :default => v), …)."""
+    k = 0
+    while k < len(rest):
+        names = rest[k]
+        names = [names] if isinstance(names, str) else [n for n in iterate(names)]
+        props = {}
+        if k + 1 < len(rest) and isinstance(rest[k + 1], dict):
+            props = {(key.name if isinstance(key, Sym) else key): v for key, v in rest[k + 1].items()}
+            k += 1
+        settings.entries.append((names, props))
+        k += 1
+    return settings
+
+
 def parse_args(*a):
     settings = a[-1]
     argv = list(a[0]) if len(a) == 2 else list(_interp.genv.vars["ARGS"])
@@ -681,7 +716,7 @@ def install(interp: Interp):
         "div": lambda a, b: (abs(a) // abs(b)) * (1 if (a >= 0) == (b >= 0) else -1), "iseven": lambda x: x % 2 == 0, "isodd": lambda x: x % 2 == 1,
         "zeros": zeros, "ones": ones, "fill": fill, "length": length, "size": size, "sum": jl_sum, "prod": jl_prod,
         "cumsum": cumsum, "map": jl_map, "foreach": foreach, "dot": dot, "hcat": hcat, "vcat": vcat, "reshape": reshape,
-        "transpose": transpose, "copy": jl_copy, "deepcopy": jl_copy, "view": view, "collect": collect, "findnext": findnext,
+        "transpose": transpose, "permutedims": permutedims, "copy": jl_copy, "deepcopy": jl_copy, "view": view, "collect": collect, "findnext": findnext,
         "findfirst": findfirst, "push!": push_, "popfirst!": popfirst_, "pop!": pop_, "append!": append_, "empty!": empty_,
         "isempty": isempty, "eigvals": eigvals, "norm": norm, "maximum": jl_maximum, "minimum": jl_minimum, "any": jl_any,
         "all": jl_all, "first": first, "last": last, "vec": lambda x: _arr(x).reshape(-1, order="F").copy(),
@@ -693,7 +728,7 @@ def install(interp: Interp):
         "error": jl_error, "exit": jl_exit, "typeof": jl_typeof, "isa": jl_isa, "isnothing": lambda x: x is None,
         "convert": convert, "eval": jl_eval, "haskey": haskey, "get": jl_get, "keys": jl_keys, "values": jl_values,
         "include": include, "rand": jl_rand, "time": _time.time, "isapprox": jl_isapprox,
-        "ArgParseSettings": lambda *a, **k: ArgSettings(), "parse_args": parse_args,
+        "ArgParseSettings": lambda *a, **k: ArgSettings(), "parse_args": parse_args, "add_arg_table!": add_arg_table_fn,
         "global_logger": global_logger, "ConsoleLogger": console_logger,
         "Meta": ModuleNS("Meta", {"parse": parse_expression}),
         "Logging": ModuleNS("Logging", {"Info": LogLevel(0), "Warn": LogLevel(1000), "Error": LogLevel(2000),

@@ -85,6 +85,9 @@ class JStruct:
         return f"{self.jtype.name}({', '.join(jl_repr(v) for v in self.f.values())})"
 
 
+_FIXED_INTS = ("Int32", "UInt32", "UInt64", "Int8", "UInt8")
+
+
 class Sym:
     def __init__(self, name):
         self.name = name
@@ -258,7 +261,10 @@ class Interp:
         self._init_types()
         from . import builtins as B
         B.install(self)
+        from . import ffi as F
+        F.install(self)
         self.genv.vars["ARGS"] = JList(argv or [])
+        self.genv.vars["PROGRAM_FILE"] = ""
 
     # ---- types ---------------------------------------------------------------------------------------------------
     def _init_types(self):
@@ -448,6 +454,11 @@ class Interp:
         finally:
             self.cur_file.pop()
 
+    def run_main(self, path):
+        """`julia path args…`: PROGRAM_FILE is the script, so its `abspath(PROGRAM_FILE) == @__FILE__ && main()` fires."""
+        self.genv.vars["PROGRAM_FILE"] = os.path.abspath(path)
+        return self.run_file(path)
+
     def run_string(self, src, name="<string>"):
         ast = parse(src, name)
         res = None
@@ -550,6 +561,8 @@ class Interp:
             return float(v)
         if ft is self.types["Float64"] and isinstance(v, bool):
             return float(v)
+        if getattr(ft, "name", None) in _FIXED_INTS and isinstance(v, (int, bool)):
+            return self.convert_to(ft, [v])     # range-checked; values of every integer width are Python ints here
         return v
 
     def construct(self, t: JType, args, kwargs=None):
@@ -570,7 +583,7 @@ class Interp:
         for name, ft, a in zip(t.fields, t.ftypes, args):
             if isinstance(ft, (JType, JTypeApp)):
                 a = self.convert_field(ft, a)
-                if not self.isa(a, ft):
+                if not (getattr(ft, "name", None) in _FIXED_INTS and isinstance(a, int)) and not self.isa(a, ft):
                     raise JlError(f"MethodError: Cannot `convert` an object of type {self.full_typeof(a)} to an object of "
                                   f"type {ft} (field {name} of {t.name})")
             f[name] = a
@@ -583,6 +596,20 @@ class Interp:
         T = self.types
         if base is T["Dict"]:
             return self._dict_ctor(*args)
+        if base.name == "Ref":
+            return self.ffi_ref(args[0] if args else None, t.params[0] if t.params else None)
+        if base in (T["Array"], T["Vector"], T["AbstractVector"], T["Matrix"]) and args and args[0] is None and \
+                self.genv.vars.get("undef", 0) is None:
+            # Array{T}(undef, dims...): uninitialised column-major storage
+            el = t.params[0] if t.params else T["Float64"]
+            dt = {"Float64": np.float64, "Int64": np.int64, "Int32": np.int32, "UInt32": np.uint32, "UInt64": np.uint64,
+                  "Bool": np.bool_, "Float32": np.float32}.get(getattr(el, "name", None))
+            if dt is None:
+                raise JlError(f"unsupported element type in {t}(undef, ...)")
+            dims = args[1:]
+            if len(dims) == 1 and isinstance(dims[0], tuple):
+                dims = dims[0]
+            return np.zeros(tuple(int(d) for d in dims), dtype=dt, order="F")
         if base in (T["Vector"], T["AbstractVector"]) and len(args) == 0:
             out = JList()
             out.eltype = t.params[0] if t.params else None
@@ -599,6 +626,9 @@ class Interp:
                 return out
         raise JlError(f"unsupported constructor call {t}")
 
+    def ffi_ref(self, value, eltype):
+        return self.JRef(value, eltype)
+
     def convert_to(self, t: JType, args):
         T = self.types
         if len(args) == 1:
@@ -608,6 +638,17 @@ class Interp:
                 if isinstance(x, np.ndarray):
                     return x.astype(np.float64)
                 return float(x)
+            if t.name in ("Int32", "UInt32", "UInt64", "Int8", "UInt8"):
+                if isinstance(x, float) and x != math.floor(x):
+                    raise JlError(f"InexactError: {t.name}({x})")
+                v = int(x)
+                lo, hi = {"Int32": (-2 ** 31, 2 ** 31 - 1), "UInt32": (0, 2 ** 32 - 1), "UInt64": (0, 2 ** 64 - 1),
+                          "Int8": (-128, 127), "UInt8": (0, 255)}[t.name]
+                if not lo <= v <= hi:
+                    raise JlError(f"InexactError: {t.name}({x})")
+                return v
+            if t.name in ("Ref",):
+                return self.ffi_ref(x, None)
             if t in (T["Int64"], T["Signed"], T["Integer"]):
                 if isinstance(x, float):
                     if x != math.floor(x):
@@ -1446,7 +1487,29 @@ def _norm_index(i, dimlen):
     raise JlError(f"ArgumentError: invalid index {i!r}")
 
 
+def _getindex_nd(o, idxs):
+    """A[i, j, k, …] with scalars, ranges and colons in any position (trailing 1s allowed, as in Julia)."""
+    while len(idxs) > o.ndim and idxs[-1] == 1:
+        idxs = idxs[:-1]
+    if len(idxs) != o.ndim:
+        raise JlError(f"unsupported indexing of a {o.ndim}-d array with {len(idxs)} indices")
+    norm = [_norm_index(i, o.shape[k]) for k, i in enumerate(idxs)]
+    if all(sc for _, sc in norm):
+        return o[tuple(ix for ix, _ in norm)].item()
+    sel = np.ix_(*[np.atleast_1d(np.arange(o.shape[k])[ix] if not isinstance(ix, np.ndarray) else ix) for k, (ix, _) in enumerate(norm)])
+    r = o[sel]
+    keep = tuple(k for k, (_, sc) in enumerate(norm) if not sc)
+    r = r.reshape([r.shape[k] for k in keep])
+    return np.asfortranarray(r).copy(order="F") if r.ndim > 1 else r.copy()
+
+
 def getindex(o, idxs):
+    if hasattr(o, "value") and type(o).__name__ == "JRef":
+        if idxs:
+            raise JlError("Ref is indexed with r[]")
+        return o.value
+    if isinstance(o, np.ndarray) and (o.ndim > 2 or (len(idxs) > 2 and o.ndim == 2)):
+        return _getindex_nd(o, list(idxs))
     if isinstance(o, np.ndarray):
         if len(idxs) == 1:
             i = idxs[0]
@@ -1509,6 +1572,11 @@ def getindex(o, idxs):
 
 
 def setindex(o, v, idxs):
+    if hasattr(o, "value") and type(o).__name__ == "JRef":
+        if idxs:
+            raise JlError("Ref is assigned with r[] = v")
+        o.value = v
+        return
     if isinstance(o, np.ndarray):
         if isinstance(v, JRange):
             v = np.array(list(v))

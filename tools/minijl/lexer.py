@@ -165,6 +165,13 @@ def lex(src: str):
             i = j
             continue
         if ch.isdigit() or (ch == "." and i + 1 < n and src[i + 1].isdigit() and not prev_is_value()):
+            if ch == "0" and i + 1 < n and src[i + 1] in "xX":   # hexadecimal literal (an unsigned integer in Julia)
+                j = i + 2
+                while j < n and (src[j] in "0123456789abcdefABCDEF_"):
+                    j += 1
+                push("num", int(src[i + 2:j].replace("_", ""), 16))
+                i = j
+                continue
             j = i
             while j < n and (src[j].isdigit() or src[j] == "_"):
                 j += 1
