@@ -76,9 +76,12 @@ struct pmc_handle {
   int sm_count = 148;
   int64_t shape_chains = 0;   // ensemble size the launch shape is chosen for (0 = nchains), pmc_set_ensemble_hint
   int ws_cfg = 0;             // warp-specialised run kernel variant (0 = classic kernel)
-  long long warp_mode_below = 20000;
+  // O(1)-ΔU chains of the plain driver: one chain per warp below this many chains, else one per lane.  Measured
+  // crossover (profiles/r02c_tune_lane_vs_warp.txt): non-interacting 14.8 vs 12.6 G updates/s at 65 536 chains and 14.5 vs
+  // 17.5 at 262 144; Ising level at 65 536.  Set from the energy type in launch_run_lane.
+  long long warp_mode_below = 0;
   long long warp_cluster_below = 11000;  // composite trials: chain per warp below this many chains, else per lane
-  int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)  // chain count under which O(1)-ΔU chains run one per warp
+  int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)
   int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;
   bool dyn_fresh = false, dynx_fresh = false;   // the host copies equal the device's (no launch since they were fetched)

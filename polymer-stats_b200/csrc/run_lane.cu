@@ -9,7 +9,8 @@ int fail(int code, const std::string& msg) { return pmc_fail(code, msg); }
 int launch_run_lane(pmc_handle* h, const RunArgs& a) {
     // few chains: one chain per warp with 32-trial windows fills the machine; many chains: one per lane
     const int mode = env_int("PMC_LANE_MODE", 0);  // 1 = lane, 2 = warp, 0 = by chain count
-    const bool use_warp = mode == 2 || (mode == 0 && packing_chains(h) < h->warp_mode_below);
+    const long long below = h->warp_mode_below > 0 ? h->warp_mode_below : (h->energy_type == PMC_ENERGY_ISING ? 65536 : 120000);
+    const bool use_warp = mode == 2 || (mode == 0 && packing_chains(h) < below);
     // PMC_LANE_CFG = minblocks*10 + compensated selects a tuning variant (experiments only)
     const int lcfg = env_int("PMC_LANE_CFG", -1);
     const bool comp = lcfg >= 0 ? (lcfg % 10) != 0 : h->compensated != 0;

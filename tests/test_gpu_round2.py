@@ -125,7 +125,7 @@ def test_packing_follows_the_ensemble_hint(pm):
     block size does, so a shard of a large sweep runs the kernel the whole ensemble would and its results are
     bit-identical to the unsharded run — across the lane/warp threshold."""
     c = pm.make_case(n=16, E0=1.0, Fz=0.5, energy_type="Ising")
-    R = 24576                                  # above the chain-per-lane threshold
+    R = 81920                                  # above the chain-per-lane threshold (65 536 for Ising chains)
     with pm.Ensemble(c, replicas=R, seed=6) as whole:
         assert whole.kernel_name().startswith("k_run_lane<")
         whole.run(400, 0)
