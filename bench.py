@@ -69,6 +69,10 @@ def c4_grid():
 WORKLOADS = {
     "C2": dict(cases=[C2_KW], replicas=4096, S=500, stepout=500, scaling="weak", e2e="state",
                desc="C2: interacting dielectric chains n=512, 4096 replicas per GPU"),
+    # opt-in precision of north_star's "ΔU in fp64, or in fp32 with a stated tolerance" (pmc_set_pair_precision): the
+    # rectangle of every trial in FP32, state / row / acceptance / accumulators FP64.  Never the headline.
+    "C2f32": dict(cases=[C2_KW], replicas=4096, S=500, stepout=500, scaling="weak", e2e="state", precision="fp32",
+                  desc="C2 with the FP32 rectangle (stated tolerance: include/polymc.h pmc_set_pair_precision)"),
     "C3": dict(cases=c3_grid(), replicas=64, S=500, stepout=500, scaling="weak", e2e="sweep",
                desc="C3: polar chains n=512 with dipole-dipole coupling, 4 mu x 4 E0 x 4 Fz sweep (64 points) x 64 replicas "
                     "per GPU"),
@@ -309,6 +313,9 @@ def measure(cx: Ctx, name: str, steps: int, warmup: int, want_e2e=True, chains_o
     cases = [pm.make_case(**kw) for kw in my_cases]
     ens = pm.Ensemble(cases, replicas=rep, seed=SEED, device=cx.local_rank, chain_id_base=base)
     ens.set_stream(cx.stream.cuda_stream)
+    fp32 = W.get("precision") == "fp32"
+    if fp32:
+        ens.set_pair_precision("fp32")
     kernel = ens.kernel_name()
     if clustering:
         ens.begin_stage(1.0)   # a fresh mcmc(nsteps, pargs, chain) call (mcmc_clustering_eap_chain.jl:171-265)
@@ -367,6 +374,13 @@ def measure(cx: Ctx, name: str, steps: int, warmup: int, want_e2e=True, chains_o
         "flop_per_update": F, "updates_per_launch": mine * S, "kernel_ms_avg": kavg_ms,
         "kernel_share_of_step": kavg_ms * len(kernel_ms) / sum(step_ms),
     }
+    if fp32:   # the rectangle runs on the FP32 pipe: 128 FMA per clock per SM (no measured FP32 figure in MEASURED_PEAKS.json)
+        peak32 = 148 * 128 * 2 * 1.965e9 / 1e12
+        roofline.update({"bound": "fp32", "peak": peak32, "frac": achieved_tf / peak32, "peak_derived": peak32,
+                         "frac_of_derived": achieved_tf / peak32,
+                         "peak_source": "derived: 148 SMs x 128 FP32 FMA per clock x 1.965 GHz",
+                         "tolerance": "relative error <= 5e-7 (1 + amplification) per pair term, include/polymc.h; "
+                                      "tests/test_gpu_fp32.py"})
     if not pair_bound:
         roofline["note"] = ("O(1)-energy chains are latency / transcendental bound (2 Philox, 2 sincos, log, exp per trial): "
                             "the flop fraction is informational, updates/s is the figure (SURVEY §8d)")
@@ -569,8 +583,9 @@ def main():
     workloads, strong, multi_abi = {}, {}, None
     if extras:
         xs = max(2, min(args.steps, 3))
-        for nm in ("C3", "C4", "C5", "K1"):
+        for nm in ("C3", "C4", "C5", "K1", "C2f32"):
             workloads[nm] = measure(cx, nm, xs, 3, want_e2e=not args.no_e2e)
+        workloads["C2f32"]["dtype"] = "f32 rectangle pair terms; f64 state, row terms, acceptance and accumulators (opt-in, not the headline)"
         workloads["C4"]["limiter"] = ("device-timed: latency / transcendental bound (2 Philox, 2 sincos, log, exp per trial); e2e through "
                                       "run_sweep: a fixed ~8-25 ms per call of handle set-up, result fetch and gather next to a kernel that "
                                       "shrinks with the GPU count (21 ms per call at 8 GPUs)")

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PMC_ABI_VERSION 3
+#define PMC_ABI_VERSION 4
 
 typedef enum pmc_status {
   PMC_OK = 0,
@@ -111,6 +111,28 @@ int64_t pmc_num_monomers(const pmc_handle* h);
  * (polymc.sweep does); 0 = this handle's own chain count (the default).  No counterpart in the reference (its
  * launchers run one single-threaded process per case, run/K1_Fz_long.jl:45). */
 int32_t pmc_set_ensemble_hint(pmc_handle* h, int64_t ensemble_chains);
+/* Precision of the dipole–dipole pair sums of a single-monomer trial (ABI v4).  PMC_PAIR_FP64 (the default) evaluates
+ * every changed pair in FP64 — the reference's Float64 (inc/eap_chain.jl:196-211).  PMC_PAIR_FP32 evaluates the
+ * RECTANGLE of a trial — the idx·(n−1−idx) pairs (i < idx < j) whose dipoles are unchanged and whose separation
+ * changes by the rigid translation of the tail — in FP32 from positions mirrored relative to the rotated monomer, and
+ * everything else (the row {idx}×rest, state, running energy, acceptance test, accumulators) in FP64 as before.
+ * Stated tolerance (tests/test_gpu_fp32.py): every pair term of the rectangle carries an error of at most
+ * 2e-6 · (1 + a) · m, m = (|μi·μj| + 3|μi·r̂||μj·r̂|) / (4π r³) the magnitude of its two parts, a = (|r| + |D|) / |r − D|
+ * for the new term (a ≲ 2 unless the trial brings the two monomers much closer than they were — then the new term is
+ * huge and decides the trial by itself) and a = 0 for the old one, i.e.
+ * |ΔU_fp32 − ΔU_fp64| ≤ 2e-6 · Σ_pairs (m_old + (1 + a) m_new): a few 1e-6 of the pair-term magnitudes of the trial.
+ * Use it while that is small against kT — extended or coiled chains.  Chains that have collapsed onto themselves
+ * (|U| of 1e5 kT and more, where point dipoles without excluded volume end up at low temperature) need FP64; the
+ * library re-synchronises the running energy with an FP64 evaluation after every FP32 launch and pmc_diagnostics
+ * column 7 reports the largest drift it found, a direct measure of the accumulated error.  Averages agree with the FP64
+ * path within 3σ and a few hundred trials reproduce its decisions (same test); long trajectories are not
+ * decision-identical.  Served by the windowed CTA-per-chain kernel of interacting chains of the plain
+ * driver on one SM per chain (n ≤ 768 in a full ensemble); every other launch ignores the setting and stays FP64.  pmc_pair_precision returns what the
+ * next pmc_run will use.  No counterpart in the reference. */
+#define PMC_PAIR_FP64 0
+#define PMC_PAIR_FP32 1
+int32_t pmc_set_pair_precision(pmc_handle* h, int32_t mode);
+int32_t pmc_pair_precision(const pmc_handle* h);
 int32_t pmc_block_threads(const pmc_handle* h);   /* the block size in use (diagnostics) */
 /* Work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
 int32_t pmc_set_stream(pmc_handle* h, void* cuda_stream);
@@ -243,6 +265,7 @@ const char* pmc_multi_gather_backend(const pmc_multi* m);   /* "nccl", "peer" or
  * pmc_reinit, pmc_checkpoint_*, ...), the device it lives on and its block of global chain ids. */
 pmc_handle* pmc_multi_shard(pmc_multi* m, int32_t slot, int32_t* device, int64_t* first_chain, int64_t* nchains);
 int32_t pmc_multi_set_ensemble_hint(pmc_multi* m, int64_t ensemble_chains);
+int32_t pmc_multi_set_pair_precision(pmc_multi* m, int32_t mode);   /* pmc_set_pair_precision on every device handle */
 int32_t pmc_multi_begin_stage(pmc_multi* m, double kT_scale);
 int32_t pmc_multi_set_state_all(pmc_multi* m, const double* phi, const double* theta);   /* [chains][n] */
 int32_t pmc_multi_get_state_all(pmc_multi* m, double* phi, double* theta);

@@ -387,6 +387,13 @@ __device__ __forceinline__ double cta_delta_pairs(const CtaView& S, int n, int e
   return block_sum<T>(acc, S.part, /*trailing_sync=*/false);
 }
 
+}  // namespace pmc
+
+#define PMC_CTA_BUILDING_BLOCKS 1
+#include "cta_f32.cuh"
+
+namespace pmc {
+
 // ---------------------------------------------------------------------------------------------
 // Kernels
 // ---------------------------------------------------------------------------------------------
@@ -551,15 +558,18 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "mem
 constexpr int kWin = 32;
 
 __host__ __device__ inline size_t cta_smem_bytes_win(int n) {
-  return cta_smem_bytes(n) + kWin * sizeof(Proposal) + 16;
+  return (cta_smem_bytes(n) + kWin * sizeof(Proposal) + 16 + 15) & ~(size_t)15;
 }
+__host__ __device__ inline size_t cta_smem_bytes_win_f32(int n) { return cta_smem_bytes_win(n) + f32_smem_bytes(n); }
 
-template <int T, int MINB, int UNROLL = 2>
+// PREC = 1: the rectangle of every trial in FP32 (cta_f32.cuh; pmc_set_pair_precision), everything else as PREC = 0.
+template <int T, int MINB, int UNROLL = 2, int PREC = 0>
 __global__ void __launch_bounds__(T, MINB) k_run_cta_win(const RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const CtaView S = carve(smem_raw, a.n);
   Proposal* win = reinterpret_cast<Proposal*>(smem_raw + cta_smem_bytes(a.n));
   unsigned* dirty = reinterpret_cast<unsigned*>(win + kWin);
+  const F32View F = carve_f32(smem_raw + cta_smem_bytes_win(a.n), PREC ? a.n : 0);
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
   const int n = a.n;
@@ -571,6 +581,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_win(const RunArgs a) {
   __syncthreads();
   const ChainParams& P = *S.par;
   load_chain<T>(mono, P, n, S);
+  if (PREC) fill_mu_f32<Team<T / 32, 0>>(S, F, n);   // visible after the window barrier below
   const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
   const double b = P.b, inv_kT = P.inv_kT;
   const long long step0 = S.dyn->step;
@@ -612,7 +623,8 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_win(const RunArgs a) {
       double dsum = 0.0;
       bool accept = false;
       if (!skip) {
-        const double t = cta_delta_pairs<T, UNROLL>(S, n, 1, b, idx, q->mx, q->my, q->mz, dnx, dny, dnz);
+        const double t = PREC ? cta_delta_pairs_f32<T>(S, F, n, b, idx, q->mx, q->my, q->mz, dnx, dny, dnz)
+                              : cta_delta_pairs<T, UNROLL>(S, n, 1, b, idx, q->mx, q->my, q->mz, dnx, dny, dnz);
         accept = decide(q->single, t, inv_kT, q->eps, dsum);
       }
       if (accept) {  // apply move!: x_idx += (b/2)Δn̂, x_{j>idx} += bΔn̂, μ_idx = μ'
@@ -630,6 +642,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_win(const RunArgs a) {
         if (accept) {
           S.sx[idx] += 0.5 * b * dnx; S.sy[idx] += 0.5 * b * dny; S.sz[idx] += 0.5 * b * dnz;
           S.mx[idx] = q->mx; S.my[idx] = q->my; S.mz[idx] = q->mz;
+          if (PREC) F.pb[idx] = make_float4((float)q->mx, (float)q->my, (float)q->mz, 0.0f);
           MonoRec rec;
           rec.phi = q->phi; rec.theta = q->theta;
           rec.nx = q->nx; rec.ny = q->ny; rec.nz = q->nz; rec.sth = q->sth;
@@ -942,6 +955,31 @@ __global__ void __launch_bounds__(T) k_delta_cta(const DeltaArgs a) {
   const Proposal* q = &S.prop[0];
   const double dsum =
       kInv4Pi * cta_delta_pairs<T>(S, n, a.energy_type, P.b, a.idx, q->mx, q->my, q->mz, q->dnx, q->dny, q->dnz);
+  if (tid == 0) {
+    a.out[0] = q->du + q->drF + dsum;
+    a.out[1] = q->dOmega;
+    a.out[2] = (double)q->clamped;
+    a.out[3] = dsum;
+  }
+}
+
+// The same with the rectangle in FP32 (cta_f32.cuh): what k_run_cta_win<…, PREC = 1> evaluates for this move.
+template <int T>
+__global__ void __launch_bounds__(T) k_delta_cta_f32(const DeltaArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  const F32View F = carve_f32(smem_raw + ((cta_smem_bytes(a.n) + 15) & ~(size_t)15), a.n);
+  const int tid = threadIdx.x, n = a.n;
+  const MonoRec* mono = a.mono + (size_t)a.chain * n;
+  if (tid == 0) *S.par = a.par[a.chain];
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  fill_mu_f32<Team<T / 32, 0>>(S, F, n);
+  if (tid == 0) build_proposal(P, mono[a.idx], a.idx, a.dphi, a.dtheta, 0.0, S.prop[0]);
+  __syncthreads();
+  const Proposal* q = &S.prop[0];
+  const double dsum = kInv4Pi * cta_delta_pairs_f32<T>(S, F, n, P.b, a.idx, q->mx, q->my, q->mz, q->dnx, q->dny, q->dnz);
   if (tid == 0) {
     a.out[0] = q->du + q->drF + dsum;
     a.out[1] = q->dOmega;

@@ -82,6 +82,7 @@ struct pmc_handle {
   long long warp_mode_below = 0;
   long long warp_cluster_below = 11000;  // composite trials: chain per warp below this many chains, else per lane
   int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)
+  int pair_precision = 0;     // 0: FP64 everywhere; 1: the rectangle of single-monomer trials in FP32 where a kernel exists (cta_f32.cuh)
   int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;
   bool dyn_fresh = false, dynx_fresh = false;   // the host copies equal the device's (no launch since they were fetched)
@@ -143,6 +144,8 @@ inline int cluster_fit128(int n) {
 
 // ---- launch helpers, one translation unit per kernel family -------------------------------------------------
 int launch_run_cta(pmc_handle* h, const pmc::RunArgs& a);                    // run_cta.cu
+bool use_f32_rect(const pmc_handle* h);
+int launch_delta_cta_f32(pmc_handle* h, const DeltaArgs& a);
 int launch_run_pair(pmc_handle* h, const pmc::RunArgs& a);                   // run_pair.cu
 bool use_pair_kernel(const pmc_handle* h);                                   // run_pair.cu
 int launch_run_lane(pmc_handle* h, const pmc::RunArgs& a);                   // run_lane.cu

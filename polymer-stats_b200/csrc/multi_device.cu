@@ -266,6 +266,14 @@ int32_t pmc_multi_set_ensemble_hint(pmc_multi* m, int64_t ensemble_chains) {
   return PMC_OK;
 }
 
+int32_t pmc_multi_set_pair_precision(pmc_multi* m, int32_t mode) {
+  int rc = check_multi(m);
+  if (rc) return rc;
+  for (pmc_handle* h : m->shard)
+    if ((rc = pmc_set_pair_precision(h, mode))) return rc;
+  return PMC_OK;
+}
+
 int32_t pmc_multi_begin_stage(pmc_multi* m, double kT_scale) {
   int rc = check_multi(m);
   if (rc) return rc;

@@ -487,6 +487,16 @@ int32_t pmc_set_ensemble_hint(pmc_handle* h, int64_t ensemble_chains) {
   return PMC_OK;
 }
 
+int32_t pmc_set_pair_precision(pmc_handle* h, int32_t mode) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (mode != PMC_PAIR_FP64 && mode != PMC_PAIR_FP32) return fail(PMC_ERR_INVALID, "pair precision must be PMC_PAIR_FP64 or PMC_PAIR_FP32");
+  h->pair_precision = mode;
+  return PMC_OK;
+}
+
+int32_t pmc_pair_precision(const pmc_handle* h) { return h && use_f32_rect(h) ? PMC_PAIR_FP32 : PMC_PAIR_FP64; }
+
 int32_t pmc_block_threads(const pmc_handle* h) { return h ? h->cta_threads : 0; }
 
 int32_t pmc_set_stream(pmc_handle* h, void* cuda_stream) {
@@ -653,7 +663,7 @@ int32_t pmc_delta_u(pmc_handle* h, int64_t chain, int64_t idx0, double dphi, dou
   a.n = h->n; a.energy_type = h->energy_type; a.chain = (int)chain; a.idx = (int)idx0;
   a.dphi = dphi; a.dtheta = dtheta;
   if (h->energy_type == PMC_ENERGY_INTERACTING) {
-    if ((rc = launch_delta_cta(h, a))) return rc;
+    if ((rc = use_f32_rect(h) ? launch_delta_cta_f32(h, a) : launch_delta_cta(h, a))) return rc;
   } else {
     k_delta_lane<<<1, 32, 0, h->stream>>>(a);
     ++h->launches;
@@ -741,6 +751,9 @@ static int run_impl(pmc_handle* h, int64_t nsteps, int64_t stepout, double* traj
   a.compensated = h->compensated;
   PMC_CU(cudaEventRecord(h->ev0, h->stream));
   if ((rc = dispatch_run(h, a))) return rc;
+  // FP32 rectangle: the running energy is the sum of FP32-rounded ΔU of the accepted moves; put it back on the exact
+  // energy of the chain after every launch (one FP64 energy evaluation per chain ≈ three trials' worth of pairs)
+  if (use_f32_rect(h) && (rc = refresh(h, /*rebind_gauge=*/false))) return rc;
   PMC_CU(cudaEventRecord(h->ev1, h->stream));
   if (traj && rows > 0)
     PMC_CU(cudaMemcpyAsync(traj, h->traj, ntraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -5,8 +5,56 @@ namespace {
 int fail(int code, const std::string& msg) { return pmc_fail(code, msg); }
 }  // namespace
 
+// FP32 rectangle (pmc_set_pair_precision): served by the windowed one-CTA kernel; every other launch stays FP64.
+bool use_f32_rect(const pmc_handle* h) {
+  if (h->pair_precision != 1 || h->energy_type != PMC_ENERGY_INTERACTING || h->cluster_mode) return false;
+  if (use_pair_kernel(h) || !env_int("PMC_RUN_WIN", h->use_win) || env_int("PMC_RUN_CFG", 0)) return false;
+  if (h->cta_threads != 64 && h->cta_threads != 128 && h->cta_threads != 256 && h->cta_threads != 512) return false;
+  return cta_smem_bytes_win_f32(h->n) <= (size_t)kSmemMax;
+}
+
+int launch_delta_cta_f32(pmc_handle* h, const DeltaArgs& a) {
+  const size_t smem = ((cta_smem_bytes(h->n) + 15) & ~(size_t)15) + f32_smem_bytes(h->n);
+#define PMC_CASE(TT)                                            \
+  case TT: {                                                    \
+    int rc = set_smem(k_delta_cta_f32<TT>, smem);               \
+    if (rc) return rc;                                          \
+    k_delta_cta_f32<TT><<<1, TT, smem, h->stream>>>(a);         \
+    ++h->launches;                                              \
+    break;                                                      \
+  }
+  switch (h->cta_threads) {
+    PMC_CASE(64) PMC_CASE(128) PMC_CASE(256) PMC_CASE(512)
+    default: return fail(PMC_ERR_INVALID, "bad cta_threads");
+  }
+#undef PMC_CASE
+  PMC_CU(cudaGetLastError());
+  return PMC_OK;
+}
+
 int launch_run_cta(pmc_handle* h, const RunArgs& a) {
   if (use_pair_kernel(h)) return launch_run_pair(h, a);
+  if (use_f32_rect(h)) {
+    const size_t smem32 = cta_smem_bytes_win_f32(h->n);
+    const int nb = (int)h->nchains;
+#define PMC_LAUNCH_F32(TT, MB)                                                   \
+  {                                                                              \
+    PMC_PICK("k_run_cta_win<" #TT "," #MB ",2,fp32>");                           \
+    int rc = set_smem(k_run_cta_win<TT, MB, 2, 1>, smem32);                      \
+    if (rc) return rc;                                                           \
+    k_run_cta_win<TT, MB, 2, 1><<<nb, TT, smem32, h->stream>>>(a);               \
+    ++h->launches;                                                               \
+    PMC_CU(cudaGetLastError());                                                  \
+    return PMC_OK;                                                               \
+  }
+    switch (h->cta_threads) {
+      case 64: PMC_LAUNCH_F32(64, 8)
+      case 128: PMC_LAUNCH_F32(128, 4)
+      case 256: PMC_LAUNCH_F32(256, 2)
+      default: PMC_LAUNCH_F32(512, 1)
+    }
+#undef PMC_LAUNCH_F32
+  }
   const size_t smem = cta_smem_bytes(h->n);
   const int nblocks = (int)h->nchains;
   // PMC_RUN_CFG = threads*100 + minblocks*10 + unroll selects a tuning variant (experiments only)

@@ -47,6 +47,8 @@ const OPTIONS = [
   ("--replicas", nothing, Int, 1), ("--seed", nothing, Int, -1), ("--device", nothing, Int, 0),
   # [B200 path] number of GPUs of this box the replicas are spread over (pmc_multi_*, ABI v3); 0 = all of them
   ("--devices", nothing, Int, 1),
+  # [B200 path] fp32: the rectangle of unchanged-dipole pairs of a trial in FP32 (pmc_set_pair_precision); else FP64
+  ("--pair-precision", nothing, String, "fp64"),
 ]
 const FLAGS = [("--force-init", "-I"), ("--do-flips", nothing), ("--umbrella-sampling", "-B"), ("--profile", "-Z")]
 
@@ -130,6 +132,13 @@ function mcmc(nsteps::Int, p)
   else
     check(ccall((:pmc_create, LIBPOLYMC), Int32, (Ptr{PmcCase}, Int64, Int32, UInt64, Int32, UInt32, Ptr{Ptr{Cvoid}}),
                 cases, 1, R, seed, p["device"], 0, h))
+  end
+  prec = Dict("fp64" => 0, "fp32" => 1)
+  haskey(prec, p["pair-precision"]) || error("pair-precision is not understood.")
+  if multi
+    check(ccall((:pmc_multi_set_pair_precision, LIBPOLYMC), Int32, (Ptr{Cvoid}, Int32), h[], prec[p["pair-precision"]]))
+  else
+    check(ccall((:pmc_set_pair_precision, LIBPOLYMC), Int32, (Ptr{Cvoid}, Int32), h[], prec[p["pair-precision"]]))
   end
   traj_io = open("$(p["prefix"])_trajectory.csv", "w"); rolling_io = open("$(p["prefix"])_rolling.csv", "w")
   writedlm(traj_io, ["step" "r1" "r2" "r3" "p1" "p2" "p3" "U"], ',')

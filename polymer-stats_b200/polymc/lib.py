@@ -20,13 +20,14 @@ CSRC_DIR = os.path.join(_ROOT, "csrc")
 
 CHAIN_TYPES = {"dielectric": 0, "polar": 1}
 ENERGY_TYPES = {"noninteracting": 0, "interacting": 1, "Ising": 2, "cutoff": 3}
+PAIR_PRECISIONS = {"fp64": 0, "fp32": 1}
 
 AVG_NAMES = ["r1", "r2", "r3", "r1sq", "r2sq", "r3sq", "rsq",
              "p1", "p2", "p3", "p1sq", "p2sq", "p3sq", "psq", "U", "Usq"]
 
 EXPORTS = [
     "pmc_abi_version", "pmc_last_error", "pmc_device_count", "pmc_create", "pmc_destroy",
-    "pmc_num_chains", "pmc_num_monomers", "pmc_set_stream", "pmc_set_ensemble_hint", "pmc_block_threads", "pmc_set_state", "pmc_get_state",
+    "pmc_num_chains", "pmc_num_monomers", "pmc_set_stream", "pmc_set_ensemble_hint", "pmc_set_pair_precision", "pmc_pair_precision", "pmc_block_threads", "pmc_set_state", "pmc_get_state",
     "pmc_set_state_all", "pmc_get_state_all", "pmc_energy", "pmc_energy_all", "pmc_observables",
     "pmc_delta_u", "pmc_run", "pmc_rows_for", "pmc_last_run_ms", "pmc_reinit", "pmc_averages",
     "pmc_accumulators", "pmc_diagnostics", "pmc_fp64_peak_probe", "pmc_launch_count",
@@ -36,7 +37,7 @@ EXPORTS = [
     # ABI v3: kernel name, checkpoints, double-double accumulators, one ensemble over several GPUs
     "pmc_kernel_name", "pmc_checkpoint_bytes", "pmc_checkpoint_save", "pmc_checkpoint_load", "pmc_accumulators_dd",
     "pmc_multi_create", "pmc_multi_destroy", "pmc_multi_num_devices", "pmc_multi_num_chains",
-    "pmc_multi_gather_backend", "pmc_multi_shard", "pmc_multi_set_ensemble_hint", "pmc_multi_begin_stage",
+    "pmc_multi_gather_backend", "pmc_multi_shard", "pmc_multi_set_ensemble_hint", "pmc_multi_set_pair_precision", "pmc_multi_begin_stage",
     "pmc_multi_set_state_all", "pmc_multi_get_state_all", "pmc_multi_rows_for", "pmc_multi_run", "pmc_multi_run_ex",
     "pmc_multi_run_async", "pmc_multi_wait", "pmc_multi_gather", "pmc_multi_last_run_ms", "pmc_multi_launch_count",
     "pmc_release_cached_memory",
@@ -158,6 +159,8 @@ def load():
                              C.POINTER(hp)]
     L.pmc_destroy.argtypes = [hp]
     L.pmc_destroy.restype = None
+    L.pmc_set_pair_precision.argtypes = [hp, C.c_int32]
+    L.pmc_pair_precision.argtypes = [hp]
     L.pmc_num_chains.argtypes = [hp]
     L.pmc_num_chains.restype = C.c_int64
     L.pmc_num_monomers.argtypes = [hp]
@@ -213,6 +216,7 @@ def load():
     L.pmc_multi_shard.argtypes = [hp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pmc_multi_shard.restype = C.c_void_p
     L.pmc_multi_set_ensemble_hint.argtypes = [hp, C.c_int64]
+    L.pmc_multi_set_pair_precision.argtypes = [hp, C.c_int32]
     L.pmc_multi_begin_stage.argtypes = [hp, C.c_double]
     L.pmc_multi_set_state_all.argtypes = [hp, dp, dp]
     L.pmc_multi_get_state_all.argtypes = [hp, dp, dp]
@@ -230,7 +234,7 @@ def load():
         f = getattr(L, name)
         if f.restype is C.c_int:  # default restype: every status-returning entry point
             f.restype = C.c_int32
-    if L.pmc_abi_version() != 3:
+    if L.pmc_abi_version() != 4:
         raise PolymcError(-1, "ABI version mismatch")
     _lib = L
     return L
@@ -289,6 +293,17 @@ class Ensemble:
         """Choose the launch shape for an ensemble of `ensemble_chains` chains (a shard passes the unsharded
         count so that results do not depend on the sharding, bit for bit); 0 = this handle's own count."""
         _check(load().pmc_set_ensemble_hint(self._h, int(ensemble_chains)))
+
+    def set_pair_precision(self, precision: str):
+        """"fp64" (default) or "fp32": the rectangle of a single-monomer trial in FP32 with the tolerance stated in
+        include/polymc.h (pmc_set_pair_precision); launches without an FP32 kernel stay FP64."""
+        if precision not in PAIR_PRECISIONS:
+            raise PolymcError(-1, "pair-precision is not understood.")
+        _check(load().pmc_set_pair_precision(self._h, PAIR_PRECISIONS[precision]))
+
+    def pair_precision(self) -> str:
+        """What the next run uses: "fp32" only where the FP32 kernel serves this handle."""
+        return {v: k for k, v in PAIR_PRECISIONS.items()}[int(load().pmc_pair_precision(self._h))]
 
     def block_threads(self) -> int:
         return int(load().pmc_block_threads(self._h))
@@ -534,6 +549,11 @@ class MultiEnsemble:
 
     def set_ensemble_hint(self, chains):
         _check(load().pmc_multi_set_ensemble_hint(self._h, int(chains)))
+
+    def set_pair_precision(self, precision: str):
+        if precision not in PAIR_PRECISIONS:
+            raise PolymcError(-1, "pair-precision is not understood.")
+        _check(load().pmc_multi_set_pair_precision(self._h, PAIR_PRECISIONS[precision]))
 
     def begin_stage(self, kT_scale=1.0):
         _check(load().pmc_multi_begin_stage(self._h, float(kT_scale)))

@@ -5,7 +5,7 @@ The reference's toolchain (Julia) is not present in this image, so this Python m
 role of the Julia host; polymer-stats_b200/julia/mcmc_eap_chain.jl is the `ccall` twin.
 
 Same option names, defaults, argument meaning and error behaviour as the reference.  Additive
-options (not in the reference): --replicas, --seed, --device.
+options (not in the reference): --replicas, --seed, --device, --pair-precision.
 """
 from __future__ import annotations
 
@@ -65,6 +65,9 @@ def build_parser() -> argparse.ArgumentParser:
     a("--replicas", type=int, default=1, help="[B200 path] independent replica chains run concurrently and pooled")
     a("--seed", type=int, default=None, help="[B200 path] Philox seed (default: time-based, like the unseeded reference)")
     a("--device", type=int, default=0, help="[B200 path] CUDA device index")
+    a("--pair-precision", default="fp64", choices=["fp64", "fp32"],
+      help="[B200 path] fp32: the rectangle of unchanged-dipole pairs of a trial in FP32 (tolerance in include/polymc.h); "
+           "everything else FP64")
     return p
 
 
@@ -178,6 +181,7 @@ def mcmc(nsteps: int, pargs: dict):
     start = time.time()
     last_update = start
     with lib.Ensemble(case, replicas=R, seed=seed, device=pargs.get("device", 0)) as ens:
+        ens.set_pair_precision(pargs.get("pair-precision", "fp64"))
         with open(f"{pargs['prefix']}_trajectory.csv", "w") as outfile, \
                 open(f"{pargs['prefix']}_rolling.csv", "w") as rollfile:
             outfile.write(TRAJ_HEADER + "\n")

@@ -51,6 +51,7 @@ class MockLib:
         self.step = 0
         self.R = 0
         self.n = 0
+        self.precision = None
 
     # ---- single device ------------------------------------------------------------------------------------------
     def pmc_last_error(self):
@@ -68,6 +69,13 @@ class MockLib:
         rc = self.pmc_create(cases, ncases, replicas, seed, C.c_int32(-1), C.c_uint32(0), out)
         self.calls[-1] = ("pmc_multi_create", _v(ncases), _v(replicas), _v(seed), _v(devices), _v(ndev))
         return rc
+
+    def pmc_set_pair_precision(self, h, mode):
+        self._check(h)
+        self.precision = _v(mode)
+        return 0
+
+    pmc_multi_set_pair_precision = pmc_set_pair_precision
 
     def _check(self, h):
         assert _v(h) == 0x1234, "host passed a wrong handle"

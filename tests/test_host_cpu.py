@@ -181,7 +181,7 @@ def test_abi_exports_every_declared_symbol(pm):
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(pm.lib.EXPORTS) == declared
-    assert pm.load().pmc_abi_version() == 3
+    assert pm.load().pmc_abi_version() == 4
     assert ctypes.sizeof(pm.PmcCase) == 13 * 8 + 2 * 8 + 6 * 4 + 4 * 8 + 4 * 4
 
 
