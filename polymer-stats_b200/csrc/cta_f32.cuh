@@ -93,9 +93,58 @@ __device__ __forceinline__ float rect_pair_f32(const LaneItemF& it, const float4
 
 // FP32 partial sums are folded into FP64 after this many terms: once a large term is in a float accumulator every later
 // addition rounds at 6e-8 of the PARTIAL SUM, so the error grows with the number of terms that follow it
-#ifndef PMC_F32_ACC
-#define PMC_F32_ACC 0   // 0: chunk sums converted and added in FP64; 1: float-pair two-sum (experiments)
+// Two lane items in the two halves of packed f32x2 operands (Blackwell add/mul/fma.f32x2: one issue slot for two FP32
+// operations); the broadcast item is replicated into both halves.  Same operations in the same order as rect_pair_f32,
+// bit-identical results.  MEASURED NEGATIVE, off by default (-DPMC_F32_PACKED=1 to build it): the loop is bound by the
+// FP32 pipe, not by issue slots — FFMA2 occupies the pipe twice as long as FFMA — so the rectangle alone gains 2.5 %
+// (607 vs 592 G pairs/s, tools/rect_bench_f32.cu) and the full kernel spills 68 B at its 128 registers.
+#ifndef PMC_F32_PACKED
+#define PMC_F32_PACKED 0
 #endif
+struct LanePairF {
+  float2 x, y, z, lx, ly, lz, ax, ay, az, tx, ty, tz, c;
+};
+
+__device__ __forceinline__ LanePairF pack_lane_items(const LaneItemF& p, const LaneItemF& q) {
+  LanePairF r;
+  r.x = make_float2(p.x, q.x); r.y = make_float2(p.y, q.y); r.z = make_float2(p.z, q.z);
+  r.lx = make_float2(p.lx, q.lx); r.ly = make_float2(p.ly, q.ly); r.lz = make_float2(p.lz, q.lz);
+  r.ax = make_float2(p.ax, q.ax); r.ay = make_float2(p.ay, q.ay); r.az = make_float2(p.az, q.az);
+  r.tx = make_float2(p.tx, q.tx); r.ty = make_float2(p.ty, q.ty); r.tz = make_float2(p.tz, q.tz);
+  r.c = make_float2(p.c, q.c);
+  return r;
+}
+
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+
+__device__ __forceinline__ float2 rect_pair_f32x2(const LanePairF& it, const float4 a, const float4 u, const float4 l,
+                                                  float2 Dx, float2 Dy, float2 Dz, float2 acc) {
+  // −(broadcast) once per item and half: a − b = a + (−b) keeps every step a packed add
+  const float2 nax = dup2(-a.x), nay = dup2(-a.y), naz = dup2(-a.z);
+  const float2 nlx = dup2(-l.x), nly = dup2(-l.y), nlz = dup2(-l.z);
+  const float2 ux = dup2(u.x), uy = dup2(u.y), uz = dup2(u.z);
+  const float2 rx = __fadd2_rn(__fadd2_rn(it.x, nax), __fadd2_rn(it.lx, nlx));
+  const float2 ry = __fadd2_rn(__fadd2_rn(it.y, nay), __fadd2_rn(it.ly, nly));
+  const float2 rz = __fadd2_rn(__fadd2_rn(it.z, naz), __fadd2_rn(it.lz, nlz));
+  const float2 mm = __ffma2_rn(it.az, uz, __ffma2_rn(it.ay, uy, __fmul2_rn(it.ax, ux)));
+  const float2 r2 = __ffma2_rn(rz, rz, __ffma2_rn(ry, ry, __fmul2_rn(rx, rx)));
+  const float2 a3 = __ffma2_rn(it.tz, rz, __ffma2_rn(it.ty, ry, __fmul2_rn(it.tx, rx)));
+  const float2 bb = __ffma2_rn(uz, rz, __ffma2_rn(uy, ry, __fmul2_rn(ux, rx)));
+  const float2 qx = sub2(rx, Dx), qy = sub2(ry, Dy), qz = sub2(rz, Dz);
+  const float2 q2 = __ffma2_rn(qz, qz, __ffma2_rn(qy, qy, __fmul2_rn(qx, qx)));
+  const float2 a3n = sub2(a3, it.c);
+  const float2 bn = __fadd2_rn(bb, dup2(-a.w));
+  const float2 y = make_float2(rsqrt_f32(r2.x), rsqrt_f32(r2.y));
+  const float2 yn = make_float2(rsqrt_f32(q2.x), rsqrt_f32(q2.y));
+  const float2 y2 = __fmul2_rn(y, y), yn2 = __fmul2_rn(yn, yn);
+  const float2 t = __ffma2_rn(__fmul2_rn(a3, bb), y2, mm);
+  const float2 tn = __ffma2_rn(__fmul2_rn(a3n, bn), yn2, mm);
+  acc = __ffma2_rn(tn, __fmul2_rn(yn2, yn), acc);
+  return __ffma2_rn(neg2(t), __fmul2_rn(y2, y), acc);
+}
+
 #ifndef PMC_KFLUSH
 #define PMC_KFLUSH 32
 #endif
@@ -111,6 +160,7 @@ __device__ __forceinline__ double rect_pass_f32(const F32View& F, int baseA, int
   const float4* __restrict__ pa = F.pa + baseB;
   const float4* __restrict__ pb = F.pb + baseB;
   const float4* __restrict__ pc = F.pc + baseB;
+  const float2 D2x = make_float2(Dx, Dx), D2y = make_float2(Dy, Dy), D2z = make_float2(Dz, Dz);
   const int U = nb * B;
   int u = (int)(((long long)U * warp) / W);
   const int u1 = (int)(((long long)U * (warp + 1)) / W);
@@ -127,44 +177,43 @@ __device__ __forceinline__ double rect_pass_f32(const F32View& F, int baseA, int
       valid[j] = l < A;
       it[j] = load_lane_item_f32(F, baseA + min(l, A - 1), Dx, Dy, Dz);
     }
+    LanePairF pk[NL >= 2 ? NL / 2 : 1];
+    if (NL >= 2 && PMC_F32_PACKED) {
+#pragma unroll
+      for (int j = 0; j < NL / 2; ++j) pk[j] = pack_lane_items(it[2 * j], it[2 * j + 1]);
+    }
     const int kend = min(B, k + (u1 - u));
     u += kend - k;
-#if PMC_F32_ACC == 1
-    // chunk sums (≤ kFlush terms each, plain FP32) are added into a float PAIR (hi, lo) by an error-free two-sum: six
-    // FP32 operations per chunk and lane item, no conversion and no FP64 in the loop; the pair goes to FP64 once per
-    // segment
-    float hi[NL], lo[NL];
-#pragma unroll
-    for (int j = 0; j < NL; ++j) hi[j] = lo[j] = 0.0f;
-#endif
     while (k < kend) {
       const int kc = min(kend, k + kFlush);
-      float a[NL];
+      if (NL >= 2 && PMC_F32_PACKED) {
+        // two lane items per packed operand: add/mul/fma.f32x2 (sm_100) halve the FP32 issue slots; MUFU per half
+        float2 a2[NL >= 2 ? NL / 2 : 1];
 #pragma unroll
-      for (int j = 0; j < NL; ++j) a[j] = 0.0f;
+        for (int j = 0; j < NL / 2; ++j) a2[j] = make_float2(0.0f, 0.0f);
 #pragma unroll(NL >= 4 ? 1 : 2)
-      for (; k < kc; ++k) {
-        const float4 va = pa[k], vu = pb[k], vl = pc[k];
+        for (; k < kc; ++k) {
+          const float4 va = pa[k], vu = pb[k], vl = pc[k];
 #pragma unroll
-        for (int j = 0; j < NL; ++j) a[j] = rect_pair_f32(it[j], va, vu, vl, Dx, Dy, Dz, a[j]);
+          for (int j = 0; j < NL / 2; ++j) a2[j] = rect_pair_f32x2(pk[j], va, vu, vl, D2x, D2y, D2z, a2[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NL / 2; ++j)   // chunk sums leave FP32 here
+          acc += (valid[2 * j] ? (double)a2[j].x : 0.0) + (valid[2 * j + 1] ? (double)a2[j].y : 0.0);
+      } else {
+        float a[NL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) a[j] = 0.0f;
+#pragma unroll(NL >= 4 ? 1 : 2)
+        for (; k < kc; ++k) {
+          const float4 va = pa[k], vu = pb[k], vl = pc[k];
+#pragma unroll
+          for (int j = 0; j < NL; ++j) a[j] = rect_pair_f32(it[j], va, vu, vl, Dx, Dy, Dz, a[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NL; ++j) acc += valid[j] ? (double)a[j] : 0.0;   // chunk sums leave FP32 here
       }
-#if PMC_F32_ACC == 1
-#pragma unroll
-      for (int j = 0; j < NL; ++j) {   // two-sum: hi + a = s + err exactly
-        const float s = hi[j] + a[j];
-        const float bb = s - hi[j];
-        lo[j] += (hi[j] - (s - bb)) + (a[j] - bb);
-        hi[j] = s;
-      }
-#else
-#pragma unroll
-      for (int j = 0; j < NL; ++j) acc += valid[j] ? (double)a[j] : 0.0;   // chunk sums leave FP32 here
-#endif
     }
-#if PMC_F32_ACC == 1
-#pragma unroll
-    for (int j = 0; j < NL; ++j) acc += valid[j] ? (double)hi[j] + (double)lo[j] : 0.0;
-#endif
     k = 0;
     ++bundle;
   }
