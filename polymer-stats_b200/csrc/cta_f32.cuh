@@ -15,7 +15,7 @@
 //     (|r| + |D|) / |r'| when a trial brings two monomers much closer than they were — then the new term is huge.
 // Stated tolerance (include/polymc.h, tests/test_gpu_fp32.py): error ≤ 2e-6·(1 + amplification) of the magnitude of
 // each pair term (the sum of the magnitudes of its two parts, μ·μ/r³ and 3(μ·r̂)(μ·r̂)/r³).
-// Measured on C2 (4096 chains × 500 trials): 13.2 M updates/s against 7.8 M in FP64; rectangle alone 1.84×
+// Measured on C2 (4096 chains × 500 trials): 14.0 M updates/s against 7.8 M in FP64; rectangle alone 1.89×
 // (tools/rect_bench_f32.cu).  Without the lo parts it would be 16.0 M (rectangle 2.25×) — and wrong by 6e-8·|offset|/|r| per
 // term, i.e. useless for long stretched chains; chunk length and accumulation scheme (profiles/r02c_tune_kflush.txt)
 // change the speed by < 4 %.
@@ -29,20 +29,22 @@
 
 namespace pmc {
 
-// Mirrors of the staged chain in shared memory, 48 B per monomer.
+// Mirrors of the staged chain in shared memory, 40 B per monomer: two float4 arrays of their own and a float2 array
+// that lives in the FP64 E array of the staged chain (8 B per monomer, unused by this path) — 32 B per monomer of extra
+// shared memory, which is what lets four CTAs of the C2 shape share an SM (52 KB each).
 struct F32View {
   float4* pa;   // hi parts of {x − x_idx, y − y_idx, z − z_idx}, w: e = μ·D_eff — rebuilt every trial
-  float4* pb;   // {μx, μy, μz, 0} — follows the FP64 dipoles (written at load and on accept)
-  float4* pc;   // lo parts of the offsets, w: 0 — rebuilt every trial
+  float4* pb;   // {μx, μy, μz} — follows the FP64 dipoles (written at load and on accept); w: lo part of the x offset
+  float2* pc;   // lo parts of the y and z offsets — rebuilt every trial
 };
 
-__host__ __device__ inline size_t f32_smem_bytes(int n) { return (size_t)n * 3 * sizeof(float4); }
+__host__ __device__ inline size_t f32_smem_bytes(int n) { return (size_t)n * 2 * sizeof(float4); }
 
-__device__ __forceinline__ F32View carve_f32(unsigned char* base, int n) {
+__device__ __forceinline__ F32View carve_f32(unsigned char* base, int n, double* E) {
   F32View F;
   F.pa = reinterpret_cast<float4*>(base);
   F.pb = F.pa + n;
-  F.pc = F.pb + n;
+  F.pc = reinterpret_cast<float2*>(E);
   return F;
 }
 
@@ -61,10 +63,11 @@ struct LaneItemF {
 };
 
 __device__ __forceinline__ LaneItemF load_lane_item_f32(const F32View& F, int L, float Dx, float Dy, float Dz) {
-  const float4 a = F.pa[L], u = F.pb[L], l = F.pc[L];
+  const float4 a = F.pa[L], u = F.pb[L];
+  const float2 l = F.pc[L];
   LaneItemF it;
   it.x = a.x; it.y = a.y; it.z = a.z;
-  it.lx = l.x; it.ly = l.y; it.lz = l.z;
+  it.lx = u.w; it.ly = l.x; it.lz = l.y;
   it.ax = u.x; it.ay = u.y; it.az = u.z;
   it.tx = -3.0f * u.x; it.ty = -3.0f * u.y; it.tz = -3.0f * u.z;
   it.c = fmaf(it.tz, Dz, fmaf(it.ty, Dy, it.tx * Dx));
@@ -72,9 +75,9 @@ __device__ __forceinline__ LaneItemF load_lane_item_f32(const F32View& F, int L,
 }
 
 // new − old of one pair, the same 43-operation form as rect_pair (cta_kernels.cuh) with MUFU.RSQ for 1/|r|.
-__device__ __forceinline__ float rect_pair_f32(const LaneItemF& it, const float4 a, const float4 u, const float4 l,
+__device__ __forceinline__ float rect_pair_f32(const LaneItemF& it, const float4 a, const float4 u, const float2 l,
                                                float Dx, float Dy, float Dz, float acc) {
-  const float rx = (it.x - a.x) + (it.lx - l.x), ry = (it.y - a.y) + (it.ly - l.y), rz = (it.z - a.z) + (it.lz - l.z);
+  const float rx = (it.x - a.x) + (it.lx - u.w), ry = (it.y - a.y) + (it.ly - l.x), rz = (it.z - a.z) + (it.lz - l.y);
   const float mm = fmaf(it.az, u.z, fmaf(it.ay, u.y, it.ax * u.x));
   const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
   const float a3 = fmaf(it.tz, rz, fmaf(it.ty, ry, it.tx * rx));
@@ -119,11 +122,11 @@ __device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
 
-__device__ __forceinline__ float2 rect_pair_f32x2(const LanePairF& it, const float4 a, const float4 u, const float4 l,
+__device__ __forceinline__ float2 rect_pair_f32x2(const LanePairF& it, const float4 a, const float4 u, const float2 l,
                                                   float2 Dx, float2 Dy, float2 Dz, float2 acc) {
   // −(broadcast) once per item and half: a − b = a + (−b) keeps every step a packed add
   const float2 nax = dup2(-a.x), nay = dup2(-a.y), naz = dup2(-a.z);
-  const float2 nlx = dup2(-l.x), nly = dup2(-l.y), nlz = dup2(-l.z);
+  const float2 nlx = dup2(-u.w), nly = dup2(-l.x), nlz = dup2(-l.y);
   const float2 ux = dup2(u.x), uy = dup2(u.y), uz = dup2(u.z);
   const float2 rx = __fadd2_rn(__fadd2_rn(it.x, nax), __fadd2_rn(it.lx, nlx));
   const float2 ry = __fadd2_rn(__fadd2_rn(it.y, nay), __fadd2_rn(it.ly, nly));
@@ -159,7 +162,7 @@ __device__ __forceinline__ double rect_pass_f32(const F32View& F, int baseA, int
   const int lane = TEAM::lane(), warp = TEAM::warp();
   const float4* __restrict__ pa = F.pa + baseB;
   const float4* __restrict__ pb = F.pb + baseB;
-  const float4* __restrict__ pc = F.pc + baseB;
+  const float2* __restrict__ pc = F.pc + baseB;
   const float2 D2x = make_float2(Dx, Dx), D2y = make_float2(Dy, Dy), D2z = make_float2(Dz, Dz);
   const int U = nb * B;
   int u = (int)(((long long)U * warp) / W);
@@ -193,7 +196,8 @@ __device__ __forceinline__ double rect_pass_f32(const F32View& F, int baseA, int
         for (int j = 0; j < NL / 2; ++j) a2[j] = make_float2(0.0f, 0.0f);
 #pragma unroll(NL >= 4 ? 1 : 2)
         for (; k < kc; ++k) {
-          const float4 va = pa[k], vu = pb[k], vl = pc[k];
+          const float4 va = pa[k], vu = pb[k];
+          const float2 vl = pc[k];
 #pragma unroll
           for (int j = 0; j < NL / 2; ++j) a2[j] = rect_pair_f32x2(pk[j], va, vu, vl, D2x, D2y, D2z, a2[j]);
         }
@@ -206,7 +210,8 @@ __device__ __forceinline__ double rect_pass_f32(const F32View& F, int baseA, int
         for (int j = 0; j < NL; ++j) a[j] = 0.0f;
 #pragma unroll(NL >= 4 ? 1 : 2)
         for (; k < kc; ++k) {
-          const float4 va = pa[k], vu = pb[k], vl = pc[k];
+          const float4 va = pa[k], vu = pb[k];
+          const float2 vl = pc[k];
 #pragma unroll
           for (int j = 0; j < NL; ++j) a[j] = rect_pair_f32(it[j], va, vu, vl, Dx, Dy, Dz, a[j]);
         }
@@ -243,15 +248,15 @@ __device__ __forceinline__ void build_mirrors_f32(const CtaView& S, const F32Vie
                                                   float ez) {
   const double xi = S.sx[idx], yi = S.sy[idx], zi = S.sz[idx];
   for (int k = TEAM::ltid(); k < n; k += TEAM::kLocalThreads) {
-    const float4 u = F.pb[k];
+    float4 u = F.pb[k];
     const double dx = S.sx[k] - xi, dy = S.sy[k] - yi, dz = S.sz[k] - zi;
-    float4 a, l;
+    float4 a;
     a.x = (float)dx; a.y = (float)dy; a.z = (float)dz;
-    l.x = (float)(dx - (double)a.x); l.y = (float)(dy - (double)a.y); l.z = (float)(dz - (double)a.z);
     a.w = fmaf(u.z, ez, fmaf(u.y, ey, u.x * ex));
-    l.w = 0.0f;
+    u.w = (float)(dx - (double)a.x);
     F.pa[k] = a;
-    F.pc[k] = l;
+    F.pb[k] = u;
+    F.pc[k] = make_float2((float)(dy - (double)a.y), (float)(dz - (double)a.z));
   }
 }
 

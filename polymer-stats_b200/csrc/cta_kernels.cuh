@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_win(const RunArgs a) {
   const CtaView S = carve(smem_raw, a.n);
   Proposal* win = reinterpret_cast<Proposal*>(smem_raw + cta_smem_bytes(a.n));
   unsigned* dirty = reinterpret_cast<unsigned*>(win + kWin);
-  const F32View F = carve_f32(smem_raw + cta_smem_bytes_win(a.n), PREC ? a.n : 0);
+  const F32View F = carve_f32(smem_raw + cta_smem_bytes_win(a.n), PREC ? a.n : 0, S.E);
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
   const int n = a.n;
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_win(const RunArgs a) {
         if (accept) {
           S.sx[idx] += 0.5 * b * dnx; S.sy[idx] += 0.5 * b * dny; S.sz[idx] += 0.5 * b * dnz;
           S.mx[idx] = q->mx; S.my[idx] = q->my; S.mz[idx] = q->mz;
-          if (PREC) F.pb[idx] = make_float4((float)q->mx, (float)q->my, (float)q->mz, 0.0f);
+          if (PREC) F.pb[idx] = make_float4((float)q->mx, (float)q->my, (float)q->mz, 0.0f);   // w is rebuilt per trial
           MonoRec rec;
           rec.phi = q->phi; rec.theta = q->theta;
           rec.nx = q->nx; rec.ny = q->ny; rec.nz = q->nz; rec.sth = q->sth;
@@ -968,7 +968,7 @@ template <int T>
 __global__ void __launch_bounds__(T) k_delta_cta_f32(const DeltaArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const CtaView S = carve(smem_raw, a.n);
-  const F32View F = carve_f32(smem_raw + ((cta_smem_bytes(a.n) + 15) & ~(size_t)15), a.n);
+  const F32View F = carve_f32(smem_raw + ((cta_smem_bytes(a.n) + 15) & ~(size_t)15), a.n, S.E);
   const int tid = threadIdx.x, n = a.n;
   const MonoRec* mono = a.mono + (size_t)a.chain * n;
   if (tid == 0) *S.par = a.par[a.chain];
