@@ -58,4 +58,42 @@ for n, R, steps in ((512, 444, 20000), (1024, 300, 6000), (200, 1000, 40000)):
           "count: %d" % (n, R, steps, "ok " if same else "DIFF", counts["windowed"][1], counts["windowed"][2], counts["classic"][1],
                          counts["classic"][2], counts["pair"][1], counts["pair"][2], diff), flush=True)
     bad += not same
+for k in ("PMC_RUN_PAIR", "PMC_RUN_WIN"):
+    os.environ.pop(k, None)
+
+# Chain per lane against chain per warp (32 speculative trials per window, resolved in order): both are the reference's
+# sequential Markov chain on the same Philox stream, so the final STATES must be equal bit for bit and the acceptance
+# counts equal — over long runs, with flips, with step adaptation on, for equal-idx (non-interacting) and neighbour
+# (Ising) conflicts.
+for kw, R, steps in ((dict(n=100, E0=1.0, Fz=0.5), 4096, 300000), (dict(n=100, E0=1.0, Fz=0.5, energy_type="Ising"), 4096, 300000),
+                     (dict(n=12, E0=2.0, Fz=0.2, kT=0.5, energy_type="Ising", chain_type="polar", mu=0.7, do_flips=True), 2048, 400000),
+                     (dict(n=7, E0=0.5, Fz=1.0, steps_per_adjust=333), 2048, 400000)):
+    res = {}
+    for tag, mode in (("lane", "1"), ("warp", "2")):
+        os.environ["PMC_LANE_MODE"] = mode
+        with pm.Ensemble(pm.make_case(**kw), replicas=R, seed=777) as ens:
+            name = ens.kernel_name()
+            t0 = time.time()
+            ens.run(steps // 3, 0, fetch_rows=False)
+            ens.run(steps - steps // 3, 1000, fetch_rows=False)
+            res[tag] = (ens.diagnostics()[:, 4].copy(), ens.get_state_all(), name, time.time() - t0)
+    os.environ.pop("PMC_LANE_MODE", None)
+    same = np.array_equal(res["lane"][0], res["warp"][0]) and all(np.array_equal(a, b) for a, b in zip(res["lane"][1], res["warp"][1]))
+    print("lane vs warp %s, %d chains x %d trials: %s (%s %.1f s, %s %.1f s)" % (
+        {k: v for k, v in kw.items() if k in ("n", "energy_type", "do_flips")}, R, steps, "ok  states and acceptance counts identical"
+        if same else "DIFF", res["lane"][2], res["lane"][3], res["warp"][2], res["warp"][3]), flush=True)
+    bad += not same
+
+# The opt-in FP32 rectangle on a chain that stays extended (weak coupling): drift of the running energy per launch
+with pm.Ensemble(pm.make_case(n=512, E0=0.3, Fz=1.0, energy_type="interacting"), replicas=1024, seed=5) as ens:
+    ens.set_pair_precision("fp32")
+    t0 = time.time()
+    for _ in range(4):
+        ens.run(5000, 0, fetch_rows=False)
+    d = ens.diagnostics()
+    ok = bool(np.isfinite(d).all() and np.all(d[:, 5] == 20000))
+    print("fp32 rectangle n=512 E0=0.3: %s  %s, 1024 chains x 20000 trials in %.1f s (%.1f M updates/s); acceptance %.3f; |U| up to %.2e; "
+          "max drift within 5000 trials %.2e" % ("ok " if ok else "BAD", ens.kernel_name(), time.time() - t0, 1024 * 20000 / (time.time() - t0) / 1e6,
+                                                 d[:, 4].sum() / d[:, 5].sum(), np.abs(d[:, 6]).max(), d[:, 7].max()), flush=True)
+    bad += not ok
 sys.exit(1 if bad else 0)
