@@ -586,11 +586,12 @@ def main():
         for nm in ("C3", "C4", "C5", "K1", "C2f32"):
             workloads[nm] = measure(cx, nm, xs, 3, want_e2e=not args.no_e2e)
         workloads["C2f32"]["dtype"] = "f32 rectangle pair terms; f64 state, row terms, acceptance and accumulators (opt-in, not the headline)"
-        workloads["C4"]["limiter"] = ("device-timed: latency / transcendental bound (2 Philox, 2 sincos, log, exp per trial); e2e through "
-                                      "run_sweep: a fixed ~8-25 ms per call of handle set-up, result fetch and gather next to a kernel that "
-                                      "shrinks with the GPU count (21 ms per call at 8 GPUs)")
-        workloads["K1"]["limiter"] = ("one warp per chain, 12 chains per SM: instruction mix (0.24 FP64 of 0.53 instructions issued per cycle "
-                                      "per scheduler) and dependent-issue latency, DESIGN.md section 8")
+        workloads["C4"]["limiter"] = ("device-timed: one chain per warp, 32 speculative trials per window; issue slots 61 % busy, the "
+                                      "transcendental core (2 sincos, log, exp, 2 Philox per trial) is a quarter of the samples; at 8 GPUs "
+                                      "2048 chains per GPU are 0.86 of one wave (13.8 warps per SM); e2e through run_sweep adds ~1 ms of host "
+                                      "work per call (contiguous case table, one all-gather)")
+        workloads["K1"]["limiter"] = ("one warp per chain, 12 chains per SM (registers and shared memory): 3450 FP64 of 5984 warp instructions per "
+                                      "trial, FP64 pipe 53 % busy, dependent-issue latency at 3 warps per scheduler; DESIGN.md section 8")
         for nm in ("C2s", "C5s"):
             r = measure(cx, nm, xs, 3, want_e2e=not args.no_e2e)
             r["limiter"] = ("148 chains per GPU at 8 GPUs are one wave: two SMs per chain and the work-ordered queue keep the FP64 "
