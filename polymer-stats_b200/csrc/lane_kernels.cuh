@@ -104,18 +104,21 @@ __global__ void __launch_bounds__(T, MINB) k_run_lane(const RunArgs a) {
 // trial — needed by the averagers, which record every trial — are inclusive prefix sums of the
 // accepted increments.  Each lane keeps its own compensated accumulators; they are combined at output
 // rows and at the end.  Windows never cross an adaptation boundary or an output row.
-template <int ISING, int MINB, bool COMP>
-__global__ void __launch_bounds__(128, MINB) k_run_warp(const RunArgs a) {
+// CPB chains per CTA: 4 (128 threads) for ensembles of several waves; 1 for an ensemble that is at most one wave of
+// warps — 2048 chains (the share of an 8-GPU phase-diagram sweep) are 512 CTAs of four = 3.46 per SM, i.e. 16 warps on
+// some SMs and 12 on others, and the launch ends with the fullest SM; as 2048 one-warp CTAs they spread 14 / 13.
+template <int ISING, int MINB, bool COMP, int CPB = 4>
+__global__ void __launch_bounds__(32 * CPB, MINB) k_run_warp(const RunArgs a) {
   // The per-chain constants and running scalars are warp-uniform: they live in shared memory (one slot per warp),
   // not in every lane's registers — with them in registers the kernel spilled 0.5–0.9 KB per thread at the 128
   // registers that four CTAs per SM allow.  Lane 0 owns the writes; __syncwarp() publishes them.
-  __shared__ ChainParams sP[4];
-  __shared__ ChainDyn sD[4];
+  __shared__ ChainParams sP[CPB];
+  __shared__ ChainDyn sD[CPB];
   // per-lane partial accumulators, [accumulator][lane] (conflict-free): another 34–68 registers otherwise
-  __shared__ double sAcc[4][kNumAcc][32];
-  __shared__ double sComp[COMP ? 4 : 1][COMP ? kNumAcc : 1][32];
+  __shared__ double sAcc[CPB][kNumAcc][32];
+  __shared__ double sComp[COMP ? CPB : 1][COMP ? kNumAcc : 1][32];
   const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
-  const int c = (int)((blockIdx.x * 128u + threadIdx.x) >> 5);
+  const int c = (int)((blockIdx.x * (unsigned)(32 * CPB) + threadIdx.x) >> 5);
   if (c >= a.nchains) return;
   constexpr unsigned FULL = 0xffffffffu;
   const int n = a.n;

@@ -18,10 +18,17 @@ int launch_run_lane(pmc_handle* h, const RunArgs& a) {
     if (use_warp) {
       const unsigned nb = (unsigned)((h->nchains + 3) / 4);
       const bool ising = h->energy_type == PMC_ENERGY_ISING;
-#define PMC_W(IS, MB, CP)                                \
-  {                                                      \
-    PMC_PICK("k_run_warp<" #IS "," #MB "," #CP ">");      \
-    k_run_warp<IS, MB, CP><<<nb, 128, 0, h->stream>>>(a); \
+      // at most one wave of warps (16 per SM): one chain per CTA, so that the block scheduler spreads the warps evenly
+      const bool one_wave = packing_chains(h) <= (long long)h->sm_count * 16 && env_int("PMC_WARP_CPB", 1) == 1;
+#define PMC_W(IS, MB, CP)                                                           \
+  {                                                                                 \
+    if (one_wave) {                                                                 \
+      PMC_PICK("k_run_warp<" #IS ",16," #CP ",1>");                                  \
+      k_run_warp<IS, 16, CP, 1><<<(unsigned)h->nchains, 32, 0, h->stream>>>(a);     \
+    } else {                                                                        \
+      PMC_PICK("k_run_warp<" #IS "," #MB "," #CP ">");                               \
+      k_run_warp<IS, MB, CP><<<nb, 128, 0, h->stream>>>(a);                         \
+    }                                                                               \
   }
 #define PMC_WSEL(MB)                                                        \
   {                                                                         \
