@@ -74,7 +74,11 @@ def test_polar_n512_trajectory(pm, O):
             _compare_run(ens, O.Run(oc, 303, chain, 1), chain, traj, roll, 500, 100, scale_pairs=True)
 
 
-def test_c2_parameters_three_sigma_vs_reference_algorithm(pm, O):
+_C2_CPU = {}   # the CPU arm of the C2 statistics test, computed once for both precisions
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_c2_parameters_three_sigma_vs_reference_algorithm(pm, O, precision):
     """north_star's statistical gate at the headline configuration itself: interacting dielectric n=512, E0=1, kT=1,
     Fz=0.5 (C2).  GPU: 4096 replicas; CPU: the oracle's algo 0 (= the reference's own algorithm: full recompute,
     stateful acceptor) on all host cores with a different seed.  Both sides follow the reference protocol (averages
@@ -88,6 +92,9 @@ def test_c2_parameters_three_sigma_vs_reference_algorithm(pm, O):
     Rg = 4096
     Rc = max(32, 2 * (os.cpu_count() or 8))
     with pm.Ensemble(pc, replicas=Rg, seed=777) as ens:
+        # fp32: the opt-in FP32 rectangle (pmc_set_pair_precision) must pass the same gate against the FP64 reference algorithm
+        ens.set_pair_precision(precision)
+        assert ens.pair_precision() == precision
         _, groll = ens.run(steps, stepout)
         g_avg, g_ar, _ = ens.averages()
 
@@ -96,8 +103,10 @@ def test_c2_parameters_three_sigma_vs_reference_algorithm(pm, O):
         _, rl = run.steps(steps, stepout)
         a, ar, _ = run.averages()
         return a, ar, rl
-    with ThreadPoolExecutor(max_workers=os.cpu_count() or 8) as ex:   # ctypes releases the GIL
-        res = list(ex.map(one, range(Rc)))
+    if "res" not in _C2_CPU:
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 8) as ex:   # ctypes releases the GIL
+            _C2_CPU["res"] = list(ex.map(one, range(Rc)))
+    res = _C2_CPU["res"]
     c_avg = np.array([r[0] for r in res])
     c_ar = np.array([r[1] for r in res])
     croll = np.array([r[2] for r in res])
