@@ -111,7 +111,7 @@ def _segments(mine: np.ndarray, replicas: int):
 
 
 def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
-              rank: int = 0, world: int = 1, protocol=None, bit_identical: bool = False):
+              rank: int = 0, world: int = 1, protocol=None, bit_identical: bool = False, pair_precision: str = "fp64"):
     """Run this rank's contiguous block of every (n, energy) bucket.  Returns a list of
     (global chain ids of the bucket, lo, block [hi-lo][NCOL]).  No communication.
 
@@ -135,6 +135,8 @@ def run_shard(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
             # size instead, and the results are then the same bit for bit for any rank count.
             with lib.Ensemble(cases[case0:case0 + ncases], replicas=nrep, seed=seed, device=device,
                               chain_id_base=int(mine[pos]), ensemble_chains=len(gids) if bit_identical else 0) as ens:
+                if pair_precision != "fp64":   # opt-in FP32 rectangle where a kernel serves it (include/polymc.h)
+                    ens.set_pair_precision(pair_precision)
                 if protocol is None or protocol.get("plain"):
                     # mcmc_eap_chain.jl:276-361: num-inits passes of nsteps trials with the re-initialisation rule between
                     inits = int(protocol.get("num_inits", 1)) if protocol else 1
@@ -181,7 +183,7 @@ def assemble(total: int, parts):
 
 
 def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0, device: int = 0,
-              torch_device=None, protocol=None, bit_identical: bool = False):
+              torch_device=None, protocol=None, bit_identical: bool = False, pair_precision: str = "fp64"):
     """Run every (case, replica) chain of a sweep for nsteps trials, sharded over the ranks of the
     current torch.distributed group (or a single process), then gather the final per-chain results on
     every rank.  Chain order = case-major: avg [ncases*replicas][16], acc_rate, normalizer, sums [..][17]."""
@@ -191,7 +193,8 @@ def run_sweep(cases, replicas: int, nsteps: int, stepout: int = 0, seed: int = 0
     if not isinstance(cases, lib.CaseTable):
         cases = list(cases)
     parts = []
-    for gids, lo, block in run_shard(cases, replicas, nsteps, stepout, seed, device, rank, world, protocol, bit_identical):
+    for gids, lo, block in run_shard(cases, replicas, nsteps, stepout, seed, device, rank, world, protocol, bit_identical,
+                                     pair_precision):
         parts.append((gids, gather_rows(block, len(gids), lo, device=torch_device)))
     return assemble(len(cases) * replicas, parts)
 
@@ -247,7 +250,8 @@ def sweep_table(pargs_list, driver: str = "plain", runs: int = 1, seed: int = 0,
             raise lib.PolymcError(-1, f"cases {seen[pre]} and {i} share the output prefix '{pre}': the swept option is not "
                                       "part of the file-name tokens (aggregate_mcmc.jl:40-57; use --kappaflag for bend-mod)")
         seen[pre] = i
-    res = run_sweep(cases, runs, p0["num-steps"], 0, seed, device, torch_device, protocol, bit_identical)
+    res = run_sweep(cases, runs, p0["num-steps"], 0, seed, device, torch_device, protocol, bit_identical,
+                    p0.get("pair-precision", "fp64"))
     runflag = runs > 1
     entries, texts = [], []
     for i, p in enumerate(pargs_list):
