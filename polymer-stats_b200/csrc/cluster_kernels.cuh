@@ -664,6 +664,231 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_cluster(const RunArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small ensembles: G one-warp teams per chain, each evaluating a DIFFERENT trial of the window at the same time.
+//
+// The reference's studies are a few hundred chains of n ≈ 100: one warp per chain leaves a B200 idle, and more warps
+// on the same trial (k_run_cta_cluster<64|128>) stop paying at the serial head of a trial.  But at the parameters of
+// those studies a trial is rejected far more often than not (acceptance 1–40 %), and a rejected trial leaves the chain
+// as it was — so trial k+1 can be evaluated on the current chain while trial k is still open, and its evaluation stands
+// unless k is accepted.  Here the G warps of a CTA evaluate trials k … k+G−1 of the proposal window against the shared,
+// read-only chain, each into its own scratch arrays; then the trials are committed in order by the whole CTA: a
+// rejected trial only does its bookkeeping, the first accepted one is applied and ends the batch (the speculations
+// behind it saw a stale chain and are evaluated again).  Every decision is taken on exactly the state the sequential
+// chain would show it: same trajectories as the one-team kernels (tests/test_gpu_cluster.py run through this kernel
+// whenever the ensemble is small).
+struct SpecResult {
+  double sums[kNumRed];
+  SegDecision dec;
+  double Dx, Dy, Dz;
+  int lo, hi, reflect, accept;
+};
+
+__host__ __device__ inline size_t cluster_spec_group_bytes(int n) {   // private arrays of one extra team
+  size_t b = (size_t)8 * n * sizeof(double) + sizeof(ClusterCtl);
+  return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t cluster_spec_smem_bytes(int n, int groups) {
+  return cta_smem_bytes_compact(n, 32 * groups) + cluster_extra_bytes(n, 32 * groups) +
+         (size_t)(groups - 1) * cluster_spec_group_bytes(n) + (((size_t)groups * sizeof(SpecResult) + 15) & ~(size_t)15);
+}
+
+template <int G, int MINB, bool CUT>
+__global__ void __launch_bounds__(32 * G, MINB) k_run_cta_cluster_spec(const RunArgs a) {
+  constexpr int T = 32 * G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve_compact(smem_raw, a.n, T);
+  const ClView X = carve_cluster(smem_raw + cta_smem_bytes_compact(a.n, T), a.n, T);
+  unsigned char* extra = smem_raw + cta_smem_bytes_compact(a.n, T) + cluster_extra_bytes(a.n, T);
+  SpecResult* res = reinterpret_cast<SpecResult*>(extra + (size_t)(G - 1) * cluster_spec_group_bytes(a.n));
+  double* rowbuf = S.rowbuf;
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int n = a.n;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  // this team's views: the chain (x, μ, n̂, ψ) is shared and read-only while trials are evaluated; sinθ'/E, n̂', x', ψ',
+  // the reduction slots and the cluster control block are the team's own
+  CtaView Sg = S;
+  ClView Xg = X;
+  Sg.part = S.part + 3 * g;
+  Xg.red = X.red + kNumRed * g;
+  if (g > 0) {
+    double* d = reinterpret_cast<double*>(extra + (size_t)(g - 1) * cluster_spec_group_bytes(n));
+    Sg.E = d;
+    Xg.nnx = d + n; Xg.nny = d + 2 * n; Xg.nnz = d + 3 * n;
+    Xg.xnx = d + 4 * n; Xg.xny = d + 5 * n; Xg.xnz = d + 6 * n;
+    Xg.psn = d + 7 * n;
+    Xg.ctl = reinterpret_cast<ClusterCtl*>(d + 8 * n);
+  }
+  if (tid == 0) {
+    *S.par = a.par[c];
+    *S.dyn = a.dyn[c];
+    *X.dx = a.dynx[c];
+  }
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  load_nhat<T>(mono, n, X);
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const long long step0 = S.dyn->step;
+  const uint32_t init = (uint32_t)S.dyn->init;
+  const bool adapt_on = P.adj_scale != 1.0 && P.steps_per_adjust > 0;
+  long long row = 0;
+  Countdown row_due, adapt_due;
+  row_due.start(step0, a.stepout);
+  adapt_due.start(step0, adapt_on ? P.steps_per_adjust : 0);
+
+  long long s = 1;
+  while (s <= a.nsteps) {
+    // ---- window [s, s+wlen): never across an adaptation boundary --------------------------------------------
+    long long wl = a.nsteps - s + 1;
+    if (wl > kClWin) wl = kClWin;
+    if (adapt_on && wl > adapt_due.left) wl = adapt_due.left;
+    const int wlen = (int)wl;
+    if (tid < 32) {
+      if (tid < wlen) make_window_entry(a, P, *S.dyn, mono, chain_id, step0 + s + tid, X.win[tid]);
+      if (tid == 0) X.ctl->dirty = 0u;
+    }
+    __syncthreads();  // window visible
+    int k = 0;
+    while (k < wlen) {
+      const int nb = min(G, wlen - k);
+      // ---- phase 1: team g evaluates trial k+g on the current chain ------------------------------------------
+      if (g < nb) {
+        const int kk = k + g;
+        const long long step = step0 + s + kk;
+        if ((X.ctl->dirty >> kk) & 1u) {  // an accepted trial of this window moved this monomer: rebuild the entry
+          if (lane == 0) make_window_entry(a, P, *S.dyn, mono, chain_id, step, X.win[kk]);
+          __syncwarp();
+        }
+        const ClProposal* q = &X.win[kk];
+        double acc[kNumRed], sums[kNumRed];
+#pragma unroll
+        for (int r = 0; r < kNumRed; ++r) acc[r] = 0.0;
+        warp_cluster_grow(Xg, *q, q->reflect, P, n, a.seed, chain_id, init, step, *Xg.ctl);
+        __syncwarp();
+        if (Xg.ctl->hi - Xg.ctl->lo < 32)
+          warp_segment_build(Sg, Xg, mono, P, *q, Xg.ctl->lo, Xg.ctl->hi, Xg.ctl->reflect != 0, acc, *Xg.ctl);
+        __syncwarp();
+        const int lo = Xg.ctl->lo, hi = Xg.ctl->hi;
+        const bool reflect = Xg.ctl->reflect != 0;
+        double Dx = Xg.ctl->Dx, Dy = Xg.ctl->Dy, Dz = Xg.ctl->Dz;
+        if (hi - lo >= 32) cta_segment_build<32>(Sg, Xg, mono, P, *q, lo, hi, reflect, acc, Dx, Dy, Dz);
+        segment_sums<32, CUT>(Sg, Xg, P, n, a.energy_type, lo, hi, Dx, Dy, Dz, acc, sums);
+        const double la = reflect ? cluster_log_alpha(Xg, n, lo, hi, Xg.ctl->up, Xg.ctl->lp) : 0.0;
+        // the α carry changes only when a trial is accepted: valid for every trial that is committed from this batch
+        const SegDecision dec = segment_decision(P, a.energy_type, sums, Dx, Dz, la, X.dx->carry);
+        const bool accept = metropolis(dec.dlogpi, q->eps);
+        if (lane == 0) {
+          SpecResult& R = res[g];
+#pragma unroll
+          for (int r = 0; r < kNumRed; ++r) R.sums[r] = sums[r];
+          R.dec = dec;
+          R.Dx = Dx; R.Dy = Dy; R.Dz = Dz;
+          R.lo = lo; R.hi = hi; R.reflect = reflect ? 1 : 0; R.accept = accept ? 1 : 0;
+        }
+      }
+      __syncthreads();  // all evaluations of the batch are in
+      // ---- phase 2: commit in order, by the whole CTA; the first accepted trial ends the batch ------------------
+      int committed = 0;
+      for (int b = 0; b < nb; ++b) {
+        const SpecResult& R = res[b];
+        const int kk = k + b;
+        const long long step = step0 + s + kk;
+        const ClProposal* q = &X.win[kk];
+        const bool accept = R.accept != 0, reflect = R.reflect != 0;
+        const int lo = R.lo, hi = R.hi;
+        if (accept) {  // the trial chain of team b becomes the chain (mcmc_clustering_eap_chain.jl:274-275)
+          const double* bE = S.E;
+          const double *bnx = X.nnx, *bny = X.nny, *bnz = X.nnz, *bxx = X.xnx, *bxy = X.xny, *bxz = X.xnz, *bps = X.psn;
+          if (b > 0) {
+            const double* d = reinterpret_cast<const double*>(extra + (size_t)(b - 1) * cluster_spec_group_bytes(n));
+            bE = d; bnx = d + n; bny = d + 2 * n; bnz = d + 3 * n; bxx = d + 4 * n; bxy = d + 5 * n; bxz = d + 6 * n;
+            bps = d + 7 * n;
+          }
+          const double Dx = R.Dx, Dy = R.Dy, Dz = R.Dz;
+          for (int m = lo + tid; m <= hi; m += T) {
+            double phi, theta, sb;
+            segment_angles(mono, *q, m, reflect, P.planar, phi, theta, sb);
+            MonoRec rec;
+            rec.phi = phi; rec.theta = theta;
+            rec.nx = bnx[m]; rec.ny = bny[m]; rec.nz = bnz[m];
+            rec.sth = (bE[m] == kKeepSinTheta) ? sb : bE[m];
+            mono[m] = rec;
+            X.nhx[m] = rec.nx; X.nhy[m] = rec.ny; X.nhz[m] = rec.nz;
+            S.sx[m] = bxx[m]; S.sy[m] = bxy[m]; S.sz[m] = bxz[m];
+            double ux, uy, uz;
+            mu_of(P, rec.nx, rec.ny, rec.nz, ux, uy, uz);
+            S.mx[m] = ux; S.my[m] = uy; S.mz[m] = uz;
+          }
+          for (int j = hi + 1 + tid; j < n; j += T) {
+            S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
+          }
+          for (int i = max(lo - 1, 0) + tid; i <= min(hi, n - 2); i += T) X.psi[i] = bps[i];
+          if (tid < 32) {  // later entries of the window on a monomer of the segment are stale now
+            const int widx = X.win[tid].idx;
+            const bool stale = tid > kk && tid < wlen && widx >= lo && widx <= hi;
+            const unsigned m = __ballot_sync(0xffffffffu, stale);
+            if (tid == 0 && m) X.ctl->dirty |= m;
+          }
+        }
+        if (tid == 0) {
+          ChainDyn& D = *S.dyn;
+          ChainDynX& DX = *X.dx;
+          if (accept) {
+            D.U += R.dec.dU;
+            D.Omega += R.sums[R_OMEGA];
+            D.su += R.dec.dsu;
+            D.r[0] += R.Dx; D.r[1] += R.Dy; D.r[2] += R.Dz;
+            D.p[0] += R.sums[R_PX]; D.p[1] += R.sums[R_PY]; D.p[2] += R.sums[R_PZ];
+            DX.spsi += R.sums[R_PSI];
+            DX.scos2 += R.sums[R_COS2];
+            DX.carry = P.alpha_carry ? R.dec.la : 0.0;  // logπ_prev = logπ + log α (acceptance.jl:32-33)
+            D.nacc += 1;
+            D.nacc_total += 1;
+          }
+          D.natt += 1;
+          D.steps_total += 1;
+          D.step = step;
+          if (reflect) {
+            const double sz = (double)(hi - lo + 1);
+            DX.ncluster += 1.0; DX.cluster_sum += sz; DX.cluster_max = fmax(DX.cluster_max, sz);
+          }
+        }
+        const bool adapt_now = adapt_due.tick();   // every thread keeps the same countdowns
+        if (tid == 0) bookkeep_cluster(P, *S.dyn, *X.dx, adapt_now, n, a.compensated != 0);
+        const bool isrow = row_due.tick();
+        if (isrow) {
+          __syncthreads();  // records of this trial are visible
+          if (row < a.rows) {
+            if (tid == 0) stage_row_cluster(*S.dyn, *X.dx, step, rowbuf);
+            if (a.state) {
+              double* st = a.state + ((size_t)c * a.rows + row) * 2 * (size_t)n;
+              for (int m = tid; m < n; m += T) {
+                const MonoRec r = mono[m];
+                st[2 * m] = r.phi; st[2 * m + 1] = r.theta;
+              }
+            }
+            __syncthreads();
+            if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = rowbuf[tid];
+            if (tid < a.roll_cols) a.roll[((size_t)c * a.rows + row) * a.roll_cols + tid] = rowbuf[8 + tid];
+          }
+          ++row;
+        }
+        ++committed;
+        if (accept) break;  // the speculations behind this trial saw the chain before it
+      }
+      k += committed;
+      __syncthreads();  // state, records, running scalars and the dirty mask are visible
+    }
+    s += wlen;
+  }
+  if (tid == 0) {
+    a.dyn[c] = *S.dyn;
+    a.dynx[c] = *X.dx;
+  }
+}
+
 // Non-mutating changed-term sums of one scripted composite trial (same device code as the run kernel).
 struct SegDeltaArgs {
   const MonoRec* mono;

@@ -270,13 +270,13 @@ ChainParams params_of(const pmc_case& c0, double kT_scale = 1.0) {
 // A small ensemble leaves SMs idle — 148 chains of n=100 are one warp per SM — so each chain gets 2× or 4× the
 // threads until the warps resident per SM reach what the base shape has when the machine is full
 // (profiles/r01f_tune_small_ensembles.txt: +50–80 % at one chain per SM, nothing lost on large ensembles).
-static int scaled_threads(int base, int minb, size_t smem, int tmax, int64_t chains, int sms) {
+static int scaled_threads(int base, int minb, size_t smem, int tmax, int64_t chains, int sms, int max_scale = 4) {
   const int fit = (int)std::max<size_t>(1, (size_t)233472 / (smem + 1024));  // CTAs per SM that fit in shared memory
   const int resident_max = std::min(minb, fit);
   const double sat = (double)resident_max * (base / 32);                     // warps per SM, full machine
   const double res = std::min((double)chains / sms, (double)resident_max) * (base / 32);
   int scale = 1;
-  while (scale < 4 && base * scale * 2 <= tmax && res * scale * 2 <= sat) scale *= 2;
+  while (scale < max_scale && base * scale * 2 <= tmax && res * scale * 2 <= sat) scale *= 2;
   return base * scale;
 }
 
@@ -287,8 +287,25 @@ static void choose_shape(pmc_handle* h) {
   if (h->cluster_mode && cta_pairs) {
     const int base = pick_cluster_threads(h->n);
     const int minb = base == 32 ? (h->n <= 40 ? 16 : h->n <= 110 ? 10 : 8) : base == 64 ? 5 : base == 128 ? cluster_fit128(h->n) : 1;
-    int t = scaled_threads(base, minb, cluster_smem_bytes(h->n, base), 256, chains, h->sm_count);
-    while (t > base && cluster_delta_smem_bytes(h->n, t) > (size_t)kSmemMax) t /= 2;
+    int t;
+    if (base == 32 && env_int("PMC_CLUSTER_SPEC", 1) != 0) {
+      // one-warp teams (n ≤ 160): the extra warps of a small ensemble run DIFFERENT trials of the same chain
+      // (k_run_cta_cluster_spec).  The largest number of teams whose CTAs are all resident at once — a second wave costs
+      // more than the teams gain (profiles/r02d_tune_spec.txt: 500 chains on 444 slots of four teams lose to two teams)
+      t = 32;
+      const int teams[3] = {8, 4, 2}, per_sm[3] = {1, 3, 5};   // launch bounds of run_cluster_cta.cu
+      for (int k = 0; k < 3; ++k) {
+        const size_t smem = cluster_spec_smem_bytes(h->n, teams[k]) + 1024;
+        const int fit = (int)std::min<size_t>((size_t)per_sm[k], (size_t)233472 / smem);
+        if (fit >= 1 && chains <= (int64_t)h->sm_count * fit && cluster_delta_smem_bytes(h->n, 32 * teams[k]) <= (size_t)kSmemMax) {
+          t = 32 * teams[k];
+          break;
+        }
+      }
+    } else {
+      t = scaled_threads(base, minb, cluster_smem_bytes(h->n, base), 256, chains, h->sm_count);
+      while (t > base && cluster_delta_smem_bytes(h->n, t) > (size_t)kSmemMax) t /= 2;
+    }
     h->cta_threads = t;
     return;
   }

@@ -25,6 +25,35 @@ int launch_run_cluster_cta(pmc_handle* h, const RunArgs& a) {
       k_run_cta_cluster<TT, MB, false><<<nblocks, TT, smem, h->stream>>>(a);              \
     }                                                                                     \
   }
+    // Small ensembles of short chains (one-warp teams, n ≤ 160): the extra warps choose_shape grants per chain evaluate
+    // DIFFERENT trials at the same time (k_run_cta_cluster_spec) instead of sharing one; PMC_CLUSTER_SPEC=0: the shared-trial
+    // kernels below (experiments)
+    if (pick_cluster_threads(h->n) == 32 && h->cta_threads > 32 && env_int("PMC_CLUSTER_SPEC", 1) && !env_int("PMC_CLUSTER_CFG", 0)) {
+      const int groups = h->cta_threads / 32;
+      const size_t smem = cluster_spec_smem_bytes(h->n, groups);
+      if (smem <= (size_t)kSmemMax) {
+#define PMC_SP(GG, MB)                                                                               \
+  {                                                                                                  \
+    PMC_PICK(cut ? "k_run_cta_cluster_spec<" #GG "," #MB ",cut>" : "k_run_cta_cluster_spec<" #GG "," #MB ">"); \
+    if (cut) {                                                                                       \
+      int rc = set_smem(k_run_cta_cluster_spec<GG, MB, true>, smem);                                 \
+      if (rc) return rc;                                                                             \
+      k_run_cta_cluster_spec<GG, MB, true><<<nblocks, 32 * GG, smem, h->stream>>>(a);                \
+    } else {                                                                                         \
+      int rc = set_smem(k_run_cta_cluster_spec<GG, MB, false>, smem);                                \
+      if (rc) return rc;                                                                             \
+      k_run_cta_cluster_spec<GG, MB, false><<<nblocks, 32 * GG, smem, h->stream>>>(a);               \
+    }                                                                                                \
+    ++h->launches;                                                                                   \
+    PMC_CU(cudaGetLastError());                                                                      \
+    return PMC_OK;                                                                                   \
+  }
+        if (groups == 2) PMC_SP(2, 5)
+        if (groups == 4) PMC_SP(4, 3)
+        if (groups == 8) PMC_SP(8, 1)
+#undef PMC_SP
+      }
+    }
     // PMC_CLUSTER_CFG = threads*100 + minblocks selects a tuning variant (experiments only)
     const int ccfg = env_int("PMC_CLUSTER_CFG", 0);
 #ifdef PMC_TUNING_VARIANTS
@@ -44,7 +73,7 @@ int launch_run_cluster_cta(pmc_handle* h, const RunArgs& a) {
 #else
     (void)ccfg;
 #endif
-    switch (h->cta_threads) {
+    switch (h->cta_threads > 256 ? 256 : h->cta_threads) {
       case 32:  // very short chains fit 16 per SM in shared memory: worth the 128-register build (+9 % at n=25)
         // registers beat occupancy for the one-warp teams (profiles/r02b_tune_k1.txt): 10 chains per SM at 204 registers are
         // +6 % over 12 at 170 for n = 64 … 100, 8 per SM +11 % at n = 150; only very short chains gain from 16 per SM

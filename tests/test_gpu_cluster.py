@@ -388,3 +388,41 @@ def test_clustering_cli_twin_end_to_end(pm, tmp_path):
     # refusals of the reference
     bad = subprocess.run(argv[:2] + ["--profile", "-v", "0"], capture_output=True, text=True, timeout=120)
     assert bad.returncode != 0 and "Not currently implemented" in bad.stderr
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=48, E0=0.6, Fz=0.3, kT=4.0, energy_type="interacting", kappa=0.5, cluster_prob=0.5),     # acceptance ≈ 0.5: many
+    dict(n=100, E0=1.0, Fz=0.25, energy_type="interacting", kappa=0.5),                             # K1 / K5's chain
+    dict(n=150, E0=1.2, Fz=0.1, kT=2.0, energy_type="cutoff", cutoff_radius=4.0, cluster_prob=0.3, chain_type="polar", mu=0.6),
+    dict(n=40, E0=0.8, Fz=0.2, kT=3.0, energy_type="interacting", planar=True),                     # 2-D tree
+])
+def test_speculative_teams_are_the_sequential_chain(pm, kw):
+    """k_run_cta_cluster_spec: 2, 4 or 8 one-warp teams evaluate different trials of the window at once and commit them
+    in order (the first accepted trial ends a batch).  Every decision is taken on the state the sequential chain would
+    show it, with the same per-team arithmetic as the one-warp kernel: acceptance counts, cluster statistics, the state
+    rows and the final chains are IDENTICAL to k_run_cta_cluster<32,…>, whatever the number of teams — also at
+    acceptance rates where most batches are cut short."""
+    case = pm.make_case(clustering=True, adj_ub=0.4, steps_per_adjust=250, **kw)
+    R, steps = 12, 3000
+    ref = None
+    for hint, teams in ((10 ** 6, 1), (600, 2), (300, 4), (0, 8)):
+        with pm.Ensemble(case, replicas=R, seed=2024, ensemble_chains=hint) as ens:
+            name = ens.kernel_name()
+            assert name.startswith("k_run_cta_cluster<32," if teams == 1 else f"k_run_cta_cluster_spec<{teams},"), name
+            ens.begin_stage(1.0)
+            traj, roll, state = ens.run_ex(steps, 500, want_state=True)
+            ens.run_ex(777, 0)                                    # a second launch: windows restart mid-adaptation-period
+            got = dict(acc=ens.diagnostics()[:, 4].copy(), stats=ens.cluster_stats().copy(), final=ens.get_state_all(),
+                       traj=traj, roll=roll, state=state, avg=ens.averages()[0], ex=ens.extra_averages())
+        if ref is None:
+            ref = got
+            assert 0 < ref["acc"].sum() < R * (steps + 777)
+            continue
+        np.testing.assert_array_equal(got["acc"], ref["acc"])
+        np.testing.assert_array_equal(got["stats"], ref["stats"])
+        for a, b in zip(got["final"], ref["final"]):
+            np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(got["state"], ref["state"])
+        # energies: the staged positions come from a block scan whose partition follows the CTA size (rounding)
+        for key in ("traj", "roll", "avg", "ex"):
+            np.testing.assert_allclose(got[key], ref[key], rtol=1e-9, atol=1e-9)

@@ -304,7 +304,10 @@ def test_block_size_follows_ensemble_size_and_results_agree(pm):
                      adj_ub=0.4, steps_per_adjust=100)
     with pm.Ensemble(k, replicas=5, seed=12) as small, \
             pm.Ensemble(k, replicas=5, seed=12, ensemble_chains=10 ** 6) as full:
-        assert small.block_threads() == 4 * full.block_threads() == 128
+        # composite trials of short chains: the extra warps are one-warp teams on DIFFERENT trials of the window
+        # (k_run_cta_cluster_spec) — eight of them when every chain's CTA is resident at once
+        assert small.block_threads() == 8 * full.block_threads() == 256
+        assert small.kernel_name().startswith("k_run_cta_cluster_spec<8,") and full.kernel_name().startswith("k_run_cta_cluster<32,")
         for e in (small, full):
             e.begin_stage(1.0)
         t1, r1, s1 = small.run_ex(600, 100, want_state=True)
