@@ -94,6 +94,9 @@ WORKLOADS = {
                desc="K4: clustering driver, Ising + bending, n=100, 500 chains"),
     "K5": dict(cases=[dict(K_KW, energy_type="interacting")], replicas=500, S=2000, stepout=250, scaling="weak",
                e2e="state", desc="K5: clustering driver, all-pairs + bending, n=100, 500 chains"),
+    "K6": dict(cases=[dict(K_KW, energy_type="interacting")], replicas=100, S=4000, stepout=500, scaling="weak",
+               e2e="state", desc="K6: clustering driver, all-pairs + bending, n=100, 100 chains per GPU — the size of one study "
+                                 "of the reference (a handful of cases x 25 runs); eight one-warp teams per chain on different trials"),
     # strong scaling: the TOTAL is fixed and split over the GPUs
     "C2s": dict(cases=[C2_KW], replicas=4096, S=500, stepout=500, scaling="strong", e2e="state",
                 desc="C2 strong: interacting dielectric n=512, 4096 chains in total"),
@@ -583,13 +586,16 @@ def main():
     workloads, strong, multi_abi = {}, {}, None
     if extras:
         xs = max(2, min(args.steps, 3))
-        for nm in ("C3", "C4", "C5", "K1", "C2f32"):
+        for nm in ("C3", "C4", "C5", "K1", "K6", "C2f32"):
             workloads[nm] = measure(cx, nm, xs, 3, want_e2e=not args.no_e2e)
         workloads["C2f32"]["dtype"] = "f32 rectangle pair terms; f64 state, row terms, acceptance and accumulators (opt-in, not the headline)"
         workloads["C4"]["limiter"] = ("device-timed: one chain per warp, 32 speculative trials per window; issue slots 61 % busy, the "
                                       "transcendental core (2 sincos, log, exp, 2 Philox per trial) is a quarter of the samples; at 8 GPUs "
                                       "2048 chains per GPU are 0.86 of one wave (13.8 warps per SM); e2e through run_sweep adds ~1 ms of host "
                                       "work per call (contiguous case table, one all-gather)")
+        workloads["K6"]["limiter"] = ("100 chains cannot fill 148 SMs with one warp each: eight teams per chain evaluate different trials of "
+                                      "the window and commit in order; a batch lasts as long as its slowest trial and ends at its first "
+                                      "accepted one (profiles/r02d_tune_spec.txt)")
         workloads["K1"]["limiter"] = ("one warp per chain, 12 chains per SM (registers and shared memory): 3450 FP64 of 5984 warp instructions per "
                                       "trial, FP64 pipe 53 % busy, dependent-issue latency at 3 warps per scheduler; DESIGN.md section 8")
         for nm in ("C2s", "C5s"):
