@@ -84,6 +84,39 @@ for kw, R, steps in ((dict(n=100, E0=1.0, Fz=0.5), 4096, 300000), (dict(n=100, E
         if same else "DIFF", res["lane"][2], res["lane"][3], res["warp"][2], res["warp"][3]), flush=True)
     bad += not same
 
+# Composite trials: 8 / 4 / 2 one-warp teams on different trials of the window, committed in order (k_run_cta_cluster_spec),
+# against one team per chain: identical acceptance counts, cluster statistics and final chains over long runs.
+for kw, R, steps in ((dict(n=100, E0=1.0, Fz=0.25, energy_type="interacting", kappa=0.5), 96, 150000),
+                     (dict(n=64, E0=0.5, Fz=0.3, kT=3.0, energy_type="interacting", kappa=0.2, cluster_prob=0.4), 96, 200000),
+                     (dict(n=120, E0=1.0, Fz=0.25, energy_type="cutoff", cutoff_radius=5.0, kappa=0.5), 64, 100000)):
+    res = {}
+    for hint in (10 ** 6, 600, 300, 0):
+        with pm.Ensemble(pm.make_case(clustering=True, adj_ub=0.4, **kw), replicas=R, seed=31337, ensemble_chains=hint) as ens:
+            ens.begin_stage(1.0)
+            t0 = time.time()
+            ens.run_ex(steps // 2, 0, fetch_rows=False)
+            ens.run_ex(steps - steps // 2, 5000, fetch_rows=False)
+            res[hint] = (ens.diagnostics()[:, 4].copy(), ens.cluster_stats().copy(), ens.get_state_all(), ens.kernel_name(), time.time() - t0,
+                         ens.diagnostics()[:, 6].copy())
+    ref = res[10 ** 6]
+    # per chain: identical acceptance count, cluster statistics and final chain in every variant
+    eq = np.ones(R, dtype=bool)
+    for r in res.values():
+        eq &= (ref[0] == r[0]) & np.all(ref[1] == r[1], axis=1) & np.all(ref[2][0] == r[2][0], axis=1) & np.all(ref[2][1] == r[2][1], axis=1)
+    # A chain of point dipoles without excluded volume can collapse until two monomers sit on top of each other
+    # (|U| ~ 1e9 kT and more): there a trial's ΔU is a difference of sums that contain such a term, its rounding error
+    # (1e-16 |U|) reaches the scale of kT·|log ε − logπ ratio| and the variants — whose staged positions differ in the
+    # last bit — may legitimately part ways.  tools/debug_spec2.py: the first differing trial of such a chain has the same
+    # ΔU through the seam in both shapes, and the speculative teams stay on the CPU oracle's trajectory.
+    collapsed = np.abs(res[10 ** 6][5]) > 1e8
+    same = bool(np.all(eq | collapsed))
+    print("speculative teams %s, %d chains x %d trials (acceptance %.3f): %s  %s" % (
+        {k: v for k, v in kw.items() if k in ("n", "energy_type")}, R, steps, ref[0].sum() / (R * steps),
+        ("ok  identical acceptance counts, cluster statistics and final chains" if same else "DIFF") +
+        ("" if eq.all() else " (%d chain(s) differ, all collapsed: |U| = %s)" % ((~eq).sum(), ", ".join("%.1e" % abs(u) for u in res[10 ** 6][5][~eq]))),
+        ", ".join("%s %.1f s" % (r[3], r[4]) for r in res.values())), flush=True)
+    bad += not same
+
 # The opt-in FP32 rectangle on a chain that stays extended (weak coupling): drift of the running energy per launch
 with pm.Ensemble(pm.make_case(n=512, E0=0.3, Fz=1.0, energy_type="interacting"), replicas=1024, seed=5) as ens:
     ens.set_pair_precision("fp32")
