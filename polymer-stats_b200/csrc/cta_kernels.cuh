@@ -668,6 +668,153 @@ __global__ void __launch_bounds__(T, MINB) k_run_cta_win(const RunArgs a) {
   if (tid == 0) a.dyn[c] = *S.dyn;
 }
 
+// Small ensembles of short chains: G one-warp teams per chain, each evaluating a DIFFERENT trial of the window at once.
+//
+// A few hundred chains of n ≈ 100 (what one study of the reference runs) cannot fill 148 SMs, and more warps on ONE trial
+// stop paying at its serial parts.  A rejected trial leaves the chain as it was — and at the parameters of those studies
+// most trials are rejected — so trials k … k+G−1 of the proposal window are evaluated at the same time against the
+// shared, read-only staged chain (each team has its own E array), and then committed in order by the whole CTA: a
+// rejected trial only does its bookkeeping, the first accepted one is applied and ends the batch (what was evaluated
+// behind it saw a stale chain and is evaluated again).  Every decision is taken on exactly the state the sequential
+// chain would show it.  The composite-trial counterpart is k_run_cta_cluster_spec (cluster_kernels.cuh).
+struct SpecTrial {
+  double dsum;
+  int accept, pad;
+};
+
+__host__ __device__ inline size_t cta_smem_bytes_spec(int n, int groups) {
+  return cta_smem_bytes_win(n) + (((size_t)(groups - 1) * n * sizeof(double) + (size_t)groups * sizeof(SpecTrial) + 15) & ~(size_t)15);
+}
+
+template <int G, int MINB>
+__global__ void __launch_bounds__(32 * G, MINB) k_run_cta_win_spec(const RunArgs a) {
+  constexpr int T = 32 * G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CtaView S = carve(smem_raw, a.n);
+  Proposal* win = reinterpret_cast<Proposal*>(smem_raw + cta_smem_bytes(a.n));
+  unsigned* dirty = reinterpret_cast<unsigned*>(win + kWin);
+  double* extraE = reinterpret_cast<double*>(smem_raw + cta_smem_bytes_win(a.n));
+  SpecTrial* res = reinterpret_cast<SpecTrial*>(extraE + (size_t)(G - 1) * a.n);
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int n = a.n;
+  MonoRec* mono = a.mono + (size_t)c * n;
+  CtaView Sg = S;                       // this team's view: its own E array, everything else shared
+  if (g > 0) Sg.E = extraE + (size_t)(g - 1) * n;
+  if (tid == 0) {
+    *S.par = a.par[c];
+    *S.dyn = a.dyn[c];
+  }
+  __syncthreads();
+  const ChainParams& P = *S.par;
+  load_chain<T>(mono, P, n, S);
+  const uint32_t chain_id = a.chain_id_base + (uint32_t)c;
+  const double b = P.b, inv_kT = P.inv_kT;
+  const long long step0 = S.dyn->step;
+  const uint32_t init = (uint32_t)S.dyn->init;
+  const bool adapt_on = P.adj_scale != 1.0 && P.steps_per_adjust > 0;
+  long long row = 0;
+  Countdown row_due, adapt_due;
+  row_due.start(step0, a.stepout);
+  adapt_due.start(step0, adapt_on ? P.steps_per_adjust : 0);
+
+  long long s = 1;
+  while (s <= a.nsteps) {
+    long long wl = a.nsteps - s + 1;
+    if (wl > kWin) wl = kWin;
+    if (adapt_on && wl > adapt_due.left) wl = adapt_due.left;   // windows never cross an adaptation boundary
+    const int wlen = (int)wl;
+    if (tid < 32) {
+      if (tid < wlen) {
+        const Draws d = draw_step(a.seed, chain_id, init, step0 + s + tid, n);
+        const MonoRec rec = mono[d.idx];
+        double dphi, dtheta;
+        increments(P, d, rec.theta, S.dyn->phi_step, S.dyn->theta_step, dphi, dtheta);
+        build_proposal(P, rec, d.idx, dphi, dtheta, d.eps, win[tid]);
+      }
+      if (tid == 0) *dirty = 0u;
+    }
+    __syncthreads();  // window visible
+    int k = 0;
+    while (k < wlen) {
+      const int nb = min(G, wlen - k);
+      // ---- phase 1: team g evaluates trial k+g on the current chain ------------------------------------------
+      if (g < nb) {
+        const int kk = k + g;
+        if ((*dirty >> kk) & 1u) {  // an accepted trial of this window moved the same monomer: rebuild the entry
+          if (lane == 0) make_proposal(a, P, *S.dyn, mono, chain_id, step0 + s + kk, win[kk]);
+          __syncwarp();
+        }
+        const Proposal* q = &win[kk];
+        double dsum = 0.0;
+        bool accept = false;
+        if (!q->skip) {
+          const double part = delta_pairs_partial<WarpTeam, 1>(Sg, n, 1, b, q->idx, q->mx, q->my, q->mz, q->dnx, q->dny, q->dnz);
+          accept = decide(q->single, warp_sum(part), inv_kT, q->eps, dsum);
+        }
+        if (lane == 0) {
+          res[g].dsum = dsum;
+          res[g].accept = accept ? 1 : 0;
+        }
+      }
+      __syncthreads();  // all evaluations of the batch are in
+      // ---- phase 2: commit in order; the first accepted trial ends the batch ---------------------------------
+      int committed = 0;
+      for (int bb = 0; bb < nb; ++bb) {
+        const int kk = k + bb;
+        const long long step = step0 + s + kk;
+        const Proposal* q = &win[kk];
+        const bool accept = res[bb].accept != 0;
+        const int idx = q->idx;
+        if (accept) {  // apply move!: x_idx += (b/2)Δn̂, x_{j>idx} += bΔn̂, μ_idx = μ'
+          const double Dx = b * q->dnx, Dy = b * q->dny, Dz = b * q->dnz;
+          for (int j = idx + 1 + tid; j < n; j += T) {
+            S.sx[j] += Dx; S.sy[j] += Dy; S.sz[j] += Dz;
+          }
+          if (tid < 32) {  // later proposals of the window on the same monomer are stale now
+            const bool stale = tid > kk && tid < wlen && win[tid].idx == idx;
+            const unsigned m = __ballot_sync(0xffffffffu, stale);
+            if (tid == 0 && m) *dirty |= m;
+          }
+        }
+        if (tid == 0) {
+          if (accept) {
+            S.sx[idx] += 0.5 * b * q->dnx; S.sy[idx] += 0.5 * b * q->dny; S.sz[idx] += 0.5 * b * q->dnz;
+            S.mx[idx] = q->mx; S.my[idx] = q->my; S.mz[idx] = q->mz;
+            MonoRec rec;
+            rec.phi = q->phi; rec.theta = q->theta;
+            rec.nx = q->nx; rec.ny = q->ny; rec.nz = q->nz; rec.sth = q->sth;
+            mono[idx] = rec;
+          }
+          apply_decision(P, *S.dyn, *q, accept, res[bb].dsum, step);
+        }
+        const bool adapt_now = adapt_due.tick();   // every thread keeps the same countdowns
+        if (tid == 0) {
+          if (adapt_now) adapt_apply(P, S.dyn->phi_step, S.dyn->theta_step, S.dyn->nacc, S.dyn->natt);
+          record_averages<true>(P, S.dyn->acc, S.dyn->comp, S.dyn->r, S.dyn->p, S.dyn->U, S.dyn->su, S.dyn->log_gauge);
+        }
+        const bool isrow = row_due.tick();
+        if (isrow && tid < 32) {
+          if (tid == 0) stage_row(*S.dyn, step, S.rowbuf);
+          __syncwarp();
+          if (row < a.rows) {
+            if (tid < 8) a.traj[((size_t)c * a.rows + row) * 8 + tid] = S.rowbuf[tid];
+            if (tid < 17) a.roll[((size_t)c * a.rows + row) * 17 + tid] = S.rowbuf[8 + tid];
+          }
+          __syncwarp();
+        }
+        if (isrow) ++row;
+        ++committed;
+        if (accept) break;  // the speculations behind this trial saw the chain before it
+      }
+      k += committed;
+      __syncthreads();  // state, records, running scalars and the dirty mask are visible
+    }
+    s += wlen;
+  }
+  if (tid == 0) a.dyn[c] = *S.dyn;
+}
+
 // Warp-specialised variant of the hot loop: warp 0 is the control warp (RNG, proposal, bookkeeping,
 // output rows), warps 1..WK are the workers that own the pair sums.  The control warp prepares the
 // proposal of trial s+1 and does the bookkeeping of trial s−1 WHILE the workers evaluate trial s, so

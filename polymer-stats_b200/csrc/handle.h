@@ -82,6 +82,7 @@ struct pmc_handle {
   long long warp_mode_below = 0;
   long long warp_cluster_below = 11000;  // composite trials: chain per warp below this many chains, else per lane
   int compensated = 0;        // Neumaier-compensated accumulators in the lane/warp kernels (CTA kernels: always)
+  int spec_teams = 0;         // > 0: small ensemble of short interacting chains — one-warp teams on different trials (k_run_cta_win_spec)
   int pair_precision = 0;     // 0: FP64 everywhere; 1: the rectangle of single-monomer trials in FP32 where a kernel exists (cta_f32.cuh)
   int use_win = 1;            // windowed run kernel (batched proposals) whenever shared memory allows
   std::vector<ChainDyn> host_dyn;

@@ -316,6 +316,23 @@ static void choose_shape(pmc_handle* h) {
   }
   const int minb = base == 64 ? 8 : base == 128 ? 4 : base == 256 ? 2 : 1;
   h->cta_threads = scaled_threads(base, minb, cta_smem_bytes_win(h->n), 512, chains, h->sm_count);
+  // Small ensembles of short interacting chains: one-warp teams on DIFFERENT trials of the window (k_run_cta_win_spec)
+  // instead of more warps on one trial.  Unlike the composite trial, the single-monomer trial has almost no serial head and
+  // shares well among warps, so this pays only where a warp is enough for a trial (profiles/r02e_tune_spec_plain.txt):
+  // n ≤ 64 with the largest number of teams whose CTAs are all resident at once (8 × 1, 4 × 3, 2 × 6 per SM: +10–70 %), and
+  // n ≤ 110 when every chain can have a whole SM (eight teams, +17–29 %); above that the one-trial kernels win.
+  h->spec_teams = 0;
+  if (h->energy_type == PMC_ENERGY_INTERACTING && !h->cluster_mode && h->n <= 110 && env_int("PMC_RUN_SPEC", 1) != 0) {
+    const int teams[3] = {8, 4, 2}, per_sm[3] = {1, 3, 6};
+    for (int k = 0; k < (h->n <= 64 ? 3 : 1); ++k) {
+      const size_t smem = cta_smem_bytes_spec(h->n, teams[k]) + 1024;
+      const int fit = (int)std::min<size_t>((size_t)per_sm[k], (size_t)233472 / smem);
+      if (fit >= 1 && chains <= (int64_t)h->sm_count * fit) {
+        h->spec_teams = teams[k];
+        break;
+      }
+    }
+  }
 }
 
 int fetch_dyn(pmc_handle* h) {

@@ -33,6 +33,25 @@ int launch_delta_cta_f32(pmc_handle* h, const DeltaArgs& a) {
 }
 
 int launch_run_cta(pmc_handle* h, const RunArgs& a) {
+  if (h->spec_teams > 0 && h->pair_precision == 0 && !env_int("PMC_RUN_CFG", 0) && env_int("PMC_RUN_WIN", h->use_win) &&
+      !env_int("PMC_RUN_WS", h->ws_cfg) && env_int("PMC_RUN_PAIR", 1) != 2) {
+    const size_t smem = cta_smem_bytes_spec(h->n, h->spec_teams);
+    const int nb = (int)h->nchains;
+#define PMC_LAUNCH_SPEC(GG, MB)                                                  \
+  {                                                                              \
+    PMC_PICK("k_run_cta_win_spec<" #GG "," #MB ">");                             \
+    int rc = set_smem(k_run_cta_win_spec<GG, MB>, smem);                         \
+    if (rc) return rc;                                                           \
+    k_run_cta_win_spec<GG, MB><<<nb, 32 * GG, smem, h->stream>>>(a);             \
+    ++h->launches;                                                               \
+    PMC_CU(cudaGetLastError());                                                  \
+    return PMC_OK;                                                               \
+  }
+    if (h->spec_teams == 8) PMC_LAUNCH_SPEC(8, 1)
+    if (h->spec_teams == 4) PMC_LAUNCH_SPEC(4, 3)
+    if (h->spec_teams == 2) PMC_LAUNCH_SPEC(2, 6)
+#undef PMC_LAUNCH_SPEC
+  }
   if (use_pair_kernel(h)) return launch_run_pair(h, a);
   if (use_f32_rect(h)) {
     const size_t smem32 = cta_smem_bytes_win_f32(h->n);

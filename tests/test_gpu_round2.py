@@ -336,3 +336,36 @@ def test_cli_numeric_type_float128_prints_double_double_averages(pm, tmp_path):
         xb = [float(x) for x in vb.strip().strip("[]").split(",")]
         np.testing.assert_allclose(xa, xb, rtol=1e-13, atol=1e-13)
     assert len(outs["float128"][3].split("=")[1].strip()) >= 40          # 36 significant digits + exponent
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=64, E0=1.0, K1=1.0, K2=0.1, Fz=0.5, Fx=0.1, steps_per_adjust=100),
+    dict(n=48, E0=0.4, Fz=0.3, kT=4.0, chain_type="polar", mu=0.5, do_flips=True, steps_per_adjust=333),   # acceptance ≈ 0.5
+    dict(n=24, E0=2.0, Fz=0.0, kT=0.5, umbrella=True),
+    dict(n=100, E0=1.0, Fz=0.5),                                                                            # eight teams only
+])
+def test_speculative_teams_of_the_plain_driver_are_the_sequential_chain(pm, kw):
+    """k_run_cta_win_spec: small ensembles of short interacting chains run 2, 4 or 8 one-warp teams per chain on different
+    trials of the window and commit them in order.  Acceptance counts and final chains are identical to the one-trial
+    kernel (k_run_cta_win), rows agree to the rounding of the pair-sum order."""
+    case = pm.make_case(energy_type="interacting", **kw)
+    R, steps = 10, 4000
+    ref = None
+    for hint, teams in ((10 ** 6, 0), (800, 2), (300, 4), (0, 8)):
+        if kw["n"] > 64 and teams in (2, 4):
+            continue                      # longer chains: speculation only when every chain can have a whole SM
+        with pm.Ensemble(case, replicas=R, seed=515, ensemble_chains=hint) as ens:
+            name = ens.kernel_name()
+            assert name.startswith(f"k_run_cta_win_spec<{teams}," if teams else "k_run_cta_win<"), name
+            traj, roll = ens.run(steps, 500)
+            ens.run(777, 0)
+            got = dict(acc=ens.diagnostics()[:, 4].copy(), final=ens.get_state_all(), traj=traj, roll=roll, avg=ens.averages()[0])
+        if ref is None:
+            ref = got
+            assert 0 < ref["acc"].sum() < R * (steps + 777)
+            continue
+        np.testing.assert_array_equal(got["acc"], ref["acc"])
+        for a, b in zip(got["final"], ref["final"]):
+            np.testing.assert_array_equal(a, b)
+        for key in ("traj", "roll", "avg"):   # the initial r, p, U come from a reduction whose order follows the block size
+            np.testing.assert_allclose(got[key], ref[key], rtol=1e-9, atol=1e-9)
