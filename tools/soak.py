@@ -117,6 +117,31 @@ for kw, R, steps in ((dict(n=100, E0=1.0, Fz=0.25, energy_type="interacting", ka
         ", ".join("%s %.1f s" % (r[3], r[4]) for r in res.values())), flush=True)
     bad += not same
 
+# The same for the plain driver's single-monomer trials (k_run_cta_win_spec) against the one-trial kernel
+for kw, R, steps, hints in ((dict(n=48, E0=1.0, Fz=0.5), 96, 300000, (10 ** 6, 800, 300, 0)),
+                            (dict(n=64, E0=0.5, Fz=0.2, kT=3.0, chain_type="polar", mu=0.6, do_flips=True), 96, 300000, (10 ** 6, 800, 300, 0)),
+                            (dict(n=100, E0=1.0, Fz=0.5), 96, 150000, (10 ** 6, 0))):
+    res = {}
+    for hint in hints:
+        with pm.Ensemble(pm.make_case(energy_type="interacting", **kw), replicas=R, seed=271828, ensemble_chains=hint) as ens:
+            t0 = time.time()
+            ens.run(steps // 2, 0, fetch_rows=False)
+            ens.run(steps - steps // 2, 5000, fetch_rows=False)
+            d = ens.diagnostics()
+            res[hint] = (d[:, 4].copy(), ens.get_state_all(), ens.kernel_name(), time.time() - t0, d[:, 6].copy())
+    ref = res[10 ** 6]
+    eq = np.ones(R, dtype=bool)
+    for r in res.values():
+        eq &= (ref[0] == r[0]) & np.all(ref[1][0] == r[1][0], axis=1) & np.all(ref[1][1] == r[1][1], axis=1)
+    collapsed = np.abs(ref[4]) > 1e8     # see above: rounding at the scale of kT once two monomers sit on top of each other
+    same = bool(np.all(eq | collapsed))
+    print("speculative teams, plain driver %s, %d chains x %d trials (acceptance %.3f): %s  %s" % (
+        {k: v for k, v in kw.items() if k in ("n", "chain_type")}, R, steps, ref[0].sum() / (R * steps),
+        ("ok  identical acceptance counts and final chains" if same else "DIFF") +
+        ("" if eq.all() else " (%d chain(s) differ, all collapsed: |U| = %s)" % ((~eq).sum(), ", ".join("%.1e" % abs(u) for u in ref[4][~eq]))),
+        ", ".join("%s %.1f s" % (r[2], r[3]) for r in res.values())), flush=True)
+    bad += not same
+
 # The opt-in FP32 rectangle on a chain that stays extended (weak coupling): drift of the running energy per launch
 with pm.Ensemble(pm.make_case(n=512, E0=0.3, Fz=1.0, energy_type="interacting"), replicas=1024, seed=5) as ens:
     ens.set_pair_precision("fp32")
