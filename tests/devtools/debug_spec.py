@@ -1,6 +1,6 @@
 """Find the first trial where a speculative-team run leaves the one-team trajectory (developer tool)."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "polymer-stats_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "polymer-stats_b200"))
 import numpy as np
 import polymc as pm
 kw = dict(n=64, E0=0.5, Fz=0.3, kT=3.0, energy_type="interacting", kappa=0.2, cluster_prob=0.4)
@@ -28,8 +28,8 @@ for hint, (s, name, acc, cs) in out.items():
               np.flatnonzero(np.abs(s[c, r] - ref[0][c, r]) > 0)[:12] // 2, "launch boundary every", steps // 4)
 
 # which of the two is the sequential chain?  the CPU oracle (ΔU algorithm) on the same Philox stream, chain 84
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "oracle"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import oracle as O
 oc = O.make_case(clustering=True, adj_ub=0.4, **kw)
 run = O.Run(oc, 31337, 84, 1)

@@ -1,6 +1,6 @@
 """The trial at which k_run_cta_cluster<32,10> and the speculative teams part ways (developer tool)."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "polymer-stats_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "polymer-stats_b200"))
 import numpy as np
 import polymc as pm
 kw = dict(n=64, E0=0.5, Fz=0.3, kT=3.0, energy_type="interacting", kappa=0.2, cluster_prob=0.4)

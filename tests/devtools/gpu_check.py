@@ -1,6 +1,6 @@
 """Developer smoke/parity script run on the GPU box (not part of the test-suite)."""
 import os, sys, time, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "polymer-stats_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np

@@ -106,7 +106,7 @@ for kw, R, steps in ((dict(n=100, E0=1.0, Fz=0.25, energy_type="interacting", ka
     # A chain of point dipoles without excluded volume can collapse until two monomers sit on top of each other
     # (|U| ~ 1e9 kT and more): there a trial's ΔU is a difference of sums that contain such a term, its rounding error
     # (1e-16 |U|) reaches the scale of kT·|log ε − logπ ratio| and the variants — whose staged positions differ in the
-    # last bit — may legitimately part ways.  tools/debug_spec2.py: the first differing trial of such a chain has the same
+    # last bit — may legitimately part ways.  tests/devtools/debug_spec2.py: the first differing trial of such a chain has the same
     # ΔU through the seam in both shapes, and the speculative teams stay on the CPU oracle's trajectory.
     collapsed = np.abs(res[10 ** 6][5]) > 1e8
     same = bool(np.all(eq | collapsed))
