@@ -1,4 +1,5 @@
-"""Developer stress test (run on the GPU box): the speculative one-warp teams of the composite-trial CTA kernel
+"""Developer stress test (run on the GPU box), PLAIN driver variant (STRESS_PLAIN=1 in the environment selects it; default: the
+composite-trial kernels): the speculative one-warp teams of the composite-trial CTA kernel
 (k_run_cta_cluster_spec, 2 / 4 / 8 teams by ensemble hint) against one team per chain (k_run_cta_cluster<32,…>) on random
 cases — all-pairs and cut-off energies, both chain types, bending, umbrella weights, α carry on / off, 2-D.  On the shared
 Philox stream they must take the same decisions and end in identical states."""
@@ -14,12 +15,19 @@ kw = json.loads(sys.argv[1]); R, steps, seed = int(sys.argv[2]), int(sys.argv[3]
 ens = pm.Ensemble(pm.make_case(**kw), replicas=R, seed=seed, ensemble_chains=int(os.environ['STRESS_HINT']))
 name = ens.kernel_name()
 out = []
-for mult in (10.0, 1.0):
-    ens.begin_stage(mult)
-    traj, roll, state = ens.run_ex(steps, steps // 3, want_state=True)
-    out.append((traj, roll, state))
+if os.environ.get("STRESS_PLAIN") == "1":
+    for _ in range(2):
+        traj, roll = ens.run(steps, steps // 3)
+        out.append((traj, roll, np.zeros(1)))
+    cs = np.zeros(1)
+else:
+    for mult in (10.0, 1.0):
+        ens.begin_stage(mult)
+        traj, roll, state = ens.run_ex(steps, steps // 3, want_state=True)
+        out.append((traj, roll, state))
+    cs = ens.cluster_stats()
 phi, th = ens.get_state_all()
-np.savez(sys.argv[5], phi=phi, th=th, traj=out[1][0], roll=out[1][1], state=out[1][2], cs=ens.cluster_stats(),
+np.savez(sys.argv[5], phi=phi, th=th, traj=out[1][0], roll=out[1][1], state=out[1][2], cs=cs,
          ar=ens.averages()[1], diag=ens.diagnostics(), name=np.array(name))
 ''' % ROOT
 rng = np.random.default_rng(7)
@@ -34,11 +42,18 @@ for t in range(int(sys.argv[1]) if len(sys.argv) > 1 else 40):
               psi0=float(rng.choice([0.0, 0.3])), clustering=True, cluster_prob=float(rng.choice([0.0, 0.3, 0.5, 0.9])),
               alpha_carry=bool(rng.integers(0, 2)), umbrella=bool(rng.integers(0, 4) == 0), adj_ub=0.4,
               steps_per_adjust=int(rng.choice([50, 77, 1000])))
+    if os.environ.get("STRESS_PLAIN") == "1":   # mcmc_eap_chain.jl: single-monomer trials, all-pairs energy
+        planar = False
+        kw = dict(n=int(rng.choice([2, 3, 5, 17, 33, 48, 64, 100, 110])), E0=float(rng.choice([0.0, 0.5, 2.0])), K1=1.0,
+                  K2=float(rng.choice([0.0, 0.3])), mu=0.5, Fz=float(rng.choice([0.0, 0.7])), Fx=float(rng.choice([0.0, 0.2])),
+                  kT=float(rng.choice([0.3, 1.0, 5.0])), chain_type=str(rng.choice(["dielectric", "polar"])), energy_type="interacting",
+                  do_flips=bool(rng.integers(0, 2)), umbrella=bool(rng.integers(0, 4) == 0),
+                  steps_per_adjust=int(rng.choice([50, 77, 1000])))
     if planar:
         kw.update(planar=True, umbrella=False, kappa=0.0, psi0=0.0, energy_type="interacting")  # the 2-D tree: no bending, no cut-off
     R, steps, seed = int(rng.choice([1, 3, 7])), int(rng.choice([300, 999, 2000])), int(rng.integers(1, 10 ** 6))
     res = {}
-    hints = ("1000000", str(rng.choice([600, 300, 0])))
+    hints = ("1000000", str(rng.choice([800 if os.environ.get("STRESS_PLAIN") == "1" else 600, 300, 0])))
     for mode in hints:
         f = "/tmp/stress_%s.npz" % mode
         env = dict(os.environ, STRESS_HINT=mode)
