@@ -179,3 +179,21 @@ def test_planar_host_against_the_python_twin(tmp_path):
     assert read(prefix + "_trajectory.csv")[0] == "step,r1,r3,p1,p3,U"
     assert read(prefix + "_rolling.csv")[0] == "step,r1,r3,r1sq,r3sq,rsq,p1,p3,p1sq,p3sq,psq,U,Usq"
     assert len(read(prefix + "_rolling.csv")) == 3
+
+
+def test_pair_precision_option_reaches_the_library(tmp_path):
+    """--pair-precision (B200-path extension): default fp64 = PMC_PAIR_FP64, fp32 = PMC_PAIR_FP32 through
+    pmc_set_pair_precision (pmc_multi_set_pair_precision with --devices); anything else is refused by both hosts."""
+    from polymc import mcmc
+    _, mock = run_host("polymc_host.jl", PLAIN + ["--prefix", str(tmp_path / "a")])
+    assert mock.precision == 0
+    _, mock = run_host("polymc_host.jl", PLAIN + ["--pair-precision", "fp32", "--prefix", str(tmp_path / "b")])
+    assert mock.precision == 1
+    _, mock = run_host("polymc_host.jl", PLAIN + ["--pair-precision", "fp32", "--devices", "2", "--prefix", str(tmp_path / "c")])
+    assert mock.precision == 1 and mock.calls[0][0] == "pmc_multi_create"
+    with pytest.raises(JlError, match="pair-precision is not understood"):
+        run_host("polymc_host.jl", PLAIN + ["--pair-precision", "fp16", "--prefix", str(tmp_path / "d")])
+    assert mcmc.parse_args(PLAIN + ["--pair-precision", "fp32"])["pair-precision"] == "fp32"
+    assert mcmc.parse_args(PLAIN)["pair-precision"] == "fp64"
+    with pytest.raises(SystemExit):
+        mcmc.parse_args(PLAIN + ["--pair-precision", "fp16"])
