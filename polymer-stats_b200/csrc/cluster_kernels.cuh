@@ -294,7 +294,7 @@ __device__ __forceinline__ void warp_segment_build(const CtaView& S, const ClVie
   double dx = 0, dy = 0, dz = 0;
   if (c <= hi) segment_monomer(S, X, mono, P, q, c, reflect, acc, dx, dy, dz);
   double ix = dx, iy = dy, iz = dz;
-#pragma unroll
+#pragma unroll 1
   for (int o = 1; o < 32; o <<= 1) {
     const double tx = __shfl_up_sync(FULL, ix, o);
     const double ty = __shfl_up_sync(FULL, iy, o);
@@ -427,10 +427,16 @@ __device__ __forceinline__ void segment_sums(const CtaView& S, const ClView& X, 
     acc[R_PAIR] += a;
   }
   // ---- reduce ------------------------------------------------------------------------------------------
+  // butterfly over the nine sums with the five steps ROLLED: a fifth of the code of nine unrolled warp_sums — these
+  // kernels are short of instruction cache, not of issue slots (profiles/r02c_hot_lines_k_run_cta_cluster_K1.txt)
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-  for (int k = 0; k < kNumRed; ++k) {
-    const double v = warp_sum(acc[k]);
-    if (lane == 0) X.red[k * W + warp] = v;
+    for (int k = 0; k < kNumRed; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNumRed; ++k) X.red[k * W + warp] = acc[k];
   }
   team_sync<T>();
 #pragma unroll
