@@ -186,3 +186,83 @@ end
 kat()""")
     assert v[0] == pytest.approx(-5.804047873024686, rel=1e-13)
     assert v[1] == pytest.approx(-2.7903233230265996, rel=1e-13)
+
+
+# ---- ccall (minijl/ffi.py): marshalling checked against a C library compiled on the spot -------------------------------
+FFI_C = r"""
+#include <stdint.h>
+#include <string.h>
+typedef struct { double a; double b; int64_t n; int32_t k; int32_t flag; double tail; } rec_t;   /* 40 bytes */
+static char msg[64];
+int32_t rec_sum(const rec_t* r, int64_t count, double* out) {     /* array of isbits structs in, one double out */
+  double s = 0; for (int64_t i = 0; i < count; ++i) s += r[i].a + 10 * r[i].b + 100 * r[i].n + 1000 * r[i].k + 10000 * r[i].flag + r[i].tail;
+  *out = s; return (int32_t)sizeof(rec_t);
+}
+int32_t fill3(double* a, int64_t d0, int64_t d1, int64_t d2) {    /* C order [d2][d1][d0] = a Julia Array{Float64}(undef, d0, d1, d2) */
+  for (int64_t k = 0; k < d2; ++k) for (int64_t j = 0; j < d1; ++j) for (int64_t i = 0; i < d0; ++i) a[(k * d1 + j) * d0 + i] = 100 * k + 10 * j + i;
+  return 0;
+}
+int32_t make_handle(void** out) { *out = (void*)0x5150; return 0; }
+int64_t use_handle(void* h, int32_t* counter) { if (counter) *counter += 7; return (int64_t)(intptr_t)h; }
+const char* last_message(void) { strcpy(msg, "from C"); return msg; }
+uint64_t mask48(uint64_t x) { return x & 0xffffffffffffULL; }
+void nothing(void) {}
+"""
+
+
+@pytest.fixture(scope="module")
+def ffi_lib(tmp_path_factory):
+    import subprocess
+    d = tmp_path_factory.mktemp("ffi")
+    src, so = d / "ffi_test.c", d / "libffi_test.so"
+    src.write_text(FFI_C)
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", str(so), str(src)])
+    return str(so)
+
+
+def test_ccall_marshals_like_julia(ffi_lib):
+    """struct arrays by field order with C alignment, column-major arrays, Ref out-parameters, Ptr{Cvoid} handles, Cstring,
+    C_NULL, unsigned 64-bit values, Cvoid returns — against a real C library (gcc)."""
+    it = Interp()
+    it.genv.vars["LIB"] = ffi_lib
+    out = it.run_string('''
+struct Rec
+  a::Cdouble; b::Float64; n::Int64; k::Int32; flag::Int32; tail::Cdouble
+end
+recs = [Rec(1.5, 2.0, 3, 4, true, 0.25), Rec(0.5, 1.0, 1, 1, false, 0.125)]
+s = Ref{Cdouble}(0.0)
+sz = ccall((:rec_sum, LIB), Int32, (Ptr{Rec}, Int64, Ptr{Cdouble}), recs, length(recs), s)
+A = Array{Float64}(undef, 2, 3, 4)
+rc = ccall((:fill3, LIB), Int32, (Ptr{Float64}, Int64, Int64, Int64), A, 2, 3, 4)
+h = Ref{Ptr{Cvoid}}(C_NULL)
+ccall((:make_handle, LIB), Int32, (Ptr{Ptr{Cvoid}},), h)
+cnt = Ref{Int32}(5)
+hv = ccall((:use_handle, LIB), Int64, (Ptr{Cvoid}, Ptr{Int32}), h[], cnt)
+hv0 = ccall((:use_handle, LIB), Int64, (Ptr{Cvoid}, Ptr{Int32}), h[], C_NULL)
+msg = unsafe_string(ccall((:last_message, LIB), Cstring, ()))
+m = ccall((:mask48, LIB), UInt64, (UInt64,), UInt64(0x123456789abcdef0) & 0xffffffffffffffff)
+nothing_back = ccall((:nothing, LIB), Cvoid, ())
+(sz, s[], rc, A[2, 3, 4], A[1, 2, 3], A[:, 1, 2], hv, cnt[], hv0, msg, m, nothing_back)
+''')
+    sz, s, rc, a234, a123, col, hv, cnt, hv0, msg, m, nb = out
+    assert sz == 40
+    assert s == (1.5 + 20 + 300 + 4000 + 10000 + 0.25) + (0.5 + 10 + 100 + 1000 + 0 + 0.125)
+    assert rc == 0 and a234 == 100 * 3 + 10 * 2 + 1 and a123 == 100 * 2 + 10 * 1 + 0
+    assert list(col) == [100.0, 101.0]
+    assert hv == 0x5150 and cnt == 12 and hv0 == 0x5150 and msg == "from C"
+    assert m == 0x123456789abcdef0 & 0xffffffffffff and nb is None
+
+
+def test_ccall_errors_are_loud(ffi_lib):
+    it = Interp()
+    it.genv.vars["LIB"] = ffi_lib
+    with pytest.raises(JlError, match="could not load symbol"):
+        it.run_string('ccall((:no_such_function, LIB), Int32, ())')
+    with pytest.raises(JlError, match="declares 2 argument types but 1 arguments"):
+        it.run_string('ccall((:use_handle, LIB), Int64, (Ptr{Cvoid}, Ptr{Int32}), C_NULL)')
+    with pytest.raises(JlError, match="could not load library"):
+        it.run_string('ccall((:f, "/nonexistent/lib.so"), Int32, ())')
+    with pytest.raises(JlError, match="InexactError"):
+        it.run_string('ccall((:fill3, LIB), Int32, (Ptr{Float64}, Int64, Int64, Int64), C_NULL, 1.5, 1, 1)')
+    with pytest.raises(JlError, match="passed as Ptr"):
+        it.run_string('ccall((:fill3, LIB), Int32, (Ptr{Float64}, Int64, Int64, Int64), [1, 2, 3], 3, 1, 1)')
