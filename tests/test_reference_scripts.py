@@ -1,0 +1,93 @@
+"""north_star: "It keeps … the output.jl tabular format, so run/* sweep scripts and scripts/aggregate_mcmc.jl work
+unchanged."  Checked literally: the UNMODIFIED reference script scripts/aggregate_mcmc.jl, executed by tools/minijl, reads
+`<prefix>.out` files written by this package (the stdout block of the CLI twins under the launchers' file names) and must
+produce the table polymc.aggregate produces directly — byte for byte.
+
+Needs /root/reference (this container only; the GPU box has none): skipped elsewhere.  CPU only."""
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "polymer-stats_b200"))
+SCRIPT = "/root/reference/scripts/aggregate_mcmc.jl"
+
+pytestmark = pytest.mark.skipif(not os.path.exists(SCRIPT), reason="the reference tree is not on this machine")
+
+
+def run_reference_aggregate(argv):
+    from minijl.interp import Interp
+    it = Interp(argv=list(argv))
+    out = io.StringIO()
+    it.stdout = out
+    it.genv.vars["stdout"] = out
+    it.run_main(SCRIPT)
+    return out.getvalue()
+
+
+def cases(rng, chain_type, count):
+    out = []
+    for k in range(count):
+        p = {"E0": float(rng.choice([0.0, 0.5, 1.25, 2.0])) + 0.001 * k, "K1": 1.0, "K2": float(rng.choice([0.0, 0.25])), "mu": 0.5,
+             "kT": float(rng.choice([0.5, 1.0])), "Fz": 0.25 * k, "Fx": 0.0, "num-monomers": int(rng.choice([50, 100])), "mlen": 1.0,
+             "bend-mod": float(rng.choice([0.0, 0.5]))}
+        out.append((p, rng.normal(size=16) * 10.0 ** rng.integers(-3, 4), rng.normal(size=2), float(rng.uniform(0.01, 0.6))))
+    return out
+
+
+@pytest.mark.parametrize("chain_type,kappaflag,runflag", [("dielectric", True, False), ("polar", False, True), ("dielectric", False, False)])
+def test_reference_aggregate_script_reads_our_out_files(tmp_path, chain_type, kappaflag, runflag):
+    from polymc import aggregate as ag
+    rng = np.random.default_rng(7)
+    text, entries = [], []
+    for k, (p, avg, ex, ar) in enumerate(cases(rng, chain_type, 5)):
+        prefix = ag.prefix_of(p, chain_type, kappaflag, run=k + 1 if runflag else None)
+        text.append((prefix, ag.out_text(avg, ar, p["mlen"], p["num-monomers"], ex)))          # the clustering driver's 12 lines
+        entries.append((prefix, ag.output_values(avg, ar, p["mlen"], p["num-monomers"], ex)))
+    outdir = tmp_path / "study"
+    ag.write_out_files(str(outdir), text)
+    ours = tmp_path / "ours.csv"
+    ag.write_table(str(ours), *ag.aggregate_table(entries, chain_type, kappaflag, runflag, 3))
+    theirs = tmp_path / "theirs.csv"
+    argv = [str(theirs), str(outdir), "*.out", chain_type, "3D", "true" if kappaflag else "false"] + (["true"] if runflag else [])
+    log = run_reference_aggregate(argv)
+    assert log.count("processing") == 5
+    assert theirs.read_text() == ours.read_text()
+
+
+def test_reference_aggregate_script_reads_our_2d_out_files(tmp_path):
+    from polymc import aggregate as ag
+    rng = np.random.default_rng(8)
+    text, entries = [], []
+    for p, avg, ex, ar in cases(rng, "dielectric", 4):
+        prefix = ag.prefix_of(p, "dielectric", False)
+        text.append((prefix, ag.out_text_2d(avg, ar, p["mlen"], p["num-monomers"])))
+        entries.append((prefix, ag.output_values_2d(avg, ar, p["mlen"], p["num-monomers"])))
+    outdir = tmp_path / "study2d"
+    ag.write_out_files(str(outdir), text)
+    ours, theirs = tmp_path / "ours.csv", tmp_path / "theirs.csv"
+    ag.write_table(str(ours), *ag.aggregate_table(entries, "dielectric", False, False, 2))
+    run_reference_aggregate([str(theirs), str(outdir), "*.out", "dielectric", "2D"])
+    assert theirs.read_text() == ours.read_text()
+
+
+def test_reference_aggregate_script_on_the_plain_drivers_ten_lines(tmp_path):
+    """mcmc_eap_chain.jl prints 10 lines (no Ealign / psi): the script then writes 20 output columns under its 22 headers —
+    upstream behaviour, reproduced by both sides."""
+    from polymc import aggregate as ag
+    rng = np.random.default_rng(9)
+    text, entries = [], []
+    for p, avg, ex, ar in cases(rng, "dielectric", 3):
+        prefix = ag.prefix_of(p, "dielectric", False)
+        text.append((prefix, ag.out_text(avg, ar, p["mlen"], p["num-monomers"])))
+        entries.append((prefix, ag.output_values(avg, ar, p["mlen"], p["num-monomers"])))
+    outdir = tmp_path / "plain"
+    ag.write_out_files(str(outdir), text)
+    ours, theirs = tmp_path / "ours.csv", tmp_path / "theirs.csv"
+    ag.write_table(str(ours), *ag.aggregate_table(entries, "dielectric", False, False, 3))
+    run_reference_aggregate([str(theirs), str(outdir), "*.out", "dielectric"])
+    assert theirs.read_text() == ours.read_text()

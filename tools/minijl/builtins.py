@@ -287,6 +287,10 @@ def reshape(x, *dims):
 
 
 def transpose(x):
+    if isinstance(x, (int, float)) and not isinstance(x, np.ndarray):
+        return x                       # transpose of a number is the number
+    if isinstance(x, (JList, list)):
+        x = np.array(list(x), dtype=object if any(isinstance(e, str) for e in x) else None)
     x = _arr(x)
     if x.ndim == 1:
         return x.reshape(1, -1)
@@ -454,12 +458,38 @@ def jl_parse(t, s):
         return float(s2)
     if t in (T["Int64"],):
         return int(s.strip())
+    if t is T["Bool"]:
+        s2 = s.strip()
+        if s2 in ("true", "1"):
+            return True
+        if s2 in ("false", "0"):
+            return False
+        raise JlError(f"ArgumentError: invalid Bool representation: {s!r}")
     raise JlError(f"parse({t}, ...) unsupported")
 
 
-def split(s, sep=None):
-    parts = s.split(sep) if sep is not None else s.split()
+def split(s, sep=None, limit=0):
+    """split(s, sep; limit=0): at most `limit` pieces (0: no limit), like Base.split."""
+    maxsplit = limit - 1 if limit and limit > 0 else -1
+    parts = s.split(sep, maxsplit) if sep is not None else s.split(None, maxsplit)
     return JList(parts)
+
+
+class GlobMatch:
+    """Glob.GlobMatch(pattern) — what readdir(pattern, dir) of Glob.jl takes."""
+
+    def __init__(self, pattern):
+        self.pattern = pattern
+
+
+def jl_readdir(*a):
+    """readdir(dir) (sorted names) and Glob's readdir(GlobMatch, dir) (sorted matching paths, joined with dir)."""
+    import fnmatch
+    if len(a) == 2 and isinstance(a[0], GlobMatch):
+        pat, d = a[0].pattern, a[1]
+        return JList([os.path.join(d, f) for f in sorted(os.listdir(d)) if fnmatch.fnmatchcase(f, pat)])
+    d = a[0] if a else "."
+    return JList(sorted(os.listdir(d)))
 
 
 def jl_open(*a):
@@ -734,6 +764,7 @@ def install(interp: Interp):
         "Logging": ModuleNS("Logging", {"Info": LogLevel(0), "Warn": LogLevel(1000), "Error": LogLevel(2000),
                                         "Debug": LogLevel(-1000), "NullLogger": null_logger}),
         "Base": ModuleNS("Base", {}),
+        "Glob": ModuleNS("Glob", {"GlobMatch": GlobMatch}), "readdir": jl_readdir,
         "identity": lambda x: x, "tuple": lambda *a: tuple(a), "Pair": lambda a, b: (a, b),
         "xor": lambda a, b: a ^ b, "trunc": lambda *a: int(a[1]) if len(a) == 2 else float(int(a[0])),
         "abs2": lambda x: x * x, "sincos": lambda x: (math.sin(x), math.cos(x)),
