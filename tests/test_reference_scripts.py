@@ -91,3 +91,34 @@ def test_reference_aggregate_script_on_the_plain_drivers_ten_lines(tmp_path):
     ag.write_table(str(ours), *ag.aggregate_table(entries, "dielectric", False, False, 3))
     run_reference_aggregate([str(theirs), str(outdir), "*.out", "dielectric"])
     assert theirs.read_text() == ours.read_text()
+
+
+REDUCE = "/root/reference/scripts/reduce_tabular_data.jl"
+
+
+@pytest.mark.skipif(not os.path.exists(REDUCE), reason="the reference tree is not on this machine")
+@pytest.mark.parametrize("chain_type,kappaflag", [("dielectric", False), ("dielectric", True), ("polar", False)])
+def test_reference_reduce_script_on_our_tables(tmp_path, chain_type, kappaflag):
+    """scripts/reduce_tabular_data.jl (unmodified, run by minijl) pools the repeated runs of a table written by
+    polymc.aggregate; polymc.aggregate.reduce_table — what run_sweep.py --pooled-out writes — gives the same file."""
+    from minijl.interp import Interp
+    from polymc import aggregate as ag
+    rng = np.random.default_rng(11)
+    entries = []
+    for k, (p, _, _, _) in enumerate(cases(rng, chain_type, 4)):
+        for run in range(1, 4 + (k % 2)):                       # 3 or 4 runs per case
+            avg, ex, ar = rng.normal(size=16), rng.normal(size=2), float(rng.uniform(0.01, 0.6))
+            entries.append((ag.prefix_of(p, chain_type, kappaflag, run=run), ag.output_values(avg, ar, p["mlen"], p["num-monomers"], ex)))
+    header, rows = ag.aggregate_table(entries, chain_type, kappaflag, True, 3)
+    indir, outdir = tmp_path / "tables", tmp_path / "reduced"
+    indir.mkdir()
+    ag.write_table(str(indir / "study.csv"), header, rows)
+    nparams = len(ag.input_headers(chain_type, kappaflag))
+    ours = tmp_path / "ours.csv"
+    ag.write_table(str(ours), *ag.reduce_table(header, rows, nparams))
+    it = Interp(argv=[str(indir), str(outdir), chain_type] + (["true"] if kappaflag else []))
+    sink = io.StringIO()
+    it.stdout = sink
+    it.genv.vars["stdout"] = sink
+    it.run_main(REDUCE)
+    assert (outdir / "study.csv").read_text() == ours.read_text()

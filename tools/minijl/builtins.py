@@ -289,7 +289,7 @@ def reshape(x, *dims):
 def transpose(x):
     if isinstance(x, (int, float)) and not isinstance(x, np.ndarray):
         return x                       # transpose of a number is the number
-    if isinstance(x, (JList, list)):
+    if isinstance(x, (JList, list, tuple)):   # a tuple: a vector that served as a Dict key (interp.dict_key)
         x = np.array(list(x), dtype=object if any(isinstance(e, str) for e in x) else None)
     x = _arr(x)
     if x.ndim == 1:
@@ -482,6 +482,49 @@ class GlobMatch:
         self.pattern = pattern
 
 
+def readdlm(path, delim=None, header=False):
+    """readdlm(file, delim; header=false): numbers become Float64; a table with text or ragged rows becomes a matrix of
+    Any with "" for the missing cells, as DelimitedFiles does.  With header=true returns (data, 1×n header matrix)."""
+    with open(path, encoding="utf-8") as f:
+        lines = [ln.rstrip("\n") for ln in f if ln.strip() != ""]
+    rows = [ln.split(delim) if delim is not None else ln.split() for ln in lines]
+    head = None
+    if header:
+        head, rows = rows[0], rows[1:]
+    width = max([len(r) for r in rows] + ([len(head)] if head else [0]))
+
+    def cell(x):
+        x = x.strip()
+        try:
+            return float(x)
+        except ValueError:
+            return x
+    data = [[cell(x) for x in r] + [""] * (width - len(r)) for r in rows]
+    if all(isinstance(x, float) for r in data for x in r):
+        arr = np.array(data, dtype=np.float64).reshape(len(data), width)
+    else:
+        arr = np.empty((len(data), width), dtype=object)
+        for i, r in enumerate(data):
+            for j, x in enumerate(r):
+                arr[i, j] = x
+    arr = np.asfortranarray(arr)
+    if header:
+        h = np.empty((1, len(head)), dtype=object)
+        for j, x in enumerate(head):
+            h[0, j] = x.strip()
+        return (arr, h)
+    return arr
+
+
+def jl_filter(f, xs):
+    keep = [x for x in iterate(xs) if _interp.call(f, [x]) is True]
+    return make_vector(keep)
+
+
+def jl_sort(xs, rev=False):
+    return make_vector(sorted(iterate(xs), reverse=bool(rev)))
+
+
 def jl_readdir(*a):
     """readdir(dir) (sorted names) and Glob's readdir(GlobMatch, dir) (sorted matching paths, joined with dir)."""
     import fnmatch
@@ -524,6 +567,9 @@ def _dlm_cell(v):
 
 
 def writedlm(io, A, delim="\t"):
+    if isinstance(io, str):                      # writedlm(path, A, delim)
+        with open(io, "w", encoding="utf-8") as f:
+            return writedlm(f, A, delim)
     A = _arr(A)
     if isinstance(A, np.ndarray) and A.ndim == 2:
         for row in A:
@@ -571,7 +617,8 @@ def jl_eval(ast):
 
 
 def haskey(d, k):
-    return k in d
+    from .interp import dict_key
+    return dict_key(k) in d
 
 
 def jl_get(d, k, default):
@@ -764,7 +811,7 @@ def install(interp: Interp):
         "Logging": ModuleNS("Logging", {"Info": LogLevel(0), "Warn": LogLevel(1000), "Error": LogLevel(2000),
                                         "Debug": LogLevel(-1000), "NullLogger": null_logger}),
         "Base": ModuleNS("Base", {}),
-        "Glob": ModuleNS("Glob", {"GlobMatch": GlobMatch}), "readdir": jl_readdir,
+        "Glob": ModuleNS("Glob", {"GlobMatch": GlobMatch}), "readdir": jl_readdir, "readdlm": readdlm, "filter": jl_filter, "sort": jl_sort,
         "identity": lambda x: x, "tuple": lambda *a: tuple(a), "Pair": lambda a, b: (a, b),
         "xor": lambda a, b: a ^ b, "trunc": lambda *a: int(a[1]) if len(a) == 2 else float(int(a[0])),
         "abs2": lambda x: x * x, "sincos": lambda x: (math.sin(x), math.cos(x)),

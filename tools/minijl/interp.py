@@ -1548,7 +1548,7 @@ def getindex(o, idxs):
             return JList(o)
         raise JlError(f"invalid index {i!r}")
     if isinstance(o, dict):
-        k = idxs[0]
+        k = dict_key(idxs[0])
         if k not in o:
             raise JlError(f"KeyError: key {jl_repr(k)} not found")
         return o[k]
@@ -1621,7 +1621,7 @@ def setindex(o, v, idxs):
             o[i - 1] = v
             return
     if isinstance(o, dict):
-        o[idxs[0]] = v
+        o[dict_key(idxs[0])] = v
         return
     raise JlError(f"MethodError: no method matching setindex!({o!r:.60}, ...)")
 
@@ -1631,7 +1631,20 @@ def _isnum(x):
     return isinstance(x, (int, float)) and not isinstance(x, bool) or isinstance(x, bool)
 
 
+def dict_key(k):
+    """A vector used as a Dict key (Julia hashes arrays by content): stored as a tuple of its elements."""
+    if isinstance(k, np.ndarray):
+        return tuple(x.item() if hasattr(x, "item") else x for x in k.reshape(-1, order="F"))
+    if isinstance(k, JList):
+        return tuple(k)
+    return k
+
+
 def op_add(a, b):
+    if isinstance(a, JList) and isinstance(b, JList):      # Vector{Any} + Vector{Any}: elementwise
+        if len(a) != len(b):
+            raise JlError("DimensionMismatch: dimensions must match")
+        return JList([op_add(x, y) for x, y in zip(a, b)])
     if isinstance(a, np.ndarray) and isinstance(b, np.ndarray):
         if a.shape != b.shape:
             raise JlError(f"DimensionMismatch: dimensions must match: a has dims {a.shape}, b has dims {b.shape}")
@@ -1670,6 +1683,8 @@ def op_mul(a, b):
 
 
 def op_div(a, b):
+    if isinstance(a, np.ndarray) and a.dtype == object and not isinstance(b, np.ndarray):
+        return np.array([x / b for x in a.reshape(-1)], dtype=np.float64).reshape(a.shape)
     if isinstance(b, np.ndarray):
         raise JlError("MethodError: no method matching /(x, array)")
     if isinstance(a, np.ndarray):

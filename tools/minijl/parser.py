@@ -654,6 +654,11 @@ class Parser:
         if k == "sym":
             return ("sym", t.val)
         if k == "id":
+            nt = self.toks[self.pos]
+            if t.val == "glob" and nt.kind == "str" and not nt.sp_before:
+                # the string macro glob"pattern" of Glob.jl: a GlobMatch
+                self.pos += 1
+                return ("call", ("field", ("name", "Glob"), "GlobMatch"), [("str", list(nt.parts))], [])
             return ("name", t.val)
         if k == "macro":
             return self.parse_macro(t)
@@ -838,6 +843,8 @@ class Parser:
             body = self.parse_block()
             self.expect_kw("end")
             return ("macrocall", name, [settings, body])
+        if name == "show":   # @show expr — an assignment or a top-level tuple is one argument
+            return ("macrocall", name, [self.parse_expr_stmt()])
         # space-separated arguments up to the end of the statement; commas make a tuple
         args = []
         while True:
