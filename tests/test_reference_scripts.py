@@ -122,3 +122,41 @@ def test_reference_reduce_script_on_our_tables(tmp_path, chain_type, kappaflag):
     it.genv.vars["stdout"] = sink
     it.run_main(REDUCE)
     assert (outdir / "study.csv").read_text() == ours.read_text()
+
+
+BY = "/root/reference/scripts/aggregate_by.jl"
+
+
+@pytest.mark.skipif(not os.path.exists(BY), reason="the reference tree is not on this machine")
+@pytest.mark.parametrize("param,runflag", [("E0", False), ("Fz", False), ("FxFz", False), ("E0", True)])
+def test_reference_aggregate_by_script_on_our_out_files(tmp_path, monkeypatch, param, runflag):
+    """scripts/aggregate_by.jl (unmodified, run by minijl — including the `julia scripts/aggregate_mcmc.jl …` command it
+    spawns per group, which a nested interpreter runs) splits a study into one table per combination of the other
+    parameters; polymc.aggregate.aggregate_by gives the same files, upstream quirks included (with the run flag the glob
+    wildcards only the last digit of the run number)."""
+    from minijl.interp import Interp
+    from polymc import aggregate as ag
+    rng = np.random.default_rng(13)
+    text, entries = [], []
+    for e0 in (0.0, 0.5, 1.0):
+        for fz, fx in ((0.0, 0.0), (0.25, 0.0), (0.25, 0.1)):
+            for run in ((1, 2, 11) if runflag else (None,)):
+                p = {"E0": e0, "K1": 1.0, "K2": 0.25, "kT": 1.0, "Fz": fz, "Fx": fx, "num-monomers": 100, "mlen": 1.0}
+                avg, ex, ar = rng.normal(size=16), rng.normal(size=2), float(rng.uniform(0.01, 0.6))
+                prefix = ag.prefix_of(p, "dielectric", False, run=run)
+                text.append((prefix, ag.out_text(avg, ar, 1.0, 100, ex)))
+                entries.append((prefix, ag.output_values(avg, ar, 1.0, 100, ex)))
+    indir, outdir = tmp_path / "study", tmp_path / "by"
+    ag.write_out_files(str(indir), text)
+    monkeypatch.chdir("/root/reference")            # the script spawns `julia scripts/aggregate_mcmc.jl` relative to the tree
+    it = Interp(argv=[str(outdir), str(indir), param, "dielectric", "3D", "false"] + (["true"] if runflag else []))
+    sink = io.StringIO()
+    it.stdout = sink
+    it.genv.vars["stdout"] = sink
+    it.run_main(BY)
+    ours = ag.aggregate_by(entries, param, "dielectric", False, runflag, 3)
+    assert sorted(os.listdir(outdir)) == sorted(ours.keys()) and len(ours) >= 3
+    for name, (header, rows) in ours.items():
+        mine = tmp_path / ("ours_" + name)
+        ag.write_table(str(mine), header, rows)
+        assert (outdir / name).read_text() == mine.read_text(), name

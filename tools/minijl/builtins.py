@@ -342,6 +342,9 @@ def collect(x):
 
 
 def findnext(pred, A, i):
+    if isinstance(pred, str) and isinstance(A, str):     # findnext(pattern, string, start): the range of the match
+        k = A.find(pred, i - 1)
+        return None if k < 0 else JRange(k + 1, k + len(pred))
     items = list(iterate(A))
     for k in range(i - 1, len(items)):
         if _interp.call(pred, [items[k]]) is True:
@@ -552,7 +555,33 @@ def jl_close(io):
     return None
 
 
+class Cmd:
+    """A command literal.  `julia script.jl args…` is run by a nested interpreter (there is no julia here); anything else
+    is refused — the interpreter is test infrastructure, not a shell."""
+
+    def __init__(self, argv):
+        self.argv = list(argv)
+
+    def __repr__(self):
+        return "`" + " ".join(self.argv) + "`"
+
+
+def run_cmd_lines(cmd: Cmd):
+    import io as _io
+    from .interp import Interp as _Interp
+    if len(cmd.argv) < 2 or cmd.argv[0] != "julia" or not cmd.argv[1].endswith(".jl"):
+        raise JlError(f"minijl: cannot run {cmd!r}")
+    child = _Interp(argv=cmd.argv[2:])
+    out = _io.StringIO()
+    child.stdout = out
+    child.genv.vars["stdout"] = out
+    child.run_main(os.path.abspath(cmd.argv[1]))
+    return JList(out.getvalue().splitlines())
+
+
 def readlines(x):
+    if isinstance(x, Cmd):
+        return run_cmd_lines(x)
     if isinstance(x, str):
         with open(x, encoding="utf-8") as f:
             return JList(f.read().splitlines())
@@ -812,6 +841,8 @@ def install(interp: Interp):
                                         "Debug": LogLevel(-1000), "NullLogger": null_logger}),
         "Base": ModuleNS("Base", {}),
         "Glob": ModuleNS("Glob", {"GlobMatch": GlobMatch}), "readdir": jl_readdir, "readdlm": readdlm, "filter": jl_filter, "sort": jl_sort,
+        "startswith": lambda s, p: s.startswith(p), "endswith": lambda s, p: s.endswith(p),
+        "display": lambda x: println(x),
         "identity": lambda x: x, "tuple": lambda *a: tuple(a), "Pair": lambda a, b: (a, b),
         "xor": lambda a, b: a ^ b, "trunc": lambda *a: int(a[1]) if len(a) == 2 else float(int(a[0])),
         "abs2": lambda x: x * x, "sincos": lambda x: (math.sin(x), math.cos(x)),

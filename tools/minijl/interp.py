@@ -674,6 +674,33 @@ class Interp:
     def c_paren(self, node):
         return self.comp(node[1])
 
+    def c_cmd(self, node):
+        """`prog arg $x "quoted $y"`: words split on blanks outside quotes; an interpolated value stays inside its word."""
+        parts = [p if isinstance(p, str) else self.comp(p) for p in node[1]]
+
+        def f(env):
+            words, cur, inq, started = [], [], False, False
+            for p in parts:
+                if isinstance(p, str):
+                    for ch in p:
+                        if ch == '"':
+                            inq = not inq
+                            started = True
+                        elif ch in " \t\n" and not inq:
+                            if started:
+                                words.append("".join(cur))
+                            cur, started = [], False
+                        else:
+                            cur.append(ch)
+                            started = True
+                else:
+                    cur.append(jl_str(p(env)))
+                    started = True
+            if started:
+                words.append("".join(cur))
+            return self.B.Cmd(words)
+        return f
+
     def c_num(self, node):
         v = node[1]
         return lambda env: v
@@ -752,6 +779,8 @@ class Interp:
                     raise JlError(f"type {o.jtype.name} has no field {name}")
             if isinstance(o, ModuleNS):
                 return o.get(name)
+            if isinstance(o, JRange) and name in ("start", "stop", "step"):
+                return getattr(o, name)
             raise JlError(f"getfield: unsupported object {o!r} . {name}")
         return f
 

@@ -53,9 +53,10 @@ def is_id_char(ch: str) -> bool:
     return unicodedata.category(ch) in ("Mn", "Mc", "Nd", "Pc", "Sk", "Me", "No") or ch in "′″‴"
 
 
-def _scan_string(src: str, i: int, line: int):
-    """src[i] is the opening quote.  Returns (parts, next index, line) — parts: str pieces and ('expr', text)."""
-    assert src[i] == '"'
+def _scan_string(src: str, i: int, line: int, term: str = '"'):
+    """src[i] is the opening quote (or backtick: term = "`").  Returns (parts, next index, line) — parts: str pieces and
+    ('expr', text)."""
+    assert src[i] == term
     i += 1
     parts, buf = [], []
     n = len(src)
@@ -63,7 +64,7 @@ def _scan_string(src: str, i: int, line: int):
         if i >= n:
             raise JlSyntaxError(f"unterminated string (line {line})")
         ch = src[i]
-        if ch == '"':
+        if ch == term:
             i += 1
             break
         if ch == "\\":
@@ -161,6 +162,12 @@ def lex(src: str):
         if ch == '"':
             parts, j, line2 = _scan_string(src, i, line)
             push("str", None, parts)
+            line = line2
+            i = j
+            continue
+        if ch == "`":      # command literal: interpolation as in a string; split into words when it is run
+            parts, j, line2 = _scan_string(src, i, line, "`")
+            push("cmd", None, parts)
             line = line2
             i = j
             continue

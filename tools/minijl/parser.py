@@ -649,6 +649,16 @@ class Parser:
                 else:
                     parts.append(p)
             return ("str", parts)
+        if k == "cmd":
+            parts = []
+            for p in t.parts:
+                if isinstance(p, tuple):
+                    sub = Parser(lex(p[1]), self.filename)
+                    sub.nl_skip = [True]
+                    parts.append(sub.parse_expr(1))
+                else:
+                    parts.append(p)
+            return ("cmd", parts)
         if k == "char":
             return ("char", t.val)
         if k == "sym":
