@@ -160,3 +160,68 @@ def test_reference_aggregate_by_script_on_our_out_files(tmp_path, monkeypatch, p
         mine = tmp_path / ("ours_" + name)
         ag.write_table(str(mine), header, rows)
         assert (outdir / name).read_text() == mine.read_text(), name
+
+
+LAUNCHERS = sorted(__import__("glob").glob("/root/reference/run/*.jl"))
+# two launchers draw their cases from Distributions.jl (no scripted stream here); one is not valid Julia upstream
+# (`zip(a, b; c; d)`: positional arguments after the semicolon)
+NOT_RUN = {"phases-random_2023-05-15.jl", "phases-random_2023-07-11.jl", "phases_2023-05-15.jl"}
+
+
+@pytest.mark.skipif(not LAUNCHERS, reason="the reference tree is not on this machine")
+def test_every_reference_launcher_command_is_accepted_by_the_cli_twins(tmp_path):
+    """north_star: "It keeps the existing CLI options … so run/* sweep scripts … work unchanged."  Every launcher of the
+    reference's run/ directory is executed UNMODIFIED by minijl with the `julia <driver>.jl …` commands it spawns
+    intercepted: a sample of each launcher's cases (first, last, every k-th) is checked — the driver is one of the two the
+    package twins, the twin's parser accepts the whole command line, the values arrive, and the `<prefix>.out` file the
+    launcher writes is named the way polymc.aggregate.prefix_of names it (so aggregate_mcmc.jl finds the parameters)."""
+    from minijl.interp import Interp
+    from minijl import builtins as B
+    from polymc import aggregate as ag, mcmc, mcmc_clustering
+    twins = {"mcmc_eap_chain.jl": mcmc, "mcmc_clustering_eap_chain.jl": mcmc_clustering}
+    ran = commands = 0
+    for path in LAUNCHERS:
+        name = os.path.basename(path)
+        if name in NOT_RUN:
+            continue
+        work = tmp_path / name
+        work.mkdir()                          # (a few launchers expect their work directory to exist)
+        it = Interp(argv=[str(work)])
+        sink = io.StringIO()
+        it.stdout = it.stderr = sink
+        it.genv.vars["stdout"] = sink
+        cmds = []
+        it.cmd_runner = lambda argv, cmds=cmds: (cmds.append(list(argv)) or "<r>    =   [0.0, 0.0, 0.0]\\n")
+
+        def sampled_pmap(f, cases, it=it):     # the launchers fan out with pmap: run a sample of the cases
+            cases = list(B.iterate(cases))
+            step = max(1, len(cases) // 25)
+            for c in cases[::step] + cases[-1:]:
+                it.call(f, [c])
+            return None
+        it.genv.vars["pmap"] = sampled_pmap
+        it.run_main(path)
+        assert cmds, name
+        ran += 1
+        for argv in cmds:
+            commands += 1
+            assert os.path.basename(argv[0]) == "julia", (name, argv[:4])
+            k = next(i for i, a in enumerate(argv) if a.endswith(".jl"))
+            driver, args = argv[k], argv[k + 1:]
+            assert driver in twins, (name, driver)
+            assert all(a in ("-t", "-O", "-p") or a.isdigit() for a in argv[1:k]), (name, argv[:k])    # julia's own flags
+            p = twins[driver].parse_args(args)            # argparse exits on an option it does not know
+            assert p["num-monomers"] == int(args[args.index("-n") + 1]) if "-n" in args else True
+            assert p["E0"] == float(args[args.index("--E0") + 1])
+            # the file the launcher writes: <workdir>/<prefix>.out with the tokens aggregate_mcmc.jl parses back
+            prefix = os.path.basename(p["prefix"])
+            tokens = dict(t.split("-", 1) for t in prefix.split("_"))
+            chain = p["chain-type"]
+            want = ag.prefix_of(p, chain, "kappa" in tokens, run=int(tokens["run"]) if "run" in tokens else None)
+            wtok = dict(t.split("-", 1) for t in want.split("_"))
+            if set(tokens) == set(wtok):      # (the older launchers write the run number unpadded: compare it as a number)
+                assert {k: v for k, v in tokens.items() if k != "run"} == {k: v for k, v in wtok.items() if k != "run"}, (name, prefix, want)
+                assert "run" not in tokens or int(tokens["run"]) == int(wtok["run"])
+            # (some launchers run several variants per case: <prefix>_umbrella.out, or standard/<prefix>.out, …)
+            assert any(f.startswith(prefix) and f.endswith(".out") for _, _, fs in os.walk(work) for f in fs), (name, prefix)
+    assert ran >= 35 and commands >= 500

@@ -566,9 +566,29 @@ class Cmd:
         return "`" + " ".join(self.argv) + "`"
 
 
+def run_cmd_text(cmd: Cmd):
+    """stdout of a command.  interp.cmd_runner(argv) -> str, when set, stands in for the process (tests)."""
+    runner = getattr(_interp, "cmd_runner", None)
+    if runner is not None:
+        return runner(cmd.argv)
+    return "\n".join(run_cmd_lines(cmd)) + "\n"
+
+
+def jl_read(x, t=None):
+    if isinstance(x, Cmd):
+        return run_cmd_text(x)
+    if isinstance(x, str):
+        with open(x, encoding="utf-8") as f:
+            return f.read()
+    return x.read()
+
+
 def run_cmd_lines(cmd: Cmd):
     import io as _io
     from .interp import Interp as _Interp
+    runner = getattr(_interp, "cmd_runner", None)
+    if runner is not None:
+        return JList(runner(cmd.argv).splitlines())
     if len(cmd.argv) < 2 or cmd.argv[0] != "julia" or not cmd.argv[1].endswith(".jl"):
         raise JlError(f"minijl: cannot run {cmd!r}")
     child = _Interp(argv=cmd.argv[2:])
@@ -612,6 +632,9 @@ def writedlm(io, A, delim="\t"):
 
 
 def jl_write(io, *a):
+    if isinstance(io, str):                      # write(path, content)
+        with open(io, "w", encoding="utf-8") as f:
+            return jl_write(f, *a)
     for x in a:
         io.write(jl_str(x))
     return None
@@ -841,6 +864,8 @@ def install(interp: Interp):
                                         "Debug": LogLevel(-1000), "NullLogger": null_logger}),
         "Base": ModuleNS("Base", {}),
         "Glob": ModuleNS("Glob", {"GlobMatch": GlobMatch}), "readdir": jl_readdir, "readdlm": readdlm, "filter": jl_filter, "sort": jl_sort,
+        "zip": lambda *xs: JList([tuple(t) for t in zip(*[list(iterate(x)) for x in xs])]),
+        "read": jl_read, "pmap": jl_map, "run": lambda cmd: run_cmd_text(cmd) and None,
         "startswith": lambda s, p: s.startswith(p), "endswith": lambda s, p: s.endswith(p),
         "display": lambda x: println(x),
         "identity": lambda x: x, "tuple": lambda *a: tuple(a), "Pair": lambda a, b: (a, b),

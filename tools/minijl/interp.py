@@ -1406,6 +1406,18 @@ class Interp:
                 self.B.add_arg_table(settings(env), entries, env)
                 return None
             return f
+        if name == "sprintf":
+            # @sprintf(fmt, args…): C formatting; round-to-nearest-even of %d arguments is the caller's business, as in Julia
+            parts = [self.comp(a) for a in args]
+
+            def f(env):
+                vals = [p(env) for p in parts]
+                fmt, rest = vals[0], tuple(int(v) if isinstance(v, float) and v == int(v) and "d" in vals[0] else v for v in vals[1:])
+                try:
+                    return fmt % rest
+                except (TypeError, ValueError) as e:
+                    raise JlError(f"@sprintf: {e}")
+            return f
         if name in ("show", "time", "elapsed"):
             inner = self.comp(args[0])
             return lambda env: inner(env)

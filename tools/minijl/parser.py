@@ -557,7 +557,7 @@ class Parser:
         idxs = []
         while not self.is_op("]"):
             idxs.append(self.parse_expr(1))
-            if self.is_op(","):
+            if self.is_op(",") or self.is_op(";"):   # `;`: the typed vertical concatenation T[a; b] of scalars
                 self.next()
         self.nl_skip.pop()
         self.in_bracket.pop()
@@ -807,10 +807,21 @@ class Parser:
         if not ((t.kind == "op" and t.val == "=") or (t.kind == "kw" and t.val == "in")):
             self.err("expected = or in after the loop variable", t)
         it = self.parse_expr(1)
+        loops = [(var, it)]
+        while self.is_op(","):          # for a in A, b in B, …: nested loops, the first iterator outermost
+            self.next()
+            v2 = self.parse_binary(CMP_PREC + 1)
+            t = self.next()
+            if not ((t.kind == "op" and t.val == "=") or (t.kind == "kw" and t.val == "in")):
+                self.err("expected = or in after the loop variable", t)
+            loops.append((v2, self.parse_expr(1)))
         self.nl_skip.pop(); self.in_bracket.pop(); self.in_index.pop()
         body = self.parse_block()
         self.expect_kw("end")
-        return ("for", var, it, body)
+        node = None
+        for v, itx in reversed(loops):
+            node = ("for", v, itx, body if node is None else ("block", [node]))
+        return node
 
     def parse_function(self):
         # function name(args; kw) ... end   |   function (f::T)(args) ... end
@@ -839,7 +850,7 @@ class Parser:
 
     def parse_macro(self, t: Tok):
         name = t.val
-        if name in ("inline", "inbounds", "simd", "fastmath", "views", "noinline", "propagate_inbounds", "eval"):
+        if name in ("inline", "inbounds", "simd", "fastmath", "views", "noinline", "propagate_inbounds", "eval", "everywhere"):
             return self.parse_statement() if not self.nl_skip[-1] else self.parse_expr(0)
         if name in ("__DIR__", "__FILE__"):
             return ("macrocall", name, [])
