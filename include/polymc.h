@@ -251,6 +251,8 @@ int32_t pmc_accumulators_dd(pmc_handle* h, double* hi, double* lo);
  * devices.  Every device is driven from its own internal host thread; there is no data-path collective.  The only
  * exchange is pmc_multi_gather: the final per-chain result rows, one ncclAllGather over NVLink (libnccl.so.2 is
  * opened with dlopen; without it the rows travel by device-to-device copies).
+ * All cases must share n, the energy type and the driver (plain / composite trials / 2-D) — PMC_ERR_INVALID otherwise —
+ * so that the kernel a case runs on does not depend on which other cases share its device.
  * devices = NULL: devices 0..ndevices-1; ndevices <= 0: every device of the box. */
 typedef struct pmc_multi pmc_multi;
 #define PMC_RESULT_COLS 24 /* one gathered row: 16 averages (rolling.csv order), acc_rate, normalizer, phi_step,

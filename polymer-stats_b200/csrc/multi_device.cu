@@ -146,6 +146,17 @@ int32_t pmc_multi_create(const pmc_case* cases, int64_t ncases, int32_t replicas
   const int64_t R = ncases * (int64_t)replicas_per_case;
   if (R > (int64_t)0x7fffffff) return fail(PMC_ERR_INVALID, "too many chains");
   if ((int64_t)ndevices > R) ndevices = (int)R;
+  // pmc_create checks a shard's cases against the shard's own first case only.  The state offsets below assume one n, and
+  // every shard must pick the same kernel family: a handle runs the composite-trial kernels as soon as ONE of its cases has
+  // cluster flips or bending (polymc.cu needs_cluster_path), so a mixed list would make a case's kernel — and the rounding
+  // of its sums — depend on which other cases share its device.
+  auto composite = [](const pmc_case& c) { return c.clustering != 0 || c.kappa != 0.0; };
+  for (int64_t c = 1; c < ncases; ++c)
+    if (cases[c].n != cases[0].n || cases[c].energy_type != cases[0].energy_type || cases[c].planar != cases[0].planar ||
+        composite(cases[c]) != composite(cases[0]))
+      return fail(PMC_ERR_INVALID,
+                  "all cases of one multi-device ensemble must share num-monomers, energy-type and driver "
+                  "(plain / clustering / 2-D); bucket the sweep");
   pmc_multi* m = new (std::nothrow) pmc_multi();
   if (!m) return fail(PMC_ERR_NOMEM, "host allocation failed");
   for (int g = 0; g < ndevices; ++g) {

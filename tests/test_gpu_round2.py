@@ -255,6 +255,17 @@ def test_multi_device_abi_on_one_gpu(pm, kw, steps):
     _check_multi_against_single(pm, [0, 0, 0], 5, kw, steps, 100, expect_backend="peer")
 
 
+def test_multi_device_ensemble_refuses_cases_that_would_pick_different_kernels(pm):
+    """A shard validates its cases against its own first case only, and a handle runs the composite-trial kernels as soon
+    as one of its cases bends: the ensemble-wide check keeps a case's kernel independent of the device split."""
+    base = dict(E0=1.0, Fz=0.5, energy_type="interacting")
+    for a, b in [(dict(base, n=48), dict(base, n=64)),
+                 (dict(base, n=48), dict(base, n=48, energy_type="Ising")),
+                 (dict(base, n=48), dict(base, n=48, kappa=0.5))]:
+        with pytest.raises(pm.PolymcError, match="must share"):
+            pm.MultiEnsemble([pm.make_case(**a), pm.make_case(**b)], replicas=2, seed=1, devices=[0, 0])
+
+
 def test_multi_device_abi_over_all_gpus(pm):
     """≥ 2 GPUs: one process drives every device through pmc_multi_*, the result rows are gathered with ONE
     ncclAllGather over NVLink, and the results equal the single-device run bit for bit."""
