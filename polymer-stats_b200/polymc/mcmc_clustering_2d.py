@@ -14,8 +14,6 @@ import math
 import sys
 import time
 
-import numpy as np
-
 from . import lib
 from .mcmc import Average, _log, pool_replicas
 from .mcmc_clustering import parse_julia_vector
