@@ -137,15 +137,6 @@ int32_t pmc_multi_create(const pmc_case* cases, int64_t ncases, int32_t replicas
   if (!out) return fail(PMC_ERR_INVALID, "null out handle");
   *out = nullptr;
   if (!cases || ncases < 1 || replicas_per_case < 1) return fail(PMC_ERR_INVALID, "need >= 1 case and >= 1 replica");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
-    cudaGetLastError();
-    return fail(PMC_ERR_NO_DEVICE, "no CUDA device available (libpolymc_b200 has no CPU fallback)");
-  }
-  if (ndevices <= 0) ndevices = ndev;  // all devices of the box
-  const int64_t R = ncases * (int64_t)replicas_per_case;
-  if (R > (int64_t)0x7fffffff) return fail(PMC_ERR_INVALID, "too many chains");
-  if ((int64_t)ndevices > R) ndevices = (int)R;
   // pmc_create checks a shard's cases against the shard's own first case only.  The state offsets below assume one n, and
   // every shard must pick the same kernel family: a handle runs the composite-trial kernels as soon as ONE of its cases has
   // cluster flips or bending (polymc.cu needs_cluster_path), so a mixed list would make a case's kernel — and the rounding
@@ -157,6 +148,15 @@ int32_t pmc_multi_create(const pmc_case* cases, int64_t ncases, int32_t replicas
       return fail(PMC_ERR_INVALID,
                   "all cases of one multi-device ensemble must share num-monomers, energy-type and driver "
                   "(plain / clustering / 2-D); bucket the sweep");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return fail(PMC_ERR_NO_DEVICE, "no CUDA device available (libpolymc_b200 has no CPU fallback)");
+  }
+  if (ndevices <= 0) ndevices = ndev;  // all devices of the box
+  const int64_t R = ncases * (int64_t)replicas_per_case;
+  if (R > (int64_t)0x7fffffff) return fail(PMC_ERR_INVALID, "too many chains");
+  if ((int64_t)ndevices > R) ndevices = (int)R;
   pmc_multi* m = new (std::nothrow) pmc_multi();
   if (!m) return fail(PMC_ERR_NOMEM, "host allocation failed");
   for (int g = 0; g < ndevices; ++g) {

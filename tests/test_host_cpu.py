@@ -340,6 +340,19 @@ def test_multi_device_entry_points_fail_loudly_without_a_device(pm):
     assert ei.value.code == -2
 
 
+def test_multi_device_ensemble_validates_the_case_list_before_it_looks_for_a_device(pm):
+    """pmc_multi_create: cases that would make the shards pick different kernels (mixed n, energy type, or plain next to
+    composite trials) are refused with PMC_ERR_INVALID — argument validation needs no GPU (include/polymc.h)."""
+    base = dict(E0=1.0, Fz=0.5, energy_type="interacting")
+    for a, b in [(dict(base, n=48), dict(base, n=64)),
+                 (dict(base, n=48), dict(base, n=48, energy_type="Ising")),
+                 (dict(base, n=48), dict(base, n=48, kappa=0.5)),
+                 (dict(base, n=48), dict(base, n=48, clustering=True))]:
+        with pytest.raises(pm.PolymcError, match="must share") as ei:
+            pm.MultiEnsemble([pm.make_case(**a), pm.make_case(**b)], replicas=2, seed=1, devices=[0, 0])
+        assert ei.value.code == -1
+
+
 # ---- static checks of the Julia ccall hosts (no Julia runtime in the image) ------------------------------------------
 def _c_prototypes():
     hdr = open(os.path.join(ROOT, "include", "polymc.h")).read()
