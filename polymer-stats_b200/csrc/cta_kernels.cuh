@@ -243,9 +243,15 @@ __device__ __forceinline__ double rect_pair(const LaneItem& it, double bx, doubl
   const double q2 = fma(qz, qz, fma(qy, qy, qx * qx));
   const double a3n = a3 - it.c;
   const double bn = bb - e;
+#if PMC_RSQ_PAR
+  double y, y2, yn, yn2;
+  rsqrt_y_y2(r2, y, y2);
+  rsqrt_y_y2(q2, yn, yn2);
+#else
   const double y = rsqrt_fast(r2);
   const double yn = rsqrt_fast(q2);
   const double y2 = y * y, yn2 = yn * yn;
+#endif
   const double t = fma(a3 * bb, y2, mm);
   const double tn = fma(a3n * bn, yn2, mm);
   if constexpr (CUT) {
